@@ -1,0 +1,396 @@
+// bwt.cuh -- stage B: Burrows-Wheeler transform of every block's cyclic rotations (reference: DivSufSortBWT,
+// /root/reference/kernel.cpp:2429-2456 and everything it calls, :61-2427 -- a sequential divsufsort per work-item).
+//
+// B200 formulation: all blocks of a batch are sorted together, segment by segment (a block = a segment of `stride`
+// element slots), by prefix doubling:
+//   round 0   key = first KEY0_BYTES bytes of the rotation; segmented LSD radix sort (8-bit digits)
+//   regroup   equal keys form groups; rank[i] = first sorted position of i's group; singletons are final
+//   round h   only rotations in groups of size > 1 stay "active": key = (group << nbits) | rank[(i+h) mod n],
+//             segmented LSD radix sort of the active list, scatter back into the group's positions, regroup.
+//   stop      when no block has active rotations, or 2h >= n (non-primitive block: ties are final).
+//   finish    L[j] = T[(SA[j]-1) mod n]; origPtr = rank[0] = first position of rotation 0's tie group.
+// The LSD radix pass is hist -> per-block scan -> stable scatter (warp match_any multi-split, shared-memory staged
+// so that the global writes of one digit are contiguous).
+#pragma once
+#include "util.cuh"
+
+namespace bz {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 4096 elements per radix tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_WARP_ELEMS = 32 * RS_ITEMS;
+
+constexpr int RG_THREADS = 256;
+constexpr int RG_ITEMS = 8;
+constexpr int RG_TILE = RG_THREADS * RG_ITEMS; // 2048 elements per regroup tile
+
+// ------------------------------------------------------------------------------------------------ radix: histogram
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t stride,
+                                                            int shift, uint32_t mask, uint32_t *__restrict__ hist, int tiles_per_block)
+{
+    __shared__ uint32_t h[256];
+    const uint32_t b = blockIdx.y, tile = blockIdx.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t base = tile * RS_TILE;
+    if (base >= cnt) return;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const K *kp = keys + (uint64_t)b * stride;
+    const int lane = lane_id();
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+        bool valid = idx < cnt;
+        unsigned vm = __ballot_sync(FULL, valid);
+        if (valid) {
+            uint32_t d = (uint32_t)(kp[idx] >> shift) & mask;
+            unsigned peers = __match_any_sync(vm, d);
+            if (lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+        }
+    }
+    __syncthreads();
+    hist[((uint64_t)b * tiles_per_block + tile) * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------ radix: per-block scan
+// hist[b][tile][d] -> exclusive prefix over tiles (per digit); digit_base[b][d] = exclusive prefix over digits of the totals.
+__global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist, const uint32_t *__restrict__ counts, int tiles_per_block,
+                                                     uint32_t *__restrict__ digit_base)
+{
+    __shared__ uint32_t scratch[33];
+    const uint32_t b = blockIdx.x, d = threadIdx.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t nt = (cnt + RS_TILE - 1) / RS_TILE;
+    uint32_t *hp = hist + (uint64_t)b * tiles_per_block * 256 + d;
+    uint32_t run = 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+        uint32_t v = hp[(uint64_t)t * 256];
+        hp[(uint64_t)t * 256] = run;
+        run += v;
+    }
+    uint32_t ex = block_excl_sum(run, scratch, nullptr);
+    digit_base[b * 256 + d] = ex;
+}
+
+// ------------------------------------------------------------------------------------------------ radix: stable scatter
+template <typename K>
+struct ScatterSmem {
+    uint32_t warp_hist[RS_WARPS][256];
+    uint32_t tile_base[256];
+    uint32_t gofs[256];
+    uint32_t scratch[34];
+    uint32_t vals[RS_TILE];
+    K keys[RS_TILE];
+};
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, K *__restrict__ keys_out,
+                                                               uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ counts, uint64_t stride, int shift,
+                                                               uint32_t mask, const uint32_t *__restrict__ hist, int tiles_per_block,
+                                                               const uint32_t *__restrict__ digit_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem<K> &sm = *reinterpret_cast<ScatterSmem<K> *>(smem_raw);
+    const uint32_t b = blockIdx.y, tile = blockIdx.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t base = tile * RS_TILE;
+    if (base >= cnt) return;
+    const uint32_t tcnt = min((uint32_t)RS_TILE, cnt - base);
+    const int lane = lane_id(), w = warp_id();
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+
+    const K *kp = keys_in + (uint64_t)b * stride + base;
+    const uint32_t *vp = vals_in + (uint64_t)b * stride + base;
+    K key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+    uint16_t rnk[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        bool valid = li < tcnt;
+        key[i] = valid ? kp[li] : (K)0;
+        val[i] = valid ? vp[li] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        bool valid = li < tcnt;
+        uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
+        unsigned peers = __match_any_sync(FULL, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = sm.warp_hist[w][d];
+            sm.warp_hist[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rnk[i] = (uint16_t)(old + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            uint32_t t = sm.warp_hist[ww][d];
+            sm.warp_hist[ww][d] = sum;
+            sum += t;
+        }
+        uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr);
+        sm.tile_base[d] = tb;
+        sm.gofs[d] = digit_base[b * 256 + d] + hist[((uint64_t)b * tiles_per_block + tile) * 256 + d] - tb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        if (li < tcnt) {
+            uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            uint32_t p = sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i];
+            sm.keys[p] = key[i];
+            sm.vals[p] = val[i];
+        }
+    }
+    __syncthreads();
+    K *ko = keys_out + (uint64_t)b * stride;
+    uint32_t *vo = vals_out + (uint64_t)b * stride;
+    for (uint32_t p = threadIdx.x; p < tcnt; p += RS_THREADS) {
+        K k = sm.keys[p];
+        uint32_t d = (uint32_t)(k >> shift) & mask;
+        uint32_t dst = sm.gofs[d] + p;
+        ko[dst] = k;
+        vo[dst] = sm.vals[p];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ round 0 keys
+// key = first `nbytes` (<= 4) bytes of rotation i, big-endian; val = i.
+__global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride, int nbytes,
+                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = n_arr[b];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *T = rle + (uint64_t)b * stride;
+    uint32_t key = 0, p = i;
+    for (int k = 0; k < nbytes; ++k) {
+        key = (key << 8) | T[p];
+        if (++p == n) p = 0;
+    }
+    keys[(uint64_t)b * stride + i] = key;
+    vals[(uint64_t)b * stride + i] = i;
+}
+
+// ------------------------------------------------------------------------------------------------ regroup
+// Sorted (keys, vals) of the active list of each block -> scatter SA, find new groups, update ranks, compact the
+// still-ambiguous rotations into the next round's sort input.
+struct RegroupArgs {
+    const uint32_t *counts;   // [G] active elements sorted this round
+    const uint32_t *n_arr;    // [G] block lengths
+    uint64_t stride;
+    const uint32_t *vals;     // sorted rotation indices
+    const uint32_t *pos_old;  // position in SA of active element a (nullptr: identity, round 0)
+    uint32_t *sa;             // [G*stride]
+    uint32_t *rank;           // [G*stride]
+    int32_t *tile_last;       // [G*tiles] last flagged index per tile (-1: none)
+    uint32_t *tile_keep;      // [G*tiles] kept (still active) elements per tile, later exclusive prefix
+    int32_t *tile_carry;      // [G*tiles] last flagged index before the tile
+    int tiles_per_block;      // regroup tiles per block
+    uint32_t *counts_new;     // [G]
+    uint32_t *pos_new;        // compacted positions
+    uint32_t *vals_new;       // compacted rotation indices
+    uint64_t *keys_new;       // (group position << nbits), rank of the second half OR-ed in by k_bwt_gather
+    int nbits;
+    uint32_t sorted_len;      // rotations are now ordered by their first sorted_len bytes
+    unsigned long long *total_active; // sum of counts_new over blocks
+};
+
+template <typename K>
+__device__ __forceinline__ void load_flags(const K *kp, uint32_t a0, uint32_t cnt, bool (&flag)[RG_ITEMS], bool (&nxt)[RG_ITEMS])
+{
+    // flag[i]: element a0+i starts a group; nxt[i]: element a0+i ends a group
+    K prev = a0 > 0 && a0 - 1 < cnt ? kp[a0 - 1] : (K)0;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i) {
+        uint32_t a = a0 + i;
+        K cur = a < cnt ? kp[a] : (K)0;
+        flag[i] = (a == 0) || (cur != prev);
+        prev = cur;
+    }
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS - 1; ++i) nxt[i] = (a0 + i + 1 >= cnt) || flag[i + 1];
+    {
+        uint32_t a = a0 + RG_ITEMS;
+        nxt[RG_ITEMS - 1] = (a >= cnt) || (kp[a] != prev);
+    }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const K *__restrict__ keys, RegroupArgs A)
+{
+    __shared__ int s_last[RG_THREADS / 32];
+    __shared__ uint32_t s_keep[RG_THREADS / 32];
+    const uint32_t b = blockIdx.y, tile = blockIdx.x;
+    const uint32_t cnt = A.counts[b];
+    const uint32_t base = tile * RG_TILE;
+    if (base >= cnt) return;
+    const K *kp = keys + (uint64_t)b * A.stride;
+    const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
+    bool flag[RG_ITEMS], nxt[RG_ITEMS];
+    int last = -1;
+    uint32_t keep = 0;
+    if (a0 < cnt) {
+        load_flags(kp, a0, cnt, flag, nxt);
+        const uint32_t *vp = A.vals + (uint64_t)b * A.stride;
+        const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
+        uint32_t *sa = A.sa + (uint64_t)b * A.stride;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            uint32_t a = a0 + i;
+            if (a < cnt) {
+                if (flag[i]) last = (int)a;
+                if (!(flag[i] && nxt[i])) ++keep;
+                sa[pp ? pp[a] : a] = vp[a];
+            }
+        }
+    }
+    last = __reduce_max_sync(FULL, last);
+    keep = __reduce_add_sync(FULL, keep);
+    if (lane_id() == 0) { s_last[warp_id()] = last; s_keep[warp_id()] = keep; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int l = -1; uint32_t k = 0;
+        for (int w = 0; w < RG_THREADS / 32; ++w) { l = max(l, s_last[w]); k += s_keep[w]; }
+        A.tile_last[(uint64_t)b * A.tiles_per_block + tile] = l;
+        A.tile_keep[(uint64_t)b * A.tiles_per_block + tile] = k;
+    }
+}
+
+// one warp per block
+__global__ void __launch_bounds__(256) k_bwt_tilescan(RegroupArgs A, uint32_t n_blocks)
+{
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (b >= n_blocks) return;
+    const int lane = lane_id();
+    const uint32_t cnt = A.counts[b];
+    const uint32_t nt = (cnt + RG_TILE - 1) / RG_TILE;
+    int carry_last = -1;
+    uint32_t carry_keep = 0;
+    for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+        uint32_t t = t0 + lane;
+        uint64_t idx = (uint64_t)b * A.tiles_per_block + t;
+        int l = t < nt ? A.tile_last[idx] : -1;
+        uint32_t k = t < nt ? A.tile_keep[idx] : 0;
+        int li = warp_incl_max(l);
+        uint32_t ki = warp_incl_sum(k);
+        int lprev = __shfl_up_sync(FULL, li, 1);
+        if (lane == 0) lprev = -1;
+        if (t < nt) {
+            A.tile_carry[idx] = max(carry_last, lprev);
+            A.tile_keep[idx] = carry_keep + ki - k;
+        }
+        carry_last = max(carry_last, __shfl_sync(FULL, li, 31));
+        carry_keep += __shfl_sync(FULL, ki, 31);
+    }
+    if (lane == 0) {
+        uint32_t nc = (A.sorted_len >= A.n_arr[b]) ? 0u : carry_keep;
+        A.counts_new[b] = nc;
+        if (nc) atomicAdd(A.total_active, (unsigned long long)nc);
+    }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const K *__restrict__ keys, RegroupArgs A)
+{
+    __shared__ int s_i[34];
+    __shared__ uint32_t s_u[34];
+    const uint32_t b = blockIdx.y, tile = blockIdx.x;
+    const uint32_t cnt = A.counts[b];
+    const uint32_t base = tile * RG_TILE;
+    if (base >= cnt) return;
+    const K *kp = keys + (uint64_t)b * A.stride;
+    const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
+    bool flag[RG_ITEMS], nxt[RG_ITEMS];
+    int last = -1;
+    uint32_t keep = 0;
+    if (a0 < cnt) {
+        load_flags(kp, a0, cnt, flag, nxt);
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            uint32_t a = a0 + i;
+            if (a < cnt) {
+                if (flag[i]) last = (int)a;
+                if (!(flag[i] && nxt[i])) ++keep;
+            }
+        }
+    }
+    const uint64_t tidx = (uint64_t)b * A.tiles_per_block + tile;
+    int prev_last = block_excl_max(last, s_i, nullptr);
+    prev_last = max(prev_last, A.tile_carry[tidx]);
+    uint32_t keep_off = A.tile_keep[tidx] + block_excl_sum(keep, s_u, nullptr);
+    if (a0 >= cnt) return;
+    const uint32_t *vp = A.vals + (uint64_t)b * A.stride;
+    const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
+    uint32_t *rank = A.rank + (uint64_t)b * A.stride;
+    uint32_t *pn = A.pos_new + (uint64_t)b * A.stride;
+    uint32_t *vn = A.vals_new + (uint64_t)b * A.stride;
+    uint64_t *kn = A.keys_new + (uint64_t)b * A.stride;
+    int g = prev_last;
+    uint32_t gpos = 0;
+    bool gpos_valid = false;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i) {
+        uint32_t a = a0 + i;
+        if (a < cnt) {
+            uint32_t mypos = pp ? pp[a] : a;
+            if (flag[i]) { g = (int)a; gpos = mypos; gpos_valid = true; }
+            else if (!gpos_valid) { gpos = pp ? pp[g] : (uint32_t)g; gpos_valid = true; }
+            uint32_t v = vp[a];
+            rank[v] = gpos;
+            if (!(flag[i] && nxt[i])) {
+                pn[keep_off] = mypos;
+                vn[keep_off] = v;
+                kn[keep_off] = (uint64_t)gpos << A.nbits;
+                ++keep_off;
+            }
+        }
+    }
+}
+
+// key |= rank[(i + h) mod n]
+__global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ counts,
+                                                     const uint32_t *__restrict__ n_arr, uint64_t stride, const uint32_t *__restrict__ rank, uint32_t h)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t cnt = counts[b];
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cnt) return;
+    const uint32_t n = n_arr[b];
+    uint64_t o = (uint64_t)b * stride;
+    uint32_t p = vals[o + a] + h; // h < n for every block that is still active
+    if (p >= n) p -= n;
+    keys[o + a] |= rank[o + p];
+}
+
+// L[j] = T[(SA[j] - 1) mod n]; origPtr = rank[0]
+__global__ void __launch_bounds__(256) k_bwt_finish(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rank,
+                                                     const uint32_t *__restrict__ n_arr, uint64_t stride, uint8_t *__restrict__ L, uint32_t *__restrict__ orig)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = n_arr[b];
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t o = (uint64_t)b * stride;
+    if (j == 0 && n > 0) orig[b] = rank[o];
+    if (j >= n) return;
+    uint32_t i = sa[o + j];
+    L[o + j] = rle[o + (i ? i - 1 : n - 1)];
+}
+
+} // namespace bz

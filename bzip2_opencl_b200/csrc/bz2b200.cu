@@ -1,0 +1,743 @@
+// bz2b200.cu -- host orchestration + C ABI (include/bz2b200.h) of the B200-native bzip2 block compressor.
+// Replaces OutputStream::closeBlocks()'s device boundary (OutputStream.hpp:190-240) and include/opencl.hpp.
+// No CPU fallback: every stage is a CUDA kernel from rle.cuh / bwt.cuh / mtf.cuh / huff.cuh / emit.cuh.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/bz2b200.h"
+#include "rle.cuh"
+#include "bwt.cuh"
+#include "mtf.cuh"
+#include "huff.cuh"
+#include "emit.cuh"
+
+using namespace bz;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct CudaErr {
+    cudaError_t e;
+    const char *what;
+};
+
+} // namespace
+
+struct bz2b200 {
+    int device = 0;
+    int base = 0, mult = 0, bs = 0;
+    uint32_t G = 0;       // blocks per batch
+    uint64_t S = 0;       // element stride per block
+    int nbits = 0;        // bits needed for a position inside a block
+    int key0_bytes = 4;
+    cudaStream_t stream = 0;
+    std::string err;
+    std::vector<DevBuf *> all;
+
+    // per-call (grow only)
+    DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
+    // per-batch, fixed size
+    DevBuf rle, L, ranks, kA, kB, vA, vB, sa, rank, pA, pB, mtf, hist, digit_base, tile_last, tile_keep, tile_carry, cnt0, cnt1, scalars,
+        lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
+        databits, nbits_b, bitoff, datastart, tilebits;
+    int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
+    uint64_t sel_stride = 0;
+    uint64_t *h_pinned = nullptr; // small pinned scratch (16 u64)
+
+    // last call
+    bz2b200_stats_t stats{};
+    uint64_t last_b0 = 0, last_nb = 0, last_total_blocks = 0;
+    std::vector<uint64_t> h_starts;
+    cudaEvent_t ev[16] = {};
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return (e_ == cudaErrorMemoryAllocation) ? BZ2B200_E_NOMEM : BZ2B200_E_CUDA;           \
+        }                                                                                          \
+    } while (0)
+
+static int ensure(bz2b200 *h, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return BZ2B200_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes + 256);
+        want = bytes + 256;
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        b.p = nullptr;
+        return BZ2B200_E_NOMEM;
+    }
+    b.cap = want;
+    if (std::find(h->all.begin(), h->all.end(), &b) == h->all.end()) h->all.push_back(&b);
+    return BZ2B200_OK;
+}
+#define ENSURE(buf, bytes)                                   \
+    do {                                                     \
+        int rc_ = ensure(h, (buf), (size_t)(bytes));         \
+        if (rc_ != BZ2B200_OK) return rc_;                   \
+    } while (0)
+
+template <typename T>
+static T *ptr(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+static int ilog2_ceil(uint64_t v)
+{
+    int b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+
+static bool g_const_ready[64] = {};
+
+static int upload_constants(bz2b200 *h)
+{
+    if (h->device < 64 && g_const_ready[h->device]) return BZ2B200_OK;
+    uint32_t table[256], pow8[48], lane_shift[256];
+    crc_build_table(table);
+    crc_build_pow8(pow8, 48);
+    for (int t = 0; t < 256; ++t) lane_shift[t] = crc_xpow8_host(64ull * (255 - t), pow8);
+    CK(cudaMemcpyToSymbol(c_crc_table, table, sizeof(table)));
+    CK(cudaMemcpyToSymbol(c_crc_pow8, pow8, sizeof(pow8)));
+    CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
+    CK(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint64_t>)));
+    CK(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint32_t>)));
+    if (h->device < 64) g_const_ready[h->device] = true;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *bz2b200_strerror(int code)
+{
+    switch (code) {
+    case BZ2B200_OK: return "ok";
+    case BZ2B200_E_BLOCKSIZE: return "Invalid block size";
+    case BZ2B200_E_PARALLEL: return "Invalid parallel block count";
+    case BZ2B200_E_ARG: return "invalid argument";
+    case BZ2B200_E_CUDA: return "CUDA error";
+    case BZ2B200_E_NOMEM: return "out of device memory";
+    case BZ2B200_E_OUTPUT: return "output buffer too small";
+    case BZ2B200_E_STATE: return "requested block is not resident";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *bz2b200_last_error(const bz2b200_t *h) { return h ? h->err.c_str() : ""; }
+
+extern "C" void bz2b200_destroy(bz2b200_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (DevBuf *b : h->all)
+        if (b->p) cudaFree(b->p);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    delete h;
+}
+
+static int create_impl(bz2b200 *h)
+{
+    CK(cudaSetDevice(h->device));
+    int rc = upload_constants(h);
+    if (rc) return rc;
+    const uint64_t G = h->G, S = h->S;
+    h->tilesR = (int)((S + RS_TILE - 1) / RS_TILE);
+    h->tilesG = (int)((S + RG_TILE - 1) / RG_TILE);
+    h->tilesM = (int)((S + MTF_TILE - 1) / MTF_TILE);
+    h->tilesR2 = (int)((S + R2_TILE - 1) / R2_TILE);
+    h->tilesD = (int)((S + HP_SYMS - 1) / HP_SYMS);
+    h->sel_stride = ((uint64_t)h->tilesD * HP_THREADS + 63) / 64 * 64;
+    ENSURE(h->rle, G * S + 64);
+    ENSURE(h->L, G * S + 64);
+    ENSURE(h->ranks, G * S + 64);
+    ENSURE(h->kA, G * S * 8);
+    ENSURE(h->kB, G * S * 8);
+    ENSURE(h->vA, G * S * 4);
+    ENSURE(h->vB, G * S * 4);
+    ENSURE(h->sa, G * S * 4);
+    ENSURE(h->rank, G * S * 4);
+    ENSURE(h->pA, G * S * 4);
+    ENSURE(h->pB, G * S * 4);
+    ENSURE(h->mtf, G * S * 2);
+    ENSURE(h->hist, G * h->tilesR * 256 * 4);
+    ENSURE(h->digit_base, G * 256 * 4);
+    ENSURE(h->tile_last, G * h->tilesG * 4);
+    ENSURE(h->tile_keep, G * h->tilesG * 4);
+    ENSURE(h->tile_carry, G * h->tilesG * 4);
+    ENSURE(h->cnt0, G * 4);
+    ENSURE(h->cnt1, G * 4);
+    ENSURE(h->scalars, 64 * 8);
+    ENSURE(h->lists, G * h->tilesM * 256);
+    ENSURE(h->dcount, G * h->tilesM * 4);
+    ENSURE(h->r2tiles, G * h->tilesR2 * sizeof(R2Tile));
+    ENSURE(h->zin, G * h->tilesR2 * 4);
+    ENSURE(h->obase, G * h->tilesR2 * 4);
+    ENSURE(h->present, G * 8 * 4);
+    ENSURE(h->crc, G * 4);
+    ENSURE(h->orig, G * 4);
+    ENSURE(h->freq, G * 258 * 4);
+    ENSURE(h->m_arr, G * 4);
+    ENSURE(h->alpha_arr, G * 4);
+    ENSURE(h->hb, G * sizeof(HuffBlock));
+    ENSURE(h->lens, G * HUFF_MAXTABLES * HUFF_LEN_STRIDE);
+    ENSURE(h->tf, G * HUFF_MAXTABLES * HUFF_MAXALPHA * 4);
+    ENSURE(h->codes, G * HUFF_MAXTABLES * HUFF_MAXALPHA * 4);
+    ENSURE(h->sel, G * h->sel_stride);
+    ENSURE(h->selpos, G * h->sel_stride);
+    ENSURE(h->selbits, G * 4);
+    ENSURE(h->tabbits, G * 4);
+    ENSURE(h->databits, G * 4);
+    ENSURE(h->nbits_b, G * 8);
+    ENSURE(h->bitoff, G * 8);
+    ENSURE(h->datastart, G * 8);
+    ENSURE(h->tilebits, G * h->tilesD * 4);
+    CK(cudaMallocHost(&h->h_pinned, 64 * sizeof(uint64_t)));
+    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_size, int multiplier, int max_blocks_in_flight)
+{
+    if (!out) return BZ2B200_E_ARG;
+    *out = nullptr;
+    if (multiplier < 1 || multiplier > 9 || base_block_size < 1000 || base_block_size > 100000) return BZ2B200_E_BLOCKSIZE;
+    if (max_blocks_in_flight < 1) return BZ2B200_E_PARALLEL;
+    int ndev = bz2b200_device_count();
+    if (ndev <= 0 || device_id < 0 || device_id >= ndev) return BZ2B200_E_CUDA;
+    bz2b200 *h = new bz2b200();
+    h->device = device_id;
+    h->base = base_block_size;
+    h->mult = multiplier;
+    h->bs = base_block_size * multiplier;
+    h->G = (uint32_t)max_blocks_in_flight;
+    h->S = ((uint64_t)h->bs + 2 + 63) / 64 * 64;
+    h->nbits = ilog2_ceil((uint64_t)h->bs + 1);
+    if (const char *e = getenv("BZ2B200_KEY0_BYTES")) {
+        int k = atoi(e);
+        if (k >= 1 && k <= 4) h->key0_bytes = k;
+    }
+    int rc = create_impl(h);
+    if (rc != BZ2B200_OK) {
+        // keep the message reachable through a static for the failing create
+        static thread_local std::string last;
+        last = h->err;
+        fprintf(stderr, "bz2b200_create: %s\n", last.c_str());
+        bz2b200_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return BZ2B200_OK;
+}
+
+extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
+{
+    if (!h) return 0;
+    // RLE1 expands by at most 5/4, Huffman codes are at most 20 bits per symbol but a block never codes worse than
+    // ~8.6 bits per RLE1 byte with 258 symbols; keep a generous bound: 1.3 n + per-block tables/selectors.
+    size_t blocks = n / (size_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
+    return n + n / 3 + blocks * (size_t)(2048 + h->bs / 50) + 4096;
+}
+
+template <typename K>
+static void radix_pass(bz2b200 *h, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *counts, int shift, int bits, uint32_t nb,
+                       uint32_t max_count)
+{
+    uint32_t tiles = (max_count + RS_TILE - 1) / RS_TILE;
+    if (tiles == 0) return;
+    dim3 grid(tiles, nb);
+    uint32_t mask = (1u << bits) - 1u;
+    k_radix_hist<K><<<grid, RS_THREADS, 0, h->stream>>>(kin, counts, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR);
+    k_radix_scan<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->hist), counts, h->tilesR, ptr<uint32_t>(h->digit_base));
+    k_radix_scatter<K><<<grid, RS_THREADS, sizeof(ScatterSmem<K>), h->stream>>>(kin, vin, kout, vout, counts, h->S, shift, mask, ptr<uint32_t>(h->hist),
+                                                                                   h->tilesR, ptr<uint32_t>(h->digit_base));
+    h->stats.kernel_launches += 3;
+}
+
+// sorts `total_bits` low bits of the keys; returns 0 if the result is in (k0,v0), 1 if in (k1,v1)
+template <typename K>
+static int radix_sort(bz2b200 *h, K *k0, uint32_t *v0, K *k1, uint32_t *v1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count)
+{
+    int npass = (total_bits + 7) / 8;
+    int basebits = total_bits / npass, extra = total_bits % npass;
+    int shift = 0, cur = 0;
+    for (int p = 0; p < npass; ++p) {
+        int bits = basebits + (p < extra ? 1 : 0);
+        if (cur == 0) radix_pass<K>(h, k0, v0, k1, v1, counts, shift, bits, nb, max_count);
+        else radix_pass<K>(h, k1, v1, k0, v0, counts, shift, bits, nb, max_count);
+        cur ^= 1;
+        shift += bits;
+    }
+    return cur;
+}
+
+struct Scalars { // layout of h->scalars (u64 each)
+    enum { TOTAL_ACTIVE = 0, BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 2 entries */ };
+};
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+static int is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Stage A over the whole input: tree of summaries + sequential walk. Leaves starts / rle_len on the device and the
+// starts on the host (h->h_starts, n_blocks + 1 entries).
+static int scan_input(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final, uint64_t *n_blocks, uint64_t *consumed)
+{
+    *n_blocks = 0;
+    *consumed = 0;
+    h->h_starts.assign(1, 0);
+    if (n == 0) return BZ2B200_OK;
+    const uint64_t limit = (uint64_t)h->bs - 6;
+    uint64_t cnt[RLE_MAX_LEVELS];
+    int nl = 0;
+    cnt[0] = (n + RLE_TILE - 1) / RLE_TILE;
+    nl = 1;
+    while (cnt[nl - 1] > 1 && nl < RLE_MAX_LEVELS) { cnt[nl] = (cnt[nl - 1] + RLE_FANOUT - 1) / RLE_FANOUT; ++nl; }
+    for (int l = 0; l < nl; ++l) ENSURE(h->seg[l], cnt[l] * sizeof(Seg));
+    const uint64_t cap = n / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
+    ENSURE(h->starts, (cap + 2) * 8);
+    ENSURE(h->rle_len, (cap + 2) * 4);
+    k_rle_tile_seg<<<(unsigned)((cnt[0] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(d_in, n, ptr<Seg>(h->seg[0]), cnt[0]);
+    for (int l = 1; l < nl; ++l)
+        k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
+                                                                                                           cnt[l]);
+    WalkLevels lv;
+    for (int l = 0; l < RLE_MAX_LEVELS; ++l) lv.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr;
+    lv.n_levels = nl;
+    uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
+    k_rle_walk<<<1, 32, 0, h->stream>>>(d_in, n, limit, is_final, lv, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), cap, d_info);
+    h->stats.kernel_launches += nl + 1;
+    CK(cudaMemcpyAsync(h->h_pinned, d_info, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    uint64_t nb = h->h_pinned[0];
+    if (nb > cap) { h->err = "internal: block count bound exceeded"; return BZ2B200_E_CUDA; }
+    *n_blocks = nb;
+    *consumed = h->h_pinned[1];
+    h->h_starts.resize(nb + 1);
+    CK(cudaMemcpy(h->h_starts.data(), h->starts.p, (nb + 1) * 8, cudaMemcpyDeviceToHost));
+    return BZ2B200_OK;
+}
+
+// resolves `input` to a 16-byte aligned device pointer (copying when it is host memory or misaligned)
+static int stage_input(bz2b200 *h, const uint8_t *input, size_t n, const uint8_t **d_in)
+{
+    if (n == 0) { *d_in = nullptr; return BZ2B200_OK; }
+    const bool dev = is_device_ptr(input);
+    if (dev && (reinterpret_cast<uintptr_t>(input) & 15u) == 0) { *d_in = input; return BZ2B200_OK; }
+    ENSURE(h->in, n + 64);
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaMemcpyAsync(h->in.p, input, n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.ms_h2d = ev_ms(h->ev[0], h->ev[1]);
+    *d_in = ptr<uint8_t>(h->in);
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint64_t *block_starts, size_t capacity, uint64_t *n_blocks)
+{
+    if (!h || (!input && n_bytes) || !n_blocks) return BZ2B200_E_ARG;
+    CK(cudaSetDevice(h->device));
+    h->stats = bz2b200_stats_t{};
+    const uint8_t *d_in = nullptr;
+    int rc = stage_input(h, input, n_bytes, &d_in);
+    if (rc) return rc;
+    uint64_t nb = 0, consumed = 0;
+    rc = scan_input(h, d_in, n_bytes, 1, &nb, &consumed);
+    if (rc) return rc;
+    *n_blocks = nb;
+    for (uint64_t i = 0; i < nb && i < capacity; ++i) block_starts[i] = h->h_starts[i];
+    return nb > capacity ? BZ2B200_E_OUTPUT : BZ2B200_OK;
+}
+
+static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words)
+{
+    cudaStream_t st = h->stream;
+    const uint64_t S = h->S;
+    uint64_t max_len = 0;
+    for (uint32_t i = 0; i < nb; ++i) max_len = std::max(max_len, h->h_starts[b0 + i + 1] - h->h_starts[b0 + i]);
+    const uint64_t max_tiles = (max_len + RLE_TILE - 1) / RLE_TILE;
+    ENSURE(h->segB, (uint64_t)nb * max_tiles * sizeof(Seg));
+    ENSURE(h->tstate, (uint64_t)nb * max_tiles * 8);
+    uint64_t *d_scal = ptr<uint64_t>(h->scalars);
+    const uint64_t *d_starts = ptr<uint64_t>(h->starts);
+    const uint32_t *d_n = ptr<uint32_t>(h->rle_len) + b0;
+    auto &stt = h->stats;
+
+    CK(cudaMemsetAsync(h->present.p, 0, (size_t)nb * 32, st));
+    CK(cudaMemsetAsync(h->crc.p, 0, (size_t)nb * 4, st));
+    CK(cudaMemsetAsync(h->freq.p, 0, (size_t)nb * 258 * 4, st));
+    CK(cudaMemsetAsync(h->tf.p, 0, (size_t)nb * HUFF_MAXTABLES * HUFF_MAXALPHA * 4, st));
+    CK(cudaMemsetAsync(h->tabbits.p, 0, (size_t)nb * 4, st));
+    CK(cudaMemsetAsync(h->databits.p, 0, (size_t)nb * 4, st));
+
+    // ---- stage A: RLE1 + presence + CRC
+    CK(cudaEventRecord(h->ev[2], st));
+    {
+        dim3 grid((unsigned)((max_tiles + RLE_WARPS - 1) / RLE_WARPS), nb);
+        k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles);
+        k_rle_btile_scan<<<(nb + RLE_WARPS - 1) / RLE_WARPS, RLE_WARPS * 32, 0, st>>>(ptr<Seg>(h->segB), d_starts, (uint32_t)b0, nb, ptr<uint64_t>(h->tstate),
+                                                                                       max_tiles);
+        k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S,
+                                                     ptr<uint32_t>(h->present));
+        dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), nb);
+        k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint32_t>(h->crc));
+        k_crc_finish<<<(nb + 127) / 128, 128, 0, st>>>(d_starts, (uint32_t)b0, nb, ptr<uint32_t>(h->crc));
+        stt.kernel_launches += 5;
+    }
+    CK(cudaEventRecord(h->ev[3], st));
+
+    // ---- stage B: BWT
+    uint32_t max_n = 0;
+    {
+        // rle_len is on the device; the host knows only an upper bound per block: min(bs, 5/4 * input + 5)
+        for (uint32_t i = 0; i < nb; ++i) {
+            uint64_t len = h->h_starts[b0 + i + 1] - h->h_starts[b0 + i];
+            uint64_t ub = std::min<uint64_t>((uint64_t)h->bs, len + len / 4 + 5);
+            max_n = std::max<uint32_t>(max_n, (uint32_t)ub);
+        }
+    }
+    uint32_t *cntA = ptr<uint32_t>(h->cnt0), *cntB = ptr<uint32_t>(h->cnt1);
+    {
+        dim3 g((max_n + 255) / 256, nb);
+        k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA));
+        stt.kernel_launches += 1;
+    }
+    int res = radix_sort<uint32_t>(h, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA), ptr<uint32_t>(h->kB), ptr<uint32_t>(h->vB), d_n, 8 * h->key0_bytes, nb,
+                                   max_n);
+    CK(cudaEventRecord(h->ev[4], st));
+
+    RegroupArgs A;
+    A.stride = S;
+    A.n_arr = d_n;
+    A.sa = ptr<uint32_t>(h->sa);
+    A.rank = ptr<uint32_t>(h->rank);
+    A.tile_last = ptr<int32_t>(h->tile_last);
+    A.tile_keep = ptr<uint32_t>(h->tile_keep);
+    A.tile_carry = ptr<int32_t>(h->tile_carry);
+    A.tiles_per_block = h->tilesG;
+    A.nbits = h->nbits;
+    A.total_active = reinterpret_cast<unsigned long long *>(d_scal + Scalars::TOTAL_ACTIVE);
+
+    uint32_t sorted_len = (uint32_t)h->key0_bytes;
+    uint32_t max_count = max_n;
+    const uint32_t *counts = d_n;
+    uint32_t *counts_next = cntA;
+    uint32_t *pos_old = nullptr, *pos_new = ptr<uint32_t>(h->pA);
+    uint64_t rounds = 0;
+    bool first = true;
+    for (;;) {
+        // sorted keys/vals are in buffer `res`; the next round's input goes to the other buffer
+        void *ks = res ? h->kB.p : h->kA.p;
+        uint32_t *vs = res ? ptr<uint32_t>(h->vB) : ptr<uint32_t>(h->vA);
+        uint64_t *kn = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
+        uint32_t *vn = res ? ptr<uint32_t>(h->vA) : ptr<uint32_t>(h->vB);
+        A.counts = counts;
+        A.vals = vs;
+        A.pos_old = pos_old;
+        A.counts_new = counts_next;
+        A.pos_new = pos_new;
+        A.vals_new = vn;
+        A.keys_new = kn;
+        A.sorted_len = sorted_len;
+        CK(cudaMemsetAsync(d_scal + Scalars::TOTAL_ACTIVE, 0, 8, st));
+        dim3 g((max_count + RG_TILE - 1) / RG_TILE, nb);
+        if (first) k_bwt_flags<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A);
+        else k_bwt_flags<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A);
+        k_bwt_tilescan<<<(nb + 7) / 8, 256, 0, st>>>(A, nb);
+        if (first) k_bwt_regroup<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A);
+        else k_bwt_regroup<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A);
+        stt.kernel_launches += 3;
+        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::TOTAL_ACTIVE, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t active = h->h_pinned[0];
+        if (active == 0) break;
+        stt.bwt_active_volume += active;
+        ++rounds;
+        first = false;
+        // next round: sort the active lists by (group, rank of the rotation sorted_len further on)
+        counts = counts_next;
+        counts_next = (counts_next == cntA) ? cntB : cntA;
+        pos_old = pos_new;
+        pos_new = (pos_new == ptr<uint32_t>(h->pA)) ? ptr<uint32_t>(h->pB) : ptr<uint32_t>(h->pA);
+        max_count = (uint32_t)std::min<uint64_t>(max_n, active);
+        dim3 gg((max_count + 255) / 256, nb);
+        k_bwt_gather<<<gg, 256, 0, st>>>(kn, vn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len);
+        stt.kernel_launches += 1;
+        int r2 = radix_sort<uint64_t>(h, kn, vn, reinterpret_cast<uint64_t *>(ks), vs, counts, 2 * h->nbits, nb, max_count);
+        // r2 == 0: result in (kn, vn) which is buffer !res ; r2 == 1: result in (ks, vs) = buffer res
+        res = r2 == 0 ? !res : res;
+        sorted_len *= 2;
+    }
+    stt.bwt_rounds = std::max<uint64_t>(stt.bwt_rounds, rounds);
+    CK(cudaEventRecord(h->ev[5], st));
+    {
+        dim3 g((max_n + 255) / 256, nb);
+        k_bwt_finish<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), ptr<uint32_t>(h->sa), ptr<uint32_t>(h->rank), d_n, S, ptr<uint8_t>(h->L), ptr<uint32_t>(h->orig));
+        stt.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(h->ev[6], st));
+
+    // ---- stage C: MTF + RLE2
+    {
+        dim3 gm((max_n + MTF_WARPS * MTF_TILE - 1) / (MTF_WARPS * MTF_TILE), nb);
+        k_mtf_sim<false><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+                                                         h->tilesM, nullptr);
+        k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb);
+        k_mtf_sim<true><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+                                                        h->tilesM, ptr<uint8_t>(h->ranks));
+        dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
+        k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2);
+        k_rle2_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<R2Tile>(h->r2tiles), d_n, h->tilesR2, nb, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase),
+                                                       ptr<uint32_t>(h->present), ptr<uint16_t>(h->mtf), S, ptr<uint32_t>(h->freq), ptr<uint32_t>(h->m_arr),
+                                                       ptr<uint32_t>(h->alpha_arr));
+        k_rle2_emit<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase), h->tilesR2, ptr<uint16_t>(h->mtf), S,
+                                                ptr<uint32_t>(h->freq));
+        stt.kernel_launches += 6;
+    }
+    CK(cudaEventRecord(h->ev[7], st));
+
+    // ---- stage D: Huffman tables
+    const uint32_t max_m = max_n + 1;
+    dim3 gh((max_m + HP_SYMS - 1) / HP_SYMS, nb);
+    {
+        k_huff_seeds<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->m_arr), ptr<uint32_t>(h->alpha_arr), ptr<uint32_t>(h->freq), nb, ptr<HuffBlock>(h->hb),
+                                                        ptr<uint8_t>(h->lens));
+        for (int it = 0; it < 4; ++it) {
+            k_huff_pass<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->sel),
+                                                    h->sel_stride);
+            k_huff_lengths<<<dim3(HUFF_MAXTABLES, nb), 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->databits),
+                                                                     it == 3);
+        }
+        k_huff_codes<<<(nb * HUFF_MAXTABLES + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->codes), ptr<uint32_t>(h->tabbits),
+                                                                      nb);
+        k_huff_selmtf<<<(nb + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbits),
+                                                      nb);
+        stt.kernel_launches += 11;
+    }
+    CK(cudaEventRecord(h->ev[8], st));
+
+    // ---- stage E: bit emission at the final stream offsets
+    {
+        k_block_bits<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->selbits), ptr<uint32_t>(h->tabbits),
+                                                        ptr<uint32_t>(h->databits), nb, ptr<uint64_t>(h->nbits_b));
+        k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, d_scal + Scalars::BITPOS, ptr<uint64_t>(h->bitoff));
+        k_emit_header<<<(nb + 31) / 32, 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
+                                                      ptr<uint8_t>(h->selpos), h->sel_stride, ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
+                                                      ptr<uint64_t>(h->datastart));
+        k_data_tilebits<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint8_t>(h->sel), h->sel_stride,
+                                                    ptr<uint32_t>(h->tilebits), h->tilesD);
+        k_data_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tilebits), h->tilesD, nb);
+        k_emit_data<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->codes), ptr<uint8_t>(h->sel), h->sel_stride,
+                                                ptr<uint32_t>(h->tilebits), h->tilesD, ptr<uint64_t>(h->datastart), d_out_words);
+        stt.kernel_launches += 6;
+        CK(cudaMemcpyAsync(ptr<uint32_t>(h->all_crc) + b0, h->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ptr<uint64_t>(h->all_nbits) + b0, h->nbits_b.p, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaEventRecord(h->ev[9], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    stt.ms_rle += ev_ms(h->ev[2], h->ev[3]);
+    stt.ms_bwt_sort0 += ev_ms(h->ev[3], h->ev[4]);
+    stt.ms_bwt_rounds += ev_ms(h->ev[4], h->ev[5]);
+    stt.ms_bwt_finish += ev_ms(h->ev[5], h->ev[6]);
+    stt.ms_mtf += ev_ms(h->ev[6], h->ev[7]);
+    stt.ms_huffman += ev_ms(h->ev[7], h->ev[8]);
+    stt.ms_emit += ev_ms(h->ev[8], h->ev[9]);
+    h->last_b0 = b0;
+    h->last_nb = nb;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
+                                       size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                       size_t block_capacity, uint64_t *n_blocks)
+{
+    if (!h) return BZ2B200_E_ARG;
+    if ((!input && n_bytes) || !out_nbits || !consumed || !n_blocks || start_bit > 7 || (!out && out_capacity)) {
+        h->err = "bad argument";
+        return BZ2B200_E_ARG;
+    }
+    CK(cudaSetDevice(h->device));
+    h->err.clear();
+    h->stats = bz2b200_stats_t{};
+    h->last_nb = 0;
+    *out_nbits = 0; *consumed = 0; *n_blocks = 0;
+    cudaStream_t st = h->stream;
+    const uint8_t *d_in = nullptr;
+    int rc = stage_input(h, input, n_bytes, &d_in);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[10], st));
+    uint64_t nb = 0, used = 0;
+    rc = scan_input(h, d_in, n_bytes, is_final, &nb, &used);
+    if (rc) return rc;
+    h->last_total_blocks = nb;
+    *n_blocks = nb;
+    *consumed = (size_t)used;
+    h->stats.n_input = used;
+    h->stats.n_blocks = nb;
+    if ((block_crcs || block_nbits) && nb > block_capacity) return BZ2B200_E_OUTPUT;
+    const size_t need = bz2b200_max_output_bytes(h, (size_t)used) + 8;
+    const size_t dcap = (need + 3) / 4 * 4;
+    ENSURE(h->out, dcap + 16);
+    ENSURE(h->all_crc, (nb + 1) * 4);
+    ENSURE(h->all_nbits, (nb + 1) * 8);
+    uint64_t *d_scal = ptr<uint64_t>(h->scalars);
+    h->h_pinned[8] = start_bit;
+    CK(cudaMemcpyAsync(d_scal + Scalars::BITPOS, h->h_pinned + 8, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->out.p, 0, dcap, st));
+    for (uint64_t b0 = 0; b0 < nb; b0 += h->G) {
+        uint32_t cnt = (uint32_t)std::min<uint64_t>(h->G, nb - b0);
+        rc = run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out));
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(h->ev[11], st));
+    CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::BITPOS, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t endbit = h->h_pinned[0];
+    const uint64_t bits = endbit - start_bit;
+    const size_t out_bytes = (size_t)((endbit + 7) / 8);
+    h->stats.ms_total = ev_ms(h->ev[10], h->ev[11]);
+    h->stats.n_out_bits = bits;
+    if (out_bytes > dcap) { h->err = "internal: output bound exceeded"; return BZ2B200_E_CUDA; }
+    if (out_bytes > out_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    *out_nbits = bits;
+    if (out_bytes) {
+        const bool dev = is_device_ptr(out);
+        CK(cudaEventRecord(h->ev[12], st));
+        CK(cudaMemcpyAsync(out, h->out.p, out_bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        h->stats.ms_d2h = ev_ms(h->ev[12], h->ev[13]);
+    }
+    if (block_crcs && nb) CK(cudaMemcpy(block_crcs, h->all_crc.p, nb * 4, cudaMemcpyDeviceToHost));
+    if (block_nbits && nb) CK(cudaMemcpy(block_nbits, h->all_nbits.p, nb * 8, cudaMemcpyDeviceToHost));
+    {   // n_rle / n_mtf totals for the roofline model (last batch only holds m; rle lengths cover the call)
+        std::vector<uint32_t> tmp(nb);
+        if (nb) CK(cudaMemcpy(tmp.data(), h->rle_len.p, nb * 4, cudaMemcpyDeviceToHost));
+        uint64_t s = 0;
+        for (uint32_t v : tmp) s += v;
+        h->stats.n_rle = s;
+    }
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_compress_stream(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes)
+{
+    if (!h || !out || !out_bytes) return BZ2B200_E_ARG;
+    if (out_capacity < 14) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    if (is_device_ptr(out)) { h->err = "compress_stream needs a host output buffer"; return BZ2B200_E_ARG; }
+    // stream header (OutputStream.hpp:126-128)
+    out[0] = 'B'; out[1] = 'Z'; out[2] = 'h'; out[3] = (uint8_t)('0' + h->mult);
+    uint64_t nbits = 0, nblocks = 0;
+    size_t consumed = 0;
+    std::vector<uint32_t> crcs(n_bytes / (size_t)std::max(1, (h->bs - 5) * 4 / 5) + 4);
+    int rc = bz2b200_compress_blocks(h, input, n_bytes, 1, 0, out + 4, out_capacity - 4, &nbits, &consumed, crcs.data(), nullptr, crcs.size(), &nblocks);
+    if (rc) return rc;
+    // trailer (OutputStream.hpp:163-176): end magic, combined CRC (fold :202), zero padding
+    uint32_t scrc = 0;
+    for (uint64_t i = 0; i < nblocks; ++i) scrc = ((scrc << 1) | (scrc >> 31)) ^ crcs[i];
+    uint64_t bitpos = 32 + nbits;
+    if ((bitpos + 80 + 7) / 8 > out_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    if ((bitpos & 7) == 0) out[bitpos >> 3] = 0;
+    auto put = [&](int count, uint64_t value) {
+        for (int i = count - 1; i >= 0; --i) {
+            if ((bitpos & 7) == 0) out[bitpos >> 3] = 0;
+            if ((value >> i) & 1) out[bitpos >> 3] |= (uint8_t)(0x80u >> (bitpos & 7));
+            ++bitpos;
+        }
+    };
+    put(24, 0x177245); put(24, 0x385090); put(32, scrc);
+    *out_bytes = (size_t)((bitpos + 7) / 8);
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage, void *dst, size_t cap, size_t *len_bytes)
+{
+    if (!h || !dst || !len_bytes) return BZ2B200_E_ARG;
+    if (block_index < h->last_b0 || block_index >= h->last_b0 + h->last_nb) return BZ2B200_E_STATE;
+    CK(cudaSetDevice(h->device));
+    const uint64_t bl = block_index - h->last_b0, S = h->S;
+    uint32_t n = 0;
+    CK(cudaMemcpy(&n, ptr<uint32_t>(h->rle_len) + block_index, 4, cudaMemcpyDeviceToHost));
+    HuffBlock hb;
+    CK(cudaMemcpy(&hb, ptr<HuffBlock>(h->hb) + bl, sizeof(hb), cudaMemcpyDeviceToHost));
+    const void *src = nullptr;
+    size_t len = 0;
+    switch (stage) {
+    case BZ2B200_STAGE_RLE1: src = ptr<uint8_t>(h->rle) + bl * S; len = n; break;
+    case BZ2B200_STAGE_BWT: src = ptr<uint8_t>(h->L) + bl * S; len = n; break;
+    case BZ2B200_STAGE_ORIGPTR: src = ptr<uint32_t>(h->orig) + bl; len = 4; break;
+    case BZ2B200_STAGE_MTF: src = ptr<uint16_t>(h->mtf) + bl * S; len = (size_t)hb.m * 2; break;
+    case BZ2B200_STAGE_FREQ: src = ptr<uint32_t>(h->freq) + bl * 258; len = 258 * 4; break;
+    case BZ2B200_STAGE_SELECTORS: src = ptr<uint8_t>(h->sel) + bl * h->sel_stride; len = hb.nsel; break;
+    case BZ2B200_STAGE_SA: src = ptr<uint32_t>(h->sa) + bl * S; len = (size_t)n * 4; break;
+    case BZ2B200_STAGE_PRESENT: {
+        uint32_t bm[8];
+        CK(cudaMemcpy(bm, ptr<uint32_t>(h->present) + bl * 8, 32, cudaMemcpyDeviceToHost));
+        if (cap < 256) return BZ2B200_E_OUTPUT;
+        for (int v = 0; v < 256; ++v) ((uint8_t *)dst)[v] = (bm[v >> 5] >> (v & 31)) & 1;
+        *len_bytes = 256;
+        return BZ2B200_OK;
+    }
+    case BZ2B200_STAGE_LENGTHS: {
+        std::vector<uint8_t> tmp((size_t)HUFF_MAXTABLES * HUFF_LEN_STRIDE);
+        CK(cudaMemcpy(tmp.data(), ptr<uint8_t>(h->lens) + bl * HUFF_MAXTABLES * HUFF_LEN_STRIDE, tmp.size(), cudaMemcpyDeviceToHost));
+        len = (size_t)hb.ntab * 258;
+        if (cap < len) return BZ2B200_E_OUTPUT;
+        memset(dst, 0, len);
+        for (uint32_t t = 0; t < hb.ntab; ++t) memcpy((uint8_t *)dst + t * 258, tmp.data() + t * HUFF_LEN_STRIDE, hb.alpha);
+        *len_bytes = len;
+        return BZ2B200_OK;
+    }
+    default: return BZ2B200_E_ARG;
+    }
+    if (cap < len) return BZ2B200_E_OUTPUT;
+    if (len) CK(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToHost));
+    *len_bytes = len;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_get_stats(const bz2b200_t *h, bz2b200_stats_t *s)
+{
+    if (!h || !s) return BZ2B200_E_ARG;
+    *s = h->stats;
+    return BZ2B200_OK;
+}

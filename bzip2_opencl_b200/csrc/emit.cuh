@@ -1,0 +1,259 @@
+// emit.cuh -- stage E: bit emission.  Bits are MSB-first (BitOutputStream.hpp:101-113).  The output buffer is an array of
+// bytes in stream order; kernels build big-endian 32-bit words and OR their byte-swapped image into a zero-initialised
+// buffer, so neighbouring producers (header thread, data tiles, the next block) may share a word without coordination.
+// Every block is written directly at its final bit offset in the stream (exclusive scan of exact block bit lengths), which
+// replaces the reference's bool-per-bit buffers and the host's writeFileBytes/getLeftBuffer carry loop
+// (OutputStream.hpp:225-239, BitOutputStream.hpp:30-99).
+#pragma once
+#include "util.cuh"
+#include "huff.cuh"
+
+namespace bz {
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// Serial MSB-first bit writer used by one thread; flushes with atomicOr.
+struct BitWriter {
+    uint32_t *out;   // word array of the stream buffer
+    uint64_t word;   // index of the word being filled
+    uint32_t acc;    // bits collected for that word (big-endian image), already positioned
+    uint32_t used;   // bits used in acc (0..31)
+    __device__ void init(uint32_t *o, uint64_t bitpos) { out = o; word = bitpos >> 5; used = (uint32_t)(bitpos & 31); acc = 0; }
+    __device__ void put(uint32_t count, uint32_t value) // count 1..32, value < 2^count
+    {
+        uint32_t room = 32 - used;
+        if (count <= room) {
+            acc |= (count == 32 ? value : (value << (room - count)));
+            used += count;
+            if (used == 32) flush_word();
+        } else {
+            uint32_t hi = value >> (count - room);
+            acc |= hi;
+            used = 32;
+            flush_word();
+            uint32_t rest = count - room;
+            acc = (value & ((1u << rest) - 1u)) << (32 - rest);
+            used = rest;
+        }
+    }
+    __device__ void flush_word()
+    {
+        if (acc) atomicOr(out + word, bswap32(acc));
+        ++word; acc = 0; used = 0;
+    }
+    __device__ void finish() { if (used && acc) atomicOr(out + word, bswap32(acc)); }
+};
+
+// exact bit length of every block
+__global__ void __launch_bounds__(128) k_block_bits(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ sel_bits,
+                                                     const uint32_t *__restrict__ table_bits, const uint32_t *__restrict__ data_bits, uint32_t n_blocks,
+                                                     uint64_t *__restrict__ nbits)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t ranges = 0;
+    for (int w = 0; w < 8; ++w) {
+        uint32_t p = present[b * 8 + w];
+        if (p & 0xffffu) ++ranges;
+        if (p >> 16) ++ranges;
+    }
+    uint64_t bits = 48 + 32 + 1 + 24 + 16 + 16ull * ranges + 3 + 15;
+    bits += sel_bits[b];
+    bits += table_bits[b];
+    bits += data_bits[b];
+    nbits[b] = bits;
+}
+
+// single CTA: bitoff[b] = *bitpos + exclusive sum; *bitpos advances by the batch total (so batches chain without a host sync)
+__global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict__ nbits, uint32_t n_blocks, uint64_t *__restrict__ bitpos,
+                                                       uint64_t *__restrict__ bitoff)
+{
+    __shared__ uint64_t s_w[33];
+    __shared__ uint64_t s_carry;
+    if (threadIdx.x == 0) s_carry = *bitpos;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += blockDim.x) {
+        uint32_t b = b0 + threadIdx.x;
+        uint64_t v = b < n_blocks ? nbits[b] : 0;
+        uint64_t inc = warp_incl_sum64(v);
+        if (lane_id() == 31) s_w[warp_id()] = inc;
+        __syncthreads();
+        if (warp_id() == 0) {
+            uint64_t x = s_w[lane_id()];
+            uint64_t xi = warp_incl_sum64(x);
+            s_w[lane_id()] = xi - x;
+            if (lane_id() == 31) s_w[32] = xi;
+        }
+        __syncthreads();
+        if (b < n_blocks) bitoff[b] = s_carry + s_w[warp_id()] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *bitpos = s_carry;
+}
+
+// one thread per block: everything in front of the coded symbols
+__global__ void __launch_bounds__(32) k_emit_header(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ crc,
+                                                     const uint32_t *__restrict__ orig, const uint8_t *__restrict__ selpos, uint64_t sel_stride,
+                                                     const uint8_t *__restrict__ lens, const uint64_t *__restrict__ bitoff, uint32_t n_blocks,
+                                                     uint32_t *__restrict__ out, uint64_t *__restrict__ data_start)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const HuffBlock h = hb[b];
+    BitWriter w;
+    w.init(out, bitoff[b]);
+    w.put(24, 0x314159u); w.put(24, 0x265359u);       // OutputStream.hpp:208-209
+    w.put(32, crc[b]);                                  // :210 writeInteger
+    w.put(1, 0);                                        // :211 randomised = 0
+    w.put(24, orig[b]);                                 // kernel.cpp:3116
+    // writeSymbolMap, kernel.cpp:2483-2511: value v is bit (v & 31) of present[v >> 5]
+    uint32_t used16 = 0;
+    for (int r = 0; r < 16; ++r) {
+        uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+        if (bits16) used16 |= 1u << (15 - r);
+    }
+    w.put(16, used16);
+    for (int r = 0; r < 16; ++r) {
+        uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+        if (bits16) w.put(16, __brev(bits16) >> 16); // value k of the range goes out k-th: MSB first
+    }
+    w.put(3, h.ntab);                                   // kernel.cpp:3001
+    w.put(15, h.nsel);                                  // :3002
+    const uint8_t *sp = selpos + (uint64_t)b * sel_stride;
+    for (uint32_t g = 0; g < h.nsel; ++g) {             // writeUnary, :3010
+        uint32_t p = sp[g];
+        w.put(p + 1, ((1u << p) - 1u) << 1);
+    }
+    for (uint32_t t = 0; t < h.ntab; ++t) {             // :3015-3040
+        const uint8_t *L = lens + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_LEN_STRIDE;
+        int cur = L[0];
+        w.put(5, (uint32_t)cur);
+        for (uint32_t j = 0; j < h.alpha; ++j) {
+            int l = L[j];
+            while (cur < l) { w.put(2, 2); ++cur; }
+            while (cur > l) { w.put(2, 3); --cur; }
+            w.put(1, 0);
+        }
+    }
+    data_start[b] = (w.word << 5) + w.used;
+    w.finish();
+}
+
+// bits of the coded symbols per tile of HP_SYMS symbols
+__global__ void __launch_bounds__(HP_THREADS) k_data_tilebits(const uint16_t *__restrict__ mtf, uint64_t mtf_stride, const HuffBlock *__restrict__ hb,
+                                                               const uint8_t *__restrict__ lens, const uint8_t *__restrict__ sel, uint64_t sel_stride,
+                                                               uint32_t *__restrict__ tile_bits, int tiles_per_block)
+{
+    __shared__ uint8_t s_len[HUFF_MAXTABLES][HUFF_LEN_STRIDE];
+    __shared__ uint16_t s_sym[HP_SYMS];
+    __shared__ uint32_t s_red[HP_THREADS / 32];
+    const uint32_t b = blockIdx.y;
+    const HuffBlock h = hb[b];
+    const uint32_t sym0 = blockIdx.x * HP_SYMS;
+    if (sym0 >= h.m) return;
+    const uint32_t nsym = min((uint32_t)HP_SYMS, h.m - sym0);
+    const uint8_t *L = lens + (uint64_t)b * HUFF_MAXTABLES * HUFF_LEN_STRIDE;
+    for (uint32_t i = threadIdx.x; i < h.ntab * HUFF_LEN_STRIDE; i += HP_THREADS) (&s_len[0][0])[i] = L[i];
+    const uint16_t *src = mtf + (uint64_t)b * mtf_stride + sym0;
+    for (uint32_t i = threadIdx.x; i < nsym; i += HP_THREADS) s_sym[i] = src[i];
+    __syncthreads();
+    uint32_t bits = 0;
+    const uint32_t g0 = threadIdx.x * HUFF_GROUP;
+    if (g0 < nsym) {
+        const uint32_t gc = min((uint32_t)HUFF_GROUP, nsym - g0);
+        const uint32_t t = sel[(uint64_t)b * sel_stride + blockIdx.x * HP_THREADS + threadIdx.x];
+        for (uint32_t k = 0; k < gc; ++k) bits += s_len[t][s_sym[g0 + k]];
+    }
+    bits = __reduce_add_sync(FULL, bits);
+    if (lane_id() == 0) s_red[warp_id()] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < HP_THREADS / 32; ++w) s += s_red[w];
+        tile_bits[(uint64_t)b * tiles_per_block + blockIdx.x] = s;
+    }
+}
+
+// one thread per block: exclusive prefix of tile bits
+__global__ void __launch_bounds__(128) k_data_scan(const HuffBlock *__restrict__ hb, uint32_t *__restrict__ tile_bits, int tiles_per_block, uint32_t n_blocks)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t nt = (hb[b].m + HP_SYMS - 1) / HP_SYMS;
+    uint32_t run = 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+        uint32_t v = tile_bits[(uint64_t)b * tiles_per_block + t];
+        tile_bits[(uint64_t)b * tiles_per_block + t] = run;
+        run += v;
+    }
+}
+
+constexpr int ED_STAGE_WORDS = HP_SYMS * HUFF_MAXLEN / 32 + 4; // 4004 words
+
+// one thread per 50-symbol group assembles its codes; the CTA stages the tile's bits in shared memory and stores words
+__global__ void __launch_bounds__(HP_THREADS) k_emit_data(const uint16_t *__restrict__ mtf, uint64_t mtf_stride, const HuffBlock *__restrict__ hb,
+                                                           const uint32_t *__restrict__ codes, const uint8_t *__restrict__ sel, uint64_t sel_stride,
+                                                           const uint32_t *__restrict__ tile_bits, int tiles_per_block, const uint64_t *__restrict__ data_start,
+                                                           uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t s_code[HUFF_MAXTABLES][HUFF_MAXALPHA];
+    __shared__ uint16_t s_sym[HP_SYMS];
+    __shared__ uint32_t s_stage[ED_STAGE_WORDS];
+    __shared__ uint32_t s_u[34];
+    const uint32_t b = blockIdx.y;
+    const HuffBlock h = hb[b];
+    const uint32_t sym0 = blockIdx.x * HP_SYMS;
+    if (sym0 >= h.m) return;
+    const uint32_t nsym = min((uint32_t)HP_SYMS, h.m - sym0);
+    const uint32_t *C = codes + (uint64_t)b * HUFF_MAXTABLES * HUFF_MAXALPHA;
+    for (uint32_t i = threadIdx.x; i < h.ntab * HUFF_MAXALPHA; i += HP_THREADS) (&s_code[0][0])[i] = C[i];
+    const uint16_t *src = mtf + (uint64_t)b * mtf_stride + sym0;
+    for (uint32_t i = threadIdx.x; i < nsym; i += HP_THREADS) s_sym[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < ED_STAGE_WORDS; i += HP_THREADS) s_stage[i] = 0;
+    __syncthreads();
+    const uint32_t g0 = threadIdx.x * HUFF_GROUP;
+    uint32_t gc = 0, t = 0, bits = 0;
+    if (g0 < nsym) {
+        gc = min((uint32_t)HUFF_GROUP, nsym - g0);
+        t = sel[(uint64_t)b * sel_stride + blockIdx.x * HP_THREADS + threadIdx.x];
+        for (uint32_t k = 0; k < gc; ++k) bits += s_code[t][s_sym[g0 + k]] >> 24;
+    }
+    uint32_t total;
+    uint32_t off = block_excl_sum(bits, s_u, &total);
+    const uint64_t tile_bit0 = data_start[b] + tile_bits[(uint64_t)b * tiles_per_block + blockIdx.x];
+    const uint32_t lead = (uint32_t)(tile_bit0 & 31); // bit offset of the tile inside its first word
+    if (gc) {
+        uint32_t pos = lead + off; // bit position relative to the first staged word
+        uint32_t wi = pos >> 5, used = pos & 31, acc = 0;
+        for (uint32_t k = 0; k < gc; ++k) {
+            uint32_t cs = s_code[t][s_sym[g0 + k]];
+            uint32_t len = cs >> 24, code = cs & 0xffffffu;
+            uint32_t room = 32 - used;
+            if (len <= room) {
+                acc |= code << (room - len);
+                used += len;
+                if (used == 32) { atomicOr(&s_stage[wi], acc); ++wi; acc = 0; used = 0; }
+            } else {
+                acc |= code >> (len - room);
+                atomicOr(&s_stage[wi], acc);
+                ++wi;
+                uint32_t rest = len - room;
+                acc = (code & ((1u << rest) - 1u)) << (32 - rest);
+                used = rest;
+            }
+        }
+        if (used) atomicOr(&s_stage[wi], acc);
+    }
+    __syncthreads();
+    const uint32_t nwords = (lead + total + 31) >> 5;
+    uint32_t *dst = out + (tile_bit0 >> 5);
+    for (uint32_t i = threadIdx.x; i < nwords; i += HP_THREADS) {
+        uint32_t v = s_stage[i];
+        if (i == 0 || i == nwords - 1) { if (v) atomicOr(dst + i, bswap32(v)); }
+        else dst[i] = bswap32(v);
+    }
+}
+
+} // namespace bz

@@ -1,0 +1,372 @@
+// rle.cuh -- stage A: block boundaries + RLE1 + symbol presence + block CRC32 on the device.
+//
+// Replaces the reference's per-byte host loop: app.cpp:108-116 -> OutputStream::write(int) (OutputStream.hpp:131-142)
+// -> BlockCompressor::write / writeRun / finishRLE (BlockCompressor.hpp:69-154) and CRC32::updateCRC (CRC32.hpp:75-86).
+// See rle_seg.h for the algebra.  Kernels:
+//   k_rle_tile_seg      one warp summarises one 2 KiB tile of the raw input                  (parallel)
+//   k_rle_reduce        64-ary tree of summaries                                             (parallel)
+//   k_rle_walk          ONE warp walks the blocks through the tree -> block start offsets     (sequential over blocks)
+//   k_rle_btile_seg     summaries of block-relative tiles                                    (parallel)
+//   k_rle_btile_scan    one warp per block: machine state at every block-relative tile start  (parallel over blocks)
+//   k_rle_emit          one warp per block-relative tile writes the RLE1 bytes + presence bits(parallel)
+//   k_crc_chunks        per-block CRC32 by chunk CRCs combined with x^(8k) mod P shifts       (parallel)
+#pragma once
+#include "util.cuh"
+#include "rle_seg.h"
+#include "crc_math.h"
+
+namespace bz {
+
+constexpr int RLE_SM_STRIDE = 68; // bytes of shared memory per lane (64 + 4 pad: conflict-free lane-strided byte reads)
+constexpr int RLE_WARPS = 8;
+
+__device__ __forceinline__ Seg shfl_seg(const Seg &s, int src)
+{
+    Seg r;
+    r.len = shfl_u64(s.len, src);
+    r.lead = shfl_u64(s.lead, src);
+    r.trail = shfl_u64(s.trail, src);
+    r.mid = shfl_u64(s.mid, src);
+    r.first = __shfl_sync(FULL, s.first, src);
+    r.last = __shfl_sync(FULL, s.last, src);
+    r.uniform = __shfl_sync(FULL, s.uniform, src);
+    r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ Seg shfl_up_seg(const Seg &s, int d)
+{
+    Seg r;
+    r.len = shfl_up_u64(s.len, d);
+    r.lead = shfl_up_u64(s.lead, d);
+    r.trail = shfl_up_u64(s.trail, d);
+    r.mid = shfl_up_u64(s.mid, d);
+    r.first = __shfl_up_sync(FULL, s.first, d);
+    r.last = __shfl_up_sync(FULL, s.last, d);
+    r.uniform = __shfl_up_sync(FULL, s.uniform, d);
+    r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ Seg warp_seg_incl_scan(Seg s)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Seg o = shfl_up_seg(s, d);
+        if (lane_id() >= d) s = seg_combine(o, s);
+    }
+    return s;
+}
+__device__ __forceinline__ RleState shfl_state(const RleState &s, int src)
+{
+    RleState r;
+    r.bl = shfl_u64(s.bl, src);
+    r.cur = __shfl_sync(FULL, s.cur, src);
+    r.run = __shfl_sync(FULL, s.run, src);
+    return r;
+}
+
+// Stage n (<= RLE_TILE) bytes in[lo..lo+n) into the warp's padded shared-memory tile.
+__device__ __forceinline__ void warp_load_tile(const uint8_t *__restrict__ in, uint64_t lo, uint32_t n, uint8_t *sm)
+{
+    const int lane = lane_id();
+    if (n == RLE_TILE && ((lo & 15ull) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0)) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + lo);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int idx = k * 32 + lane; // uint4 index inside the tile
+            uint4 v = __ldg(src + idx);
+            int byte = idx * 16;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sm + (byte >> 6) * RLE_SM_STRIDE + (byte & 63));
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    } else {
+        for (uint32_t k = lane; k < n; k += 32) sm[(k >> 6) * RLE_SM_STRIDE + (k & 63)] = __ldg(in + lo + k);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t lane_count(uint32_t n)
+{
+    int c = (int)n - lane_id() * (int)RLE_LANE_BYTES;
+    return c < 0 ? 0u : (c > (int)RLE_LANE_BYTES ? RLE_LANE_BYTES : (uint32_t)c);
+}
+
+__device__ __forceinline__ Seg lane_seg(const uint8_t *sm, uint32_t cnt)
+{
+    const uint8_t *p = sm + lane_id() * RLE_SM_STRIDE;
+    return seg_from_bytes([p](uint32_t i) { return (uint32_t)p[i]; }, cnt);
+}
+
+// ---------------------------------------------------------------- level 0 summaries of the raw input
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_tile_seg(const uint8_t *__restrict__ in, uint64_t n_bytes, Seg *__restrict__ seg0, uint64_t n_tiles)
+{
+    __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
+    uint64_t tile = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    if (tile >= n_tiles) return;
+    uint8_t *sm = sm_all[warp_id()];
+    uint64_t lo = tile * RLE_TILE;
+    uint32_t n = (uint32_t)min((uint64_t)RLE_TILE, n_bytes - lo);
+    warp_load_tile(in, lo, n, sm);
+    Seg s = warp_seg_incl_scan(lane_seg(sm, lane_count(n)));
+    if (lane_id() == 31) seg0[tile] = s;
+}
+
+// ---------------------------------------------------------------- tree level k -> k+1
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_reduce(const Seg *__restrict__ child, uint64_t n_child, Seg *__restrict__ parent, uint64_t n_parent)
+{
+    uint64_t p = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    if (p >= n_parent) return;
+    uint64_t c0 = p * RLE_FANOUT + 2 * lane_id();
+    Seg a = c0 < n_child ? child[c0] : seg_empty();
+    Seg b = c0 + 1 < n_child ? child[c0 + 1] : seg_empty();
+    Seg s = warp_seg_incl_scan(seg_combine(a, b));
+    if (lane_id() == 31) parent[p] = s;
+}
+
+// ---------------------------------------------------------------- the sequential walk (one warp)
+struct WalkLevels {
+    const Seg *seg[RLE_MAX_LEVELS];
+    int n_levels;
+};
+
+struct DevTileScan {
+    const uint8_t *in;
+    uint8_t *sm;
+    __device__ TileScanResult operator()(uint64_t lo, uint64_t hi, RleState st, uint64_t limit) const
+    {
+        const int lane = lane_id();
+        uint32_t n = (uint32_t)(hi - lo);
+        __syncwarp();
+        warp_load_tile(in, lo, n, sm);
+        uint32_t cnt = lane_count(n);
+        Seg incl = warp_seg_incl_scan(lane_seg(sm, cnt));
+        Seg excl = shfl_up_seg(incl, 1);
+        if (lane == 0) excl = seg_empty();
+        RleState s = state_apply(excl, st);
+        bool found = false;
+        uint64_t fpos = hi;
+        const uint8_t *p = sm + lane * RLE_SM_STRIDE;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            if (s.bl > limit) { found = true; fpos = lo + (uint64_t)lane * RLE_LANE_BYTES + i; break; }
+            state_step(s, p[i]);
+        }
+        unsigned ballot = __ballot_sync(FULL, found);
+        int src = ballot ? (__ffs(ballot) - 1) : (int)((n - 1) / RLE_LANE_BYTES);
+        TileScanResult r;
+        r.pos = shfl_u64(fpos, src);
+        r.st = shfl_state(s, src);
+        if (!ballot) r.pos = hi;
+        __syncwarp();
+        return r;
+    }
+};
+
+struct DevSegLoad {
+    WalkLevels lv;
+    __device__ Seg operator()(int level, uint64_t idx) const { return lv.seg[level][idx]; }
+};
+
+// info[0] = number of complete blocks, info[1] = bytes consumed by them.
+// starts[b] for b <= min(n_blocks, cap): start offset of block b; starts[n_blocks] = consumed. rle_len[b] = RLE1 length.
+__global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t limit, int is_final, WalkLevels lv,
+                                                  uint64_t *__restrict__ starts, uint32_t *__restrict__ rle_len, uint64_t cap, uint64_t *__restrict__ info)
+{
+    __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
+    DevTileScan scan{in, sm};
+    DevSegLoad load{lv};
+    uint64_t s = 0, nb = 0;
+    while (s < n_bytes) {
+        RleState st;
+        uint64_t e = walk_block(s, n_bytes, limit, lv.n_levels, load, scan, st);
+        bool complete = (e < n_bytes) || is_final; // e == n_bytes without a refusal: flushed only when the stream ends
+        if (!complete) break;
+        if (lane_id() == 0 && nb < cap) {
+            starts[nb] = s;
+            rle_len[nb] = (uint32_t)state_final_length(st);
+        }
+        ++nb;
+        s = e;
+    }
+    if (lane_id() == 0) {
+        if (nb <= cap) starts[nb] = s;
+        info[0] = nb;
+        info[1] = s;
+    }
+}
+
+// ---------------------------------------------------------------- block-relative tiles
+// Tile k of block b covers input [starts[b] + k*RLE_TILE, min(.., starts[b+1])).
+__device__ __forceinline__ bool btile_range(const uint64_t *starts, uint32_t b, uint64_t k, uint64_t &lo, uint32_t &n)
+{
+    uint64_t s = starts[b], e = starts[b + 1];
+    lo = s + k * RLE_TILE;
+    if (lo >= e) return false;
+    n = (uint32_t)min((uint64_t)RLE_TILE, e - lo);
+    return true;
+}
+
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_btile_seg(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
+                                                                    Seg *__restrict__ segB, uint64_t max_tiles)
+{
+    __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
+    uint64_t k = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    uint32_t bl = blockIdx.y;
+    uint64_t lo; uint32_t n;
+    if (k >= max_tiles || !btile_range(starts, b0 + bl, k, lo, n)) return;
+    uint8_t *sm = sm_all[warp_id()];
+    warp_load_tile(in, lo, n, sm);
+    Seg s = warp_seg_incl_scan(lane_seg(sm, lane_count(n)));
+    if (lane_id() == 31) segB[(uint64_t)bl * max_tiles + k] = s;
+}
+
+__device__ __forceinline__ uint64_t pack_state(const RleState &s) { return (s.bl & 0xffffffffull) | ((uint64_t)(s.run & 0xff) << 32) | ((uint64_t)(s.cur & 0xff) << 40); }
+__device__ __forceinline__ RleState unpack_state(uint64_t v)
+{
+    RleState s;
+    s.bl = v & 0xffffffffull;
+    s.run = (uint32_t)(v >> 32) & 0xff;
+    s.cur = (uint32_t)(v >> 40) & 0xff;
+    return s;
+}
+
+// one warp per block: state of the machine at the first byte of every block-relative tile
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_btile_scan(const Seg *__restrict__ segB, const uint64_t *__restrict__ starts, uint32_t b0, uint32_t nb,
+                                                                     uint64_t *__restrict__ tstate, uint64_t max_tiles)
+{
+    uint32_t bl = blockIdx.x * RLE_WARPS + warp_id();
+    if (bl >= nb) return;
+    uint64_t len = starts[b0 + bl + 1] - starts[b0 + bl];
+    uint64_t nt = (len + RLE_TILE - 1) / RLE_TILE;
+    Seg carry = seg_empty();
+    const int lane = lane_id();
+    for (uint64_t k0 = 0; k0 < nt; k0 += 32) {
+        uint64_t k = k0 + lane;
+        Seg mine = k < nt ? segB[(uint64_t)bl * max_tiles + k] : seg_empty();
+        Seg incl = warp_seg_incl_scan(mine);
+        Seg excl = shfl_up_seg(incl, 1);
+        if (lane == 0) excl = seg_empty();
+        if (k < nt) tstate[(uint64_t)bl * max_tiles + k] = pack_state(state_apply(seg_combine(carry, excl), state_fresh()));
+        carry = seg_combine(carry, shfl_seg(incl, 31));
+    }
+}
+
+__device__ __forceinline__ void bm_set(uint32_t (&bm)[8], uint32_t v)
+{
+#pragma unroll
+    for (int w = 0; w < 8; ++w) bm[w] |= (w == (int)(v >> 5)) ? (1u << (v & 31)) : 0u;
+}
+
+__device__ __forceinline__ void emit_run(uint8_t *dst, uint32_t v, uint32_t len, uint32_t (&bm)[8])
+{
+    // writeRun, BlockCompressor.hpp:134-154
+    bm_set(bm, v);
+    dst[0] = (uint8_t)v;
+    if (len > 1) dst[1] = (uint8_t)v;
+    if (len > 2) dst[2] = (uint8_t)v;
+    if (len > 3) {
+        dst[3] = (uint8_t)v;
+        dst[4] = (uint8_t)(len - 4);
+        bm_set(bm, len - 4);
+    }
+}
+
+// one warp per block-relative tile: RLE1 bytes into rle[bl*stride ...], presence bitmap into present[bl*8 ...]
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
+                                                               const uint64_t *__restrict__ tstate, uint64_t max_tiles, uint8_t *__restrict__ rle,
+                                                               uint64_t stride, uint32_t *__restrict__ present)
+{
+    __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
+    uint64_t k = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    uint32_t bl = blockIdx.y;
+    uint64_t lo; uint32_t n;
+    if (k >= max_tiles || !btile_range(starts, b0 + bl, k, lo, n)) return;
+    const int lane = lane_id();
+    uint8_t *sm = sm_all[warp_id()];
+    warp_load_tile(in, lo, n, sm);
+    uint32_t cnt = lane_count(n);
+    Seg incl = warp_seg_incl_scan(lane_seg(sm, cnt));
+    Seg excl = shfl_up_seg(incl, 1);
+    if (lane == 0) excl = seg_empty();
+    RleState s = state_apply(excl, unpack_state(tstate[(uint64_t)bl * max_tiles + k]));
+    uint8_t *out = rle + (uint64_t)bl * stride;
+    uint32_t bm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint8_t *p = sm + lane * RLE_SM_STRIDE;
+    uint32_t blen = (uint32_t)s.bl, cur = s.cur, run = s.run;
+    for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t v = p[i];
+        if (run == 0) { cur = v; run = 1; }
+        else if (cur == v) {
+            if (++run > 254) { emit_run(out + blen, cur, 255, bm); blen += 5; run = 0; }
+        } else {
+            emit_run(out + blen, cur, run, bm);
+            blen += rle_enc_small(run);
+            cur = v; run = 1;
+        }
+    }
+    // finishRLE (BlockCompressor.hpp:112-118): the lane holding the block's last byte flushes the pending run
+    bool last_lane = cnt > 0 && (lo + (uint64_t)lane * RLE_LANE_BYTES + cnt == starts[b0 + bl + 1]);
+    if (last_lane && run > 0) emit_run(out + blen, cur, run, bm);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t r = __reduce_or_sync(FULL, bm[w]);
+        if (lane == 0 && r) atomicOr(&present[bl * 8 + w], r);
+    }
+}
+
+// ---------------------------------------------------------------- CRC32 (CRC32.hpp:30-92): MSB-first, poly 0x04C11DB7
+constexpr int CRC_THREADS = 256;
+constexpr int CRC_BYTES_PER_THREAD = 64;
+constexpr int CRC_CHUNK = CRC_THREADS * CRC_BYTES_PER_THREAD; // 16 KiB
+
+__constant__ uint32_t c_crc_table[256];      // CRC32.hpp:33-65
+__constant__ uint32_t c_crc_pow8[48];        // x^(8 * 2^j) mod P
+__constant__ uint32_t c_crc_lane_shift[256]; // x^(8 * 64 * (255 - t)) mod P
+
+__device__ __forceinline__ uint32_t crc_xpow8(uint64_t k)
+{
+    return crc_xpow8_t(k, [](int j) { return c_crc_pow8[j]; });
+}
+
+// Chunks are aligned to the END of each block so every thread's shift is a compile-time-known multiple of 64 bytes.
+// crc_acc[bl] accumulates (XOR) the "pure" CRC (register started at 0); k_crc_finish folds in the 0xFFFFFFFF start value.
+__global__ void __launch_bounds__(CRC_THREADS) k_crc_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
+                                                             uint32_t *__restrict__ crc_acc)
+{
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t red[CRC_THREADS / 32];
+    tab[threadIdx.x] = c_crc_table[threadIdx.x];
+    __syncthreads();
+    uint32_t bl = blockIdx.y;
+    uint64_t s = starts[b0 + bl], e = starts[b0 + bl + 1];
+    uint64_t c = blockIdx.x;
+    if (c * CRC_CHUNK >= e - s) return;
+    uint64_t chunk_end = e - c * CRC_CHUNK;
+    // thread t covers [chunk_end - 64*(256-t), chunk_end - 64*(255-t)) clipped to >= s
+    int64_t hi = (int64_t)chunk_end - (int64_t)CRC_BYTES_PER_THREAD * (255 - (int)threadIdx.x);
+    int64_t lo = hi - CRC_BYTES_PER_THREAD;
+    if (lo < (int64_t)s) lo = (int64_t)s;
+    uint32_t crc = 0;
+    for (int64_t q = lo; q < hi; ++q) crc = (crc << 8) ^ tab[((crc >> 24) ^ __ldg(in + q)) & 0xff];
+    if (crc) crc = crc_mulmod(crc, c_crc_lane_shift[threadIdx.x]);
+    crc = __reduce_xor_sync(FULL, crc);
+    if (lane_id() == 0) red[warp_id()] = crc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t x = 0;
+        for (int w = 0; w < CRC_THREADS / 32; ++w) x ^= red[w];
+        if (x) {
+            x = crc_mulmod(x, crc_xpow8(c * CRC_CHUNK));
+            atomicXor(&crc_acc[bl], x);
+        }
+    }
+}
+
+// crc[bl] = ~(pure ^ 0xFFFFFFFF * x^(8 len))   (CRC32.hpp:67,70-73)
+__global__ void k_crc_finish(const uint64_t *__restrict__ starts, uint32_t b0, uint32_t nb, uint32_t *__restrict__ crc_acc)
+{
+    uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bl >= nb) return;
+    uint64_t len = starts[b0 + bl + 1] - starts[b0 + bl];
+    crc_acc[bl] = ~(crc_acc[bl] ^ crc_mulmod(0xffffffffu, crc_xpow8(len)));
+}
+
+} // namespace bz

@@ -1,0 +1,256 @@
+// rle_seg.h -- algebra of the reference's RLE1 / block-boundary state machine, usable on host and device.
+//
+// The reference decides block boundaries with a sequential per-byte state machine
+// (BlockCompressor::write, /root/reference/include/BlockCompressor.hpp:69-96): a byte is refused when
+// blockLength > blockSize-6 at entry (:71-74), runs are cut at 255 (:84-88), a run of L >= 4 is stored as
+// 4 bytes + the count byte L-4 (writeRun, :134-154), and a new block restarts the chunking.
+//
+// To run that machine in parallel we summarise any byte range by a `Seg` whose composition is associative,
+// and we can push the machine's state (blockLength, current value, pending run length) through a Seg in
+// O(1).  Tiles of the input are summarised independently, combined in a 64-ary tree, and the (short)
+// sequential walk over blocks steps through that tree instead of through bytes.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BZ_HD __host__ __device__ __forceinline__
+#else
+#define BZ_HD inline
+#endif
+
+namespace bz {
+
+// encoded size of a pending run of r (0..254) bytes when it is flushed: writeRun(value, r)
+BZ_HD uint32_t rle_enc_small(uint32_t r) { return r < 4u ? r : 5u; }
+// encoded size of a maximal run of `len` equal bytes chunked from its first byte: full 255-chunks (4+1 bytes) + rest
+BZ_HD uint64_t rle_enc_run(uint64_t len) { return 5ull * (len / 255ull) + rle_enc_small((uint32_t)(len % 255ull)); }
+
+struct Seg {
+    uint64_t len;   // bytes covered (0 = empty segment, the identity)
+    uint64_t lead;  // length of the leading run of equal bytes (== len when uniform)
+    uint64_t trail; // length of the trailing run of equal bytes (== len when uniform)
+    uint64_t mid;   // encoded bytes of every maximal run that touches neither end of the segment
+    uint32_t first, last;
+    uint32_t uniform; // all bytes equal
+    uint32_t pad;
+};
+
+BZ_HD Seg seg_empty()
+{
+    Seg s;
+    s.len = s.lead = s.trail = s.mid = 0;
+    s.first = s.last = 0;
+    s.uniform = 1;
+    s.pad = 0;
+    return s;
+}
+
+BZ_HD Seg seg_byte_run(uint32_t v, uint64_t n)
+{
+    Seg s;
+    s.len = s.lead = s.trail = n;
+    s.mid = 0;
+    s.first = s.last = v;
+    s.uniform = 1;
+    s.pad = 0;
+    return s;
+}
+
+// A followed by B.
+BZ_HD Seg seg_combine(const Seg &A, const Seg &B)
+{
+    if (A.len == 0) return B;
+    if (B.len == 0) return A;
+    Seg R;
+    R.pad = 0;
+    R.len = A.len + B.len;
+    R.first = A.first;
+    R.last = B.last;
+    const bool join = (A.last == B.first);
+    if (A.uniform && B.uniform && join) {
+        R.uniform = 1;
+        R.lead = R.trail = R.len;
+        R.mid = 0;
+        return R;
+    }
+    R.uniform = 0;
+    R.mid = A.mid + B.mid;
+    if (join) {
+        R.lead = A.uniform ? A.len + B.lead : A.lead;
+        R.trail = B.uniform ? A.trail + B.len : B.trail;
+        if (!A.uniform && !B.uniform) R.mid += rle_enc_run(A.trail + B.lead);
+    } else {
+        R.lead = A.lead;   // == A.len when A is uniform
+        R.trail = B.trail; // == B.len when B is uniform
+        if (!A.uniform) R.mid += rle_enc_run(A.trail);
+        if (!B.uniform) R.mid += rle_enc_run(B.lead);
+    }
+    return R;
+}
+
+// State of BlockCompressor between two write() calls.
+struct RleState {
+    uint64_t bl;  // blockLength
+    uint32_t cur; // rleCurrentValue (only meaningful when run > 0)
+    uint32_t run; // rleLength, 0..254
+};
+
+BZ_HD RleState state_fresh()
+{
+    RleState s;
+    s.bl = 0;
+    s.cur = 0xffffffffu;
+    s.run = 0;
+    return s;
+}
+
+// One accepted byte (BlockCompressor.hpp:76-95). The refusal test (:71-74) is the caller's.
+BZ_HD void state_step(RleState &s, uint32_t v)
+{
+    if (s.run == 0) {
+        s.cur = v;
+        s.run = 1;
+    } else if (s.cur == v) {
+        if (++s.run > 254) {
+            s.bl += 5;
+            s.run = 0;
+        }
+    } else {
+        s.bl += rle_enc_small(s.run);
+        s.cur = v;
+        s.run = 1;
+    }
+}
+
+// State after accepting every byte of S (valid only while no refusal happens inside S; since blockLength is
+// monotone, "bl after <= limit" proves that).
+BZ_HD RleState state_apply(const Seg &S, RleState s)
+{
+    if (S.len == 0) return s;
+    if (S.uniform) {
+        uint64_t tot;
+        if (s.run > 0 && s.cur == S.first) tot = s.run + S.len;
+        else { s.bl += rle_enc_small(s.run); tot = S.len; }
+        s.bl += 5ull * (tot / 255ull);
+        s.run = (uint32_t)(tot % 255ull);
+        s.cur = S.first;
+    } else {
+        uint64_t tot;
+        if (s.run > 0 && s.cur == S.first) tot = s.run + S.lead;
+        else { s.bl += rle_enc_small(s.run); tot = S.lead; }
+        s.bl += rle_enc_run(tot) + S.mid + 5ull * (S.trail / 255ull);
+        s.run = (uint32_t)(S.trail % 255ull);
+        s.cur = S.last;
+    }
+    return s;
+}
+
+// blockLength after finishRLE() (BlockCompressor.hpp:112-118)
+BZ_HD uint64_t state_final_length(const RleState &s) { return s.bl + rle_enc_small(s.run); }
+
+// Summary of `n` bytes read through `get(i)`.
+template <typename Get>
+BZ_HD Seg seg_from_bytes(Get get, uint32_t n)
+{
+    if (n == 0) return seg_empty();
+    Seg s;
+    s.pad = 0;
+    s.len = n;
+    s.mid = 0;
+    uint32_t cur = get(0);
+    s.first = cur;
+    uint32_t runlen = 1;
+    bool changed = false;
+    uint32_t lead = 0;
+    for (uint32_t i = 1; i < n; ++i) {
+        uint32_t v = get(i);
+        if (v == cur) {
+            ++runlen;
+        } else {
+            if (!changed) { lead = runlen; changed = true; }
+            else s.mid += rle_enc_run(runlen);
+            cur = v;
+            runlen = 1;
+        }
+    }
+    s.last = cur;
+    if (!changed) {
+        s.uniform = 1;
+        s.lead = s.trail = n;
+    } else {
+        s.uniform = 0;
+        s.lead = lead;
+        s.trail = runlen;
+    }
+    return s;
+}
+
+// ---- geometry of the summary tree ----
+constexpr uint32_t RLE_TILE = 2048;     // bytes per level-0 tile (one warp, 64 bytes per lane)
+constexpr uint32_t RLE_LANE_BYTES = 64;
+constexpr uint32_t RLE_FANOUT = 64;
+constexpr int RLE_MAX_LEVELS = 6;       // 2 KiB * 64^5 = 2 PiB
+
+} // namespace bz
+
+namespace bz {
+
+// Result of scanning bytes [lo, hi) of one tile with the machine in state `st` at lo.
+struct TileScanResult {
+    uint64_t pos;   // first q in [lo,hi) refused (st.bl > limit at entry), else hi
+    RleState st;    // state at pos
+};
+
+// One block of the sequential walk: starting with a fresh machine at `start`, find where the block ends.
+//   load(level, index)            -> Seg of tree node (level 0 = RLE_TILE bytes)
+//   scan(lo, hi, state, limit)    -> TileScanResult (lo, hi inside one tile)
+// Returns the end position e (== n_bytes, or the refused byte that starts the next block) and leaves the machine
+// state at e in `st_end` and the state at the first tile boundary after `start` in `st_tile` (for the emit pass).
+template <typename Load, typename Scan>
+BZ_HD uint64_t walk_block(uint64_t start, uint64_t n_bytes, uint64_t limit, int n_levels, Load load, Scan scan, RleState &st_end)
+{
+    RleState st = state_fresh();
+    uint64_t pos = start;
+    // 1. finish the partial tile
+    if (pos % RLE_TILE != 0) {
+        uint64_t hi = (pos / RLE_TILE + 1) * RLE_TILE;
+        if (hi > n_bytes) hi = n_bytes;
+        TileScanResult r = scan(pos, hi, st, limit);
+        if (r.pos < hi || r.st.bl > limit || hi == n_bytes) { st_end = r.st; return r.pos; }
+        st = r.st;
+        pos = hi;
+    }
+    // 2. climb: take the largest aligned node that fits; 3. once a node does not fit, only descend
+    bool descending = false;
+    int level = 0;
+    while (pos < n_bytes) {
+        if (!descending) {
+            level = 0;
+            uint64_t size = RLE_TILE;
+            while (level + 1 < n_levels && pos % (size * RLE_FANOUT) == 0) { size *= RLE_FANOUT; ++level; }
+        }
+        uint64_t size = RLE_TILE;
+        for (int l = 0; l < level; ++l) size *= RLE_FANOUT;
+        uint64_t hi = pos + size;
+        if (hi > n_bytes) hi = n_bytes;
+        Seg node = load(level, pos / size);
+        RleState nx = state_apply(node, st);
+        if (nx.bl <= limit) {
+            st = nx;
+            pos = hi;
+            continue;
+        }
+        if (level > 0) {
+            descending = true;
+            --level;
+            continue;
+        }
+        TileScanResult r = scan(pos, hi, st, limit);
+        st_end = r.st; // r.pos < hi, or refusal exactly at hi (r.st.bl > limit), or hi == n_bytes
+        return r.pos;
+    }
+    st_end = st;
+    return pos;
+}
+
+} // namespace bz

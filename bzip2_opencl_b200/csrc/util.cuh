@@ -1,0 +1,98 @@
+// util.cuh -- shared device helpers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bz {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
+{
+    uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src), hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d)
+{
+    uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, d), hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), d);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// inclusive warp scans
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= d) v += o;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_max(int v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= d) v = max(v, o);
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_sum64(uint64_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = shfl_up_u64(v, d);
+        if (lane_id() >= d) v += o;
+    }
+    return v;
+}
+
+// Block-wide exclusive sum over one value per thread (blockDim.x <= 1024, multiple of 32).
+// `scratch` needs 33 uint32_t.  Returns exclusive prefix; *total gets the block total.
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t *scratch, uint32_t *total)
+{
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    uint32_t inc = warp_incl_sum(v);
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < nw ? scratch[lane] : 0;
+        uint32_t xi = warp_incl_sum(x);
+        scratch[lane] = xi - x;
+        if (lane == 31) scratch[32] = xi;
+    }
+    __syncthreads();
+    uint32_t res = scratch[w] + inc - v;
+    if (total) *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+// Block-wide inclusive max over one value per thread, returns the exclusive max of all PREVIOUS threads (-1 if none).
+__device__ __forceinline__ int block_excl_max(int v, int *scratch, int *total)
+{
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    int inc = warp_incl_max(v);
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = lane < nw ? scratch[lane] : -1;
+        int xi = warp_incl_max(x);
+        int ex = __shfl_up_sync(FULL, xi, 1);
+        if (lane == 0) ex = -1;
+        scratch[lane] = ex;
+        if (lane == 31) scratch[32] = xi;
+    }
+    __syncthreads();
+    int prev = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) prev = -1;
+    int res = max(scratch[w], prev);
+    if (total) *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+} // namespace bz

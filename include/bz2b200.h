@@ -1,0 +1,141 @@
+/*
+ * bz2b200.h -- C ABI of the B200-native bzip2 block compressor (libbz2b200.so).
+ *
+ * This is the drop-in boundary for the compress path of Stan1slav337/Bzip2-OpenCL.  It replaces everything
+ * that reference keeps behind include/opencl.hpp -- Device / Memory<T> / Kernel (opencl.hpp:145-539), the
+ * 14 mirrored buffers and the blocking upload / kernel_close->run() / download sequence of
+ * OutputStream::closeBlocks() (OutputStream.hpp:83-116,215-223) -- AND the per-byte host RLE1 loop that feeds
+ * it (BlockCompressor.hpp:69-154 driven by app.cpp:108-116): raw input bytes go in, the concatenated
+ * bit-exact block bit streams come out.  The reference-named C++ facade (Config.hpp, CRC32.hpp,
+ * BlockCompressor.hpp, BitOutputStream.hpp, OutputStream.hpp in bzip2_opencl_b200/include/) sits on top of
+ * these entry points; INTEGRATION.md shows the binding.
+ *
+ * Plain pointers and sizes only.  Every `input` / `out` pointer may be a host pointer (pageable or pinned)
+ * or a device pointer on the handle's device; the library detects which.  All work is CUDA (sm_100a); there
+ * is no CPU fallback: without a usable device bz2b200_create fails with BZ2B200_E_CUDA.
+ *
+ * Threading: one handle = one host thread at a time.  One handle drives one GPU; multi-GPU jobs use one
+ * handle (one process) per GPU over disjoint block ranges (blocks share no state -- SURVEY 8(e)).
+ */
+#ifndef BZ2B200_H
+#define BZ2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bz2b200 bz2b200_t;
+
+enum {
+    BZ2B200_OK = 0,
+    BZ2B200_E_BLOCKSIZE = -1, /* multiplier outside 1..9 / bad base -> facade throws std::invalid_argument("Invalid block size") (OutputStream.hpp:73-76) */
+    BZ2B200_E_PARALLEL = -2,  /* max_blocks_in_flight < 1 -> std::invalid_argument("Invalid parallel block count") (OutputStream.hpp:78-81) */
+    BZ2B200_E_ARG = -3,       /* null pointer, bad start_bit, bad stage id ... */
+    BZ2B200_E_CUDA = -4,      /* no device / CUDA runtime error (text in bz2b200_last_error) */
+    BZ2B200_E_NOMEM = -5,     /* device or pinned allocation failed */
+    BZ2B200_E_OUTPUT = -6,    /* out_capacity / block_capacity too small; nothing useful was written */
+    BZ2B200_E_STATE = -7      /* stage dump asked for a block that is not in the last batch */
+};
+
+/* Number of CUDA devices visible (0 when there is none or the driver is unusable). */
+int bz2b200_device_count(void);
+
+/*
+ * Create a compressor on CUDA device `device_id`.
+ *   base_block_size       BLOCKSIZE_DEFAULT of the reference (Config.hpp:30): 10000 for the stock reference,
+ *                         100000 for real bzip2 block sizes (BASELINE configs).  Any value in [1000, 100000].
+ *   multiplier            1..9 (OutputStream.hpp:65-76); block size = base_block_size * multiplier.
+ *   max_blocks_in_flight  the reference's parallelBlockCnt (-p, OutputStream.hpp:67): how many blocks one
+ *                         device batch holds.  Output never depends on it.
+ * Replaces: Device{select_device_with_most_flops()} + the Memory<> / Kernel constructors (OutputStream.hpp:61,83-116).
+ */
+int bz2b200_create(bz2b200_t **handle, int device_id, int base_block_size, int multiplier, int max_blocks_in_flight);
+
+/* Releases every device and pinned buffer (Memory<T>::~Memory, opencl.hpp:276-278). NULL is allowed. */
+void bz2b200_destroy(bz2b200_t *handle);
+
+/* Upper bound for the bits bz2b200_compress_blocks can produce for n_bytes of input, in BYTES. */
+size_t bz2b200_max_output_bytes(const bz2b200_t *handle, size_t n_bytes);
+
+/*
+ * Find the block boundaries the reference's sequential RLE1 state machine would produce
+ * (BlockCompressor::write refusal rule, BlockCompressor.hpp:71-74; OutputStream::getNextCompressor,
+ * OutputStream.hpp:179-188) for `n_bytes` of input, without compressing.
+ *   block_starts[i] = input offset of the first byte of block i; *n_blocks = number of blocks (0 for empty input).
+ * If more than `capacity` blocks exist only the first `capacity` starts are stored and BZ2B200_E_OUTPUT is returned
+ * (*n_blocks is still the true count).  Used by multi-GPU callers to shard block ranges.
+ */
+int bz2b200_scan_blocks(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint64_t *block_starts, size_t capacity,
+                        uint64_t *n_blocks);
+
+/*
+ * The hot path.  Compress input[0..n_bytes) into bzip2 blocks: RLE1 + CRC32 + symbol map, BWT, MTF/RLE2,
+ * 6-table Huffman, bit packing -- everything closeBlocks() + kernel_close produce for every block
+ * (OutputStream.hpp:190-240, kernel.cpp:3099-3159), i.e. per block
+ *   48b magic | 32b block CRC | 1b 0 | 24b origPtr | symbol map | tables | selectors | codes     
+ * concatenated at BIT granularity with no padding between blocks.  The stream header ("BZh9") and trailer
+ * (end magic, stream CRC, padding) are NOT written -- OutputStream does that (OutputStream.hpp:126-128,169-172),
+ * or use bz2b200_compress_stream.
+ *
+ *   is_final     non-zero: the input ends here; the last partial block is flushed (finishRLE, BlockCompressor.hpp:112-118).
+ *                zero: only blocks that are complete (their refusing byte was seen) are produced; *consumed tells the
+ *                caller how many input bytes they covered -- the rest must be presented again at the start of the next call.
+ *   start_bit    0..7: bit offset inside out[0] at which the first block starts (the carry of the previous call, the
+ *                reference's leftBuffer, BitOutputStream.hpp:30-45).  The top start_bit bits of out[0] are written as 0
+ *                for the caller to OR its carry bits in.
+ *   out          receives ceil((start_bit + *out_nbits)/8) bytes; unused low bits of the last byte are 0.
+ *   out_nbits    number of bits produced (excluding start_bit).
+ *   block_crcs / block_nbits   per-block CRC (as written in the header) and bit length; may be NULL.  block_capacity
+ *                entries each; BZ2B200_E_OUTPUT if there are more blocks.
+ */
+int bz2b200_compress_blocks(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit,
+                            uint8_t *out, size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs,
+                            uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks);
+
+/*
+ * Whole .bz2 stream in one call: "BZh" + ('0'+multiplier), all blocks, end-of-stream magic, combined CRC
+ * (crc = rotl(crc,1) ^ blockCRC, OutputStream.hpp:202), zero padding.  == OutputStream ctor + write* + close().
+ */
+int bz2b200_compress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity,
+                            size_t *out_bytes);
+
+/* Per-stage device time (CUDA events on the handle's stream) and counters of the LAST compress call. */
+typedef struct {
+    float ms_total;       /* first kernel to last kernel, device side, excludes host<->device copies */
+    float ms_h2d, ms_d2h; /* copies done by the call (0 for device-resident buffers) */
+    float ms_rle, ms_bwt_sort0, ms_bwt_rounds, ms_bwt_finish, ms_mtf, ms_huffman, ms_emit;
+    uint64_t n_input, n_rle, n_mtf, n_out_bits, n_blocks;
+    uint64_t bwt_rounds;        /* prefix-doubling rounds executed (max over batches) */
+    uint64_t bwt_active_volume; /* sum over rounds of active (unresolved) rotations: rho * n_rle of SURVEY 8(d) */
+    uint64_t kernel_launches;   /* kernels launched by the call */
+} bz2b200_stats_t;
+int bz2b200_get_stats(const bz2b200_t *handle, bz2b200_stats_t *stats);
+
+/*
+ * Test hook: copy one intermediate of block `block_index` (index within the last
+ * compress call) to host memory.  Only blocks of the LAST device batch are available.
+ */
+enum {
+    BZ2B200_STAGE_RLE1 = 1,      /* uint8  [n]      RLE1'd block bytes          (BlockCompressor.hpp:134-154) */
+    BZ2B200_STAGE_PRESENT = 2,   /* uint8  [256]    blockValuesPresent          (BlockCompressor.hpp:136,148) */
+    BZ2B200_STAGE_BWT = 3,       /* uint8  [n]      BWT last column L           (kernel.cpp:2429) */
+    BZ2B200_STAGE_ORIGPTR = 4,   /* uint32 [1]      origPtr                     (kernel.cpp:3114-3116) */
+    BZ2B200_STAGE_MTF = 5,       /* uint16 [m]      MTF/RLE2 symbols incl. EOB  (kernel.cpp:2561-2649) */
+    BZ2B200_STAGE_FREQ = 6,      /* int32  [258]    mtfSymbolFrequencies        (kernel.cpp:2613,2641-2643) */
+    BZ2B200_STAGE_SELECTORS = 7, /* uint8  [nsel]   final selectors             (kernel.cpp:2940-2943) */
+    BZ2B200_STAGE_LENGTHS = 8,   /* uint8  [T*258]  final code lengths          (kernel.cpp:2947-2950) */
+    BZ2B200_STAGE_SA = 9         /* uint32 [n]      sorted rotation start indices (debug) */
+};
+int bz2b200_stage_dump(bz2b200_t *handle, uint64_t block_index, int stage, void *dst, size_t dst_capacity, size_t *len_bytes);
+
+const char *bz2b200_strerror(int code);
+/* Detail text of the last failure on this handle (CUDA error string ...); "" if none. */
+const char *bz2b200_last_error(const bz2b200_t *handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BZ2B200_H */

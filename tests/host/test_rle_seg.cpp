@@ -1,0 +1,142 @@
+// Host check of the RLE1 segment algebra + block walk (bzip2_opencl_b200/csrc/rle_seg.h) against a literal
+// byte-at-a-time run of the reference state machine (BlockCompressor.hpp:69-96).  Pure CPU; run by tests/test_host_logic.py.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cstring>
+#include "../../bzip2_opencl_b200/csrc/rle_seg.h"
+using namespace bz;
+
+static std::vector<Seg> level0(const std::vector<uint8_t> &in)
+{
+    size_t nt = (in.size() + RLE_TILE - 1) / RLE_TILE;
+    std::vector<Seg> out(nt);
+    for (size_t t = 0; t < nt; ++t) {
+        Seg acc = seg_empty();
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            size_t lo = t * RLE_TILE + lane * RLE_LANE_BYTES, hi = lo + RLE_LANE_BYTES;
+            if (hi > in.size()) hi = in.size();
+            if (lo >= hi) break;
+            const uint8_t *p = in.data() + lo;
+            acc = seg_combine(acc, seg_from_bytes([&](uint32_t i) { return (uint32_t)p[i]; }, (uint32_t)(hi - lo)));
+        }
+        out[t] = acc;
+    }
+    return out;
+}
+
+struct Blocks { std::vector<uint64_t> starts, lens; };
+
+static Blocks reference_walk(const std::vector<uint8_t> &in, uint64_t limit)
+{
+    Blocks b;
+    RleState st = state_fresh();
+    uint64_t start = 0;
+    for (size_t i = 0; i < in.size(); ++i) {
+        if (st.bl > limit) {
+            b.starts.push_back(start); b.lens.push_back(state_final_length(st));
+            st = state_fresh(); start = i;
+        }
+        state_step(st, in[i]);
+    }
+    if (!(st.bl == 0 && st.run == 0)) { b.starts.push_back(start); b.lens.push_back(state_final_length(st)); }
+    return b;
+}
+
+static Blocks tree_walk(const std::vector<uint8_t> &in, uint64_t limit)
+{
+    std::vector<std::vector<Seg>> lv;
+    lv.push_back(level0(in));
+    while (lv.back().size() > 1 && (int)lv.size() < RLE_MAX_LEVELS) {
+        const auto &c = lv.back();
+        std::vector<Seg> up((c.size() + RLE_FANOUT - 1) / RLE_FANOUT);
+        for (size_t j = 0; j < up.size(); ++j) {
+            Seg acc = seg_empty();
+            for (size_t k = j * RLE_FANOUT; k < (j + 1) * RLE_FANOUT && k < c.size(); ++k) acc = seg_combine(acc, c[k]);
+            up[j] = acc;
+        }
+        lv.push_back(up);
+    }
+    auto load = [&](int level, uint64_t idx) { return lv[level][idx]; };
+    auto scan = [&](uint64_t lo, uint64_t hi, RleState st, uint64_t lim) {
+        // emulate the warp: 32 lanes x 64 bytes from lo
+        Seg segs[32]; RleState sts[32];
+        Seg acc = seg_empty();
+        TileScanResult res; res.pos = hi;
+        bool found = false;
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            uint64_t a = lo + lane * RLE_LANE_BYTES, e = a + RLE_LANE_BYTES;
+            if (e > hi) e = hi;
+            sts[lane] = state_apply(acc, st);
+            if (a < e) {
+                const uint8_t *p = in.data() + a;
+                segs[lane] = seg_from_bytes([&](uint32_t i) { return (uint32_t)p[i]; }, (uint32_t)(e - a));
+                RleState s = sts[lane];
+                for (uint64_t q = a; q < e && !found; ++q) {
+                    if (s.bl > lim) { found = true; res.pos = q; res.st = s; break; }
+                    state_step(s, in[q]);
+                }
+                // consistency of apply vs step
+                if (!found) {
+                    RleState viaSeg = state_apply(segs[lane], sts[lane]);
+                    if (viaSeg.bl != s.bl || viaSeg.run != s.run || (s.run && viaSeg.cur != s.cur)) { printf("apply/step mismatch\n"); exit(2); }
+                }
+                acc = seg_combine(acc, segs[lane]);
+            }
+        }
+        if (!found) res.st = state_apply(acc, st);
+        return res;
+    };
+    Blocks b;
+    uint64_t s = 0, n = in.size();
+    while (s < n) {
+        RleState st;
+        uint64_t e = walk_block(s, n, limit, (int)lv.size(), load, scan, st);
+        b.starts.push_back(s); b.lens.push_back(state_final_length(st));
+        s = e;
+    }
+    return b;
+}
+
+static uint64_t rng = 88172645463325252ull;
+static uint32_t rnd() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 11); }
+
+int main()
+{
+    int cases = 0;
+    for (int iter = 0; iter < 400; ++iter) {
+        size_t n = rnd() % 300000 + 1;
+        if (iter % 7 == 0) n = rnd() % 5000 + 1;
+        std::vector<uint8_t> in(n);
+        int mode = iter % 6;
+        size_t i = 0;
+        while (i < n) {
+            uint32_t v = rnd() & 0xff;
+            size_t run;
+            switch (mode) {
+            case 0: run = 1; break;
+            case 1: run = rnd() % 6 + 1; break;
+            case 2: run = rnd() % 600 + 1; break;
+            case 3: run = (rnd() % 3 == 0) ? rnd() % 70000 + 1 : rnd() % 4 + 1; break;
+            case 4: run = n; v = 0; break;
+            default: run = (rnd() % 50 == 0) ? 255 * (rnd() % 5 + 1) + (rnd() % 3) - 1 : rnd() % 9 + 1; break;
+            }
+            if (mode == 1) v &= 3;
+            for (size_t k = 0; k < run && i < n; ++k) in[i++] = (uint8_t)v;
+        }
+        uint64_t bss[] = {20, 100, 1000, 10000, 90000, 300000};
+        for (uint64_t bs : bss) {
+            uint64_t limit = bs - 6;
+            Blocks a = reference_walk(in, limit), b = tree_walk(in, limit);
+            if (a.starts != b.starts || a.lens != b.lens) {
+                printf("MISMATCH iter %d mode %d n %zu bs %llu: ref %zu blocks, tree %zu blocks\n", iter, mode, n, (unsigned long long)bs, a.starts.size(), b.starts.size());
+                for (size_t k = 0; k < a.starts.size() && k < b.starts.size(); ++k)
+                    if (a.starts[k] != b.starts[k] || a.lens[k] != b.lens[k]) { printf(" first diff at block %zu: ref (%llu,%llu) tree (%llu,%llu)\n", k, (unsigned long long)a.starts[k], (unsigned long long)a.lens[k], (unsigned long long)b.starts[k], (unsigned long long)b.lens[k]); break; }
+                return 1;
+            }
+            ++cases;
+        }
+    }
+    printf("OK %d cases\n", cases);
+    return 0;
+}
