@@ -19,7 +19,7 @@ STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAG
 
 EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200_max_output_bytes", "bz2b200_scan_blocks",
            "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
-           "bz2b200_last_error"]
+           "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times"]
 
 
 class Stats(C.Structure):
@@ -66,6 +66,10 @@ def load_library() -> C.CDLL:
     L.bz2b200_strerror.argtypes = [C.c_int]
     L.bz2b200_last_error.restype = C.c_char_p
     L.bz2b200_last_error.argtypes = [vp]
+    L.bz2b200_set_profiling.restype = C.c_int
+    L.bz2b200_set_profiling.argtypes = [vp, C.c_int]
+    L.bz2b200_kernel_times.restype = C.c_int
+    L.bz2b200_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, u64p]
     _lib = L
     return L
 
@@ -165,6 +169,21 @@ class Compressor:
         s = Stats()
         self._check(self.lib.bz2b200_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def set_profiling(self, on: bool = True):
+        self._check(self.lib.bz2b200_set_profiling(self.h, int(on)))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total ms, launches, algorithmic bytes)} since profiling was switched on."""
+        out = {}
+        i = 0
+        while True:
+            name, ms, cnt, nbytes = C.c_char_p(), C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+            if self.lib.bz2b200_kernel_times(self.h, i, C.byref(name), C.byref(ms), C.byref(cnt), C.byref(nbytes)) != OK:
+                break
+            out[name.value.decode()] = (ms.value, cnt.value, nbytes.value)
+            i += 1
+        return out
 
     def stage(self, block_index: int, stage: int) -> np.ndarray:
         dtype = {STAGE_ORIGPTR: np.uint32, STAGE_MTF: np.uint16, STAGE_FREQ: np.int32, STAGE_SA: np.uint32}.get(stage, np.uint8)

@@ -192,22 +192,33 @@ def binary_records(n: int, seed: int) -> bytes:
     return rec.reshape(-1)[:n].tobytes()
 
 
-def mixed_corpus(n: int, seg: int = 16 << 20) -> bytes:
-    """Config C2: segments of `seg` bytes cycling text (seed 200+k) / code (300+k) / binary (400+k)."""
-    parts = []
-    k = 0
+def _mixed_segment(args):
+    k, m = args
+    kind = k % 3
+    if kind == 0:
+        return word_text(m, 200 + k)
+    if kind == 1:
+        return code_text(m, 300 + k)
+    return binary_records(m, 400 + k)
+
+
+def mixed_corpus(n: int, seg: int = 16 << 20, workers: int = 1) -> bytes:
+    """Config C2: segments of `seg` bytes cycling text (seed 200+k) / code (300+k) / binary (400+k).
+    Segments are independent, so `workers` > 1 generates them in a process pool (same bytes)."""
+    jobs = []
     have = 0
+    k = 0
     while have < n:
         m = min(seg, n - have)
-        kind = k % 3
-        if kind == 0:
-            parts.append(word_text(m, 200 + k))
-        elif kind == 1:
-            parts.append(code_text(m, 300 + k))
-        else:
-            parts.append(binary_records(m, 400 + k))
+        jobs.append((k, m))
         have += m
         k += 1
+    if workers > 1 and len(jobs) > 1:
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(max_workers=min(workers, len(jobs))) as ex:
+            parts = list(ex.map(_mixed_segment, jobs))
+    else:
+        parts = [_mixed_segment(j) for j in jobs]
     return b"".join(parts)
 
 

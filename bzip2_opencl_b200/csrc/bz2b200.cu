@@ -19,6 +19,9 @@
 
 using namespace bz;
 
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_flags, KID_k_bwt_tilescan, KID_k_bwt_regroup, KID_k_bwt_gather, KID_k_bwt_finish, KID_k_mtf_sim, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_flags", "k_bwt_tilescan", "k_bwt_regroup", "k_bwt_gather", "k_bwt_finish", "k_mtf_sim", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+
 namespace {
 
 struct DevBuf {
@@ -58,8 +61,51 @@ struct bz2b200 {
     bz2b200_stats_t stats{};
     uint64_t last_b0 = 0, last_nb = 0, last_total_blocks = 0;
     std::vector<uint64_t> h_starts;
+    std::vector<uint32_t> h_rle_len;
     cudaEvent_t ev[16] = {};
+
+    // optional per-kernel timing (bz2b200_set_profiling): CUDA events around every launch on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<int> prof_ids;
+    size_t prof_used = 0;
+    double k_ms[KID_COUNT] = {};
+    uint64_t k_launches[KID_COUNT] = {};
+    uint64_t k_bytes[KID_COUNT] = {};   // algorithmic bytes (one read or write of each operand) of the profiled launches
 };
+
+static inline void prof_mark(bz2b200 *h, int id)
+{
+    if (h->prof_used == h->prof_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_pool.push_back(e);
+    }
+    cudaEventRecord(h->prof_pool[h->prof_used++], h->stream);
+    if (id >= 0) h->prof_ids.push_back(id);
+}
+// all recorded launches have completed (caller synchronised): fold the event pairs into the per-kernel totals
+static void prof_collect(bz2b200 *h)
+{
+    for (size_t i = 0; i < h->prof_ids.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prof_pool[2 * i], h->prof_pool[2 * i + 1]);
+        h->k_ms[h->prof_ids[i]] += ms;
+        h->k_launches[h->prof_ids[i]] += 1;
+    }
+    h->prof_ids.clear();
+    h->prof_used = 0;
+}
+#define KBYTES(id, bytes)                            \
+    do {                                             \
+        if (h->profiling) h->k_bytes[id] += (uint64_t)(bytes); \
+    } while (0)
+#define KL(id, ...)                                  \
+    do {                                             \
+        if (h->profiling) prof_mark(h, id);          \
+        __VA_ARGS__;                                 \
+        if (h->profiling) prof_mark(h, -1);          \
+    } while (0)
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -266,30 +312,33 @@ extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
 
 template <typename K>
 static void radix_pass(bz2b200 *h, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *counts, int shift, int bits, uint32_t nb,
-                       uint32_t max_count)
+                       uint32_t max_count, uint64_t total_elems)
 {
     uint32_t tiles = (max_count + RS_TILE - 1) / RS_TILE;
     if (tiles == 0) return;
     dim3 grid(tiles, nb);
     uint32_t mask = (1u << bits) - 1u;
-    k_radix_hist<K><<<grid, RS_THREADS, 0, h->stream>>>(kin, counts, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR);
-    k_radix_scan<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->hist), counts, h->tilesR, ptr<uint32_t>(h->digit_base));
-    k_radix_scatter<K><<<grid, RS_THREADS, sizeof(ScatterSmem<K>), h->stream>>>(kin, vin, kout, vout, counts, h->S, shift, mask, ptr<uint32_t>(h->hist),
-                                                                                   h->tilesR, ptr<uint32_t>(h->digit_base));
+    KL(KID_k_radix_hist, k_radix_hist<K><<<grid, RS_THREADS, 0, h->stream>>>(kin, counts, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR));
+    KL(KID_k_radix_scan, k_radix_scan<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->hist), counts, h->tilesR, ptr<uint32_t>(h->digit_base)));
+    KL(KID_k_radix_scatter, k_radix_scatter<K><<<grid, RS_THREADS, sizeof(ScatterSmem<K>), h->stream>>>(kin, vin, kout, vout, counts, h->S, shift, mask,
+                                                                                                      ptr<uint32_t>(h->hist), h->tilesR, ptr<uint32_t>(h->digit_base)));
     h->stats.kernel_launches += 3;
+    KBYTES(KID_k_radix_hist, total_elems * sizeof(K));
+    KBYTES(KID_k_radix_scatter, total_elems * (2 * sizeof(K) + 8));
 }
 
 // sorts `total_bits` low bits of the keys; returns 0 if the result is in (k0,v0), 1 if in (k1,v1)
 template <typename K>
-static int radix_sort(bz2b200 *h, K *k0, uint32_t *v0, K *k1, uint32_t *v1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count)
+static int radix_sort(bz2b200 *h, K *k0, uint32_t *v0, K *k1, uint32_t *v1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count,
+                      uint64_t total_elems)
 {
     int npass = (total_bits + 7) / 8;
     int basebits = total_bits / npass, extra = total_bits % npass;
     int shift = 0, cur = 0;
     for (int p = 0; p < npass; ++p) {
         int bits = basebits + (p < extra ? 1 : 0);
-        if (cur == 0) radix_pass<K>(h, k0, v0, k1, v1, counts, shift, bits, nb, max_count);
-        else radix_pass<K>(h, k1, v1, k0, v0, counts, shift, bits, nb, max_count);
+        if (cur == 0) radix_pass<K>(h, k0, v0, k1, v1, counts, shift, bits, nb, max_count, total_elems);
+        else radix_pass<K>(h, k1, v1, k0, v0, counts, shift, bits, nb, max_count, total_elems);
         cur ^= 1;
         shift += bits;
     }
@@ -322,6 +371,7 @@ static int scan_input(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final,
     *n_blocks = 0;
     *consumed = 0;
     h->h_starts.assign(1, 0);
+    h->h_rle_len.clear();
     if (n == 0) return BZ2B200_OK;
     const uint64_t limit = (uint64_t)h->bs - 6;
     uint64_t cnt[RLE_MAX_LEVELS];
@@ -333,25 +383,28 @@ static int scan_input(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final,
     const uint64_t cap = n / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
     ENSURE(h->starts, (cap + 2) * 8);
     ENSURE(h->rle_len, (cap + 2) * 4);
-    k_rle_tile_seg<<<(unsigned)((cnt[0] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(d_in, n, ptr<Seg>(h->seg[0]), cnt[0]);
+    KL(KID_k_rle_tile_seg, k_rle_tile_seg<<<(unsigned)((cnt[0] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(d_in, n, ptr<Seg>(h->seg[0]), cnt[0]));
     for (int l = 1; l < nl; ++l)
-        k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
-                                                                                                           cnt[l]);
+        KL(KID_k_rle_reduce, k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
+                                                                                                           cnt[l]));
     WalkLevels lv;
     for (int l = 0; l < RLE_MAX_LEVELS; ++l) lv.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr;
     lv.n_levels = nl;
     uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
-    k_rle_walk<<<1, 32, 0, h->stream>>>(d_in, n, limit, is_final, lv, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), cap, d_info);
+    KL(KID_k_rle_walk, k_rle_walk<<<1, 32, 0, h->stream>>>(d_in, n, limit, is_final, lv, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), cap, d_info));
     h->stats.kernel_launches += nl + 1;
     CK(cudaMemcpyAsync(h->h_pinned, d_info, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    if (h->profiling) prof_collect(h);
     uint64_t nb = h->h_pinned[0];
     if (nb > cap) { h->err = "internal: block count bound exceeded"; return BZ2B200_E_CUDA; }
     *n_blocks = nb;
     *consumed = h->h_pinned[1];
     h->h_starts.resize(nb + 1);
     CK(cudaMemcpy(h->h_starts.data(), h->starts.p, (nb + 1) * 8, cudaMemcpyDeviceToHost));
+    h->h_rle_len.resize(nb);
+    if (nb) CK(cudaMemcpy(h->h_rle_len.data(), h->rle_len.p, nb * 4, cudaMemcpyDeviceToHost));
     return BZ2B200_OK;
 }
 
@@ -412,36 +465,33 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     CK(cudaEventRecord(h->ev[2], st));
     {
         dim3 grid((unsigned)((max_tiles + RLE_WARPS - 1) / RLE_WARPS), nb);
-        k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles);
-        k_rle_btile_scan<<<(nb + RLE_WARPS - 1) / RLE_WARPS, RLE_WARPS * 32, 0, st>>>(ptr<Seg>(h->segB), d_starts, (uint32_t)b0, nb, ptr<uint64_t>(h->tstate),
-                                                                                       max_tiles);
-        k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S,
-                                                     ptr<uint32_t>(h->present));
+        KL(KID_k_rle_btile_seg, k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles));
+        KL(KID_k_rle_btile_scan, k_rle_btile_scan<<<(nb + RLE_WARPS - 1) / RLE_WARPS, RLE_WARPS * 32, 0, st>>>(ptr<Seg>(h->segB), d_starts, (uint32_t)b0, nb, ptr<uint64_t>(h->tstate),
+                                                                                       max_tiles));
+        KL(KID_k_rle_emit, k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S,
+                                                     ptr<uint32_t>(h->present)));
         dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), nb);
-        k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint32_t>(h->crc));
-        k_crc_finish<<<(nb + 127) / 128, 128, 0, st>>>(d_starts, (uint32_t)b0, nb, ptr<uint32_t>(h->crc));
+        KL(KID_k_crc_chunks, k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint32_t>(h->crc)));
+        KL(KID_k_crc_finish, k_crc_finish<<<(nb + 127) / 128, 128, 0, st>>>(d_starts, (uint32_t)b0, nb, ptr<uint32_t>(h->crc)));
         stt.kernel_launches += 5;
     }
     CK(cudaEventRecord(h->ev[3], st));
 
     // ---- stage B: BWT
     uint32_t max_n = 0;
-    {
-        // rle_len is on the device; the host knows only an upper bound per block: min(bs, 5/4 * input + 5)
-        for (uint32_t i = 0; i < nb; ++i) {
-            uint64_t len = h->h_starts[b0 + i + 1] - h->h_starts[b0 + i];
-            uint64_t ub = std::min<uint64_t>((uint64_t)h->bs, len + len / 4 + 5);
-            max_n = std::max<uint32_t>(max_n, (uint32_t)ub);
-        }
+    uint64_t sum_n = 0;
+    for (uint32_t i = 0; i < nb; ++i) {
+        max_n = std::max(max_n, h->h_rle_len[b0 + i]);
+        sum_n += h->h_rle_len[b0 + i];
     }
     uint32_t *cntA = ptr<uint32_t>(h->cnt0), *cntB = ptr<uint32_t>(h->cnt1);
     {
         dim3 g((max_n + 255) / 256, nb);
-        k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA));
+        KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA)));
         stt.kernel_launches += 1;
     }
     int res = radix_sort<uint32_t>(h, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA), ptr<uint32_t>(h->kB), ptr<uint32_t>(h->vB), d_n, 8 * h->key0_bytes, nb,
-                                   max_n);
+                                   max_n, sum_n);
     CK(cudaEventRecord(h->ev[4], st));
 
     RegroupArgs A;
@@ -479,14 +529,15 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         A.sorted_len = sorted_len;
         CK(cudaMemsetAsync(d_scal + Scalars::TOTAL_ACTIVE, 0, 8, st));
         dim3 g((max_count + RG_TILE - 1) / RG_TILE, nb);
-        if (first) k_bwt_flags<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A);
-        else k_bwt_flags<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A);
-        k_bwt_tilescan<<<(nb + 7) / 8, 256, 0, st>>>(A, nb);
-        if (first) k_bwt_regroup<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A);
-        else k_bwt_regroup<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A);
+        if (first) KL(KID_k_bwt_flags, k_bwt_flags<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
+        else KL(KID_k_bwt_flags, k_bwt_flags<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
+        KL(KID_k_bwt_tilescan, k_bwt_tilescan<<<(nb + 7) / 8, 256, 0, st>>>(A, nb));
+        if (first) KL(KID_k_bwt_regroup, k_bwt_regroup<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
+        else KL(KID_k_bwt_regroup, k_bwt_regroup<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
         stt.kernel_launches += 3;
         CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::TOTAL_ACTIVE, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (h->profiling) prof_collect(h);
         uint64_t active = h->h_pinned[0];
         if (active == 0) break;
         stt.bwt_active_volume += active;
@@ -499,9 +550,9 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         pos_new = (pos_new == ptr<uint32_t>(h->pA)) ? ptr<uint32_t>(h->pB) : ptr<uint32_t>(h->pA);
         max_count = (uint32_t)std::min<uint64_t>(max_n, active);
         dim3 gg((max_count + 255) / 256, nb);
-        k_bwt_gather<<<gg, 256, 0, st>>>(kn, vn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len);
+        KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(kn, vn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len));
         stt.kernel_launches += 1;
-        int r2 = radix_sort<uint64_t>(h, kn, vn, reinterpret_cast<uint64_t *>(ks), vs, counts, 2 * h->nbits, nb, max_count);
+        int r2 = radix_sort<uint64_t>(h, kn, vn, reinterpret_cast<uint64_t *>(ks), vs, counts, 2 * h->nbits, nb, max_count, active);
         // r2 == 0: result in (kn, vn) which is buffer !res ; r2 == 1: result in (ks, vs) = buffer res
         res = r2 == 0 ? !res : res;
         sorted_len *= 2;
@@ -510,7 +561,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     CK(cudaEventRecord(h->ev[5], st));
     {
         dim3 g((max_n + 255) / 256, nb);
-        k_bwt_finish<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), ptr<uint32_t>(h->sa), ptr<uint32_t>(h->rank), d_n, S, ptr<uint8_t>(h->L), ptr<uint32_t>(h->orig));
+        KL(KID_k_bwt_finish, k_bwt_finish<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), ptr<uint32_t>(h->sa), ptr<uint32_t>(h->rank), d_n, S, ptr<uint8_t>(h->L), ptr<uint32_t>(h->orig)));
         stt.kernel_launches += 1;
     }
     CK(cudaEventRecord(h->ev[6], st));
@@ -518,19 +569,20 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     // ---- stage C: MTF + RLE2
     {
         dim3 gm((max_n + MTF_WARPS * MTF_TILE - 1) / (MTF_WARPS * MTF_TILE), nb);
-        k_mtf_sim<false><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
-                                                         h->tilesM, nullptr);
-        k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb);
-        k_mtf_sim<true><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
-                                                        h->tilesM, ptr<uint8_t>(h->ranks));
+        KL(KID_k_mtf_sim, k_mtf_sim<false><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+                                                         h->tilesM, nullptr));
+        KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
+        KL(KID_k_mtf_sim, k_mtf_sim<true><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+                                                        h->tilesM, ptr<uint8_t>(h->ranks)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
-        k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2);
-        k_rle2_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<R2Tile>(h->r2tiles), d_n, h->tilesR2, nb, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase),
+        KL(KID_k_rle2_tiles, k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2));
+        KL(KID_k_rle2_scan, k_rle2_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<R2Tile>(h->r2tiles), d_n, h->tilesR2, nb, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase),
                                                        ptr<uint32_t>(h->present), ptr<uint16_t>(h->mtf), S, ptr<uint32_t>(h->freq), ptr<uint32_t>(h->m_arr),
-                                                       ptr<uint32_t>(h->alpha_arr));
-        k_rle2_emit<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase), h->tilesR2, ptr<uint16_t>(h->mtf), S,
-                                                ptr<uint32_t>(h->freq));
+                                                       ptr<uint32_t>(h->alpha_arr)));
+        KL(KID_k_rle2_emit, k_rle2_emit<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase), h->tilesR2, ptr<uint16_t>(h->mtf), S,
+                                                ptr<uint32_t>(h->freq)));
         stt.kernel_launches += 6;
+        KBYTES(KID_k_mtf_sim, 3 * sum_n); // two passes read L, the second writes the ranks
     }
     CK(cudaEventRecord(h->ev[7], st));
 
@@ -538,35 +590,35 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     const uint32_t max_m = max_n + 1;
     dim3 gh((max_m + HP_SYMS - 1) / HP_SYMS, nb);
     {
-        k_huff_seeds<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->m_arr), ptr<uint32_t>(h->alpha_arr), ptr<uint32_t>(h->freq), nb, ptr<HuffBlock>(h->hb),
-                                                        ptr<uint8_t>(h->lens));
+        KL(KID_k_huff_seeds, k_huff_seeds<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->m_arr), ptr<uint32_t>(h->alpha_arr), ptr<uint32_t>(h->freq), nb, ptr<HuffBlock>(h->hb),
+                                                        ptr<uint8_t>(h->lens)));
         for (int it = 0; it < 4; ++it) {
-            k_huff_pass<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->sel),
-                                                    h->sel_stride);
-            k_huff_lengths<<<dim3(HUFF_MAXTABLES, nb), 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->databits),
-                                                                     it == 3);
+            KL(KID_k_huff_pass, k_huff_pass<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->sel),
+                                                    h->sel_stride));
+            KL(KID_k_huff_lengths, k_huff_lengths<<<dim3(HUFF_MAXTABLES, nb), 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->databits),
+                                                                     it == 3));
         }
-        k_huff_codes<<<(nb * HUFF_MAXTABLES + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->codes), ptr<uint32_t>(h->tabbits),
-                                                                      nb);
-        k_huff_selmtf<<<(nb + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbits),
-                                                      nb);
+        KL(KID_k_huff_codes, k_huff_codes<<<(nb * HUFF_MAXTABLES + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->codes), ptr<uint32_t>(h->tabbits),
+                                                                      nb));
+        KL(KID_k_huff_selmtf, k_huff_selmtf<<<(nb + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbits),
+                                                      nb));
         stt.kernel_launches += 11;
     }
     CK(cudaEventRecord(h->ev[8], st));
 
     // ---- stage E: bit emission at the final stream offsets
     {
-        k_block_bits<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->selbits), ptr<uint32_t>(h->tabbits),
-                                                        ptr<uint32_t>(h->databits), nb, ptr<uint64_t>(h->nbits_b));
-        k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, d_scal + Scalars::BITPOS, ptr<uint64_t>(h->bitoff));
-        k_emit_header<<<(nb + 31) / 32, 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
+        KL(KID_k_block_bits, k_block_bits<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->selbits), ptr<uint32_t>(h->tabbits),
+                                                        ptr<uint32_t>(h->databits), nb, ptr<uint64_t>(h->nbits_b)));
+        KL(KID_k_bit_offsets, k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, d_scal + Scalars::BITPOS, ptr<uint64_t>(h->bitoff)));
+        KL(KID_k_emit_header, k_emit_header<<<(nb + 31) / 32, 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
                                                       ptr<uint8_t>(h->selpos), h->sel_stride, ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
-                                                      ptr<uint64_t>(h->datastart));
-        k_data_tilebits<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint8_t>(h->sel), h->sel_stride,
-                                                    ptr<uint32_t>(h->tilebits), h->tilesD);
-        k_data_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tilebits), h->tilesD, nb);
-        k_emit_data<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->codes), ptr<uint8_t>(h->sel), h->sel_stride,
-                                                ptr<uint32_t>(h->tilebits), h->tilesD, ptr<uint64_t>(h->datastart), d_out_words);
+                                                      ptr<uint64_t>(h->datastart)));
+        KL(KID_k_data_tilebits, k_data_tilebits<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint8_t>(h->sel), h->sel_stride,
+                                                    ptr<uint32_t>(h->tilebits), h->tilesD));
+        KL(KID_k_data_scan, k_data_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tilebits), h->tilesD, nb));
+        KL(KID_k_emit_data, k_emit_data<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->codes), ptr<uint8_t>(h->sel), h->sel_stride,
+                                                ptr<uint32_t>(h->tilebits), h->tilesD, ptr<uint64_t>(h->datastart), d_out_words));
         stt.kernel_launches += 6;
         CK(cudaMemcpyAsync(ptr<uint32_t>(h->all_crc) + b0, h->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(ptr<uint64_t>(h->all_nbits) + b0, h->nbits_b.p, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
@@ -574,6 +626,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     CK(cudaEventRecord(h->ev[9], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (h->profiling) prof_collect(h);
     stt.ms_rle += ev_ms(h->ev[2], h->ev[3]);
     stt.ms_bwt_sort0 += ev_ms(h->ev[3], h->ev[4]);
     stt.ms_bwt_rounds += ev_ms(h->ev[4], h->ev[5]);
@@ -732,6 +785,25 @@ extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage,
     if (cap < len) return BZ2B200_E_OUTPUT;
     if (len) CK(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToHost));
     *len_bytes = len;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_set_profiling(bz2b200_t *h, int on)
+{
+    if (!h) return BZ2B200_E_ARG;
+    h->profiling = on != 0;
+    for (int i = 0; i < KID_COUNT; ++i) { h->k_ms[i] = 0; h->k_launches[i] = 0; h->k_bytes[i] = 0; }
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_kernel_times(const bz2b200_t *h, int index, const char **name, double *ms, uint64_t *launches, uint64_t *bytes)
+{
+    if (!h || !name || !ms || !launches || !bytes) return BZ2B200_E_ARG;
+    if (index < 0 || index >= KID_COUNT) return BZ2B200_E_STATE;
+    *name = kKernelNames[index];
+    *ms = h->k_ms[index];
+    *launches = h->k_launches[index];
+    *bytes = h->k_bytes[index];
     return BZ2B200_OK;
 }
 

@@ -115,6 +115,14 @@ typedef struct {
 int bz2b200_get_stats(const bz2b200_t *handle, bz2b200_stats_t *stats);
 
 /*
+ * Optional per-kernel timing: with profiling on, every kernel launch is bracketed by CUDA events on the launching stream;
+ * bz2b200_kernel_times(index) returns the name, summed milliseconds, launch count and (for the sort / MTF kernels) summed algorithmic bytes of kernel `index` since profiling was
+ * switched on (BZ2B200_E_STATE when index is past the last kernel).  Used by bench.py for the roofline line.
+ */
+int bz2b200_set_profiling(bz2b200_t *handle, int on);
+int bz2b200_kernel_times(const bz2b200_t *handle, int index, const char **name, double *ms, uint64_t *launches, uint64_t *algorithmic_bytes);
+
+/*
  * Test hook: copy one intermediate of block `block_index` (index within the last
  * compress call) to host memory.  Only blocks of the LAST device batch are available.
  */

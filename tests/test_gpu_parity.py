@@ -1,0 +1,271 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libbz2b200.so), against the oracle on the same inputs.
+Bar: bit-exact.  Every produced stream must also decode with libbzip2 (Python bz2) and the reference's own decoder."""
+import bz2
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bzip2_opencl_b200 import api, corpus, multi
+from oracle import oracle, refimpl
+from conftest import have_ref, ROOT
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "appendix_e.json")))
+CONFIGS = {"A": (10000, 9), "B": (100000, 9), "C": (100000, 1)}
+NAMES = [k for k in GOLD if not k.startswith("_")]
+
+_comp = {}
+
+
+def comp(mult=9, base=100000, parallel=24):
+    key = (mult, base, parallel)
+    if key not in _comp:
+        if len(_comp) > 6:
+            for c in _comp.values():
+                c.close()
+            _comp.clear()
+        _comp[key] = api.Compressor(mult, parallel, base)
+    return _comp[key]
+
+
+def test_native_library_is_what_runs():
+    lib = api.load_library()
+    assert lib.bz2b200_device_count() >= 1
+    c = comp()
+    c.compress(b"hello")
+    assert c.stats()["kernel_launches"] > 20  # the CUDA kernels ran; there is no other path
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_vectors(name, cfg):
+    base, mult = CONFIGS[cfg]
+    d = corpus.GOLDEN_INPUTS[name]()
+    out = comp(mult, base).compress(d)
+    size, sha = GOLD[name][cfg]
+    assert len(out) == size
+    assert out == oracle.compress(d, mult, base)            # bit-exact vs the oracle (same origPtr convention)
+    if GOLD[name]["primitive"]:
+        assert hashlib.sha256(out).hexdigest()[:16] == sha  # and vs the committed reference hash
+    if base == 100000:
+        assert bz2.decompress(out) == d
+    if have_ref(base):
+        assert refimpl.decompress(out, len(d) + 16, base) == d
+
+
+def _stage_check(c, d, mult, base, blocks):
+    for b in blocks:
+        o = oracle.block_stages(d, b, mult, base)
+        assert (c.stage(b, api.STAGE_RLE1) == o["rle"]).all(), f"RLE1 block {b}"
+        assert (c.stage(b, api.STAGE_PRESENT).astype(bool) == o["present"]).all(), f"presence block {b}"
+        assert (c.stage(b, api.STAGE_BWT) == o["L"]).all(), f"BWT block {b}"
+        assert int(c.stage(b, api.STAGE_ORIGPTR)[0]) == o["orig_ptr"], f"origPtr block {b}"
+        assert (c.stage(b, api.STAGE_MTF) == o["mtf"]).all(), f"MTF block {b}"
+        assert (c.stage(b, api.STAGE_FREQ) == o["freq"]).all(), f"freq block {b}"
+        assert (c.stage(b, api.STAGE_SELECTORS) == o["selectors"]).all(), f"selectors block {b}"
+        assert (c.stage(b, api.STAGE_LENGTHS).reshape(-1, 258) == o["code_lengths"]).all(), f"lengths block {b}"
+
+
+def test_stage_dumps_match_oracle():
+    d = corpus.word_text(250000, 77) + bytes(5000) + corpus.rand_bytes(140000, 3) + corpus.g_runs()[:100000]
+    for mult, base in ((1, 100000), (9, 10000)):
+        c = comp(mult, base, 64)
+        r = c.compress_blocks(d)
+        starts, lens, crcs = oracle.rle1_blocks(d, mult, base)
+        assert (c.scan_blocks(d) == starts).all()
+        assert (r["crcs"] == crcs).all()
+        _stage_check(c, d, mult, base, range(len(starts)))
+        # per-block bit lengths add up and match the oracle's
+        for b in range(len(starts)):
+            assert int(r["block_nbits"][b]) == oracle.block_stages(d, b, mult, base)["block_bits"]
+        assert int(r["block_nbits"].sum()) == r["nbits"]
+
+
+def test_empty_and_tiny_inputs():
+    c = comp(9, 100000)
+    assert c.compress(b"") == oracle.compress(b"", 9, 100000) and len(c.compress(b"")) == 14
+    for d in (b"a", b"ab", b"aa", b"aaaa", b"aaaaa", b"\x00", b"\xff" * 3, bytes(range(256)), b"abracadabra"):
+        out = c.compress(d)
+        assert out == oracle.compress(d, 9, 100000)
+        assert bz2.decompress(out) == d
+    r = c.compress_blocks(b"")
+    assert r["nbits"] == 0 and len(r["crcs"]) == 0 and r["consumed"] == 0
+
+
+@pytest.mark.parametrize("base", [1000, 3000])
+def test_block_boundary_edges(base):
+    # lengths around the refusal limit (blockLength > bs-6), long runs straddling boundaries, 255-run chunking
+    c = comp(1, base, 16)
+    bs = base
+    rng = np.random.default_rng(5)
+    cases = [bytes((i * 7 + 3) % 251 for i in range(n)) for n in (bs - 7, bs - 6, bs - 5, bs - 4, bs - 1, bs, bs + 1, 2 * bs + 3)]
+    cases += [bytes(n) for n in (254, 255, 256, 509, 510, 511, 5 * bs, 51 * bs + 17)]
+    cases += [bytes((i * 7 + 3) % 251 for i in range(bs - 20)) + b"z" * k + b"tail" * 50 for k in (1, 3, 4, 5, 6, 254, 255, 256, 300, 1000)]
+    for _ in range(6):
+        runs = rng.integers(1, 700, 60)
+        vals = rng.integers(0, 4, 60, dtype=np.uint8)
+        cases.append(np.repeat(vals, runs).tobytes())
+    for d in cases:
+        out = c.compress(d)
+        exp, offs, nonprim = oracle.compress_ex(d, 1, base)
+        assert out == exp, f"n={len(d)}"
+        s, l, crc = oracle.rle1_blocks(d, 1, base)
+        assert (c.scan_blocks(d) == s).all()
+
+
+def test_ragged_sizes_random_and_text():
+    rng = np.random.default_rng(11)
+    c = comp(2, 10000, 8)
+    for i in range(12):
+        n = int(rng.integers(1, 150000))
+        d = rng.integers(0, 256 if i % 2 else 3, n, dtype=np.uint8).tobytes() if i % 3 else corpus.word_text(n, i)
+        assert c.compress(d) == oracle.compress(d, 2, 10000), f"case {i} n={n}"
+
+
+def test_output_independent_of_parallel_block_count():
+    # the reference's output depends on -p; ours must not
+    d = corpus.word_text(700000, 21) + corpus.rand_bytes(300000, 22)
+    outs = {p: api.Compressor(1, p, 100000).compress(d) for p in (1, 3, 16)}
+    assert outs[1] == outs[3] == outs[16] == oracle.compress(d, 1, 100000)
+
+
+def test_streaming_calls_with_carry_bits():
+    # not-final calls return only complete blocks and how much input they consumed; start_bit carries the bit offset
+    d = corpus.word_text(430000, 31) + bytes(300000) + corpus.rand_bytes(150000, 32)
+    mult, base = 1, 100000
+    c = comp(mult, base, 4)
+    parts, pos, startbit = [], 0, 0
+    chunk = 260000
+    buf = b""
+    fed = 0
+    while fed < len(d) or buf:
+        take = d[fed:fed + chunk]
+        fed += len(take)
+        buf += take
+        final = fed >= len(d)
+        r = c.compress_blocks(buf, is_final=final, start_bit=startbit)
+        bits = np.unpackbits(np.frombuffer(r["bits"], dtype=np.uint8))[startbit:startbit + r["nbits"]]
+        assert not np.unpackbits(np.frombuffer(r["bits"], dtype=np.uint8))[:startbit].any()
+        parts.append((np.packbits(bits).tobytes(), int(r["nbits"]), r["crcs"]))
+        startbit = (startbit + r["nbits"]) % 8
+        buf = buf[r["consumed"]:]
+        if final:
+            assert not buf
+            break
+    assert api.stream_from_blocks(mult, parts) == oracle.compress(d, mult, base)
+
+
+def test_device_pointers_in_and_out():
+    import torch
+    d = corpus.mixed_corpus(3 << 20, 1 << 20)
+    c = comp(9, 100000)
+    t_in = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+    cap = c.max_output_bytes(len(d)) + 64
+    t_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    r = c.compress_blocks_ptr(t_in.data_ptr(), len(d), t_out.data_ptr(), cap)
+    bits = t_out[:(r["nbits"] + 7) // 8].cpu().numpy().tobytes()
+    assert api.stream_from_blocks(9, [(bits, r["nbits"], r["crcs"])]) == oracle.compress(d, 9, 100000)
+    # misaligned device input is staged internally
+    r2 = c.compress_blocks_ptr(t_in.data_ptr() + 1, len(d) - 1, t_out.data_ptr(), cap)
+    bits2 = t_out[:(r2["nbits"] + 7) // 8].cpu().numpy().tobytes()
+    assert api.stream_from_blocks(9, [(bits2, r2["nbits"], r2["crcs"])]) == oracle.compress(d[1:], 9, 100000)
+
+
+def test_output_too_small_is_reported():
+    c = comp(9, 100000)
+    d = corpus.rand_bytes(100000, 1)
+    src = np.frombuffer(d, dtype=np.uint8)
+    out = np.zeros(1000, dtype=np.uint8)
+    n = C.c_size_t(0)
+    rc = c.lib.bz2b200_compress_stream(c.h, src.ctypes.data_as(C.c_void_p), len(d), out.ctypes.data_as(C.c_void_p), 1000, C.byref(n))
+    assert rc == api.E_OUTPUT
+
+
+def test_sharded_block_ranges_reassemble_bit_exactly():
+    # the N-GPU path on one GPU: every rank's byte range goes through the C ABI separately, rank 0 concatenates
+    d = corpus.word_text(900000, 41) + bytes(200000) + corpus.rand_bytes(500000, 42)
+    mult, base = 2, 100000
+    c = comp(mult, base, 4)
+    starts = c.scan_blocks(d)
+    whole = oracle.compress(d, mult, base)
+    for world in (2, 3, 8):
+        parts = [multi.compress_shard(lambda buf, final: c.compress_blocks(buf, final), d, rng) for rng in multi.shard_byte_ranges(starts, len(d), world)]
+        assert api.stream_from_blocks(mult, parts) == whole
+
+
+@pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
+def test_config1_64mb_markov_text_vs_real_reference():
+    # BASELINE configs[0]: 64 MiB English-like Markov text, -9 (900k), against the reference's own code (oracle/_ref)
+    d = corpus.word_text(64 << 20, 101, markov=True)
+    out = api.Compressor(9, 80, 100000).compress(d)
+    ref = refimpl.compress(d, 9, 100000, threads=os.cpu_count() or 8)
+    assert out == ref
+    assert bz2.decompress(out) == d
+
+
+def test_config3_repetitive_deep_prefix_doubling():
+    # BASELINE configs[2] shapes: a full all-zero block ((0,0,0,0,251)^179999, non-primitive), period-2 blocks ((ab)^449998,
+    # non-primitive), period-3 (primitive at 899996), long-LCP text (100 kB segment repeated), near-periodic "ab" + noise
+    base_text = corpus.word_text(100_000, 500)
+    ab = np.frombuffer(b"ab" * 1_000_000, dtype=np.uint8).copy()
+    ab[65535::65536] = np.frombuffer(corpus.rand_bytes(len(ab[65535::65536]), 7), dtype=np.uint8)
+    d = bytes(46_000_000) + b"ab" * 1_400_000 + b"xyz" * 700_000 + base_text * 25 + ab.tobytes()
+    c = api.Compressor(9, 16, 100000)
+    out = c.compress(d)
+    assert c.stats()["bwt_rounds"] >= 15
+    exp, offs, nonprim = oracle.compress_ex(d, 9, 100000)
+    assert nonprim.sum() >= 3
+    assert out == exp
+    assert bz2.decompress(out) == d
+    if have_ref(100000):
+        ref = refimpl.compress(d, 9, 100000, threads=os.cpu_count() or 8)
+        assert oracle.mask_origptr(out, offs, nonprim) == oracle.mask_origptr(ref, offs, nonprim)
+        assert refimpl.decompress(out, len(d) + 16, 100000) == d
+
+
+def test_config5_block_size_sweep_roundtrip():
+    # BASELINE configs[4] scaled: every multiplier 1..9 on text; bz2 -d and the reference decoder both accept it
+    d = corpus.word_text(6 << 20, 5, markov=True)
+    for mult in range(1, 10):
+        out = comp(mult, 100000, 64).compress(d)
+        assert out == oracle.compress(d, mult, 100000), f"-{mult}"
+        assert bz2.decompress(out) == d
+        if have_ref(100000) and mult in (1, 5, 9):
+            assert refimpl.decompress(out, len(d) + 16, 100000) == d
+
+
+def test_config4_random_bytes_full_blocks_properties():
+    # BASELINE configs[3] shape at 128 MiB: incompressible bytes; size-independent properties instead of the oracle
+    d = corpus.rand_bytes(128 << 20, 4)
+    c = api.Compressor(9, 160, 100000)
+    r = c.compress_blocks(d)
+    starts = c.scan_blocks(d)
+    assert len(starts) == len(r["crcs"]) and starts[0] == 0 and (np.diff(starts.astype(np.int64)) > 0).all()
+    for b in (0, len(starts) // 2, len(starts) - 1):  # checksum of checksums: block CRCs are CRCs of the raw input ranges
+        lo = int(starts[b]); hi = int(starts[b + 1]) if b + 1 < len(starts) else len(d)
+        assert int(r["crcs"][b]) == oracle.crc32(d[lo:hi])
+    full = api.stream_from_blocks(9, [(r["bits"], r["nbits"], r["crcs"])])
+    assert bz2.decompress(full) == d
+    assert 1.0 < len(full) / len(d) < 1.01
+
+
+def test_cpp_facade_end_to_end(tmp_path):
+    # the reference-named C++ surface (OutputStream.hpp ...) driven exactly like app.cpp:103-117, both write() overloads
+    exe = str(tmp_path / "facade")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "host", "facade_smoke.cpp"), "-o", exe,
+                           "-DBZ2B200_BLOCKSIZE_DEFAULT=100000", "-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    d = corpus.word_text(1500000, 61) + bytes(700000) + corpus.rand_bytes(400000, 62)
+    src = tmp_path / "in.bin"
+    src.write_bytes(d)
+    for mult, par, bulk in ((1, 3, False), (1, 64, True), (9, 2, True)):
+        dst = tmp_path / f"out_{mult}_{par}.bz2"
+        subprocess.check_call([exe, str(src), str(dst), str(mult), str(par)] + (["bulk"] if bulk else []), env=env)
+        assert dst.read_bytes() == oracle.compress(d, mult, 100000)

@@ -1,0 +1,169 @@
+"""CPU-only checks of the host side: the RLE1 segment algebra + block walk, CRC combine arithmetic, the C++ facade surface,
+the C ABI's symbols and argument errors, and bit-granular stream concatenation (single process and world_size 2 over gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from bzip2_opencl_b200 import api, corpus, multi
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "tests", "host")
+
+
+def _compile(src, out, extra=()):
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", os.path.join(HOST, src), "-o", out, *extra]
+    subprocess.check_call(cmd)
+
+
+def test_rle_segment_algebra_and_walk(tmp_path):
+    exe = str(tmp_path / "rle_seg")
+    _compile("test_rle_seg.cpp", exe)
+    out = subprocess.check_output([exe]).decode()
+    assert out.startswith("OK")
+
+
+def test_crc_combine_math(tmp_path):
+    exe = str(tmp_path / "crc_math")
+    _compile("test_crc_math.cpp", exe)
+    assert subprocess.check_output([exe]).decode().strip() == "OK"
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bz2b200.h")).read()
+    declared = set(re.findall(r"\b(bz2b200_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("bz2b200_stage_dump)")
+    lib = api.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert set(api.EXPORTS) <= declared
+
+
+def test_c_abi_argument_errors_without_gpu():
+    lib = api.load_library()
+    h = C.c_void_p()
+    assert lib.bz2b200_create(C.byref(h), 0, 100000, 0, 4) == api.E_BLOCKSIZE
+    assert lib.bz2b200_create(C.byref(h), 0, 100000, 10, 4) == api.E_BLOCKSIZE
+    assert lib.bz2b200_create(C.byref(h), 0, 5, 9, 4) == api.E_BLOCKSIZE
+    assert lib.bz2b200_create(C.byref(h), 0, 100000, 9, 0) == api.E_PARALLEL
+    assert lib.bz2b200_strerror(api.E_BLOCKSIZE) == b"Invalid block size"
+    assert lib.bz2b200_strerror(api.E_PARALLEL) == b"Invalid parallel block count"
+    lib.bz2b200_destroy(None)
+    if lib.bz2b200_device_count() == 0:
+        # the product must fail loudly without a CUDA device -- no CPU fallback
+        assert lib.bz2b200_create(C.byref(h), 0, 100000, 9, 4) == api.E_CUDA
+        with pytest.raises(api.Bz2Error):
+            api.Compressor()
+    with pytest.raises(ValueError, match="Invalid block size"):
+        api.Compressor(multiplier=0)
+    with pytest.raises(ValueError, match="Invalid parallel block count"):
+        api.Compressor(parallel=0)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "bzip2_opencl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+                assert "libref_" not in text, f
+
+
+def test_facade_compiles_and_keeps_the_reference_error_behaviour(tmp_path):
+    exe = str(tmp_path / "facade")
+    _compile("facade_smoke.cpp", exe, ["-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"), "-I" + os.path.join(ROOT, "include"),
+                                      "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.check_output([exe, "errors"], env=env).decode()
+    assert out.startswith("errors-ok 5")
+    assert "f5d3bf25" in out and oracle.crc32(b"abbb") == 0xf5d3bf25
+
+
+def _split_blocks(stream, offs):
+    """cut an oracle stream into per-block (bits, nbits) using the oracle's block bit offsets"""
+    bits = np.unpackbits(np.frombuffer(stream, dtype=np.uint8))
+    ends = list(offs[1:]) + [len(bits) - ((len(bits) - int(offs[-1])) % 8 if False else 0)]
+    return bits, ends
+
+
+def test_stream_from_blocks_bit_concatenation():
+    d = corpus.word_text(350000, 5) + corpus.rand_bytes(120000, 9)
+    for mult, base in ((1, 100000), (2, 10000)):
+        stream, offs, _ = oracle.compress_ex(d, mult, base)
+        _, _, crcs = oracle.rle1_blocks(d, mult, base)
+        bits = np.unpackbits(np.frombuffer(stream, dtype=np.uint8))
+        nb = len(offs)
+        # the trailer starts 80 bits + padding before the end; find it: last block ends where the end magic begins
+        magic = np.unpackbits(np.frombuffer((0x177245385090).to_bytes(6, "big"), dtype=np.uint8))
+        end = None
+        for pad in range(8):
+            e = len(bits) - pad - 80
+            if e >= 0 and (bits[e:e + 48] == magic).all():
+                end = e
+        assert end is not None
+        bounds = [int(o) for o in offs] + [end]
+        for groups in (1, 2, 3, nb):
+            parts = []
+            per = -(-nb // groups)
+            for g in range(groups):
+                lo, hi = min(g * per, nb), min((g + 1) * per, nb)
+                seg = bits[bounds[lo]:bounds[hi]]
+                parts.append((np.packbits(seg).tobytes(), len(seg), crcs[lo:hi]))
+            assert api.stream_from_blocks(mult, parts) == stream
+    assert api.stream_from_blocks(9, []) == oracle.compress(b"", 9, 100000)
+
+
+def test_shard_ranges_cover_every_block_once():
+    starts = np.array([0, 100, 250, 400, 900], dtype=np.uint64)
+    for world in (1, 2, 3, 4, 8):
+        r = multi.shard_byte_ranges(starts, 1000, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == 1000
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert sum(x[3] - x[2] for x in r) == len(starts)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from bzip2_opencl_b200 import multi, corpus
+from oracle import oracle
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+data = corpus.word_text(300000, 11) + bytes(70000) + corpus.rand_bytes(90000, 12)
+mult, base = 1, 100000
+# rank 0 scans the boundaries (on a GPU box: bz2b200_scan_blocks) and broadcasts them: metadata only
+box = [oracle.rle1_blocks(data, mult, base)[0] if rank == 0 else None]
+dist.broadcast_object_list(box, src=0)
+starts = box[0]
+rng = multi.shard_byte_ranges(starts, len(data), world)[rank]
+def compress_blocks(buf, final):  # stand-in for Compressor.compress_blocks: the oracle, block by block (TEST ONLY)
+    stream, offs, _ = oracle.compress_ex(buf, mult, base)
+    bits = np.unpackbits(np.frombuffer(stream, dtype=np.uint8))
+    end = max(e for e in range(len(bits) - 87, len(bits) - 79) if e >= 32 and bits[e:e+24].tolist() == [int(c) for c in format(0x177245, "024b")])
+    seg = bits[32:end]
+    return dict(bits=np.packbits(seg).tobytes(), nbits=len(seg), crcs=oracle.rle1_blocks(buf, mult, base)[2])
+part = multi.compress_shard(compress_blocks, data, rng)
+stream = multi.gather_stream(mult, part, rank, world)
+if rank == 0:
+    assert stream == oracle.compress(data, mult, base), "sharded stream differs"
+    print("SHARDED-OK", len(stream))
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_sharding_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29531", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "SHARDED-OK" in out.stdout

@@ -1,0 +1,108 @@
+"""The oracle (oracle/bz2_oracle.c) is pinned here: golden hashes of SURVEY Appendix E, the real reference built for the
+CPU (oracle/_ref), and two independent decoders (Python's bz2 = libbzip2, and the reference's own InputStream)."""
+import bz2
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bzip2_opencl_b200 import corpus
+from oracle import oracle, refimpl
+from conftest import have_ref
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "appendix_e.json")))
+CONFIGS = {"A": (10000, 9), "B": (100000, 9), "C": (100000, 1)}
+NAMES = [k for k in GOLD if not k.startswith("_")]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_corpus_generators_are_pinned(name):
+    d = corpus.GOLDEN_INPUTS[name]()
+    assert len(d) == GOLD[name]["bytes"]
+    assert hashlib.sha256(d).hexdigest()[:16] == GOLD[name]["sha"]
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_golden(name, cfg):
+    base, mult = CONFIGS[cfg]
+    d = corpus.GOLDEN_INPUTS[name]()
+    out, offs, nonprim = oracle.compress_ex(d, mult, base)
+    size, sha = GOLD[name][cfg]
+    assert len(out) == size
+    if not nonprim.any():
+        assert hashlib.sha256(out).hexdigest()[:16] == sha  # bit-identical to the reference's output
+    elif have_ref(base):
+        # non-primitive blocks: only the 24-bit origPtr may differ
+        ref = refimpl.compress(d, mult, base, threads=4)
+        assert hashlib.sha256(ref).hexdigest()[:16] == sha
+        assert oracle.mask_origptr(out, offs, nonprim) == oracle.mask_origptr(ref, offs, nonprim)
+    if base == 100000:
+        assert bz2.decompress(out) == d
+    if have_ref(base):
+        assert refimpl.decompress(out, len(d) + 16, base) == d
+
+
+def _seeded_cases():
+    rng = np.random.default_rng(7)
+    cases = []
+    for i in range(10):
+        n = int(rng.integers(1, 400000))
+        kind = i % 5
+        if kind == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            d = rng.integers(0, 4, n, dtype=np.uint8)
+        elif kind == 2:
+            d = np.repeat(rng.integers(0, 256, n // 50 + 1, dtype=np.uint8), rng.integers(1, 400, n // 50 + 1))[:n]
+        elif kind == 3:
+            d = np.frombuffer(corpus.word_text(n, 1000 + i), dtype=np.uint8)
+        else:
+            d = np.frombuffer(corpus.binary_records(n, 2000 + i), dtype=np.uint8)
+        cases.append(d.tobytes())
+    return cases
+
+
+@pytest.mark.skipif(not have_ref(100000) or not have_ref(10000), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("idx", range(10))
+def test_oracle_equals_real_reference_on_seeded_inputs(idx):
+    d = _seeded_cases()[idx]
+    for base, mult in ((100000, 9), (100000, 1 + idx % 9), (10000, 9), (10000, 1 + (idx * 3) % 9)):
+        out, offs, nonprim = oracle.compress_ex(d, mult, base)
+        ref = refimpl.compress(d, mult, base, threads=2)
+        assert oracle.mask_origptr(out, offs, nonprim) == oracle.mask_origptr(ref, offs, nonprim)
+        if not nonprim.any():
+            assert out == ref
+        s1, l1, c1 = oracle.rle1_blocks(d, mult, base)
+        s2, l2, c2 = refimpl.rle1_blocks(d, mult, base)
+        assert (s1 == s2).all() and (l1 == l2).all() and (c1 == c2).all()
+
+
+@pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
+def test_oracle_stage_dumps_equal_reference():
+    d = corpus.word_text(250000, 77) + bytes(5000) + corpus.rand_bytes(40000, 3)
+    for b in range(3):
+        o = oracle.block_stages(d, b, 1, 100000)
+        r = refimpl.block_stages(d, b, 1, 100000)
+        assert o["length"] == r["length"] and o["orig_ptr"] == r["orig_ptr"] and o["crc"] == r["crc"]
+        assert (o["rle"] == r["rle"]).all() and (o["L"] == r["L"]).all() and (o["present"] == r["present"]).all()
+        assert (o["mtf"] == r["mtf"]).all() and (o["freq"] == r["freq"]).all() and (o["selectors"] == r["selectors"]).all()
+
+
+def test_oracle_block_boundary_edges():
+    # blocks of exactly bs, bs-1 ... bytes; refused byte starts the next block with a fresh run
+    for base in (1000, 4000):
+        bs = base
+        for n in (bs - 7, bs - 6, bs - 5, bs - 4, bs, bs + 1, 2 * bs):
+            d = bytes((i * 7 + 3) % 251 for i in range(n))
+            starts, lens, _ = oracle.rle1_blocks(d, 1, base)
+            assert int(lens.max()) <= bs
+            assert starts[0] == 0
+            out = oracle.compress(d, 1, base)
+            if base == 100000:
+                assert bz2.decompress(out) == d
+        z = bytes(5 * bs)
+        starts, lens, _ = oracle.rle1_blocks(z, 1, base)
+        assert int(lens.max()) <= bs and len(starts) >= 1
