@@ -388,7 +388,7 @@ static int scan_input(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final,
         KL(KID_k_rle_reduce, k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
                                                                                                            cnt[l]));
     WalkLevels lv;
-    for (int l = 0; l < RLE_MAX_LEVELS; ++l) lv.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr;
+    for (int l = 0; l < RLE_MAX_LEVELS; ++l) { lv.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; lv.cnt[l] = l < nl ? cnt[l] : 0; }
     lv.n_levels = nl;
     uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
     KL(KID_k_rle_walk, k_rle_walk<<<1, 32, 0, h->stream>>>(d_in, n, limit, is_final, lv, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), cap, d_info));
@@ -568,11 +568,11 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
 
     // ---- stage C: MTF + RLE2
     {
-        dim3 gm((max_n + MTF_WARPS * MTF_TILE - 1) / (MTF_WARPS * MTF_TILE), nb);
-        KL(KID_k_mtf_sim, k_mtf_sim<false><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+        dim3 gm((max_n + MS_THREADS * MTF_TILE - 1) / (MS_THREADS * MTF_TILE), nb);
+        KL(KID_k_mtf_sim, k_mtf_sim<false><<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
                                                          h->tilesM, nullptr));
         KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
-        KL(KID_k_mtf_sim, k_mtf_sim<true><<<gm, MTF_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
+        KL(KID_k_mtf_sim, k_mtf_sim<true><<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
                                                         h->tilesM, ptr<uint8_t>(h->ranks)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
         KL(KID_k_rle2_tiles, k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2));

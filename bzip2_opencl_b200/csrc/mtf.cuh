@@ -2,12 +2,13 @@
 // Reference: MTFAndRLE2StageEncoder + valueToFront, /root/reference/kernel.cpp:2513-2649 (one sequential loop per block).
 //
 // MTF is a serial dependency chain; the device formulation cuts every block into tiles of MTF_TILE symbols:
-//   k_mtf_sim<false>  one warp per tile runs MTF from the identity list and keeps only the final list; its first d
+//   k_mtf_sim<false>  one THREAD per tile runs MTF from the identity list and keeps only the final list; its first d
 //                     entries (d = distinct symbols seen) are the tile's symbols by recency -- a partial permutation
 //   k_mtf_compose     one warp per block composes those in tile order -> the exact list at every tile start
-//   k_mtf_sim<true>   one warp per tile re-runs MTF from its true start list and writes the ranks
-// The 256-entry list lives in registers: lane l holds entries 8l..8l+7 in one 64-bit word; a lookup is a SWAR
-// byte compare + ballot, the move-to-front is one shuffle + funnel shift.
+//   k_mtf_sim<true>   one thread per tile re-runs MTF from its true start list and writes the ranks
+// Each thread's 256-entry list is 32 64-bit words in shared memory (word 0 in a register); a lookup walks 8 entries per
+// step with a SWAR zero-byte test and shifts the words it passes -- typical BWT output resolves in word 0.  Symbols and
+// ranks are staged through shared memory so global traffic stays in 64-byte pieces.
 //   k_rle2_tiles / k_rle2_scan / k_rle2_emit  turn ranks into the RUNA/RUNB/rank+1/EOB symbol stream with an
 //                     exclusive scan of emission counts, and histogram the symbols (mtfSymbolFrequencies).
 #pragma once
@@ -29,75 +30,127 @@ __device__ __forceinline__ void build_symbol_map(const uint32_t *present8, uint8
     }
 }
 
-__device__ __forceinline__ uint64_t mtf_identity_lane() // entries 8l .. 8l+7
+// ---- per-thread MTF over one tile.  The 256-entry list of every thread lives in shared memory as 32 little-endian
+// 64-bit words (word k = entries 8k..8k+7), word 0 is kept in a register.  A lookup walks the list 8 entries at a time
+// with a SWAR zero-byte test; the words it passes are shifted up by one entry on the way (that IS the move-to-front).
+constexpr int MS_THREADS = 128;
+constexpr int MS_CHUNK = 64;          // symbols staged per thread per step
+constexpr int MS_STAGE_STRIDE = 68;   // bytes (17 words: conflict-free lane-strided access)
+constexpr int MS_LIST_WORDS = 33;     // 32 words + 1 pad (conflict-free 64-bit lane-strided access)
+constexpr uint64_t ONES8 = 0x0101010101010101ull;
+
+__device__ __forceinline__ uint32_t zero_byte_index(uint64_t x) // index of the lowest zero byte of x, 8 if none
 {
-    uint64_t b = (uint64_t)lane_id() * 8;
-    return (b) | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24) | ((b + 4) << 32) | ((b + 5) << 40) | ((b + 6) << 48) | ((b + 7) << 56);
+    uint64_t t = (x - ONES8) & ~x & 0x8080808080808080ull;
+    return t ? (uint32_t)(__ffsll((long long)t) - 1) >> 3 : 8u;
 }
 
-// position of symbol c in the distributed list; then move it to the front.  All 32 lanes call with the same c.
-__device__ __forceinline__ uint32_t mtf_step(uint64_t &v, uint32_t c)
+// rank of c in (w0, list[1..31]); moves c to the front
+__device__ __forceinline__ uint32_t mtf_lookup(uint64_t &w0, uint64_t *list, uint32_t c)
 {
-    const int lane = lane_id();
-    uint64_t x = v ^ (0x0101010101010101ull * c);
-    uint64_t t = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull; // lowest set bit marks the (unique) zero byte
-    unsigned hit = __ballot_sync(FULL, t != 0);
-    int hl = __ffs(hit) - 1;
-    uint32_t bi = (uint32_t)(__ffsll((long long)t) - 1) >> 3;
-    bi = __shfl_sync(FULL, bi, hl);
-    uint32_t pos = (uint32_t)hl * 8 + bi;
-    if (pos != 0) { // warp-uniform
-        uint32_t top = (uint32_t)(v >> 56);
-        uint32_t inc = __shfl_up_sync(FULL, top, 1);
-        if (lane == 0) inc = c;
-        uint64_t sh = (v << 8) | inc;
-        if (lane < hl) v = sh;
-        else if (lane == hl) {
-            uint64_t m = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
-            v = (sh & m) | (v & ~m);
-        }
+    if ((uint32_t)(w0 & 0xff) == c) return 0;
+    const uint64_t pat = ONES8 * c;
+    uint32_t bi = zero_byte_index(w0 ^ pat);
+    if (bi < 8) {
+        uint64_t m = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
+        w0 = (w0 & ~m) | (((w0 << 8) | c) & m);
+        return bi;
     }
-    return pos;
+    uint32_t carry = (uint32_t)(w0 >> 56);
+    w0 = (w0 << 8) | c;
+    for (uint32_t k = 1;; ++k) { // c is always present: the loop ends at k <= 31
+        uint64_t w = list[k];
+        bi = zero_byte_index(w ^ pat);
+        if (bi < 8) {
+            uint64_t m = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
+            list[k] = (w & ~m) | (((w << 8) | carry) & m);
+            return 8 * k + bi;
+        }
+        list[k] = (w << 8) | carry;
+        carry = (uint32_t)(w >> 56);
+    }
 }
 
-// WRITE=false: lists[tile] = final list from identity start, dcount[tile] = distinct symbols seen.
-// WRITE=true : lists[tile] is the true start list; ranks are written.
+// One THREAD per tile.  WRITE=false: lists[tile] = final list from the identity start, dcount[tile] = distinct symbols seen.
+// WRITE=true : lists[tile] is the true start list (k_mtf_compose); the ranks are written.
 template <bool WRITE>
-__global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_sim(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
-                                                             const uint32_t *__restrict__ present, uint64_t *__restrict__ lists,
-                                                             uint32_t *__restrict__ dcount, int tiles_per_block, uint8_t *__restrict__ ranks)
+__global__ void __launch_bounds__(MS_THREADS) k_mtf_sim(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                         const uint32_t *__restrict__ present, uint64_t *__restrict__ lists, uint32_t *__restrict__ dcount,
+                                                         int tiles_per_block, uint8_t *__restrict__ ranks)
 {
+    __shared__ uint64_t s_list[MS_THREADS * MS_LIST_WORDS];
+    __shared__ __align__(16) uint8_t s_stage[MS_THREADS * MS_STAGE_STRIDE];
     __shared__ uint8_t map[256];
     const uint32_t b = blockIdx.y;
     const uint32_t n = n_arr[b];
-    if ((uint64_t)blockIdx.x * MTF_WARPS * MTF_TILE >= n) return;
+    const uint32_t tile0 = blockIdx.x * MS_THREADS;
+    if ((uint64_t)tile0 * MTF_TILE >= n) return;
     build_symbol_map(present + b * 8, map);
     __syncthreads();
-    const uint32_t tile = blockIdx.x * MTF_WARPS + warp_id();
+    const int lane = lane_id(), w = warp_id();
+    const uint32_t wtile0 = tile0 + w * 32;          // first tile of this warp
+    if ((uint64_t)wtile0 * MTF_TILE >= n) return;
+    const uint32_t tile = wtile0 + lane;
     const uint32_t base = tile * MTF_TILE;
-    if (base >= n) return;
-    const uint32_t cnt = min((uint32_t)MTF_TILE, n - base);
-    const int lane = lane_id();
-    const uint64_t lidx = ((uint64_t)b * tiles_per_block + tile) * 32 + lane;
-    uint64_t v = WRITE ? lists[lidx] : mtf_identity_lane();
-    const uint8_t *src = L + (uint64_t)b * stride + base;
-    uint8_t *dst = WRITE ? ranks + (uint64_t)b * stride + base : nullptr;
-    uint32_t d = 0;
-    for (uint32_t k = 0; k < cnt; k += 32) {
-        uint32_t mine = (k + lane < cnt) ? map[src[k + lane]] : 0u;
-        uint32_t lim = min(32u, cnt - k);
-        uint32_t myrank = 0;
-        for (uint32_t j = 0; j < lim; ++j) {
-            uint32_t c = __shfl_sync(FULL, mine, j);
-            uint32_t pos = mtf_step(v, c);
-            if (WRITE) { if (lane == (int)j) myrank = pos; }
-            else if (pos >= d) ++d;
+    const uint32_t cnt = base < n ? min((uint32_t)MTF_TILE, n - base) : 0u;
+    const uint64_t lidx = ((uint64_t)b * tiles_per_block + tile) * 32;
+    uint64_t *list = s_list + threadIdx.x * MS_LIST_WORDS;
+    uint64_t w0 = 0;
+    if (cnt) {
+        if (WRITE) {
+            w0 = lists[lidx];
+            for (int k = 1; k < 32; ++k) list[k] = lists[lidx + k];
+        } else {
+            w0 = 0x0706050403020100ull;
+            for (uint64_t k = 1; k < 32; ++k) list[k] = 0x0706050403020100ull + ONES8 * (8 * k);
         }
-        if (WRITE && k + lane < cnt) dst[k + lane] = (uint8_t)myrank;
     }
-    if (!WRITE) {
-        lists[lidx] = v;
-        if (lane == 0) dcount[(uint64_t)b * tiles_per_block + tile] = d;
+    const uint8_t *src = L + (uint64_t)b * stride;
+    uint8_t *dst = WRITE ? ranks + (uint64_t)b * stride : nullptr;
+    const uint32_t wcnt = min((uint32_t)MTF_TILE, n - wtile0 * MTF_TILE); // symbols in the warp's fullest tile
+    const uint32_t nchunks = (wcnt + MS_CHUNK - 1) / MS_CHUNK;
+    uint8_t *wstage = s_stage + (w * 32) * MS_STAGE_STRIDE;
+    uint8_t *mine = s_stage + threadIdx.x * MS_STAGE_STRIDE;
+    uint32_t d = 0;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        // cooperative load: 4 lanes x 16 bytes cover one tile's 64-byte piece, 8 tiles per instruction
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
+            uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
+            if (off < n) {
+                uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + off));
+                uint32_t *sp = reinterpret_cast<uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
+                sp[0] = v.x; sp[1] = v.y; sp[2] = v.z; sp[3] = v.w;
+            }
+        }
+        __syncwarp();
+        int valid = (int)cnt - (int)(c * MS_CHUNK);
+        valid = valid < 0 ? 0 : (valid > MS_CHUNK ? MS_CHUNK : valid);
+        for (int i = 0; i < valid; ++i) {
+            uint32_t r = mtf_lookup(w0, list, map[mine[i]]);
+            if (WRITE) mine[i] = (uint8_t)r;
+            else if (r >= d) ++d;
+        }
+        __syncwarp();
+        if (WRITE) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
+                uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
+                if (off < n) {
+                    const uint32_t *sp = reinterpret_cast<const uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
+                    uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                    *reinterpret_cast<uint4 *>(dst + off) = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (!WRITE && cnt) {
+        lists[lidx] = w0;
+        for (int k = 1; k < 32; ++k) lists[lidx + k] = list[k];
+        dcount[(uint64_t)b * tiles_per_block + tile] = d;
     }
 }
 

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_reduce(const Seg *__rest
 // ---------------------------------------------------------------- the sequential walk (one warp)
 struct WalkLevels {
     const Seg *seg[RLE_MAX_LEVELS];
+    uint64_t cnt[RLE_MAX_LEVELS];
     int n_levels;
 };
 
@@ -160,9 +161,35 @@ struct DevTileScan {
     }
 };
 
-struct DevSegLoad {
+// A sibling group (<= 64 nodes of one level) in one go: lane l loads nodes 2l and 2l+1, a warp scan gives the machine
+// state in front of every node, a ballot finds the first node that overflows the block.
+struct DevSiblingStep {
     WalkLevels lv;
-    __device__ Seg operator()(int level, uint64_t idx) const { return lv.seg[level][idx]; }
+    __device__ bool operator()(int level, uint64_t i0, uint64_t iend, RleState &st, uint64_t limit, uint64_t &found) const
+    {
+        const int lane = lane_id();
+        const Seg *nodes = lv.seg[level];
+        const uint64_t ia = i0 + 2 * lane, ib = ia + 1;
+        Seg a = ia < iend ? nodes[ia] : seg_empty();
+        Seg b = ib < iend ? nodes[ib] : seg_empty();
+        Seg incl = warp_seg_incl_scan(seg_combine(a, b));
+        Seg excl = shfl_up_seg(incl, 1);
+        if (lane == 0) excl = seg_empty();
+        RleState sa = state_apply(excl, st), sb = state_apply(a, sa), sc = state_apply(b, sb);
+        const bool oa = a.len && sb.bl > limit;
+        const bool ob = !oa && b.len && sc.bl > limit;
+        const unsigned bal = __ballot_sync(FULL, oa || ob);
+        if (bal) {
+            const int f = __ffs(bal) - 1;
+            const int first_is_a = __shfl_sync(FULL, (int)oa, f);
+            found = i0 + 2 * (uint64_t)f + (first_is_a ? 0 : 1);
+            RleState pick = oa ? sa : sb;
+            st = shfl_state(pick, f);
+            return true;
+        }
+        st = shfl_state(sc, 31);
+        return false;
+    }
 };
 
 // info[0] = number of complete blocks, info[1] = bytes consumed by them.
@@ -172,11 +199,11 @@ __global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in,
 {
     __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
     DevTileScan scan{in, sm};
-    DevSegLoad load{lv};
+    DevSiblingStep step{lv};
     uint64_t s = 0, nb = 0;
     while (s < n_bytes) {
         RleState st;
-        uint64_t e = walk_block(s, n_bytes, limit, lv.n_levels, load, scan, st);
+        uint64_t e = walk_block_wide(s, n_bytes, limit, lv.n_levels, lv.cnt, step, scan, st);
         bool complete = (e < n_bytes) || is_final; // e == n_bytes without a refusal: flushed only when the stream ends
         if (!complete) break;
         if (lane_id() == 0 && nb < cap) {

@@ -253,4 +253,59 @@ BZ_HD uint64_t walk_block(uint64_t start, uint64_t n_bytes, uint64_t limit, int 
     return pos;
 }
 
+// Same walk, but every tree level is consumed a sibling group (<= 64 nodes) at a time so that a warp can evaluate the
+// whole group with one coalesced load and one scan:
+//   step(level, i0, iend, st, limit, found) -> true if pushing the machine through nodes [i0, iend) of `level` (at most 64)
+//       overflows; then `found` is the first overflowing node and `st` the state in front of it; otherwise `st` is the state
+//       behind node iend-1.
+//   cnt[level] = number of nodes at that level.
+template <typename Step, typename Scan>
+BZ_HD uint64_t walk_block_wide(uint64_t start, uint64_t n_bytes, uint64_t limit, int n_levels, const uint64_t *cnt, Step step, Scan scan,
+                               RleState &st_end)
+{
+    RleState st = state_fresh();
+    uint64_t pos = start;
+    if (pos % RLE_TILE != 0) {
+        uint64_t hi = (pos / RLE_TILE + 1) * RLE_TILE;
+        if (hi > n_bytes) hi = n_bytes;
+        TileScanResult r = scan(pos, hi, st, limit);
+        if (r.pos < hi || r.st.bl > limit || hi == n_bytes) { st_end = r.st; return r.pos; }
+        st = r.st;
+        pos = hi;
+    }
+    int level = 0;
+    uint64_t found = 0;
+    bool hit = false;
+    while (!hit) {
+        if (pos >= n_bytes) { st_end = st; return n_bytes; }
+        level = 0;
+        uint64_t i0 = pos / RLE_TILE;
+        while (level + 1 < n_levels && (i0 % RLE_FANOUT) == 0) { ++level; i0 /= RLE_FANOUT; }
+        uint64_t gend = (level == n_levels - 1) ? cnt[level] : (i0 / RLE_FANOUT + 1) * RLE_FANOUT;
+        if (gend > cnt[level]) gend = cnt[level];
+        uint64_t size = RLE_TILE;
+        for (int l = 0; l < level; ++l) size *= RLE_FANOUT;
+        while (i0 < gend && !hit) {
+            uint64_t iend = i0 + RLE_FANOUT < gend ? i0 + RLE_FANOUT : gend;
+            hit = step(level, i0, iend, st, limit, found);
+            i0 = iend;
+        }
+        if (!hit) {
+            pos = gend * size;
+            if (pos > n_bytes) pos = n_bytes;
+        }
+    }
+    while (level > 0) {
+        --level;
+        uint64_t i0 = found * RLE_FANOUT;
+        uint64_t iend = i0 + RLE_FANOUT < cnt[level] ? i0 + RLE_FANOUT : cnt[level];
+        step(level, i0, iend, st, limit, found); // must hit: the parent overflowed
+    }
+    pos = found * RLE_TILE;
+    uint64_t hi = pos + RLE_TILE < n_bytes ? pos + RLE_TILE : n_bytes;
+    TileScanResult r = scan(pos, hi, st, limit);
+    st_end = r.st;
+    return r.pos;
+}
+
 } // namespace bz

@@ -87,11 +87,23 @@ static Blocks tree_walk(const std::vector<uint8_t> &in, uint64_t limit)
         if (!found) res.st = state_apply(acc, st);
         return res;
     };
+    std::vector<uint64_t> cnt;
+    for (auto &v : lv) cnt.push_back(v.size());
+    auto step = [&](int level, uint64_t i0, uint64_t iend, RleState &st, uint64_t lim, uint64_t &found) {
+        for (uint64_t i = i0; i < iend; ++i) {
+            RleState nx = state_apply(lv[level][i], st);
+            if (nx.bl > lim) { found = i; return true; }
+            st = nx;
+        }
+        return false;
+    };
     Blocks b;
     uint64_t s = 0, n = in.size();
     while (s < n) {
-        RleState st;
+        RleState st, st2;
         uint64_t e = walk_block(s, n, limit, (int)lv.size(), load, scan, st);
+        uint64_t e2 = walk_block_wide(s, n, limit, (int)lv.size(), cnt.data(), step, scan, st2);
+        if (e != e2 || state_final_length(st) != state_final_length(st2)) { printf("walk_block_wide disagrees at start %llu: %llu vs %llu\n", (unsigned long long)s, (unsigned long long)e, (unsigned long long)e2); exit(3); }
         b.starts.push_back(s); b.lens.push_back(state_final_length(st));
         s = e;
     }
@@ -107,6 +119,7 @@ int main()
     for (int iter = 0; iter < 400; ++iter) {
         size_t n = rnd() % 300000 + 1;
         if (iter % 7 == 0) n = rnd() % 5000 + 1;
+        if (iter % 50 == 3) n = 9000000 + rnd() % 12000000; // deep tree: 4 levels
         std::vector<uint8_t> in(n);
         int mode = iter % 6;
         size_t i = 0;
