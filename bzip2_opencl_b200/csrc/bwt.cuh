@@ -209,7 +209,7 @@ struct RegroupArgs {
     uint64_t *keys_new;       // (group position << nbits), rank of the second half OR-ed in by k_bwt_gather
     int nbits;
     uint32_t sorted_len;      // rotations are now ordered by their first sorted_len bytes
-    unsigned long long *total_active; // sum of counts_new over blocks
+    unsigned long long *total_active; // [0] sum of counts_new over blocks, [3] max of counts_new (sizes the next round's grids)
 };
 
 template <typename K>
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_bwt_tilescan(RegroupArgs A, uint32_t n_
     if (lane == 0) {
         uint32_t nc = (A.sorted_len >= A.n_arr[b]) ? 0u : carry_keep;
         A.counts_new[b] = nc;
-        if (nc) atomicAdd(A.total_active, (unsigned long long)nc);
+        if (nc) { atomicAdd(A.total_active, (unsigned long long)nc); atomicMax(A.total_active + 3, (unsigned long long)nc); }
     }
 }
 

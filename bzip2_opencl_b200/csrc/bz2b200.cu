@@ -19,8 +19,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_flags, KID_k_bwt_tilescan, KID_k_bwt_regroup, KID_k_bwt_gather, KID_k_bwt_finish, KID_k_mtf_sim, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_flags", "k_bwt_tilescan", "k_bwt_regroup", "k_bwt_gather", "k_bwt_finish", "k_mtf_sim", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_flags, KID_k_bwt_tilescan, KID_k_bwt_regroup, KID_k_bwt_gather, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_flags", "k_bwt_tilescan", "k_bwt_regroup", "k_bwt_gather", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -167,6 +167,12 @@ static int upload_constants(bz2b200 *h)
     CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
     CK(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint64_t>)));
     CK(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint32_t>)));
+    // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
+    CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_emit_data, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_huff_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (h->device < 64) g_const_ready[h->device] = true;
     return BZ2B200_OK;
 }
@@ -346,7 +352,7 @@ static int radix_sort(bz2b200 *h, K *k0, uint32_t *v0, K *k1, uint32_t *v1, cons
 }
 
 struct Scalars { // layout of h->scalars (u64 each)
-    enum { TOTAL_ACTIVE = 0, BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 2 entries */ };
+    enum { TOTAL_ACTIVE = 0, BITPOS = 1, BATCH_BITS = 2, MAX_ACTIVE = 3, WALK_INFO = 4 /* 2 entries */ };
 };
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -528,6 +534,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         A.keys_new = kn;
         A.sorted_len = sorted_len;
         CK(cudaMemsetAsync(d_scal + Scalars::TOTAL_ACTIVE, 0, 8, st));
+        CK(cudaMemsetAsync(d_scal + Scalars::MAX_ACTIVE, 0, 8, st));
         dim3 g((max_count + RG_TILE - 1) / RG_TILE, nb);
         if (first) KL(KID_k_bwt_flags, k_bwt_flags<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
         else KL(KID_k_bwt_flags, k_bwt_flags<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
@@ -535,7 +542,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         if (first) KL(KID_k_bwt_regroup, k_bwt_regroup<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
         else KL(KID_k_bwt_regroup, k_bwt_regroup<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
         stt.kernel_launches += 3;
-        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::TOTAL_ACTIVE, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::TOTAL_ACTIVE, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h->profiling) prof_collect(h);
         uint64_t active = h->h_pinned[0];
@@ -548,7 +555,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         counts_next = (counts_next == cntA) ? cntB : cntA;
         pos_old = pos_new;
         pos_new = (pos_new == ptr<uint32_t>(h->pA)) ? ptr<uint32_t>(h->pB) : ptr<uint32_t>(h->pA);
-        max_count = (uint32_t)std::min<uint64_t>(max_n, active);
+        max_count = (uint32_t)std::min<uint64_t>(max_n, h->h_pinned[Scalars::MAX_ACTIVE]);
         dim3 gg((max_count + 255) / 256, nb);
         KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(kn, vn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len));
         stt.kernel_launches += 1;
@@ -569,11 +576,12 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     // ---- stage C: MTF + RLE2
     {
         dim3 gm((max_n + MS_THREADS * MTF_TILE - 1) / (MS_THREADS * MTF_TILE), nb);
-        KL(KID_k_mtf_sim, k_mtf_sim<false><<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
-                                                         h->tilesM, nullptr));
+        dim3 gq((max_n + MR_WARPS * MTF_TILE - 1) / (MR_WARPS * MTF_TILE), nb);
+        KL(KID_k_mtf_recency, k_mtf_recency<<<gq, MR_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists),
+                                                                          ptr<uint32_t>(h->dcount), h->tilesM));
         KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
-        KL(KID_k_mtf_sim, k_mtf_sim<true><<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount),
-                                                        h->tilesM, ptr<uint8_t>(h->ranks)));
+        KL(KID_k_mtf_ranks, k_mtf_ranks<<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), h->tilesM,
+                                                                   ptr<uint8_t>(h->ranks)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
         KL(KID_k_rle2_tiles, k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2));
         KL(KID_k_rle2_scan, k_rle2_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<R2Tile>(h->r2tiles), d_n, h->tilesR2, nb, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase),
@@ -582,7 +590,8 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_rle2_emit, k_rle2_emit<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase), h->tilesR2, ptr<uint16_t>(h->mtf), S,
                                                 ptr<uint32_t>(h->freq)));
         stt.kernel_launches += 6;
-        KBYTES(KID_k_mtf_sim, 3 * sum_n); // two passes read L, the second writes the ranks
+        KBYTES(KID_k_mtf_recency, sum_n);
+        KBYTES(KID_k_mtf_ranks, 2 * sum_n);
     }
     CK(cudaEventRecord(h->ev[7], st));
 

@@ -2,13 +2,13 @@
 // Reference: MTFAndRLE2StageEncoder + valueToFront, /root/reference/kernel.cpp:2513-2649 (one sequential loop per block).
 //
 // MTF is a serial dependency chain; the device formulation cuts every block into tiles of MTF_TILE symbols:
-//   k_mtf_sim<false>  one THREAD per tile runs MTF from the identity list and keeps only the final list; its first d
-//                     entries (d = distinct symbols seen) are the tile's symbols by recency -- a partial permutation
+//   k_mtf_recency     one warp per tile: the tile's distinct symbols by recency (a partial permutation), computed in parallel from
+//                     last-occurrence positions -- what running MTF over the tile would leave at the front of the list
 //   k_mtf_compose     one warp per block composes those in tile order -> the exact list at every tile start
-//   k_mtf_sim<true>   one thread per tile re-runs MTF from its true start list and writes the ranks
-// Each thread's 256-entry list is 32 64-bit words in shared memory (word 0 in a register); a lookup walks 8 entries per
-// step with a SWAR zero-byte test and shifts the words it passes -- typical BWT output resolves in word 0.  Symbols and
-// ranks are staged through shared memory so global traffic stays in 64-byte pieces.
+//   k_mtf_ranks       one THREAD per tile re-runs MTF from its true start list and writes the ranks.  The first 16 list
+//                     entries sit in four registers (typical BWT output resolves there); the other 240 live in shared memory
+//                     and are walked 16 entries per step with per-byte SIMD compares (__vcmpeq4) and __byte_perm shifts.
+//                     Symbols and ranks are staged through shared memory so global traffic stays in 64-byte pieces.
 //   k_rle2_tiles / k_rle2_scan / k_rle2_emit  turn ranks into the RUNA/RUNB/rank+1/EOB symbol stream with an
 //                     exclusive scan of emission counts, and histogram the symbols (mtfSymbolFrequencies).
 #pragma once
@@ -45,40 +45,117 @@ __device__ __forceinline__ uint32_t zero_byte_index(uint64_t x) // index of the 
     return t ? (uint32_t)(__ffsll((long long)t) - 1) >> 3 : 8u;
 }
 
-// rank of c in (w0, list[1..31]); moves c to the front
-__device__ __forceinline__ uint32_t mtf_lookup(uint64_t &w0, uint64_t *list, uint32_t c)
+__device__ __forceinline__ uint64_t low_bytes_mask(uint32_t bi) // bytes 0..bi
 {
-    if ((uint32_t)(w0 & 0xff) == c) return 0;
-    const uint64_t pat = ONES8 * c;
-    uint32_t bi = zero_byte_index(w0 ^ pat);
-    if (bi < 8) {
-        uint64_t m = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
-        w0 = (w0 & ~m) | (((w0 << 8) | c) & m);
-        return bi;
-    }
-    uint32_t carry = (uint32_t)(w0 >> 56);
-    w0 = (w0 << 8) | c;
-    for (uint32_t k = 1;; ++k) { // c is always present: the loop ends at k <= 31
-        uint64_t w = list[k];
-        bi = zero_byte_index(w ^ pat);
-        if (bi < 8) {
-            uint64_t m = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
-            list[k] = (w & ~m) | (((w << 8) | carry) & m);
-            return 8 * k + bi;
-        }
-        list[k] = (w << 8) | carry;
-        carry = (uint32_t)(w >> 56);
-    }
+    return bi >= 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
 }
 
-// One THREAD per tile.  WRITE=false: lists[tile] = final list from the identity start, dcount[tile] = distinct symbols seen.
-// WRITE=true : lists[tile] is the true start list (k_mtf_compose); the ranks are written.
-template <bool WRITE>
-__global__ void __launch_bounds__(MS_THREADS) k_mtf_sim(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
-                                                         const uint32_t *__restrict__ present, uint64_t *__restrict__ lists, uint32_t *__restrict__ dcount,
-                                                         int tiles_per_block, uint8_t *__restrict__ ranks)
+// ---- pass 1: the tile's distinct symbols ordered by recency (most recent first).  Fully parallel: last occurrence of every
+// symbol with shared-memory atomicMax (only run ends write), then a counting rank over the <= 256 present symbols.
+// lists[tile] receives the order in its first d = dcount[tile] entries; that is all k_mtf_compose reads.
+constexpr int MR_WARPS = 8;
+__global__ void __launch_bounds__(MR_WARPS * 32) k_mtf_recency(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                                const uint32_t *__restrict__ present, uint64_t *__restrict__ lists,
+                                                                uint32_t *__restrict__ dcount, int tiles_per_block)
 {
-    __shared__ uint64_t s_list[MS_THREADS * MS_LIST_WORDS];
+    __shared__ uint8_t map[256];
+    __shared__ int s_last[MR_WARPS][256];
+    __shared__ int s_cpos[MR_WARPS][256];
+    __shared__ __align__(8) uint8_t s_order[MR_WARPS][256];
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = n_arr[b];
+    if ((uint64_t)blockIdx.x * MR_WARPS * MTF_TILE >= n) return;
+    build_symbol_map(present + b * 8, map);
+    __syncthreads();
+    const int lane = lane_id(), w = warp_id();
+    const uint32_t tile = blockIdx.x * MR_WARPS + w;
+    const uint32_t base = tile * MTF_TILE;
+    if (base >= n) return;
+    const uint32_t cnt = min((uint32_t)MTF_TILE, n - base);
+    int *last = s_last[w], *cpos = s_cpos[w];
+    uint8_t *order = s_order[w];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { last[lane * 8 + j] = -1; order[lane * 8 + j] = 0; }
+    __syncwarp();
+    const uint8_t *src = L + (uint64_t)b * stride + base;
+    for (uint32_t k = 0; k < cnt; k += 32) {
+        const uint32_t p = k + lane;
+        const uint32_t sym = p < cnt ? map[src[p]] : 0xffffu;
+        const uint32_t nxt = __shfl_down_sync(FULL, sym, 1);
+        if (p < cnt && (lane == 31 || sym != nxt)) atomicMax(&last[sym], (int)p);
+    }
+    __syncwarp();
+    // compact the present symbols: (position of last occurrence) per symbol
+    int mine[8];
+    uint32_t have = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mine[j] = last[lane * 8 + j]; have += mine[j] >= 0; }
+    uint32_t off = warp_incl_sum(have) - have;
+    const uint32_t d = __shfl_sync(FULL, off + have, 31);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (mine[j] >= 0) cpos[off++] = mine[j];
+    __syncwarp();
+    // rank = number of present symbols seen later
+    uint32_t rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t i = 0; i < d; ++i) {
+        const int v = cpos[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rk[j] += v > mine[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (mine[j] >= 0) order[rk[j]] = (uint8_t)(lane * 8 + j);
+    __syncwarp();
+    const uint64_t lidx = ((uint64_t)b * tiles_per_block + tile) * 32;
+    lists[lidx + lane] = *reinterpret_cast<const uint64_t *>(order + lane * 8);
+    if (lane == 0) dcount[(uint64_t)b * tiles_per_block + tile] = d;
+}
+
+// ---- pass 2: one THREAD per tile re-runs MTF from its true start list (k_mtf_compose) and writes the ranks.
+// The list is 16 x uint4 (16 entries each).  Entries 0..15 live in four registers; the rest in shared memory.  A lookup
+// compares 16 entries per step with four per-byte SIMD compares (__vcmpeq4) and shifts the passed words by one entry with
+// __byte_perm -- that shift IS the move-to-front.
+constexpr int ML_STRIDE4 = 17; // uint4 per thread (16 + 1 pad: conflict-free 128-bit lane-strided access)
+
+struct Quad { uint32_t x, y, z, w; };
+
+// q shifted up by one entry with `in` entering at entry 0
+__device__ __forceinline__ Quad quad_shift(const Quad &q, uint32_t in)
+{
+    Quad s;
+    s.x = (q.x << 8) | in;
+    s.y = __byte_perm(q.x, q.y, 0x6543);
+    s.z = __byte_perm(q.y, q.z, 0x6543);
+    s.w = __byte_perm(q.z, q.w, 0x6543);
+    return s;
+}
+// entry index (0..15) of byte value `pat`/0x01010101 in q, or 16
+__device__ __forceinline__ uint32_t quad_find(const Quad &q, uint32_t pat)
+{
+    uint32_t m0 = __vcmpeq4(q.x, pat), m1 = __vcmpeq4(q.y, pat), m2 = __vcmpeq4(q.z, pat), m3 = __vcmpeq4(q.w, pat);
+    if ((m0 | m1 | m2 | m3) == 0) return 16;
+    if (m0) return (uint32_t)(__ffs((int)m0) - 1) >> 3;
+    if (m1) return 4 + ((uint32_t)(__ffs((int)m1) - 1) >> 3);
+    if (m2) return 8 + ((uint32_t)(__ffs((int)m2) - 1) >> 3);
+    return 12 + ((uint32_t)(__ffs((int)m3) - 1) >> 3);
+}
+// entries 0..p come from the shifted quad s, entries above p stay
+__device__ __forceinline__ Quad quad_blend(const Quad &old, const Quad &s, uint32_t p)
+{
+    const uint32_t wi = p >> 2, bi = p & 3;
+    const uint32_t m = bi == 3 ? 0xffffffffu : ((1u << (8 * (bi + 1))) - 1u);
+    Quad r;
+    r.x = wi > 0 ? s.x : ((old.x & ~m) | (s.x & m));
+    r.y = wi > 1 ? s.y : (wi == 1 ? ((old.y & ~m) | (s.y & m)) : old.y);
+    r.z = wi > 2 ? s.z : (wi == 2 ? ((old.z & ~m) | (s.z & m)) : old.z);
+    r.w = wi == 3 ? ((old.w & ~m) | (s.w & m)) : old.w;
+    return r;
+}
+
+__global__ void __launch_bounds__(MS_THREADS) k_mtf_ranks(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                           const uint32_t *__restrict__ present, const uint64_t *__restrict__ lists,
+                                                           int tiles_per_block, uint8_t *__restrict__ ranks)
+{
+    __shared__ uint4 s_list[MS_THREADS * ML_STRIDE4];
     __shared__ __align__(16) uint8_t s_stage[MS_THREADS * MS_STAGE_STRIDE];
     __shared__ uint8_t map[256];
     const uint32_t b = blockIdx.y;
@@ -88,69 +165,90 @@ __global__ void __launch_bounds__(MS_THREADS) k_mtf_sim(const uint8_t *__restric
     build_symbol_map(present + b * 8, map);
     __syncthreads();
     const int lane = lane_id(), w = warp_id();
-    const uint32_t wtile0 = tile0 + w * 32;          // first tile of this warp
+    const uint32_t wtile0 = tile0 + w * 32; // first tile of this warp
     if ((uint64_t)wtile0 * MTF_TILE >= n) return;
     const uint32_t tile = wtile0 + lane;
     const uint32_t base = tile * MTF_TILE;
     const uint32_t cnt = base < n ? min((uint32_t)MTF_TILE, n - base) : 0u;
-    const uint64_t lidx = ((uint64_t)b * tiles_per_block + tile) * 32;
-    uint64_t *list = s_list + threadIdx.x * MS_LIST_WORDS;
-    uint64_t w0 = 0;
+    const uint4 *gl = reinterpret_cast<const uint4 *>(lists + ((uint64_t)b * tiles_per_block + tile) * 32);
+    uint4 *list = s_list + threadIdx.x * ML_STRIDE4;
+    Quad r = {0, 0, 0, 0};
     if (cnt) {
-        if (WRITE) {
-            w0 = lists[lidx];
-            for (int k = 1; k < 32; ++k) list[k] = lists[lidx + k];
-        } else {
-            w0 = 0x0706050403020100ull;
-            for (uint64_t k = 1; k < 32; ++k) list[k] = 0x0706050403020100ull + ONES8 * (8 * k);
-        }
+        uint4 v = gl[0];
+        r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+        for (int k = 1; k < 16; ++k) list[k] = gl[k];
     }
     const uint8_t *src = L + (uint64_t)b * stride;
-    uint8_t *dst = WRITE ? ranks + (uint64_t)b * stride : nullptr;
-    const uint32_t wcnt = min((uint32_t)MTF_TILE, n - wtile0 * MTF_TILE); // symbols in the warp's fullest tile
+    uint8_t *dst = ranks + (uint64_t)b * stride;
+    const uint32_t wcnt = min((uint32_t)MTF_TILE, n - wtile0 * MTF_TILE); // lane 0's tile is the fullest
     const uint32_t nchunks = (wcnt + MS_CHUNK - 1) / MS_CHUNK;
     uint8_t *wstage = s_stage + (w * 32) * MS_STAGE_STRIDE;
     uint8_t *mine = s_stage + threadIdx.x * MS_STAGE_STRIDE;
-    uint32_t d = 0;
     for (uint32_t c = 0; c < nchunks; ++c) {
-        // cooperative load: 4 lanes x 16 bytes cover one tile's 64-byte piece, 8 tiles per instruction
+        // cooperative load: 4 lanes x 16 bytes cover one tile's 64-byte piece, 8 tiles per instruction; bytes are mapped to
+        // dense symbol indices on the way in (keeps the table lookup out of the serial chain)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
             uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
             if (off < n) {
                 uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + off));
+                uint32_t in[4] = {v.x, v.y, v.z, v.w};
                 uint32_t *sp = reinterpret_cast<uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
-                sp[0] = v.x; sp[1] = v.y; sp[2] = v.z; sp[3] = v.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t x = in[j];
+                    sp[j] = (uint32_t)map[x & 0xff] | ((uint32_t)map[(x >> 8) & 0xff] << 8) | ((uint32_t)map[(x >> 16) & 0xff] << 16) |
+                            ((uint32_t)map[x >> 24] << 24);
+                }
             }
         }
         __syncwarp();
         int valid = (int)cnt - (int)(c * MS_CHUNK);
         valid = valid < 0 ? 0 : (valid > MS_CHUNK ? MS_CHUNK : valid);
         for (int i = 0; i < valid; ++i) {
-            uint32_t r = mtf_lookup(w0, list, map[mine[i]]);
-            if (WRITE) mine[i] = (uint8_t)r;
-            else if (r >= d) ++d;
-        }
-        __syncwarp();
-        if (WRITE) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
-                uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
-                if (off < n) {
-                    const uint32_t *sp = reinterpret_cast<const uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
-                    uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
-                    *reinterpret_cast<uint4 *>(dst + off) = v;
+            const uint32_t sym = mine[i];
+            uint32_t rank = 0;
+            if ((r.x & 0xff) != sym) {
+                const uint32_t pat = sym * 0x01010101u;
+                uint32_t p = quad_find(r, pat);
+                Quad s = quad_shift(r, sym);
+                if (p < 16) {
+                    r = quad_blend(r, s, p);
+                    rank = p;
+                } else {
+                    uint32_t carry = r.w >> 24;
+                    r = s;
+                    for (uint32_t k = 1;; ++k) { // the symbol is present: ends at k <= 15
+                        uint4 v = list[k];
+                        Quad q = {v.x, v.y, v.z, v.w};
+                        p = quad_find(q, pat);
+                        s = quad_shift(q, carry);
+                        if (p < 16) {
+                            q = quad_blend(q, s, p);
+                            list[k] = make_uint4(q.x, q.y, q.z, q.w);
+                            rank = 16 * k + p;
+                            break;
+                        }
+                        list[k] = make_uint4(s.x, s.y, s.z, s.w);
+                        carry = q.w >> 24;
+                    }
                 }
             }
-            __syncwarp();
+            mine[i] = (uint8_t)rank;
         }
-    }
-    if (!WRITE && cnt) {
-        lists[lidx] = w0;
-        for (int k = 1; k < 32; ++k) lists[lidx + k] = list[k];
-        dcount[(uint64_t)b * tiles_per_block + tile] = d;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
+            uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
+            if (off < n) {
+                const uint32_t *sp = reinterpret_cast<const uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
+                uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                *reinterpret_cast<uint4 *>(dst + off) = v;
+            }
+        }
+        __syncwarp();
     }
 }
 
