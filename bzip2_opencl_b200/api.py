@@ -24,7 +24,7 @@ EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_total", "ms_h2d", "ms_d2h", "ms_rle", "ms_bwt_sort0", "ms_bwt_rounds", "ms_bwt_finish",
-                                         "ms_mtf", "ms_huffman", "ms_emit")] + \
+                                         "ms_mtf", "ms_huffman", "ms_emit", "ms_walk")] + \
                [(n, C.c_uint64) for n in ("n_input", "n_rle", "n_mtf", "n_out_bits", "n_blocks", "bwt_rounds", "bwt_active_volume",
                                           "kernel_launches")]
 

@@ -55,7 +55,19 @@ struct bz2b200 {
         databits, nbits_b, bitoff, datastart, tilebits;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
     uint64_t sel_stride = 0;
-    uint64_t *h_pinned = nullptr; // small pinned scratch (16 u64)
+    uint64_t *h_pinned = nullptr; // small pinned scratch (64 u64)
+
+    // boundary walk, pipelined one batch ahead on a side stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_tree = nullptr, ev_walk = nullptr, ev_w0 = nullptr, ev_w1 = nullptr;
+    uint64_t *pin_starts = nullptr; // G + 2
+    uint32_t *pin_len = nullptr;    // G + 2
+    uint64_t *pin_info = nullptr;   // 4
+    WalkLevels wl{};
+    const uint8_t *w_in = nullptr;
+    uint64_t w_n = 0, w_cap = 0, w_req = 0, w_found = 0;
+    int w_final = 0;
+    bool w_finished = true;
 
     // last call
     bz2b200_stats_t stats{};
@@ -208,6 +220,12 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
     for (DevBuf *b : h->all)
         if (b->p) cudaFree(b->p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->pin_starts) cudaFreeHost(h->pin_starts);
+    if (h->pin_len) cudaFreeHost(h->pin_len);
+    if (h->pin_info) cudaFreeHost(h->pin_info);
+    if (h->side) cudaStreamDestroy(h->side);
+    for (cudaEvent_t e : {h->ev_tree, h->ev_walk, h->ev_w0, h->ev_w1})
+        if (e) cudaEventDestroy(e);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
     delete h;
@@ -270,6 +288,14 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->datastart, G * 8);
     ENSURE(h->tilebits, G * h->tilesD * 4);
     CK(cudaMallocHost(&h->h_pinned, 64 * sizeof(uint64_t)));
+    CK(cudaMallocHost(&h->pin_starts, (G + 2) * sizeof(uint64_t)));
+    CK(cudaMallocHost(&h->pin_len, (G + 2) * sizeof(uint32_t)));
+    CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h->ev_w0));
+    CK(cudaEventCreate(&h->ev_w1));
     for (auto &e : h->ev) CK(cudaEventCreate(&e));
     return BZ2B200_OK;
 }
@@ -370,47 +396,77 @@ static int is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// Stage A over the whole input: tree of summaries + sequential walk. Leaves starts / rle_len on the device and the
-// starts on the host (h->h_starts, n_blocks + 1 entries).
-static int scan_input(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final, uint64_t *n_blocks, uint64_t *consumed)
+// Stage A over the whole input, part 1: the tree of summaries (main stream).  The sequential walk over blocks then runs in
+// chunks on a side stream (walk_launch / walk_collect), one batch ahead of the compression kernels.
+static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
 {
-    *n_blocks = 0;
-    *consumed = 0;
     h->h_starts.assign(1, 0);
     h->h_rle_len.clear();
+    h->w_in = d_in;
+    h->w_n = n;
+    h->w_final = is_final;
+    h->w_found = 0;
+    h->w_finished = (n == 0);
     if (n == 0) return BZ2B200_OK;
-    const uint64_t limit = (uint64_t)h->bs - 6;
     uint64_t cnt[RLE_MAX_LEVELS];
-    int nl = 0;
+    int nl = 1;
     cnt[0] = (n + RLE_TILE - 1) / RLE_TILE;
-    nl = 1;
     while (cnt[nl - 1] > 1 && nl < RLE_MAX_LEVELS) { cnt[nl] = (cnt[nl - 1] + RLE_FANOUT - 1) / RLE_FANOUT; ++nl; }
     for (int l = 0; l < nl; ++l) ENSURE(h->seg[l], cnt[l] * sizeof(Seg));
-    const uint64_t cap = n / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
-    ENSURE(h->starts, (cap + 2) * 8);
-    ENSURE(h->rle_len, (cap + 2) * 4);
+    h->w_cap = n / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
+    ENSURE(h->starts, (h->w_cap + 2) * 8);
+    ENSURE(h->rle_len, (h->w_cap + 2) * 4);
     KL(KID_k_rle_tile_seg, k_rle_tile_seg<<<(unsigned)((cnt[0] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(d_in, n, ptr<Seg>(h->seg[0]), cnt[0]));
     for (int l = 1; l < nl; ++l)
         KL(KID_k_rle_reduce, k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
                                                                                                            cnt[l]));
-    WalkLevels lv;
-    for (int l = 0; l < RLE_MAX_LEVELS; ++l) { lv.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; lv.cnt[l] = l < nl ? cnt[l] : 0; }
-    lv.n_levels = nl;
+    h->stats.kernel_launches += nl;
+    for (int l = 0; l < RLE_MAX_LEVELS; ++l) { h->wl.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; h->wl.cnt[l] = l < nl ? cnt[l] : 0; }
+    h->wl.n_levels = nl;
     uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
-    KL(KID_k_rle_walk, k_rle_walk<<<1, 32, 0, h->stream>>>(d_in, n, limit, is_final, lv, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), cap, d_info));
-    h->stats.kernel_launches += nl + 1;
-    CK(cudaMemcpyAsync(h->h_pinned, d_info, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemsetAsync(d_info, 0, 32, h->stream));
+    CK(cudaEventRecord(h->ev_tree, h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_tree, 0));
+    return BZ2B200_OK;
+}
+
+// side stream: find up to `max_new` (<= G) further blocks and bring their starts / lengths to pinned host memory
+static int walk_launch(bz2b200 *h, uint64_t max_new)
+{
+    uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
+    const uint64_t b0 = h->w_found;
+    h->w_req = max_new;
+    CK(cudaEventRecord(h->ev_w0, h->side));
+    k_rle_walk<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), h->w_cap,
+                                       d_info, max_new);
+    CK(cudaEventRecord(h->ev_w1, h->side));
+    h->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(h->pin_info, d_info, 32, cudaMemcpyDeviceToHost, h->side));
+    const uint64_t room = h->w_cap + 1 - std::min(b0, h->w_cap + 1); // entries of starts[] from b0 that exist
+    const uint64_t ns = std::min<uint64_t>(max_new + 1, room + 1), nl = std::min<uint64_t>(max_new, room);
+    CK(cudaMemcpyAsync(h->pin_starts, ptr<uint64_t>(h->starts) + b0, ns * 8, cudaMemcpyDeviceToHost, h->side));
+    if (nl) CK(cudaMemcpyAsync(h->pin_len, ptr<uint32_t>(h->rle_len) + b0, nl * 4, cudaMemcpyDeviceToHost, h->side));
+    CK(cudaEventRecord(h->ev_walk, h->side));
+    return BZ2B200_OK;
+}
+
+static int walk_collect(bz2b200 *h)
+{
+    CK(cudaEventSynchronize(h->ev_walk));
     CK(cudaGetLastError());
-    if (h->profiling) prof_collect(h);
-    uint64_t nb = h->h_pinned[0];
-    if (nb > cap) { h->err = "internal: block count bound exceeded"; return BZ2B200_E_CUDA; }
-    *n_blocks = nb;
-    *consumed = h->h_pinned[1];
+    const uint64_t nb = h->pin_info[0];
+    if (nb > h->w_cap || nb < h->w_found || nb - h->w_found > h->w_req) { h->err = "internal: block walk out of bounds"; return BZ2B200_E_CUDA; }
+    const uint64_t fresh = nb - h->w_found;
     h->h_starts.resize(nb + 1);
-    CK(cudaMemcpy(h->h_starts.data(), h->starts.p, (nb + 1) * 8, cudaMemcpyDeviceToHost));
     h->h_rle_len.resize(nb);
-    if (nb) CK(cudaMemcpy(h->h_rle_len.data(), h->rle_len.p, nb * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i <= fresh; ++i) h->h_starts[h->w_found + i] = h->pin_starts[i];
+    for (uint64_t i = 0; i < fresh; ++i) h->h_rle_len[h->w_found + i] = h->pin_len[i];
+    h->w_found = nb;
+    h->w_finished = h->pin_info[2] != 0;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_w0, h->ev_w1);
+    h->stats.ms_walk += ms;
+    if (h->profiling) { h->k_ms[KID_k_rle_walk] += ms; h->k_launches[KID_k_rle_walk] += 1; }
     return BZ2B200_OK;
 }
 
@@ -438,9 +494,16 @@ extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_
     const uint8_t *d_in = nullptr;
     int rc = stage_input(h, input, n_bytes, &d_in);
     if (rc) return rc;
-    uint64_t nb = 0, consumed = 0;
-    rc = scan_input(h, d_in, n_bytes, 1, &nb, &consumed);
+    rc = walk_setup(h, d_in, n_bytes, 1);
     if (rc) return rc;
+    while (!h->w_finished) {
+        rc = walk_launch(h, h->G);
+        if (rc) return rc;
+        rc = walk_collect(h);
+        if (rc) return rc;
+    }
+    if (h->profiling) { CK(cudaStreamSynchronize(h->stream)); prof_collect(h); }
+    const uint64_t nb = h->w_found;
     *n_blocks = nb;
     for (uint64_t i = 0; i < nb && i < capacity; ++i) block_starts[i] = h->h_starts[i];
     return nb > capacity ? BZ2B200_E_OUTPUT : BZ2B200_OK;
@@ -667,29 +730,53 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
     int rc = stage_input(h, input, n_bytes, &d_in);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[10], st));
-    uint64_t nb = 0, used = 0;
-    rc = scan_input(h, d_in, n_bytes, is_final, &nb, &used);
+    rc = walk_setup(h, d_in, n_bytes, is_final);
     if (rc) return rc;
+    const uint64_t cap_blocks = n_bytes / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
+    const size_t need = bz2b200_max_output_bytes(h, n_bytes) + 8;
+    const size_t dcap = (need + 3) / 4 * 4;
+    ENSURE(h->out, dcap + 16);
+    ENSURE(h->all_crc, (cap_blocks + 1) * 4);
+    ENSURE(h->all_nbits, (cap_blocks + 1) * 8);
+    uint64_t *d_scal = ptr<uint64_t>(h->scalars);
+    h->h_pinned[8] = start_bit;
+    CK(cudaMemcpyAsync(d_scal + Scalars::BITPOS, h->h_pinned + 8, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->out.p, 0, dcap, st));
+    {
+        // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
+        bool pending = false;
+        uint64_t b0 = 0;
+        if (!h->w_finished) {
+            rc = walk_launch(h, std::min<uint64_t>(h->G, 48));
+            if (rc) return rc;
+            pending = true;
+        }
+        while (pending || b0 < h->w_found) {
+            if (pending) {
+                rc = walk_collect(h);
+                if (rc) return rc;
+                pending = false;
+            }
+            if (!h->w_finished) {
+                rc = walk_launch(h, h->G);
+                if (rc) return rc;
+                pending = true;
+            }
+            if (b0 < h->w_found) {
+                uint32_t cnt = (uint32_t)std::min<uint64_t>(h->G, h->w_found - b0);
+                rc = run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out));
+                if (rc) return rc;
+                b0 += cnt;
+            }
+        }
+    }
+    const uint64_t nb = h->w_found, used = h->h_starts[nb];
     h->last_total_blocks = nb;
     *n_blocks = nb;
     *consumed = (size_t)used;
     h->stats.n_input = used;
     h->stats.n_blocks = nb;
-    if ((block_crcs || block_nbits) && nb > block_capacity) return BZ2B200_E_OUTPUT;
-    const size_t need = bz2b200_max_output_bytes(h, (size_t)used) + 8;
-    const size_t dcap = (need + 3) / 4 * 4;
-    ENSURE(h->out, dcap + 16);
-    ENSURE(h->all_crc, (nb + 1) * 4);
-    ENSURE(h->all_nbits, (nb + 1) * 8);
-    uint64_t *d_scal = ptr<uint64_t>(h->scalars);
-    h->h_pinned[8] = start_bit;
-    CK(cudaMemcpyAsync(d_scal + Scalars::BITPOS, h->h_pinned + 8, 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(h->out.p, 0, dcap, st));
-    for (uint64_t b0 = 0; b0 < nb; b0 += h->G) {
-        uint32_t cnt = (uint32_t)std::min<uint64_t>(h->G, nb - b0);
-        rc = run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out));
-        if (rc) return rc;
-    }
+    if ((block_crcs || block_nbits) && nb > block_capacity) { h->err = "block_capacity too small"; return BZ2B200_E_OUTPUT; }
     CK(cudaEventRecord(h->ev[11], st));
     CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::BITPOS, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -711,12 +798,10 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
     }
     if (block_crcs && nb) CK(cudaMemcpy(block_crcs, h->all_crc.p, nb * 4, cudaMemcpyDeviceToHost));
     if (block_nbits && nb) CK(cudaMemcpy(block_nbits, h->all_nbits.p, nb * 8, cudaMemcpyDeviceToHost));
-    {   // n_rle / n_mtf totals for the roofline model (last batch only holds m; rle lengths cover the call)
-        std::vector<uint32_t> tmp(nb);
-        if (nb) CK(cudaMemcpy(tmp.data(), h->rle_len.p, nb * 4, cudaMemcpyDeviceToHost));
-        uint64_t s = 0;
-        for (uint32_t v : tmp) s += v;
-        h->stats.n_rle = s;
+    {
+        uint64_t sum = 0;
+        for (uint32_t v : h->h_rle_len) sum += v;
+        h->stats.n_rle = sum;
     }
     return BZ2B200_OK;
 }

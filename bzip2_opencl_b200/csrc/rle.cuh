@@ -192,20 +192,27 @@ struct DevSiblingStep {
     }
 };
 
-// info[0] = number of complete blocks, info[1] = bytes consumed by them.
-// starts[b] for b <= min(n_blocks, cap): start offset of block b; starts[n_blocks] = consumed. rle_len[b] = RLE1 length.
+// Resumable: info[0] = blocks found so far, info[1] = input position reached, info[2] = 1 once the input is exhausted (or,
+// for a non-final call, the remaining bytes do not complete a block).  One launch finds at most `max_new` further blocks, so
+// the host can run it on a side stream one batch ahead of the compression kernels.
+// starts[b] = start offset of block b, starts[info[0]] = position reached; rle_len[b] = RLE1 length of block b.
 __global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t limit, int is_final, WalkLevels lv,
-                                                  uint64_t *__restrict__ starts, uint32_t *__restrict__ rle_len, uint64_t cap, uint64_t *__restrict__ info)
+                                                  uint64_t *__restrict__ starts, uint32_t *__restrict__ rle_len, uint64_t cap, uint64_t *__restrict__ info,
+                                                  uint64_t max_new)
 {
     __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
     DevTileScan scan{in, sm};
     DevSiblingStep step{lv};
-    uint64_t s = 0, nb = 0;
-    while (s < n_bytes) {
+    uint64_t nb = info[0], s = info[1];
+    const uint64_t target = nb + max_new;
+    uint64_t finished = 0;
+    __syncwarp();
+    while (nb < target) {
+        if (s >= n_bytes) { finished = 1; break; }
         RleState st;
         uint64_t e = walk_block_wide(s, n_bytes, limit, lv.n_levels, lv.cnt, step, scan, st);
         bool complete = (e < n_bytes) || is_final; // e == n_bytes without a refusal: flushed only when the stream ends
-        if (!complete) break;
+        if (!complete) { finished = 1; break; }
         if (lane_id() == 0 && nb < cap) {
             starts[nb] = s;
             rle_len[nb] = (uint32_t)state_final_length(st);
@@ -213,10 +220,13 @@ __global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in,
         ++nb;
         s = e;
     }
+    if (s >= n_bytes) finished = 1;
+    __syncwarp();
     if (lane_id() == 0) {
         if (nb <= cap) starts[nb] = s;
         info[0] = nb;
         info[1] = s;
+        info[2] = finished;
     }
 }
 

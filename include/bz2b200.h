@@ -107,6 +107,7 @@ typedef struct {
     float ms_total;       /* first kernel to last kernel, device side, excludes host<->device copies */
     float ms_h2d, ms_d2h; /* copies done by the call (0 for device-resident buffers) */
     float ms_rle, ms_bwt_sort0, ms_bwt_rounds, ms_bwt_finish, ms_mtf, ms_huffman, ms_emit;
+    float ms_walk;        /* block-boundary walk (side stream, overlapped with the previous batch) */
     uint64_t n_input, n_rle, n_mtf, n_out_bits, n_blocks;
     uint64_t bwt_rounds;        /* prefix-doubling rounds executed (max over batches) */
     uint64_t bwt_active_volume; /* sum over rounds of active (unresolved) rotations: rho * n_rle of SURVEY 8(d) */
