@@ -52,13 +52,16 @@ struct bz2b200 {
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, vA, vB, sa, rank, pA, pB, mtf, hist, digit_base, tile_last, tile_keep, tile_carry, cnt0, cnt1, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
-        databits, nbits_b, bitoff, datastart, tilebits;
+        databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
     uint64_t sel_stride = 0;
     uint64_t *h_pinned = nullptr; // small pinned scratch (64 u64)
 
     // boundary walk, pipelined one batch ahead on a side stream
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr, copy = nullptr; // walk stream; output-drain stream (finished batches leave while the next one computes)
+    uint8_t *drain_dst = nullptr;   // caller's output buffer (nullptr: no overlapped drain)
+    size_t drain_cap = 0, drained = 0;
+    bool drain_dev = false;
     cudaEvent_t ev_tree = nullptr, ev_walk = nullptr, ev_w0 = nullptr, ev_w1 = nullptr;
     uint64_t *pin_starts = nullptr; // G + 2
     uint32_t *pin_len = nullptr;    // G + 2
@@ -224,6 +227,7 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
     if (h->pin_len) cudaFreeHost(h->pin_len);
     if (h->pin_info) cudaFreeHost(h->pin_info);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->copy) cudaStreamDestroy(h->copy);
     for (cudaEvent_t e : {h->ev_tree, h->ev_walk, h->ev_w0, h->ev_w1})
         if (e) cudaEventDestroy(e);
     for (auto &e : h->ev)
@@ -281,6 +285,8 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->sel, G * h->sel_stride);
     ENSURE(h->selpos, G * h->sel_stride);
     ENSURE(h->selbits, G * 4);
+    ENSURE(h->selbitoff, G * h->sel_stride * 4);
+    ENSURE(h->pertab, G * HUFF_MAXTABLES * 4);
     ENSURE(h->tabbits, G * 4);
     ENSURE(h->databits, G * 4);
     ENSURE(h->nbits_b, G * 8);
@@ -292,6 +298,7 @@ static int create_impl(bz2b200 *h)
     CK(cudaMallocHost(&h->pin_len, (G + 2) * sizeof(uint32_t)));
     CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev_w0));
@@ -671,9 +678,9 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
                                                                      it == 3));
         }
         KL(KID_k_huff_codes, k_huff_codes<<<(nb * HUFF_MAXTABLES + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->codes), ptr<uint32_t>(h->tabbits),
-                                                                      nb));
-        KL(KID_k_huff_selmtf, k_huff_selmtf<<<(nb + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbits),
-                                                      nb));
+                                                                      ptr<uint32_t>(h->pertab), nb));
+        KL(KID_k_huff_selmtf, k_huff_selmtf<<<(nb + 7) / 8, 256, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos),
+                                                                       ptr<uint32_t>(h->selbitoff), ptr<uint32_t>(h->selbits), nb));
         stt.kernel_launches += 11;
     }
     CK(cudaEventRecord(h->ev[8], st));
@@ -683,9 +690,10 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_block_bits, k_block_bits<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->selbits), ptr<uint32_t>(h->tabbits),
                                                         ptr<uint32_t>(h->databits), nb, ptr<uint64_t>(h->nbits_b)));
         KL(KID_k_bit_offsets, k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, d_scal + Scalars::BITPOS, ptr<uint64_t>(h->bitoff)));
-        KL(KID_k_emit_header, k_emit_header<<<(nb + 31) / 32, 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
-                                                      ptr<uint8_t>(h->selpos), h->sel_stride, ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
-                                                      ptr<uint64_t>(h->datastart)));
+        KL(KID_k_emit_header, k_emit_header<<<(nb + 7) / 8, 256, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
+                                                                       ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbitoff), h->sel_stride, ptr<uint32_t>(h->selbits),
+                                                                       ptr<uint32_t>(h->pertab), ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
+                                                                       ptr<uint64_t>(h->datastart)));
         KL(KID_k_data_tilebits, k_data_tilebits<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint8_t>(h->sel), h->sel_stride,
                                                     ptr<uint32_t>(h->tilebits), h->tilesD));
         KL(KID_k_data_scan, k_data_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tilebits), h->tilesD, nb));
@@ -696,9 +704,20 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         CK(cudaMemcpyAsync(ptr<uint64_t>(h->all_nbits) + b0, h->nbits_b.p, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
     }
     CK(cudaEventRecord(h->ev[9], st));
+    CK(cudaMemcpyAsync(h->h_pinned + 16, d_scal + Scalars::BITPOS, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (h->profiling) prof_collect(h);
+    if (h->drain_dst) {
+        // every byte below the current bit position is final: ship it now, overlapped with the next batch
+        const size_t done = (size_t)(h->h_pinned[16] >> 3);
+        if (done > h->drain_cap) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+        if (done > h->drained) {
+            CK(cudaMemcpyAsync(h->drain_dst + h->drained, ptr<uint8_t>(h->out) + h->drained, done - h->drained,
+                               h->drain_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->copy));
+            h->drained = done;
+        }
+    }
     stt.ms_rle += ev_ms(h->ev[2], h->ev[3]);
     stt.ms_bwt_sort0 += ev_ms(h->ev[3], h->ev[4]);
     stt.ms_bwt_rounds += ev_ms(h->ev[4], h->ev[5]);
@@ -711,9 +730,29 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     return BZ2B200_OK;
 }
 
+static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
+                                size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                size_t block_capacity, uint64_t *n_blocks);
+
 extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                        size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
                                        size_t block_capacity, uint64_t *n_blocks)
+{
+    int rc = compress_blocks_impl(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits,
+                                  block_capacity, n_blocks);
+    if (h) {
+        // never leave copies into the caller's buffer or a walk in flight, whatever the outcome
+        cudaStreamSynchronize(h->copy);
+        cudaStreamSynchronize(h->side);
+        h->drain_dst = nullptr;
+        if (rc != BZ2B200_OK) (void)cudaGetLastError();
+    }
+    return rc;
+}
+
+static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
+                                size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                size_t block_capacity, uint64_t *n_blocks)
 {
     if (!h) return BZ2B200_E_ARG;
     if ((!input && n_bytes) || !out_nbits || !consumed || !n_blocks || start_bit > 7 || (!out && out_capacity)) {
@@ -742,6 +781,10 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
     h->h_pinned[8] = start_bit;
     CK(cudaMemcpyAsync(d_scal + Scalars::BITPOS, h->h_pinned + 8, 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(h->out.p, 0, dcap, st));
+    h->drain_dst = out;
+    h->drain_cap = out_capacity;
+    h->drained = 0;
+    h->drain_dev = out ? is_device_ptr(out) != 0 : false;
     {
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
         bool pending = false;
@@ -789,13 +832,17 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
     if (out_bytes > out_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
     *out_nbits = bits;
     if (out_bytes) {
-        const bool dev = is_device_ptr(out);
+        // the tail that was not drained while the batches ran (at least the last partial byte)
+        CK(cudaStreamSynchronize(h->copy));
         CK(cudaEventRecord(h->ev[12], st));
-        CK(cudaMemcpyAsync(out, h->out.p, out_bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (out_bytes > h->drained)
+            CK(cudaMemcpyAsync(out + h->drained, ptr<uint8_t>(h->out) + h->drained, out_bytes - h->drained,
+                               h->drain_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->ev[13], st));
         CK(cudaStreamSynchronize(st));
         h->stats.ms_d2h = ev_ms(h->ev[12], h->ev[13]);
     }
+    h->drain_dst = nullptr;
     if (block_crcs && nb) CK(cudaMemcpy(block_crcs, h->all_crc.p, nb * 4, cudaMemcpyDeviceToHost));
     if (block_nbits && nb) CK(cudaMemcpy(block_nbits, h->all_nbits.p, nb * 8, cudaMemcpyDeviceToHost));
     {

@@ -93,52 +93,90 @@ __global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict
     if (threadIdx.x == 0) *bitpos = s_carry;
 }
 
-// one thread per block: everything in front of the coded symbols
-__global__ void __launch_bounds__(32) k_emit_header(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ crc,
-                                                     const uint32_t *__restrict__ orig, const uint8_t *__restrict__ selpos, uint64_t sel_stride,
-                                                     const uint8_t *__restrict__ lens, const uint64_t *__restrict__ bitoff, uint32_t n_blocks,
-                                                     uint32_t *__restrict__ out, uint64_t *__restrict__ data_start)
+// OR `len` (1..32) bits of `value` into the stream at absolute bit position `pos`
+__device__ __forceinline__ void or_bits(uint32_t *out, uint64_t pos, uint32_t len, uint32_t value)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t w = pos >> 5;
+    const uint32_t off = (uint32_t)(pos & 31);
+    if (off + len <= 32) {
+        uint32_t x = value << (32 - off - len);
+        if (x) atomicOr(out + w, bswap32(x));
+    } else {
+        const uint32_t rest = off + len - 32;
+        uint32_t hi = value >> rest, lo = value << (32 - rest);
+        if (hi) atomicOr(out + w, bswap32(hi));
+        if (lo) atomicOr(out + w + 1, bswap32(lo));
+    }
+}
+
+// One warp per block: everything in front of the coded symbols.  Lane 0 writes the fixed fields, all lanes write the selector
+// unary codes at their precomputed offsets, lanes 0..T-1 write one delta-coded table each.
+__global__ void __launch_bounds__(256) k_emit_header(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ crc,
+                                                      const uint32_t *__restrict__ orig, const uint8_t *__restrict__ selpos,
+                                                      const uint32_t *__restrict__ selbitoff, uint64_t sel_stride, const uint32_t *__restrict__ sel_bits,
+                                                      const uint32_t *__restrict__ per_table_bits, const uint8_t *__restrict__ lens,
+                                                      const uint64_t *__restrict__ bitoff, uint32_t n_blocks, uint32_t *__restrict__ out,
+                                                      uint64_t *__restrict__ data_start)
+{
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (b >= n_blocks) return;
+    const int lane = lane_id();
     const HuffBlock h = hb[b];
-    BitWriter w;
-    w.init(out, bitoff[b]);
-    w.put(24, 0x314159u); w.put(24, 0x265359u);       // OutputStream.hpp:208-209
-    w.put(32, crc[b]);                                  // :210 writeInteger
-    w.put(1, 0);                                        // :211 randomised = 0
-    w.put(24, orig[b]);                                 // kernel.cpp:3116
-    // writeSymbolMap, kernel.cpp:2483-2511: value v is bit (v & 31) of present[v >> 5]
-    uint32_t used16 = 0;
-    for (int r = 0; r < 16; ++r) {
-        uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
-        if (bits16) used16 |= 1u << (15 - r);
+    uint32_t ranges = 0;
+    for (int w = 0; w < 8; ++w) {
+        uint32_t p = present[b * 8 + w];
+        ranges += (p & 0xffffu) ? 1u : 0u;
+        ranges += (p >> 16) ? 1u : 0u;
     }
-    w.put(16, used16);
-    for (int r = 0; r < 16; ++r) {
-        uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
-        if (bits16) w.put(16, __brev(bits16) >> 16); // value k of the range goes out k-th: MSB first
-    }
-    w.put(3, h.ntab);                                   // kernel.cpp:3001
-    w.put(15, h.nsel);                                  // :3002
-    const uint8_t *sp = selpos + (uint64_t)b * sel_stride;
-    for (uint32_t g = 0; g < h.nsel; ++g) {             // writeUnary, :3010
-        uint32_t p = sp[g];
-        w.put(p + 1, ((1u << p) - 1u) << 1);
-    }
-    for (uint32_t t = 0; t < h.ntab; ++t) {             // :3015-3040
-        const uint8_t *L = lens + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_LEN_STRIDE;
-        int cur = L[0];
-        w.put(5, (uint32_t)cur);
-        for (uint32_t j = 0; j < h.alpha; ++j) {
-            int l = L[j];
-            while (cur < l) { w.put(2, 2); ++cur; }
-            while (cur > l) { w.put(2, 3); --cur; }
-            w.put(1, 0);
+    const uint64_t sel_start = bitoff[b] + 48 + 32 + 1 + 24 + 16 + 16ull * ranges + 3 + 15;
+    if (lane == 0) {
+        BitWriter w;
+        w.init(out, bitoff[b]);
+        w.put(24, 0x314159u); w.put(24, 0x265359u);       // OutputStream.hpp:208-209
+        w.put(32, crc[b]);                                  // :210 writeInteger
+        w.put(1, 0);                                        // :211 randomised = 0
+        w.put(24, orig[b]);                                 // kernel.cpp:3116
+        // writeSymbolMap, kernel.cpp:2483-2511: value v is bit (v & 31) of present[v >> 5]
+        uint32_t used16 = 0;
+        for (int r = 0; r < 16; ++r) {
+            uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+            if (bits16) used16 |= 1u << (15 - r);
         }
+        w.put(16, used16);
+        for (int r = 0; r < 16; ++r) {
+            uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+            if (bits16) w.put(16, __brev(bits16) >> 16); // value k of the range goes out k-th: MSB first
+        }
+        w.put(3, h.ntab);                                   // kernel.cpp:3001
+        w.put(15, h.nsel);                                  // :3002
+        w.finish();
     }
-    data_start[b] = (w.word << 5) + w.used;
-    w.finish();
+    const uint8_t *sp = selpos + (uint64_t)b * sel_stride;
+    const uint32_t *so = selbitoff + (uint64_t)b * sel_stride;
+    for (uint32_t g = lane; g < h.nsel; g += 32) {          // writeUnary, :3010: p ones then a zero
+        const uint32_t p = sp[g];
+        or_bits(out, sel_start + so[g], p + 1, ((1u << p) - 1u) << 1);
+    }
+    uint64_t tstart = sel_start + sel_bits[b];
+    for (uint32_t t = 0; t < h.ntab; ++t) {                 // :3015-3040
+        const uint32_t tb = per_table_bits[b * HUFF_MAXTABLES + t];
+        if ((uint32_t)lane == t) {
+            const uint8_t *L = lens + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_LEN_STRIDE;
+            BitWriter w;
+            w.init(out, tstart);
+            int cur = L[0];
+            w.put(5, (uint32_t)cur);
+            for (uint32_t j = 0; j < h.alpha; ++j) {
+                int l = L[j];
+                while (cur < l) { w.put(2, 2); ++cur; }
+                while (cur > l) { w.put(2, 3); --cur; }
+                w.put(1, 0);
+            }
+            w.finish();
+        }
+        tstart += tb;
+    }
+    if (lane == 0) data_start[b] = tstart;
 }
 
 // bits of the coded symbols per tile of HP_SYMS symbols

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(32) k_huff_lengths(const HuffBlock *__restrict
 
 // one thread per (block, table): canonical codes, merged as (len << 24) | code; bits of the delta-coded table
 __global__ void __launch_bounds__(64) k_huff_codes(const HuffBlock *__restrict__ hb, const uint8_t *__restrict__ lens, uint32_t *__restrict__ codes,
-                                                    uint32_t *__restrict__ table_bits, uint32_t n_blocks)
+                                                    uint32_t *__restrict__ table_bits, uint32_t *__restrict__ per_table_bits, uint32_t n_blocks)
 {
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b = id / HUFF_MAXTABLES, t = id % HUFF_MAXTABLES;
@@ -247,30 +247,55 @@ __global__ void __launch_bounds__(64) k_huff_codes(const HuffBlock *__restrict__
         C[j] = ((uint32_t)l << 24) | next[l]++;
     }
     atomicAdd(&table_bits[b], tb);
+    per_table_bits[b * HUFF_MAXTABLES + t] = tb;
 }
 
-// one thread per block: MTF positions of the selectors (kernel.cpp:3004-3012) and their total unary length
-__global__ void __launch_bounds__(64) k_huff_selmtf(const HuffBlock *__restrict__ hb, const uint8_t *__restrict__ sel, uint64_t sel_stride,
-                                                     uint8_t *__restrict__ selpos, uint32_t *__restrict__ sel_bits, uint32_t n_blocks)
+// One warp per block: MTF positions of the selectors (kernel.cpp:3004-3012), the bit offset of every selector's unary code and
+// their total length.  Position of selector g = number of OTHER tables used more recently than sel[g]; "last use" per table is
+// a prefix maximum, so 32 selectors are resolved per step with six warp max-scans instead of a serial 6-entry list.
+__global__ void __launch_bounds__(256) k_huff_selmtf(const HuffBlock *__restrict__ hb, const uint8_t *__restrict__ sel, uint64_t sel_stride,
+                                                      uint8_t *__restrict__ selpos, uint32_t *__restrict__ selbitoff, uint32_t *__restrict__ sel_bits,
+                                                      uint32_t n_blocks)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (b >= n_blocks) return;
+    const int lane = lane_id();
     const uint32_t ns = hb[b].nsel;
     const uint8_t *s = sel + (uint64_t)b * sel_stride;
     uint8_t *o = selpos + (uint64_t)b * sel_stride;
-    uint32_t list = 0x543210u; // nibble k = table at position k
-    uint32_t bits = 0;
-    for (uint32_t g = 0; g < ns; ++g) {
-        uint32_t v = s[g];
+    uint32_t *bo = selbitoff + (uint64_t)b * sel_stride;
+    int last[HUFF_MAXTABLES]; // last use of table t before the current chunk; the initial list 0,1,..,5 == virtual uses at -1-t
+#pragma unroll
+    for (int t = 0; t < HUFF_MAXTABLES; ++t) last[t] = -1 - t;
+    uint32_t bits_before = 0;
+    for (uint32_t g0 = 0; g0 < ns; g0 += 32) {
+        const uint32_t g = g0 + lane;
+        const bool valid = g < ns;
+        const int v = valid ? (int)s[g] : -1;
+        int lt[HUFF_MAXTABLES]; // last use of table t strictly before g
+        int mine = 0;
+#pragma unroll
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) {
+            int x = (v == t) ? (int)g : -1000;
+            int inc = warp_incl_max(x);
+            int ex = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) ex = -1000;
+            lt[t] = max(last[t], ex);
+            last[t] = max(last[t], __shfl_sync(FULL, inc, 31));
+            if (v == t) mine = lt[t];
+        }
         uint32_t pos = 0;
-        while (((list >> (4 * pos)) & 0xfu) != v) ++pos;
-        uint32_t low = list & ((1u << (4 * pos)) - 1u);
-        uint32_t high = pos >= 7 ? 0u : (list >> (4 * (pos + 1))) << (4 * (pos + 1));
-        list = high | (low << 4) | v;
-        o[g] = (uint8_t)pos;
-        bits += pos + 1;
+#pragma unroll
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) pos += (t != v && lt[t] > mine) ? 1u : 0u;
+        const uint32_t nb_ = valid ? pos + 1 : 0u;
+        const uint32_t inc = warp_incl_sum(nb_);
+        if (valid) {
+            o[g] = (uint8_t)pos;
+            bo[g] = bits_before + inc - nb_;
+        }
+        bits_before += __shfl_sync(FULL, inc, 31);
     }
-    sel_bits[b] = bits;
+    if (lane == 0) sel_bits[b] = bits_before;
 }
 
 } // namespace bz
