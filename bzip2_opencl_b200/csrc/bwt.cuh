@@ -27,32 +27,56 @@ constexpr int RG_ITEMS = 8;
 constexpr int RG_TILE = RG_THREADS * RG_ITEMS; // 2048 elements per regroup tile
 
 // ------------------------------------------------------------------------------------------------ radix: histogram
+// Each thread owns RS_ITEMS CONSECUTIVE keys and run-length encodes their digits in registers before touching the shared
+// histogram: on the (already ordered) group half of a composite key that is one atomic per thread instead of sixteen, and the
+// unordered half has few same-address collisions inside a warp anyway.
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t stride,
                                                             int shift, uint32_t mask, uint32_t *__restrict__ hist, int tiles_per_block)
 {
-    __shared__ uint32_t h[256];
+    __shared__ uint32_t h[RS_WARPS][256];
     const uint32_t b = blockIdx.y, tile = blockIdx.x;
     const uint32_t cnt = counts[b];
     const uint32_t base = tile * RS_TILE;
     if (base >= cnt) return;
-    h[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
-    const K *kp = keys + (uint64_t)b * stride;
-    const int lane = lane_id();
-#pragma unroll 4
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-        bool valid = idx < cnt;
-        unsigned vm = __ballot_sync(FULL, valid);
-        if (valid) {
-            uint32_t d = (uint32_t)(kp[idx] >> shift) & mask;
-            unsigned peers = __match_any_sync(vm, d);
-            if (lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+    const K *kp = keys + (uint64_t)b * stride + base;
+    const uint32_t tcnt = min((uint32_t)RS_TILE, cnt - base);
+    const uint32_t i0 = threadIdx.x * RS_ITEMS;
+    uint32_t *wh = h[warp_id()];
+    if (i0 < tcnt) {
+        constexpr int VEC = 16 / sizeof(K); // keys per 128-bit load
+        uint32_t prev = 0xffffffffu, run = 0;
+        if (i0 + RS_ITEMS <= tcnt) {
+            const uint4 *vp = reinterpret_cast<const uint4 *>(kp + i0); // stride and tile base are multiples of 16 bytes
+#pragma unroll
+            for (int v = 0; v < RS_ITEMS / VEC; ++v) {
+                uint4 q = __ldg(vp + v);
+                K kk[VEC];
+                if (sizeof(K) == 8) { kk[0] = (K)(((uint64_t)q.y << 32) | q.x); kk[1 % VEC] = (K)(((uint64_t)q.w << 32) | q.z); }
+                else { kk[0] = (K)q.x; kk[1 % VEC] = (K)q.y; kk[2 % VEC] = (K)q.z; kk[3 % VEC] = (K)q.w; }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    uint32_t d = (uint32_t)(kk[j] >> shift) & mask;
+                    if (d != prev) { if (run) atomicAdd(&wh[prev], run); prev = d; run = 0; }
+                    ++run;
+                }
+            }
+        } else {
+            for (uint32_t i = i0; i < tcnt; ++i) {
+                uint32_t d = (uint32_t)(kp[i] >> shift) & mask;
+                if (d != prev) { if (run) atomicAdd(&wh[prev], run); prev = d; run = 0; }
+                ++run;
+            }
         }
+        if (run) atomicAdd(&wh[prev], run);
     }
     __syncthreads();
-    hist[((uint64_t)b * tiles_per_block + tile) * 256 + threadIdx.x] = h[threadIdx.x];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) sum += h[w][threadIdx.x];
+    hist[((uint64_t)b * tiles_per_block + tile) * 256 + threadIdx.x] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------ radix: per-block scan
