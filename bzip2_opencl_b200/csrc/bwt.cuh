@@ -9,8 +9,9 @@
 //             segmented LSD radix sort of the active list, scatter back into the group's positions, regroup.
 //   stop      when no block has active rotations, or 2h >= n (non-primitive block: ties are final).
 //   finish    L[j] = T[(SA[j]-1) mod n]; origPtr = rank[0] = first position of rotation 0's tie group.
-// The LSD radix pass is hist -> per-block scan -> stable scatter (warp match_any multi-split, shared-memory staged
-// so that the global writes of one digit are contiguous).
+// Sort elements are single 64-bit words: (sort key << 20) | rotation index (block positions fit 20 bits), so a pass moves
+// 8 bytes per element and needs no value array.  The LSD radix pass is hist -> per-block scan -> stable scatter (warp match_any
+// multi-split, shared-memory staged so that the global writes of one digit are contiguous).
 #pragma once
 #include "util.cuh"
 
@@ -21,6 +22,9 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 4096 elements per radix tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_WARP_ELEMS = 32 * RS_ITEMS;
+
+constexpr int VAL_BITS = 20;                 // low bits of a sort element: the rotation's start index inside its block
+constexpr uint64_t VAL_MASK = (1ull << VAL_BITS) - 1ull;
 
 constexpr int RG_THREADS = 256;
 constexpr int RG_ITEMS = 8;
@@ -100,24 +104,21 @@ __global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist,
 }
 
 // ------------------------------------------------------------------------------------------------ radix: stable scatter
-template <typename K>
 struct ScatterSmem {
     uint32_t warp_hist[RS_WARPS][256];
     uint32_t tile_base[256];
     uint32_t gofs[256];
     uint32_t scratch[34];
-    uint32_t vals[RS_TILE];
-    K keys[RS_TILE];
+    uint64_t keys[RS_TILE];
 };
 
-template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, K *__restrict__ keys_out,
-                                                               uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ counts, uint64_t stride, int shift,
-                                                               uint32_t mask, const uint32_t *__restrict__ hist, int tiles_per_block,
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+                                                               const uint32_t *__restrict__ counts, uint64_t stride, int shift, uint32_t mask,
+                                                               const uint32_t *__restrict__ hist, int tiles_per_block,
                                                                const uint32_t *__restrict__ digit_base)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem<K> &sm = *reinterpret_cast<ScatterSmem<K> *>(smem_raw);
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const uint32_t b = blockIdx.y, tile = blockIdx.x;
     const uint32_t cnt = counts[b];
     const uint32_t base = tile * RS_TILE;
@@ -128,17 +129,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restric
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
 
-    const K *kp = keys_in + (uint64_t)b * stride + base;
-    const uint32_t *vp = vals_in + (uint64_t)b * stride + base;
-    K key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
+    const uint64_t *kp = keys_in + (uint64_t)b * stride + base;
+    uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-        bool valid = li < tcnt;
-        key[i] = valid ? kp[li] : (K)0;
-        val[i] = valid ? vp[li] : 0u;
+        key[i] = li < tcnt ? kp[li] : 0ull;
     }
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
@@ -178,25 +175,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restric
             uint32_t d = (uint32_t)(key[i] >> shift) & mask;
             uint32_t p = sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i];
             sm.keys[p] = key[i];
-            sm.vals[p] = val[i];
         }
     }
     __syncthreads();
-    K *ko = keys_out + (uint64_t)b * stride;
-    uint32_t *vo = vals_out + (uint64_t)b * stride;
+    uint64_t *ko = keys_out + (uint64_t)b * stride;
     for (uint32_t p = threadIdx.x; p < tcnt; p += RS_THREADS) {
-        K k = sm.keys[p];
+        uint64_t k = sm.keys[p];
         uint32_t d = (uint32_t)(k >> shift) & mask;
-        uint32_t dst = sm.gofs[d] + p;
-        ko[dst] = k;
-        vo[dst] = sm.vals[p];
+        ko[sm.gofs[d] + p] = k;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ round 0 keys
-// key = first `nbytes` (<= 4) bytes of rotation i, big-endian; val = i.
+// element = (first `nbytes` (<= 4) bytes of rotation i, big-endian) << 20 | i
 __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride, int nbytes,
-                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                                                    uint64_t *__restrict__ keys)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = n_arr[b];
@@ -208,18 +201,16 @@ __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ r
         key = (key << 8) | T[p];
         if (++p == n) p = 0;
     }
-    keys[(uint64_t)b * stride + i] = key;
-    vals[(uint64_t)b * stride + i] = i;
+    keys[(uint64_t)b * stride + i] = ((uint64_t)key << VAL_BITS) | i;
 }
 
 // ------------------------------------------------------------------------------------------------ regroup
-// Sorted (keys, vals) of the active list of each block -> scatter SA, find new groups, update ranks, compact the
+// Sorted elements of the active list of each block -> scatter SA, find new groups, update ranks, compact the
 // still-ambiguous rotations into the next round's sort input.
 struct RegroupArgs {
     const uint32_t *counts;   // [G] active elements sorted this round
     const uint32_t *n_arr;    // [G] block lengths
     uint64_t stride;
-    const uint32_t *vals;     // sorted rotation indices
     const uint32_t *pos_old;  // position in SA of active element a (nullptr: identity, round 0)
     uint32_t *sa;             // [G*stride]
     uint32_t *rank;           // [G*stride]
@@ -229,22 +220,23 @@ struct RegroupArgs {
     int tiles_per_block;      // regroup tiles per block
     uint32_t *counts_new;     // [G]
     uint32_t *pos_new;        // compacted positions
-    uint32_t *vals_new;       // compacted rotation indices
-    uint64_t *keys_new;       // (group position << nbits), rank of the second half OR-ed in by k_bwt_gather
+    uint64_t *keys_new;       // (group position << (20 + nbits)) | rotation index; k_bwt_gather ORs in rank of the second half << 20
     int nbits;
     uint32_t sorted_len;      // rotations are now ordered by their first sorted_len bytes
     unsigned long long *total_active; // [0] sum of counts_new over blocks, [3] max of counts_new (sizes the next round's grids)
 };
 
-template <typename K>
-__device__ __forceinline__ void load_flags(const K *kp, uint32_t a0, uint32_t cnt, bool (&flag)[RG_ITEMS], bool (&nxt)[RG_ITEMS])
+__device__ __forceinline__ void load_flags(const uint64_t *kp, uint32_t a0, uint32_t cnt, bool (&flag)[RG_ITEMS], bool (&nxt)[RG_ITEMS],
+                                           uint32_t (&val)[RG_ITEMS])
 {
-    // flag[i]: element a0+i starts a group; nxt[i]: element a0+i ends a group
-    K prev = a0 > 0 && a0 - 1 < cnt ? kp[a0 - 1] : (K)0;
+    // flag[i]: element a0+i starts a group; nxt[i]: element a0+i ends a group; val[i]: its rotation index
+    uint64_t prev = a0 > 0 && a0 - 1 < cnt ? (kp[a0 - 1] >> VAL_BITS) : 0ull;
 #pragma unroll
     for (int i = 0; i < RG_ITEMS; ++i) {
         uint32_t a = a0 + i;
-        K cur = a < cnt ? kp[a] : (K)0;
+        uint64_t e = a < cnt ? kp[a] : 0ull;
+        uint64_t cur = e >> VAL_BITS;
+        val[i] = (uint32_t)(e & VAL_MASK);
         flag[i] = (a == 0) || (cur != prev);
         prev = cur;
     }
@@ -252,12 +244,11 @@ __device__ __forceinline__ void load_flags(const K *kp, uint32_t a0, uint32_t cn
     for (int i = 0; i < RG_ITEMS - 1; ++i) nxt[i] = (a0 + i + 1 >= cnt) || flag[i + 1];
     {
         uint32_t a = a0 + RG_ITEMS;
-        nxt[RG_ITEMS - 1] = (a >= cnt) || (kp[a] != prev);
+        nxt[RG_ITEMS - 1] = (a >= cnt) || ((kp[a] >> VAL_BITS) != prev);
     }
 }
 
-template <typename K>
-__global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const K *__restrict__ keys, RegroupArgs A)
+__global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const uint64_t *__restrict__ keys, RegroupArgs A)
 {
     __shared__ int s_last[RG_THREADS / 32];
     __shared__ uint32_t s_keep[RG_THREADS / 32];
@@ -265,14 +256,14 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const K *__restrict__ 
     const uint32_t cnt = A.counts[b];
     const uint32_t base = tile * RG_TILE;
     if (base >= cnt) return;
-    const K *kp = keys + (uint64_t)b * A.stride;
+    const uint64_t *kp = keys + (uint64_t)b * A.stride;
     const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
     bool flag[RG_ITEMS], nxt[RG_ITEMS];
+    uint32_t val[RG_ITEMS];
     int last = -1;
     uint32_t keep = 0;
     if (a0 < cnt) {
-        load_flags(kp, a0, cnt, flag, nxt);
-        const uint32_t *vp = A.vals + (uint64_t)b * A.stride;
+        load_flags(kp, a0, cnt, flag, nxt, val);
         const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
         uint32_t *sa = A.sa + (uint64_t)b * A.stride;
 #pragma unroll
@@ -281,7 +272,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const K *__restrict__ 
             if (a < cnt) {
                 if (flag[i]) last = (int)a;
                 if (!(flag[i] && nxt[i])) ++keep;
-                sa[pp ? pp[a] : a] = vp[a];
+                sa[pp ? pp[a] : a] = val[i];
             }
         }
     }
@@ -330,8 +321,7 @@ __global__ void __launch_bounds__(256) k_bwt_tilescan(RegroupArgs A, uint32_t n_
     }
 }
 
-template <typename K>
-__global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const K *__restrict__ keys, RegroupArgs A)
+__global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__restrict__ keys, RegroupArgs A)
 {
     __shared__ int s_i[34];
     __shared__ uint32_t s_u[34];
@@ -339,13 +329,14 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const K *__restrict_
     const uint32_t cnt = A.counts[b];
     const uint32_t base = tile * RG_TILE;
     if (base >= cnt) return;
-    const K *kp = keys + (uint64_t)b * A.stride;
+    const uint64_t *kp = keys + (uint64_t)b * A.stride;
     const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
     bool flag[RG_ITEMS], nxt[RG_ITEMS];
+    uint32_t val[RG_ITEMS];
     int last = -1;
     uint32_t keep = 0;
     if (a0 < cnt) {
-        load_flags(kp, a0, cnt, flag, nxt);
+        load_flags(kp, a0, cnt, flag, nxt, val);
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i) {
             uint32_t a = a0 + i;
@@ -360,12 +351,11 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const K *__restrict_
     prev_last = max(prev_last, A.tile_carry[tidx]);
     uint32_t keep_off = A.tile_keep[tidx] + block_excl_sum(keep, s_u, nullptr);
     if (a0 >= cnt) return;
-    const uint32_t *vp = A.vals + (uint64_t)b * A.stride;
     const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
     uint32_t *rank = A.rank + (uint64_t)b * A.stride;
     uint32_t *pn = A.pos_new + (uint64_t)b * A.stride;
-    uint32_t *vn = A.vals_new + (uint64_t)b * A.stride;
     uint64_t *kn = A.keys_new + (uint64_t)b * A.stride;
+    const int gshift = VAL_BITS + A.nbits;
     int g = prev_last;
     uint32_t gpos = 0;
     bool gpos_valid = false;
@@ -376,31 +366,31 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const K *__restrict_
             uint32_t mypos = pp ? pp[a] : a;
             if (flag[i]) { g = (int)a; gpos = mypos; gpos_valid = true; }
             else if (!gpos_valid) { gpos = pp ? pp[g] : (uint32_t)g; gpos_valid = true; }
-            uint32_t v = vp[a];
+            const uint32_t v = val[i];
             rank[v] = gpos;
             if (!(flag[i] && nxt[i])) {
                 pn[keep_off] = mypos;
-                vn[keep_off] = v;
-                kn[keep_off] = (uint64_t)gpos << A.nbits;
+                kn[keep_off] = ((uint64_t)gpos << gshift) | v;
                 ++keep_off;
             }
         }
     }
 }
 
-// key |= rank[(i + h) mod n]
-__global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ counts,
-                                                     const uint32_t *__restrict__ n_arr, uint64_t stride, const uint32_t *__restrict__ rank, uint32_t h)
+// element |= rank[(i + h) mod n] << 20
+__global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ n_arr,
+                                                     uint64_t stride, const uint32_t *__restrict__ rank, uint32_t h)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t cnt = counts[b];
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= cnt) return;
     const uint32_t n = n_arr[b];
-    uint64_t o = (uint64_t)b * stride;
-    uint32_t p = vals[o + a] + h; // h < n for every block that is still active
+    const uint64_t o = (uint64_t)b * stride;
+    const uint64_t e = keys[o + a];
+    uint32_t p = (uint32_t)(e & VAL_MASK) + h; // h < n for every block that is still active
     if (p >= n) p -= n;
-    keys[o + a] |= rank[o + p];
+    keys[o + a] = e | ((uint64_t)rank[o + p] << VAL_BITS);
 }
 
 // L[j] = T[(SA[j] - 1) mod n]; origPtr = rank[0]

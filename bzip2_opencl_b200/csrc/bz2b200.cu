@@ -50,7 +50,7 @@ struct bz2b200 {
     // per-call (grow only)
     DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     // per-batch, fixed size
-    DevBuf rle, L, ranks, kA, kB, vA, vB, sa, rank, pA, pB, mtf, hist, digit_base, tile_last, tile_keep, tile_carry, cnt0, cnt1, scalars,
+    DevBuf rle, L, ranks, kA, kB, sa, rank, pA, pB, mtf, hist, digit_base, tile_last, tile_keep, tile_carry, cnt0, cnt1, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
@@ -180,12 +180,10 @@ static int upload_constants(bz2b200 *h)
     CK(cudaMemcpyToSymbol(c_crc_table, table, sizeof(table)));
     CK(cudaMemcpyToSymbol(c_crc_pow8, pow8, sizeof(pow8)));
     CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
-    CK(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint64_t>)));
-    CK(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<uint32_t>)));
+    CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_emit_data, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_huff_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (h->device < 64) g_const_ready[h->device] = true;
@@ -252,8 +250,6 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->ranks, G * S + 64);
     ENSURE(h->kA, G * S * 8);
     ENSURE(h->kB, G * S * 8);
-    ENSURE(h->vA, G * S * 4);
-    ENSURE(h->vB, G * S * 4);
     ENSURE(h->sa, G * S * 4);
     ENSURE(h->rank, G * S * 4);
     ENSURE(h->pA, G * S * 4);
@@ -349,35 +345,32 @@ extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
     return n + n / 3 + blocks * (size_t)(2048 + h->bs / 50) + 4096;
 }
 
-template <typename K>
-static void radix_pass(bz2b200 *h, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *counts, int shift, int bits, uint32_t nb,
-                       uint32_t max_count, uint64_t total_elems)
+static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const uint32_t *counts, int shift, int bits, uint32_t nb, uint32_t max_count,
+                       uint64_t total_elems)
 {
     uint32_t tiles = (max_count + RS_TILE - 1) / RS_TILE;
     if (tiles == 0) return;
     dim3 grid(tiles, nb);
     uint32_t mask = (1u << bits) - 1u;
-    KL(KID_k_radix_hist, k_radix_hist<K><<<grid, RS_THREADS, 0, h->stream>>>(kin, counts, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR));
+    KL(KID_k_radix_hist, k_radix_hist<uint64_t><<<grid, RS_THREADS, 0, h->stream>>>(kin, counts, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR));
     KL(KID_k_radix_scan, k_radix_scan<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->hist), counts, h->tilesR, ptr<uint32_t>(h->digit_base)));
-    KL(KID_k_radix_scatter, k_radix_scatter<K><<<grid, RS_THREADS, sizeof(ScatterSmem<K>), h->stream>>>(kin, vin, kout, vout, counts, h->S, shift, mask,
-                                                                                                      ptr<uint32_t>(h->hist), h->tilesR, ptr<uint32_t>(h->digit_base)));
+    KL(KID_k_radix_scatter, k_radix_scatter<<<grid, RS_THREADS, sizeof(ScatterSmem), h->stream>>>(kin, kout, counts, h->S, shift, mask, ptr<uint32_t>(h->hist),
+                                                                                                h->tilesR, ptr<uint32_t>(h->digit_base)));
     h->stats.kernel_launches += 3;
-    KBYTES(KID_k_radix_hist, total_elems * sizeof(K));
-    KBYTES(KID_k_radix_scatter, total_elems * (2 * sizeof(K) + 8));
+    KBYTES(KID_k_radix_hist, total_elems * 8);
+    KBYTES(KID_k_radix_scatter, total_elems * 16);
 }
 
-// sorts `total_bits` low bits of the keys; returns 0 if the result is in (k0,v0), 1 if in (k1,v1)
-template <typename K>
-static int radix_sort(bz2b200 *h, K *k0, uint32_t *v0, K *k1, uint32_t *v1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count,
-                      uint64_t total_elems)
+// sorts bits [VAL_BITS, VAL_BITS + total_bits) of the elements; returns 0 if the result is in k0, 1 if in k1
+static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count, uint64_t total_elems)
 {
     int npass = (total_bits + 7) / 8;
     int basebits = total_bits / npass, extra = total_bits % npass;
-    int shift = 0, cur = 0;
+    int shift = VAL_BITS, cur = 0;
     for (int p = 0; p < npass; ++p) {
         int bits = basebits + (p < extra ? 1 : 0);
-        if (cur == 0) radix_pass<K>(h, k0, v0, k1, v1, counts, shift, bits, nb, max_count, total_elems);
-        else radix_pass<K>(h, k1, v1, k0, v0, counts, shift, bits, nb, max_count, total_elems);
+        if (cur == 0) radix_pass(h, k0, k1, counts, shift, bits, nb, max_count, total_elems);
+        else radix_pass(h, k1, k0, counts, shift, bits, nb, max_count, total_elems);
         cur ^= 1;
         shift += bits;
     }
@@ -563,11 +556,10 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     uint32_t *cntA = ptr<uint32_t>(h->cnt0), *cntB = ptr<uint32_t>(h->cnt1);
     {
         dim3 g((max_n + 255) / 256, nb);
-        KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA)));
+        KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint64_t>(h->kA)));
         stt.kernel_launches += 1;
     }
-    int res = radix_sort<uint32_t>(h, ptr<uint32_t>(h->kA), ptr<uint32_t>(h->vA), ptr<uint32_t>(h->kB), ptr<uint32_t>(h->vB), d_n, 8 * h->key0_bytes, nb,
-                                   max_n, sum_n);
+    int res = radix_sort(h, ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_n, 8 * h->key0_bytes, nb, max_n, sum_n);
     CK(cudaEventRecord(h->ev[4], st));
 
     RegroupArgs A;
@@ -588,29 +580,22 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     uint32_t *counts_next = cntA;
     uint32_t *pos_old = nullptr, *pos_new = ptr<uint32_t>(h->pA);
     uint64_t rounds = 0;
-    bool first = true;
     for (;;) {
-        // sorted keys/vals are in buffer `res`; the next round's input goes to the other buffer
-        void *ks = res ? h->kB.p : h->kA.p;
-        uint32_t *vs = res ? ptr<uint32_t>(h->vB) : ptr<uint32_t>(h->vA);
+        // sorted elements are in buffer `res`; the next round's input goes to the other buffer
+        uint64_t *ks = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
         uint64_t *kn = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
-        uint32_t *vn = res ? ptr<uint32_t>(h->vA) : ptr<uint32_t>(h->vB);
         A.counts = counts;
-        A.vals = vs;
         A.pos_old = pos_old;
         A.counts_new = counts_next;
         A.pos_new = pos_new;
-        A.vals_new = vn;
         A.keys_new = kn;
         A.sorted_len = sorted_len;
         CK(cudaMemsetAsync(d_scal + Scalars::TOTAL_ACTIVE, 0, 8, st));
         CK(cudaMemsetAsync(d_scal + Scalars::MAX_ACTIVE, 0, 8, st));
         dim3 g((max_count + RG_TILE - 1) / RG_TILE, nb);
-        if (first) KL(KID_k_bwt_flags, k_bwt_flags<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
-        else KL(KID_k_bwt_flags, k_bwt_flags<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
+        KL(KID_k_bwt_flags, k_bwt_flags<<<g, RG_THREADS, 0, st>>>(ks, A));
         KL(KID_k_bwt_tilescan, k_bwt_tilescan<<<(nb + 7) / 8, 256, 0, st>>>(A, nb));
-        if (first) KL(KID_k_bwt_regroup, k_bwt_regroup<uint32_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(ks), A));
-        else KL(KID_k_bwt_regroup, k_bwt_regroup<uint64_t><<<g, RG_THREADS, 0, st>>>(reinterpret_cast<const uint64_t *>(ks), A));
+        KL(KID_k_bwt_regroup, k_bwt_regroup<<<g, RG_THREADS, 0, st>>>(ks, A));
         stt.kernel_launches += 3;
         CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::TOTAL_ACTIVE, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -619,7 +604,6 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         if (active == 0) break;
         stt.bwt_active_volume += active;
         ++rounds;
-        first = false;
         // next round: sort the active lists by (group, rank of the rotation sorted_len further on)
         counts = counts_next;
         counts_next = (counts_next == cntA) ? cntB : cntA;
@@ -627,10 +611,10 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         pos_new = (pos_new == ptr<uint32_t>(h->pA)) ? ptr<uint32_t>(h->pB) : ptr<uint32_t>(h->pA);
         max_count = (uint32_t)std::min<uint64_t>(max_n, h->h_pinned[Scalars::MAX_ACTIVE]);
         dim3 gg((max_count + 255) / 256, nb);
-        KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(kn, vn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len));
+        KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(kn, counts, d_n, S, ptr<uint32_t>(h->rank), sorted_len));
         stt.kernel_launches += 1;
-        int r2 = radix_sort<uint64_t>(h, kn, vn, reinterpret_cast<uint64_t *>(ks), vs, counts, 2 * h->nbits, nb, max_count, active);
-        // r2 == 0: result in (kn, vn) which is buffer !res ; r2 == 1: result in (ks, vs) = buffer res
+        int r2 = radix_sort(h, kn, ks, counts, 2 * h->nbits, nb, max_count, active);
+        // r2 == 0: result in kn which is buffer !res ; r2 == 1: result in ks = buffer res
         res = r2 == 0 ? !res : res;
         sorted_len *= 2;
     }
