@@ -95,4 +95,35 @@ __device__ __forceinline__ int block_excl_max(int v, int *scratch, int *total)
     return res;
 }
 
+// Exclusive SUFFIX minimum over one value per thread: min of the values of all threads with a HIGHER index (INT_MAX if none).
+__device__ __forceinline__ int block_excl_min_suffix(int v, int *scratch)
+{
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    int inc = v; // min over lanes >= lane of this warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_down_sync(FULL, inc, d);
+        if (lane + d < 32) inc = min(inc, o);
+    }
+    if (lane == 0) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = lane < nw ? scratch[lane] : 0x7fffffff;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_down_sync(FULL, x, d);
+            if (lane + d < 32) x = min(x, o);
+        }
+        int ex = __shfl_down_sync(FULL, x, 1);
+        if (lane == 31) ex = 0x7fffffff;
+        scratch[lane] = ex; // min over warps > lane
+    }
+    __syncthreads();
+    int nxt = __shfl_down_sync(FULL, inc, 1);
+    if (lane == 31) nxt = 0x7fffffff;
+    int res = min(scratch[w], nxt);
+    __syncthreads();
+    return res;
+}
+
 } // namespace bz
