@@ -444,8 +444,8 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
 // START in [k*LS_STRIDE, (k+1)*LS_STRIDE); they end inside the 2*LS_STRIDE window it loads.  Inside the window the group
 // position is replaced by a dense group index, so (index, rank of the second half) fits 32 bits and is LSD-sorted in shared
 // memory (same warp match_any multi-split as the global scatter, no global traffic between passes).
-constexpr int LS_THREADS = 256;
-constexpr int LS_ITEMS = 16;
+constexpr int LS_THREADS = 512;
+constexpr int LS_ITEMS = 8;
 constexpr int LS_WIN = LS_THREADS * LS_ITEMS; // 4096
 constexpr int LS_STRIDE = LS_WIN / 2;         // == RG_TILE
 constexpr int LS_WARPS = LS_THREADS / 32;
@@ -553,13 +553,16 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_localsort(const uint64_t *__
         {
             const uint32_t d = threadIdx.x;
             uint32_t sum = 0;
+            if (d < 256) {
 #pragma unroll
-            for (int ww = 0; ww < LS_WARPS; ++ww) {
-                uint32_t t = sm.warp_hist[ww][d];
-                sm.warp_hist[ww][d] = sum;
-                sum += t;
+                for (int ww = 0; ww < LS_WARPS; ++ww) {
+                    uint32_t t = sm.warp_hist[ww][d];
+                    sm.warp_hist[ww][d] = sum;
+                    sum += t;
+                }
             }
-            sm.tile_base[d] = block_excl_sum(sum, sm.scratch, nullptr);
+            const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr); // threads >= 256 add 0 behind the digits
+            if (d < 256) sm.tile_base[d] = tb;
         }
         __syncthreads();
 #pragma unroll
