@@ -318,12 +318,16 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const uint64_t *__rest
     if (a0 < cnt) {
         const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
         uint32_t *sa = A.sa + (uint64_t)b * A.stride;
+        const bool done = A.sorted_len >= A.n_arr[b];
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i) {
             uint32_t a = a0 + i;
             if (a < cnt) {
-                if (!(v.flag[i] && v.nxt[i])) { if (v.local[i]) ++ks; else ++kb; }
-                sa[pp ? pp[a] : a] = v.val[i];
+                const bool single = v.flag[i] && v.nxt[i];
+                if (!single) { if (v.local[i]) ++ks; else ++kb; }
+                // SA is only read by k_bwt_finish: write a rotation's slot when it becomes final (alone in its group, or the
+                // block stops here); rotations that stay active are written by a later round
+                if (single || done) sa[pp ? pp[a] : a] = v.val[i];
             }
         }
     }

@@ -21,6 +21,20 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d)
     return ((uint64_t)hi << 32) | lo;
 }
 
+// Lanes of the warp that hold the same 8-bit digit as this lane (invalid lanes match nobody): eight ballots instead of
+// match.any, whose latency grows with the number of distinct values in the warp.
+__device__ __forceinline__ unsigned warp_digit_peers(uint32_t d, bool valid)
+{
+    unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (d >> bit) & 1u;
+        const unsigned b = __ballot_sync(FULL, one);
+        peers &= one ? b : ~b;
+    }
+    return valid ? peers : 0u;
+}
+
 // inclusive warp scans
 __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v)
 {
