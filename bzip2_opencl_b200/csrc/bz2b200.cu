@@ -653,12 +653,12 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
 
     // ---- stage C: MTF + RLE2
     {
-        dim3 gm((max_n + MS_THREADS * MTF_TILE - 1) / (MS_THREADS * MTF_TILE), nb);
+        dim3 gm((max_n + MW_WARPS * MTF_TILE - 1) / (MW_WARPS * MTF_TILE), nb);
         dim3 gq((max_n + MR_WARPS * MTF_TILE - 1) / (MR_WARPS * MTF_TILE), nb);
         KL(KID_k_mtf_recency, k_mtf_recency<<<gq, MR_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists),
                                                                           ptr<uint32_t>(h->dcount), h->tilesM));
         KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
-        KL(KID_k_mtf_ranks, k_mtf_ranks<<<gm, MS_THREADS, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), h->tilesM,
+        KL(KID_k_mtf_ranks, k_mtf_ranks<<<gm, MW_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), h->tilesM,
                                                                    ptr<uint8_t>(h->ranks)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
         KL(KID_k_rle2_tiles, k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2));

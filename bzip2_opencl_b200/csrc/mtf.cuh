@@ -5,10 +5,9 @@
 //   k_mtf_recency     one warp per tile: the tile's distinct symbols by recency (a partial permutation), computed in parallel from
 //                     last-occurrence positions -- what running MTF over the tile would leave at the front of the list
 //   k_mtf_compose     one warp per block composes those in tile order -> the exact list at every tile start
-//   k_mtf_ranks       one THREAD per tile re-runs MTF from its true start list and writes the ranks.  The first 16 list
-//                     entries sit in four registers (typical BWT output resolves there); the other 240 live in shared memory
-//                     and are walked 16 entries per step with per-byte SIMD compares (__vcmpeq4) and __byte_perm shifts.
-//                     Symbols and ranks are staged through shared memory so global traffic stays in 64-byte pieces.
+//   k_mtf_ranks       one WARP per tile re-runs MTF from its true start list, 32 symbols per step: ranks come from a
+//                     branch-free dominance count over the step's previous-occurrence times, then the list is rebuilt in
+//                     shared memory (recent symbols first, stable compaction of the rest).
 //   k_rle2_tiles / k_rle2_scan / k_rle2_emit  turn ranks into the RUNA/RUNB/rank+1/EOB symbol stream with an
 //                     exclusive scan of emission counts, and histogram the symbols (mtfSymbolFrequencies).
 #pragma once
@@ -28,26 +27,6 @@ __device__ __forceinline__ void build_symbol_map(const uint32_t *present8, uint8
         c += __popc(present8[v >> 5] & ((1u << (v & 31)) - 1u));
         map[v] = (uint8_t)c;
     }
-}
-
-// ---- per-thread MTF over one tile.  The 256-entry list of every thread lives in shared memory as 32 little-endian
-// 64-bit words (word k = entries 8k..8k+7), word 0 is kept in a register.  A lookup walks the list 8 entries at a time
-// with a SWAR zero-byte test; the words it passes are shifted up by one entry on the way (that IS the move-to-front).
-constexpr int MS_THREADS = 128;
-constexpr int MS_CHUNK = 64;          // symbols staged per thread per step
-constexpr int MS_STAGE_STRIDE = 68;   // bytes (17 words: conflict-free lane-strided access)
-constexpr int MS_LIST_WORDS = 33;     // 32 words + 1 pad (conflict-free 64-bit lane-strided access)
-constexpr uint64_t ONES8 = 0x0101010101010101ull;
-
-__device__ __forceinline__ uint32_t zero_byte_index(uint64_t x) // index of the lowest zero byte of x, 8 if none
-{
-    uint64_t t = (x - ONES8) & ~x & 0x8080808080808080ull;
-    return t ? (uint32_t)(__ffsll((long long)t) - 1) >> 3 : 8u;
-}
-
-__device__ __forceinline__ uint64_t low_bytes_mask(uint32_t bi) // bytes 0..bi
-{
-    return bi >= 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull);
 }
 
 // ---- pass 1: the tile's distinct symbols ordered by recency (most recent first).  Fully parallel: last occurrence of every
@@ -110,145 +89,112 @@ __global__ void __launch_bounds__(MR_WARPS * 32) k_mtf_recency(const uint8_t *__
     if (lane == 0) dcount[(uint64_t)b * tiles_per_block + tile] = d;
 }
 
-// ---- pass 2: one THREAD per tile re-runs MTF from its true start list (k_mtf_compose) and writes the ranks.
-// The list is 16 x uint4 (16 entries each).  Entries 0..15 live in four registers; the rest in shared memory.  A lookup
-// compares 16 entries per step with four per-byte SIMD compares (__vcmpeq4) and shifts the passed words by one entry with
-// __byte_perm -- that shift IS the move-to-front.
-constexpr int ML_STRIDE4 = 17; // uint4 per thread (16 + 1 pad: conflict-free 128-bit lane-strided access)
+// ---- pass 2: one WARP per tile re-runs MTF from its true start list (k_mtf_compose) and writes the ranks, 32 symbols per
+// step, branch-free.  With tau_j = lane of the previous occurrence of lane j's symbol inside the step (or the virtual time
+// -1 - v_j, v_j = position in the list at the start of the step, when there is none):
+//     rank_j = [no previous occurrence] * v_j + #{ q : tau_j < q < j, tau_q < tau_j }
+// (symbols that were behind s_j and occur before j jump in front of it; for a repeated symbol the count is the number of
+// distinct symbols in between).  The list is then rebuilt in place: the step's distinct symbols by recency, followed by the
+// untouched part of the old list in its old order (a stable compaction of the first max(v)+1 entries only).
+constexpr int MW_WARPS = 8; // tiles per CTA
 
-struct Quad { uint32_t x, y, z, w; };
+struct MtfWarpSmem {
+    uint8_t stage[MTF_TILE]; // dense symbols in, ranks out
+    uint8_t list[256];       // list[pos] = symbol
+    uint8_t inv[256];        // inv[symbol] = pos
+    uint8_t mark[256];       // symbol occurs in the current step
+};
 
-// q shifted up by one entry with `in` entering at entry 0
-__device__ __forceinline__ Quad quad_shift(const Quad &q, uint32_t in)
+__global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                              const uint32_t *__restrict__ present, const uint64_t *__restrict__ lists,
+                                                              int tiles_per_block, uint8_t *__restrict__ ranks)
 {
-    Quad s;
-    s.x = (q.x << 8) | in;
-    s.y = __byte_perm(q.x, q.y, 0x6543);
-    s.z = __byte_perm(q.y, q.z, 0x6543);
-    s.w = __byte_perm(q.z, q.w, 0x6543);
-    return s;
-}
-// entry index (0..15) of byte value `pat`/0x01010101 in q, or 16
-__device__ __forceinline__ uint32_t quad_find(const Quad &q, uint32_t pat)
-{
-    uint32_t m0 = __vcmpeq4(q.x, pat), m1 = __vcmpeq4(q.y, pat), m2 = __vcmpeq4(q.z, pat), m3 = __vcmpeq4(q.w, pat);
-    if ((m0 | m1 | m2 | m3) == 0) return 16;
-    if (m0) return (uint32_t)(__ffs((int)m0) - 1) >> 3;
-    if (m1) return 4 + ((uint32_t)(__ffs((int)m1) - 1) >> 3);
-    if (m2) return 8 + ((uint32_t)(__ffs((int)m2) - 1) >> 3);
-    return 12 + ((uint32_t)(__ffs((int)m3) - 1) >> 3);
-}
-// entries 0..p come from the shifted quad s, entries above p stay
-__device__ __forceinline__ Quad quad_blend(const Quad &old, const Quad &s, uint32_t p)
-{
-    const uint32_t wi = p >> 2, bi = p & 3;
-    const uint32_t m = bi == 3 ? 0xffffffffu : ((1u << (8 * (bi + 1))) - 1u);
-    Quad r;
-    r.x = wi > 0 ? s.x : ((old.x & ~m) | (s.x & m));
-    r.y = wi > 1 ? s.y : (wi == 1 ? ((old.y & ~m) | (s.y & m)) : old.y);
-    r.z = wi > 2 ? s.z : (wi == 2 ? ((old.z & ~m) | (s.z & m)) : old.z);
-    r.w = wi == 3 ? ((old.w & ~m) | (s.w & m)) : old.w;
-    return r;
-}
-
-__global__ void __launch_bounds__(MS_THREADS) k_mtf_ranks(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
-                                                           const uint32_t *__restrict__ present, const uint64_t *__restrict__ lists,
-                                                           int tiles_per_block, uint8_t *__restrict__ ranks)
-{
-    __shared__ uint4 s_list[MS_THREADS * ML_STRIDE4];
-    __shared__ __align__(16) uint8_t s_stage[MS_THREADS * MS_STAGE_STRIDE];
+    __shared__ __align__(16) MtfWarpSmem sm_all[MW_WARPS];
     __shared__ uint8_t map[256];
     const uint32_t b = blockIdx.y;
     const uint32_t n = n_arr[b];
-    const uint32_t tile0 = blockIdx.x * MS_THREADS;
-    if ((uint64_t)tile0 * MTF_TILE >= n) return;
+    if ((uint64_t)blockIdx.x * MW_WARPS * MTF_TILE >= n) return;
     build_symbol_map(present + b * 8, map);
     __syncthreads();
     const int lane = lane_id(), w = warp_id();
-    const uint32_t wtile0 = tile0 + w * 32; // first tile of this warp
-    if ((uint64_t)wtile0 * MTF_TILE >= n) return;
-    const uint32_t tile = wtile0 + lane;
+    const uint32_t tile = blockIdx.x * MW_WARPS + w;
     const uint32_t base = tile * MTF_TILE;
-    const uint32_t cnt = base < n ? min((uint32_t)MTF_TILE, n - base) : 0u;
-    const uint4 *gl = reinterpret_cast<const uint4 *>(lists + ((uint64_t)b * tiles_per_block + tile) * 32);
-    uint4 *list = s_list + threadIdx.x * ML_STRIDE4;
-    Quad r = {0, 0, 0, 0};
-    if (cnt) {
-        uint4 v = gl[0];
-        r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
-        for (int k = 1; k < 16; ++k) list[k] = gl[k];
+    if (base >= n) return;
+    const uint32_t cnt = min((uint32_t)MTF_TILE, n - base);
+    MtfWarpSmem &S = sm_all[w];
+    {
+        const uint64_t l8 = lists[((uint64_t)b * tiles_per_block + tile) * 32 + lane];
+        *reinterpret_cast<uint64_t *>(S.list + lane * 8) = l8;
+        *reinterpret_cast<uint64_t *>(S.mark + lane * 8) = 0ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) S.inv[(uint32_t)(l8 >> (8 * k)) & 0xffu] = (uint8_t)(lane * 8 + k);
     }
-    const uint8_t *src = L + (uint64_t)b * stride;
-    uint8_t *dst = ranks + (uint64_t)b * stride;
-    const uint32_t wcnt = min((uint32_t)MTF_TILE, n - wtile0 * MTF_TILE); // lane 0's tile is the fullest
-    const uint32_t nchunks = (wcnt + MS_CHUNK - 1) / MS_CHUNK;
-    uint8_t *wstage = s_stage + (w * 32) * MS_STAGE_STRIDE;
-    uint8_t *mine = s_stage + threadIdx.x * MS_STAGE_STRIDE;
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        // cooperative load: 4 lanes x 16 bytes cover one tile's 64-byte piece, 8 tiles per instruction; bytes are mapped to
-        // dense symbol indices on the way in (keeps the table lookup out of the serial chain)
+    const uint8_t *src = L + (uint64_t)b * stride + base;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
-            uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
-            if (off < n) {
-                uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + off));
-                uint32_t in[4] = {v.x, v.y, v.z, v.w};
-                uint32_t *sp = reinterpret_cast<uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
+    for (int q = 0; q < MTF_TILE / 512; ++q) {
+        const uint32_t off = (q * 32 + lane) * 16;
+        if (off < cnt) { // bytes past n inside the last 16 are in-bounds garbage and never used
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + off));
+            const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t x = in[j];
-                    sp[j] = (uint32_t)map[x & 0xff] | ((uint32_t)map[(x >> 8) & 0xff] << 8) | ((uint32_t)map[(x >> 16) & 0xff] << 16) |
-                            ((uint32_t)map[x >> 24] << 24);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t x = in[j];
+                o[j] = (uint32_t)map[x & 0xff] | ((uint32_t)map[(x >> 8) & 0xff] << 8) | ((uint32_t)map[(x >> 16) & 0xff] << 16) | ((uint32_t)map[x >> 24] << 24);
             }
+            *reinterpret_cast<uint4 *>(S.stage + off) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u, gt = 0xfffffffeu << lane;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const bool valid = c0 + lane < cnt;
+        const uint32_t sym = S.stage[c0 + lane];
+        const unsigned peers = __match_any_sync(FULL, valid ? sym : 256u + lane);
+        const unsigned lower = peers & lt;
+        const bool first = lower == 0;
+        const uint32_t v = S.inv[valid ? sym : 0u];
+        const int tau = first ? -1 - (int)v : 31 - __clz((int)lower);
+        const unsigned W = tau >= 0 ? (lt & ~((2u << tau) - 1u)) : lt;
+        unsigned acc = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int tq = __shfl_sync(FULL, tau, q);
+            if (tq < tau) acc |= 1u << q;
+        }
+        const uint32_t rank = __popc(acc & W) + (first ? v : 0u);
+        if (valid) S.stage[c0 + lane] = (uint8_t)rank;
+        // ---- rebuild the list
+        const bool is_last = valid && (peers & gt) == 0;
+        const unsigned Bl = __ballot_sync(FULL, is_last);
+        const int maxv = __reduce_max_sync(FULL, (valid && first) ? (int)v : -1);
+        if (is_last) S.mark[sym] = 1;
+        __syncwarp();
+        uint32_t suffix = 0; // marked entries at higher positions than the current 32-entry slice
+        for (int k = maxv >> 5; k >= 0; --k) {
+            const int x = k * 32 + lane;
+            const uint32_t e = S.list[x];
+            const bool in = x <= maxv;
+            const bool mk = in && S.mark[e];
+            const unsigned Bm = __ballot_sync(FULL, mk);
+            const uint32_t np = (uint32_t)x + suffix + __popc(Bm & gt); // old position + marked entries behind it
+            if (in && !mk) { S.list[np] = (uint8_t)e; S.inv[e] = (uint8_t)np; }
+            suffix += __popc(Bm);
+            __syncwarp();
+        }
+        if (is_last) {
+            const uint32_t r = __popc(Bl & gt);
+            S.list[r] = (uint8_t)sym;
+            S.inv[sym] = (uint8_t)r;
+            S.mark[sym] = 0;
         }
         __syncwarp();
-        int valid = (int)cnt - (int)(c * MS_CHUNK);
-        valid = valid < 0 ? 0 : (valid > MS_CHUNK ? MS_CHUNK : valid);
-        for (int i = 0; i < valid; ++i) {
-            const uint32_t sym = mine[i];
-            uint32_t rank = 0;
-            if ((r.x & 0xff) != sym) {
-                const uint32_t pat = sym * 0x01010101u;
-                uint32_t p = quad_find(r, pat);
-                Quad s = quad_shift(r, sym);
-                if (p < 16) {
-                    r = quad_blend(r, s, p);
-                    rank = p;
-                } else {
-                    uint32_t carry = r.w >> 24;
-                    r = s;
-                    for (uint32_t k = 1;; ++k) { // the symbol is present: ends at k <= 15
-                        uint4 v = list[k];
-                        Quad q = {v.x, v.y, v.z, v.w};
-                        p = quad_find(q, pat);
-                        s = quad_shift(q, carry);
-                        if (p < 16) {
-                            q = quad_blend(q, s, p);
-                            list[k] = make_uint4(q.x, q.y, q.z, q.w);
-                            rank = 16 * k + p;
-                            break;
-                        }
-                        list[k] = make_uint4(s.x, s.y, s.z, s.w);
-                        carry = q.w >> 24;
-                    }
-                }
-            }
-            mine[i] = (uint8_t)rank;
-        }
-        __syncwarp();
+    }
+    uint8_t *dst = ranks + (uint64_t)b * stride + base;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t tl = q * 8 + (lane >> 2), piece = lane & 3;
-            uint32_t off = (wtile0 + tl) * MTF_TILE + c * MS_CHUNK + piece * 16;
-            if (off < n) {
-                const uint32_t *sp = reinterpret_cast<const uint32_t *>(wstage + tl * MS_STAGE_STRIDE + piece * 16);
-                uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
-                *reinterpret_cast<uint4 *>(dst + off) = v;
-            }
-        }
-        __syncwarp();
+    for (int q = 0; q < MTF_TILE / 512; ++q) {
+        const uint32_t off = (q * 32 + lane) * 16;
+        if (off < cnt) *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(S.stage + off);
     }
 }
 

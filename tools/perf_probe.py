@@ -26,7 +26,7 @@ def probe(name, data, mult=9, base=100000, parallel=64, reps=2, verify=False):
     dt, st = best
     print(f"{name:14s} n={n/1e6:8.1f}MB P={parallel:4d} blocks={st['n_blocks']:5d} wall {dt*1e3:8.1f} ms = {n/dt/1e6:8.1f} MB/s | dev {st['ms_total']:8.1f} "
           f"rle {st['ms_rle']:6.1f} sort0 {st['ms_bwt_sort0']:6.1f} rounds {st['ms_bwt_rounds']:7.1f}[{st['bwt_rounds']:2d}, rho={st['bwt_active_volume']/max(1,st['n_rle']):.2f}] "
-          f"fin {st['ms_bwt_finish']:5.1f} mtf {st['ms_mtf']:6.1f} huf {st['ms_huffman']:6.1f} emit {st['ms_emit']:6.1f} d2h {st['ms_d2h']:5.1f} launches {st['kernel_launches']}",
+          f"fin {st['ms_bwt_finish']:5.1f} mtf {st['ms_mtf']:6.1f} huf {st['ms_huffman']:6.1f} emit {st['ms_emit']:6.1f} walk {st['ms_walk']:6.1f} d2h {st['ms_d2h']:5.1f} launches {st['kernel_launches']}",
           flush=True)
     if verify:
         nbits = res["nbits"]
