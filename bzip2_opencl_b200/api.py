@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libbz2b200.so")
 
 OK, E_BLOCKSIZE, E_PARALLEL, E_ARG, E_CUDA, E_NOMEM, E_OUTPUT, E_STATE = 0, -1, -2, -3, -4, -5, -6, -7
 
-STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAGE_SELECTORS, STAGE_LENGTHS, STAGE_SA = range(1, 10)
+STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAGE_SELECTORS, STAGE_LENGTHS, STAGE_RANK = range(1, 10)
 
 EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200_max_output_bytes", "bz2b200_scan_blocks",
            "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
@@ -186,7 +186,7 @@ class Compressor:
         return out
 
     def stage(self, block_index: int, stage: int) -> np.ndarray:
-        dtype = {STAGE_ORIGPTR: np.uint32, STAGE_MTF: np.uint16, STAGE_FREQ: np.int32, STAGE_SA: np.uint32}.get(stage, np.uint8)
+        dtype = {STAGE_ORIGPTR: np.uint32, STAGE_MTF: np.uint16, STAGE_FREQ: np.int32, STAGE_RANK: np.uint32}.get(stage, np.uint8)
         cap = (self.block_size + 64) * 4
         buf = np.zeros(cap, dtype=np.uint8)
         n = C.c_size_t(0)

@@ -217,333 +217,308 @@ __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------------ regroup
-// Sorted elements of the active list of each block -> scatter SA, find new groups, update ranks, compact the
-// still-ambiguous rotations into the next round's sort input.
-struct RegroupArgs {
-    const uint32_t *counts;   // [G] active elements sorted this round (small-group part first, then the rest)
-    const uint32_t *n_arr;    // [G] block lengths
+// After a sort, equal keys form the new groups.  For every element: rank[rotation] = SA position of its group's first element;
+// a rotation alone in its group (or any rotation once 2h >= n) is final and its BWT byte goes straight to L[position].
+// Rotations that stay ambiguous are kept for the next round in one of two places:
+//   * groups that lie inside one SA tile (RG_TILE consecutive SA positions) move to that tile's LOCAL region: all later
+//     refinements of such a group stay inside the tile, so k_bwt_local sorts and regroups them in shared memory;
+//   * the rest (groups larger than a tile or straddling a tile edge) go to the block's BAG, an unordered list that the next
+//     round sorts with the global radix sort.
+// Elements carry the SA position of their group's first element (bag: absolute, local region: relative to the tile), so a
+// sorted list needs no position array: position = group position + index inside the (old) group.
+struct RoundArgs {
+    const uint32_t *n_arr;      // [G] block lengths
     uint64_t stride;
-    const uint32_t *pos_old;  // position in SA of active element a (nullptr: identity, round 0)
-    uint32_t *sa;             // [G*stride]
-    uint32_t *rank;           // [G*stride]
-    int32_t *tile_last;       // [G*tiles] last flagged index per tile (-1: none)
-    uint32_t *tile_keep_s;    // [G*tiles] kept elements of tile-local groups per tile, later exclusive prefix
-    uint32_t *tile_keep_b;    // [G*tiles] kept elements of the other groups per tile, later exclusive prefix
-    int32_t *tile_carry;      // [G*tiles] last flagged index before the tile
-    int tiles_per_block;      // regroup tiles per block
-    uint32_t *cnt_t_new;      // [G] all still-active elements
-    uint32_t *cnt_s_new;      // [G] ... of which in tile-local groups (sorted in shared memory next round)
-    uint32_t *cnt_b_new;      // [G] ... the rest (global radix sort next round)
-    uint32_t *pos_new;        // compacted positions
-    uint64_t *keys_new;       // (list slot of the group start << (20 + nbits)) | rotation index; k_bwt_gather ORs in rank of the second half << 20
-    int nbits;
-    int split;                // 0: put every group in the global-sort part
-    uint32_t sorted_len;      // rotations are now ordered by their first sorted_len bytes
-    unsigned long long *totals; // [0] sum of cnt_t_new, [3] max cnt_t_new, [8] max cnt_s_new, [9] max cnt_b_new, [10] sum cnt_b_new
+    const uint8_t *T;           // [G*stride] RLE1 blocks
+    uint8_t *L;                 // [G*stride] BWT last column
+    uint32_t *rank;             // [G*stride]
+    uint64_t *loc;              // [G*stride] local regions: tile t of block b owns loc[b*stride + t*RG_TILE ...]
+    uint32_t *loc_cnt;          // [G*tiles] elements in each local region
+    int tiles_per_block;
+    unsigned long long *totals; // [0] rotations kept for the next round (all blocks)
+    uint32_t sorted_len;        // rotations are now ordered by their first sorted_len bytes
+    int split;                  // 0: keep every group in the bag (debug)
 };
 
-__device__ __forceinline__ void load_flags(const uint64_t *kp, uint32_t a0, uint32_t cnt, bool (&flag)[RG_ITEMS], bool (&nxt)[RG_ITEMS],
-                                           uint32_t (&val)[RG_ITEMS])
-{
-    // flag[i]: element a0+i starts a group; nxt[i]: element a0+i ends a group; val[i]: its rotation index
-    uint64_t prev = a0 > 0 && a0 - 1 < cnt ? (kp[a0 - 1] >> VAL_BITS) : 0ull;
-#pragma unroll
-    for (int i = 0; i < RG_ITEMS; ++i) {
-        uint32_t a = a0 + i;
-        uint64_t e = a < cnt ? kp[a] : 0ull;
-        uint64_t cur = e >> VAL_BITS;
-        val[i] = (uint32_t)(e & VAL_MASK);
-        flag[i] = (a == 0) || (cur != prev);
-        prev = cur;
-    }
-#pragma unroll
-    for (int i = 0; i < RG_ITEMS - 1; ++i) nxt[i] = (a0 + i + 1 >= cnt) || flag[i + 1];
-    {
-        uint32_t a = a0 + RG_ITEMS;
-        nxt[RG_ITEMS - 1] = (a >= cnt) || ((kp[a] >> VAL_BITS) != prev);
-    }
-}
+constexpr int GPOS_SHIFT = 2 * VAL_BITS;  // element = group position << 40 | rank of the second half << 20 | rotation index
+constexpr int SA_TILE_BITS = 11;
+static_assert((1 << SA_TILE_BITS) == RG_TILE, "SA tile = regroup tile");
+constexpr int INT_INF = 0x7fffffff;
 
-// Per element: does its (new) group start AND end inside this regroup tile?  Such "tile-local" groups (<= RG_TILE elements)
-// are sorted in shared memory next round; everything else goes through the global radix sort.
-struct TileView {
-    bool flag[RG_ITEMS], nxt[RG_ITEMS], local[RG_ITEMS];
-    uint32_t val[RG_ITEMS];
-    int last;          // last flagged index owned by this thread (-1)
-    int prev_last;     // last flagged index of the threads before it, inside the tile (-1)
-};
-
-__device__ __forceinline__ void tile_view(const uint64_t *kp, uint32_t a0, uint32_t cnt, int split, int *s_i, TileView &v)
+// kp[] is sorted non-decreasing by (e >> shift) and kp[pos] >> shift == key: first / last slot of the run of `key`
+// (galloping, so a short run costs a few probes).
+__device__ __forceinline__ uint32_t run_first(const uint64_t *kp, uint32_t pos, uint64_t key, int shift)
 {
-    v.last = -1;
-    int first_end = 0x7fffffff;
-    if (a0 < cnt) {
-        load_flags(kp, a0, cnt, v.flag, v.nxt, v.val);
-#pragma unroll
-        for (int i = RG_ITEMS - 1; i >= 0; --i)
-            if (a0 + i < cnt && v.nxt[i]) first_end = (int)(a0 + i);
-#pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i)
-            if (a0 + i < cnt && v.flag[i]) v.last = (int)(a0 + i);
-    }
-    v.prev_last = block_excl_max(v.last, s_i, nullptr);
-    const int next_end = block_excl_min_suffix(first_end, s_i);
-    if (a0 < cnt) {
-        bool started = v.prev_last >= 0;
-#pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i) { started = started || v.flag[i]; v.local[i] = started; }
-        bool ended = next_end != 0x7fffffff;
-#pragma unroll
-        for (int i = RG_ITEMS - 1; i >= 0; --i) {
-            if (a0 + i < cnt) ended = ended || v.nxt[i];
-            v.local[i] = v.local[i] && ended && split != 0;
+    uint32_t hi = pos, step = 1;
+    for (;;) {
+        if (hi == 0) return 0;
+        const uint32_t cand = hi >= step ? hi - step : 0u;
+        if ((kp[cand] >> shift) == key) { hi = cand; step <<= 1; continue; }
+        uint32_t lo = cand;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if ((kp[mid] >> shift) == key) hi = mid; else lo = mid;
         }
+        return hi;
+    }
+}
+__device__ __forceinline__ uint32_t run_last(const uint64_t *kp, uint32_t pos, uint32_t cnt, uint64_t key, int shift)
+{
+    uint32_t lo = pos, step = 1;
+    for (;;) {
+        if (lo + 1 >= cnt) return lo;
+        const uint32_t cand = min(lo + step, cnt - 1);
+        if ((kp[cand] >> shift) == key) { lo = cand; step <<= 1; continue; }
+        uint32_t hi = cand;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if ((kp[mid] >> shift) == key) lo = mid; else hi = mid;
+        }
+        return lo;
     }
 }
 
-__global__ void __launch_bounds__(RG_THREADS) k_bwt_flags(const uint64_t *__restrict__ keys, RegroupArgs A)
+// What a thread knows about its RG_ITEMS consecutive slots a0 .. a0+RG_ITEMS-1 of a sorted list after the block-wide scans.
+struct GroupView {
+    uint32_t P[RG_ITEMS];    // SA position of the new group's first element (relative to the list's position base)
+    uint32_t p[RG_ITEMS];    // SA position of the element
+    uint32_t size[RG_ITEMS]; // elements in the new group
+};
+
+// e[i] = slot a0+i (0 past the end); prev_e = slot a0-1 (unused when a0 == 0); next_e = slot a0+RG_ITEMS (unused past the end).
+// edge_s / edge_o: first slot of the new / old group that contains the tile's first slot; edge_e: last slot of the new group
+// that contains the tile's last slot.  ROUND0: the list is the whole block sorted by its first key (one old group at 0).
+template <bool ROUND0>
+__device__ __forceinline__ void group_view(const uint64_t (&e)[RG_ITEMS], uint64_t prev_e, uint64_t next_e, uint32_t a0, uint32_t cnt, uint32_t edge_s,
+                                           uint32_t edge_o, uint32_t edge_e, int *s_i, GroupView &v)
 {
-    __shared__ int s_i[34];
-    __shared__ int s_last[RG_THREADS / 32];
-    __shared__ uint32_t s_ks[RG_THREADS / 32], s_kb[RG_THREADS / 32];
-    const uint32_t b = blockIdx.y, tile = blockIdx.x;
-    const uint32_t cnt = A.counts[b];
-    const uint32_t base = tile * RG_TILE;
-    if (base >= cnt) return;
-    const uint64_t *kp = keys + (uint64_t)b * A.stride;
-    const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
-    TileView v;
-    tile_view(kp, a0, cnt, A.split, s_i, v);
-    uint32_t ks = 0, kb = 0;
+    bool nf[RG_ITEMS], of[RG_ITEMS], nx[RG_ITEMS];
+    int last_n = -1, last_o = -1, first_end = INT_INF;
     if (a0 < cnt) {
-        const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
-        uint32_t *sa = A.sa + (uint64_t)b * A.stride;
-        const bool done = A.sorted_len >= A.n_arr[b];
+        uint64_t prev = prev_e;
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i) {
-            uint32_t a = a0 + i;
-            if (a < cnt) {
-                const bool single = v.flag[i] && v.nxt[i];
-                if (!single) { if (v.local[i]) ++ks; else ++kb; }
-                // SA is only read by k_bwt_finish: write a rotation's slot when it becomes final (alone in its group, or the
-                // block stops here); rotations that stay active are written by a later round
-                if (single || done) sa[pp ? pp[a] : a] = v.val[i];
+            const uint32_t a = a0 + i;
+            nf[i] = (a == 0) || ((e[i] >> VAL_BITS) != (prev >> VAL_BITS));
+            of[i] = ROUND0 ? (a == 0) : ((a == 0) || ((e[i] >> GPOS_SHIFT) != (prev >> GPOS_SHIFT)));
+            prev = e[i];
+        }
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS - 1; ++i) nx[i] = (a0 + i + 1 >= cnt) || nf[i + 1];
+        nx[RG_ITEMS - 1] = (a0 + RG_ITEMS >= cnt) || ((next_e >> VAL_BITS) != (e[RG_ITEMS - 1] >> VAL_BITS));
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i)
+            if (a0 + i < cnt) {
+                if (nf[i]) last_n = (int)(a0 + i);
+                if (of[i]) last_o = (int)(a0 + i);
             }
-        }
+#pragma unroll
+        for (int i = RG_ITEMS - 1; i >= 0; --i)
+            if (a0 + i < cnt && nx[i]) first_end = (int)(a0 + i);
     }
-    int last = __reduce_max_sync(FULL, v.last);
-    ks = __reduce_add_sync(FULL, ks);
-    kb = __reduce_add_sync(FULL, kb);
-    if (lane_id() == 0) { s_last[warp_id()] = last; s_ks[warp_id()] = ks; s_kb[warp_id()] = kb; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int l = -1; uint32_t s = 0, k = 0;
-        for (int w = 0; w < RG_THREADS / 32; ++w) { l = max(l, s_last[w]); s += s_ks[w]; k += s_kb[w]; }
-        const uint64_t idx = (uint64_t)b * A.tiles_per_block + tile;
-        A.tile_last[idx] = l;
-        A.tile_keep_s[idx] = s;
-        A.tile_keep_b[idx] = k;
+    const int prev_n = block_excl_max(last_n, s_i, nullptr);
+    const int prev_o = ROUND0 ? 0 : block_excl_max(last_o, s_i, nullptr);
+    const int next_end = block_excl_min_suffix(first_end, s_i);
+    if (a0 >= cnt) return;
+    int e_run = next_end != INT_INF ? next_end : (int)edge_e;
+    int en[RG_ITEMS];
+#pragma unroll
+    for (int i = RG_ITEMS - 1; i >= 0; --i) {
+        if (a0 + i < cnt && nx[i]) e_run = (int)(a0 + i);
+        en[i] = e_run;
     }
-}
-
-// one warp per block
-__global__ void __launch_bounds__(256) k_bwt_tilescan(RegroupArgs A, uint32_t n_blocks)
-{
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (b >= n_blocks) return;
-    const int lane = lane_id();
-    const uint32_t cnt = A.counts[b];
-    const uint32_t nt = (cnt + RG_TILE - 1) / RG_TILE;
-    int carry_last = -1;
-    uint32_t carry_s = 0, carry_b = 0;
-    for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
-        uint32_t t = t0 + lane;
-        uint64_t idx = (uint64_t)b * A.tiles_per_block + t;
-        int l = t < nt ? A.tile_last[idx] : -1;
-        uint32_t ks = t < nt ? A.tile_keep_s[idx] : 0, kb = t < nt ? A.tile_keep_b[idx] : 0;
-        int li = warp_incl_max(l);
-        uint32_t si = warp_incl_sum(ks), bi = warp_incl_sum(kb);
-        int lprev = __shfl_up_sync(FULL, li, 1);
-        if (lane == 0) lprev = -1;
-        if (t < nt) {
-            A.tile_carry[idx] = max(carry_last, lprev);
-            A.tile_keep_s[idx] = carry_s + si - ks;
-            A.tile_keep_b[idx] = carry_b + bi - kb;
-        }
-        carry_last = max(carry_last, __shfl_sync(FULL, li, 31));
-        carry_s += __shfl_sync(FULL, si, 31);
-        carry_b += __shfl_sync(FULL, bi, 31);
-    }
-    if (lane == 0) {
-        const bool done = A.sorted_len >= A.n_arr[b]; // k_bwt_regroup writes no lists for a finished block
-        A.cnt_s_new[b] = done ? 0u : carry_s;
-        A.cnt_b_new[b] = done ? 0u : carry_b;
-        const uint32_t nc = done ? 0u : carry_s + carry_b;
-        A.cnt_t_new[b] = nc;
-        if (nc) {
-            atomicAdd(A.totals, (unsigned long long)nc);
-            atomicMax(A.totals + 3, (unsigned long long)nc);
-            atomicMax(A.totals + 8, (unsigned long long)carry_s);
-            atomicMax(A.totals + 9, (unsigned long long)carry_b);
-            atomicAdd(A.totals + 10, (unsigned long long)carry_b);
+    int s_run = prev_n >= 0 ? prev_n : (int)edge_s;
+    int o_run = ROUND0 ? 0 : (prev_o >= 0 ? prev_o : (int)edge_o);
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i) {
+        const uint32_t a = a0 + i;
+        if (a < cnt) {
+            if (nf[i]) s_run = (int)a;
+            if (!ROUND0 && of[i]) o_run = (int)a;
+            const uint32_t gpos = ROUND0 ? 0u : (uint32_t)(e[i] >> GPOS_SHIFT);
+            v.P[i] = gpos + (uint32_t)(s_run - o_run);
+            v.p[i] = gpos + (a - (uint32_t)o_run);
+            v.size[i] = (uint32_t)(en[i] - s_run + 1);
         }
     }
 }
 
-__global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__restrict__ keys, RegroupArgs A)
+// One CTA per RG_TILE slots of a block's sorted list (round 0: all rotations by their first key; later: the sorted bag).
+template <bool ROUND0>
+__global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, RoundArgs A,
+                                                             uint64_t *__restrict__ bag, uint32_t *__restrict__ bag_cnt)
 {
     __shared__ int s_i[34];
     __shared__ uint32_t s_u[34];
+    __shared__ uint32_t s_edge[3];
+    __shared__ uint32_t s_base;
     const uint32_t b = blockIdx.y, tile = blockIdx.x;
-    const uint32_t cnt = A.counts[b];
+    const uint32_t cnt = counts[b];
     const uint32_t base = tile * RG_TILE;
     if (base >= cnt) return;
     const uint64_t *kp = keys + (uint64_t)b * A.stride;
+    const uint32_t tile_last = min(base + (uint32_t)RG_TILE, cnt) - 1;
+    if (threadIdx.x < 3) {
+        uint32_t r = 0;
+        if (threadIdx.x == 0) r = run_first(kp, base, kp[base] >> VAL_BITS, VAL_BITS);
+        else if (threadIdx.x == 1) r = ROUND0 ? 0u : run_first(kp, base, kp[base] >> GPOS_SHIFT, GPOS_SHIFT);
+        else r = run_last(kp, tile_last, cnt, kp[tile_last] >> VAL_BITS, VAL_BITS);
+        s_edge[threadIdx.x] = r;
+    }
     const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
-    TileView v;
-    tile_view(kp, a0, cnt, A.split, s_i, v);
-    uint32_t ks = 0, kb = 0;
+    uint64_t e[RG_ITEMS];
+    uint64_t prev_e = 0, next_e = 0;
     if (a0 < cnt) {
+        if (a0 + RG_ITEMS <= cnt) {
+            const uint4 *vp = reinterpret_cast<const uint4 *>(kp + a0);
+#pragma unroll
+            for (int q = 0; q < RG_ITEMS / 2; ++q) {
+                const uint4 x = __ldg(vp + q);
+                e[2 * q] = ((uint64_t)x.y << 32) | x.x;
+                e[2 * q + 1] = ((uint64_t)x.w << 32) | x.z;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < RG_ITEMS; ++i) e[i] = a0 + i < cnt ? kp[a0 + i] : 0ull;
+        }
+        if (a0 > 0) prev_e = kp[a0 - 1];
+        if (a0 + RG_ITEMS < cnt) next_e = kp[a0 + RG_ITEMS];
+    }
+    __syncthreads(); // s_edge
+    GroupView v;
+    group_view<ROUND0>(e, prev_e, next_e, a0, cnt, s_edge[0], s_edge[1], s_edge[2], s_i, v);
+    const uint32_t n = A.n_arr[b];
+    const bool done = A.sorted_len >= n;
+    const uint64_t o = (uint64_t)b * A.stride;
+    uint32_t kg = 0, kl = 0; // kept in the bag / in local regions
+    unsigned gmask = 0, lmask = 0;
+    if (a0 < cnt) {
+        const uint8_t *T = A.T + o;
+        uint8_t *L = A.L + o;
+        uint32_t *rank = A.rank + o;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            if (a0 + i < cnt) {
+                const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
+                rank[val] = v.P[i];
+                if (v.size[i] == 1 || done) L[v.p[i]] = T[val ? val - 1 : n - 1];
+                else if (A.split && (v.P[i] >> SA_TILE_BITS) == ((v.P[i] + v.size[i] - 1) >> SA_TILE_BITS)) { lmask |= 1u << i; ++kl; }
+                else { gmask |= 1u << i; ++kg; }
+            }
+        }
+    }
+    uint32_t total_g, total_l;
+    uint32_t off = block_excl_sum(kg, s_u, &total_g);
+    (void)block_excl_sum(kl, s_u, &total_l);
+    if (threadIdx.x == 0) {
+        s_base = total_g ? atomicAdd(&bag_cnt[b], total_g) : 0u;
+        if (total_g + total_l) atomicAdd(A.totals, (unsigned long long)(total_g + total_l));
+    }
+    __syncthreads();
+    if (gmask) {
+        uint64_t *bg = bag + o + s_base;
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i)
-            if (a0 + i < cnt && !(v.flag[i] && v.nxt[i])) { if (v.local[i]) ++ks; else ++kb; }
+            if (gmask & (1u << i)) bg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
     }
-    const uint64_t tidx = (uint64_t)b * A.tiles_per_block + tile;
-    const int prev_last = max(v.prev_last, A.tile_carry[tidx]);
-    uint32_t off_s = A.tile_keep_s[tidx] + block_excl_sum(ks, s_u, nullptr);
-    uint32_t off_b = A.cnt_s_new[b] + A.tile_keep_b[tidx] + block_excl_sum(kb, s_u, nullptr);
-    if (a0 >= cnt) return;
-    const uint32_t *pp = A.pos_old ? A.pos_old + (uint64_t)b * A.stride : nullptr;
-    uint32_t *rank = A.rank + (uint64_t)b * A.stride;
-    uint32_t *pn = A.pos_new + (uint64_t)b * A.stride;
-    uint64_t *kn = A.keys_new + (uint64_t)b * A.stride;
-    const int gshift = VAL_BITS + A.nbits;
-    const bool done = A.sorted_len >= A.n_arr[b];
-    int g = prev_last;
-    uint32_t gpos = 0;
-    bool gpos_valid = false;
+    if (lmask) {
+        // one slot reservation per run of consecutive slots that go to the same SA tile
+        uint32_t *lc = A.loc_cnt + (uint64_t)b * A.tiles_per_block;
+        uint32_t tl[RG_ITEMS], len[RG_ITEMS];
 #pragma unroll
-    for (int i = 0; i < RG_ITEMS; ++i) {
-        uint32_t a = a0 + i;
-        if (a < cnt) {
-            uint32_t mypos = pp ? pp[a] : a;
-            if (v.flag[i]) { g = (int)a; gpos = mypos; gpos_valid = true; }
-            else if (!gpos_valid) { gpos = pp ? pp[g] : (uint32_t)g; gpos_valid = true; }
-            const uint32_t val = v.val[i];
-            rank[val] = gpos;
-            if (!done && !(v.flag[i] && v.nxt[i])) {
-                // key high part = list slot of the group's first element: the list is [small groups | other groups], each in
-                // SA order but not sorted as a whole, and a sort must leave every group in its own slots (pos_new is per slot).
-                // All elements of a group are kept and share a class, so their slots are consecutive.
-                const uint32_t o = v.local[i] ? off_s++ : off_b++;
-                pn[o] = mypos;
-                kn[o] = ((uint64_t)(o - (a - (uint32_t)g)) << gshift) | val;
+        for (int i = 0; i < RG_ITEMS; ++i) tl[i] = (lmask & (1u << i)) ? (v.P[i] >> SA_TILE_BITS) : 0xffffffffu;
+#pragma unroll
+        for (int i = RG_ITEMS - 1; i >= 0; --i)
+            len[i] = tl[i] == 0xffffffffu ? 0u : 1u + ((i + 1 < RG_ITEMS && tl[(i + 1) % RG_ITEMS] == tl[i]) ? len[(i + 1) % RG_ITEMS] : 0u);
+        uint64_t *reg = nullptr;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            if (tl[i] != 0xffffffffu) {
+                if (i == 0 || tl[(i + RG_ITEMS - 1) % RG_ITEMS] != tl[i]) reg = A.loc + o + (uint64_t)tl[i] * RG_TILE + atomicAdd(&lc[tl[i]], len[i]);
+                *reg++ = ((uint64_t)(v.P[i] & (RG_TILE - 1)) << GPOS_SHIFT) | (e[i] & VAL_MASK);
             }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------ shared-memory sort of small groups
-// The small-group part of an active list is a run of whole groups, each at most RG_TILE elements.  CTA k owns the groups that
-// START in [k*LS_STRIDE, (k+1)*LS_STRIDE); they end inside the 2*LS_STRIDE window it loads.  Inside the window the group
-// position is replaced by a dense group index, so (index, rank of the second half) fits 32 bits and is LSD-sorted in shared
-// memory (same warp match_any multi-split as the global scatter, no global traffic between passes).
-constexpr int LS_THREADS = 512;
-constexpr int LS_ITEMS = 8;
-constexpr int LS_WIN = LS_THREADS * LS_ITEMS; // 4096
-constexpr int LS_STRIDE = LS_WIN / 2;         // == RG_TILE
+// max / sum over blocks of the new bag sizes (grid sizing and loop control on the host)
+__global__ void __launch_bounds__(256) k_bwt_roundstats(const uint32_t *__restrict__ bag_cnt, uint32_t n_blocks, unsigned long long *__restrict__ totals)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = b < n_blocks ? bag_cnt[b] : 0u;
+    const uint32_t mx = __reduce_max_sync(FULL, c), sm = __reduce_add_sync(FULL, c);
+    if (lane_id() == 0 && mx) {
+        atomicMax(totals + 1, (unsigned long long)mx);
+        atomicAdd(totals + 2, (unsigned long long)sm);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ local regions
+// One CTA per (SA tile, block): sort the region's elements by (group position, rank of the second half) in shared memory
+// (LSD radix, warp match_any multi-split, digits that are constant over the region skipped), regroup them exactly like
+// k_bwt_regroup does, and write the still-ambiguous ones back to the front of the same region.
+constexpr int LS_THREADS = RG_THREADS;
+constexpr int LS_ITEMS = RG_ITEMS;
 constexpr int LS_WARPS = LS_THREADS / 32;
-static_assert(LS_STRIDE == RG_TILE, "small groups are classified per regroup tile");
 
 struct LocalSmem {
-    uint64_t e[LS_WIN];
+    uint64_t e[RG_TILE];
     uint32_t warp_hist[LS_WARPS][256];
     uint32_t tile_base[256];
-    uint32_t gpos_of[LS_STRIDE + 2];
     uint32_t scratch[34];
-    int first_start, end_start;
+    int scr_i[34];
+    uint32_t red[2 * LS_WARPS];
 };
 
-__global__ void __launch_bounds__(LS_THREADS) k_bwt_localsort(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, const uint32_t *__restrict__ cnt_s,
-                                                               uint64_t stride, int nbits)
+__global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    LocalSmem &sm = *reinterpret_cast<LocalSmem *>(smem_raw);
-    const uint32_t b = blockIdx.y;
-    const uint32_t cnt = cnt_s[b];
-    const uint32_t base = blockIdx.x * LS_STRIDE;
-    if (base >= cnt) return;
-    const uint32_t wcnt = min((uint32_t)LS_WIN, cnt - base);
-    const uint64_t *sp = src + (uint64_t)b * stride + base;
-    const int gshift = VAL_BITS + nbits;
+    __shared__ __align__(16) LocalSmem sm;
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    uint32_t *cnt_p = A.loc_cnt + (uint64_t)b * A.tiles_per_block + t;
+    const uint32_t c = *cnt_p;
+    if (c == 0) return;
+    const uint64_t o = (uint64_t)b * A.stride;
+    uint64_t *reg = A.loc + o + (uint64_t)t * RG_TILE;
     const int lane = lane_id(), w = warp_id();
-    for (uint32_t j = threadIdx.x; j < wcnt; j += LS_THREADS) sm.e[j] = sp[j];
-    if (threadIdx.x == 0) { sm.first_start = 0x7fffffff; sm.end_start = (int)wcnt; }
-    const uint64_t prev_g = base > 0 ? (sp[-1] >> gshift) : ~0ull;
+    // ---- load; which key bits differ inside the region?
+    uint32_t or_lo = 0, and_lo = 0xffffffffu;
+    for (uint32_t j = threadIdx.x; j < c; j += LS_THREADS) {
+        const uint64_t x = reg[j];
+        sm.e[j] = x;
+        const uint32_t k = (uint32_t)(x >> VAL_BITS); // 31 key bits
+        or_lo |= k; and_lo &= k;
+    }
+    or_lo = __reduce_or_sync(FULL, or_lo);
+    and_lo = __reduce_and_sync(FULL, and_lo);
+    if (lane == 0) { sm.red[w] = or_lo; sm.red[LS_WARPS + w] = and_lo; }
     __syncthreads();
-    // group starts among my 16 consecutive window elements
-    const uint32_t j0 = threadIdx.x * LS_ITEMS;
-    uint64_t el[LS_ITEMS];
-    bool st[LS_ITEMS];
+    uint32_t diff;
     {
-        uint64_t pg = j0 == 0 ? prev_g : (j0 - 1 < wcnt ? (sm.e[j0 - 1] >> gshift) : 0ull);
+        uint32_t x = 0, y = 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < LS_ITEMS; ++i) {
-            uint32_t j = j0 + i;
-            el[i] = j < wcnt ? sm.e[j] : 0ull;
-            uint64_t g = el[i] >> gshift;
-            st[i] = j < wcnt && (g != pg || (base == 0 && j == 0));
-            pg = g;
-            if (st[i]) {
-                if (j < (uint32_t)LS_STRIDE) atomicMin(&sm.first_start, (int)j);
-                else atomicMin(&sm.end_start, (int)j);
-            }
-        }
+        for (int ww = 0; ww < LS_WARPS; ++ww) { x |= sm.red[ww]; y &= sm.red[LS_WARPS + ww]; }
+        diff = x ^ y;
     }
-    __syncthreads();
-    const int f = sm.first_start, eend = sm.end_start;
-    if (f == 0x7fffffff) return; // no group starts in my stride: the groups here belong to the CTA on the left
-    const uint32_t m = (uint32_t)(eend - f);
-    // dense group index = (number of starts in [f, j]) - 1
-    uint32_t mystarts = 0;
-#pragma unroll
-    for (int i = 0; i < LS_ITEMS; ++i) {
-        int j = (int)(j0 + i);
-        if (st[i] && j >= f && j < eend) ++mystarts;
-    }
-    uint32_t ngroups;
-    uint32_t gid = block_excl_sum(mystarts, sm.scratch, &ngroups); // starts before my elements
-    const uint64_t lowmask = (1ull << gshift) - 1ull;
-#pragma unroll
-    for (int i = 0; i < LS_ITEMS; ++i) {
-        int j = (int)(j0 + i);
-        if (j >= f && j < eend) {
-            if (st[i]) { sm.gpos_of[gid] = (uint32_t)(el[i] >> gshift); ++gid; }
-            sm.e[j - f] = ((uint64_t)(gid - 1) << gshift) | (el[i] & lowmask); // all reads of e[] happened before the last barrier
-        }
-    }
-    __syncthreads();
-    // LSD passes over bits [VAL_BITS, VAL_BITS + nbits + gbits)
-    const int gbits = ngroups > 1 ? 32 - __clz((int)ngroups - 1) : 0;
-    const int total_bits = nbits + gbits;
     const unsigned lt = (1u << lane) - 1u;
-    for (int shift = VAL_BITS; shift < VAL_BITS + total_bits; shift += 8) {
+    for (int shift = 0; shift < 32; shift += 8) {
+        if (((diff >> shift) & 0xffu) == 0) continue; // uniform over the CTA
+        const int sh = shift + VAL_BITS;
         uint64_t key[LS_ITEMS];
         uint16_t rnk[LS_ITEMS];
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            key[i] = li < m ? sm.e[li] : 0ull;
+            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
+            key[i] = li < c ? sm.e[li] : 0ull;
         }
         for (int i = threadIdx.x; i < LS_WARPS * 256; i += LS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            bool valid = li < m;
-            uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 0xffu) : 0xffffffffu;
-            unsigned peers = __match_any_sync(FULL, d);
-            int leader = __ffs(peers) - 1;
+            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
+            const bool valid = li < c;
+            const uint32_t d = valid ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(FULL, d);
+            const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
             if (valid && lane == leader) {
                 old = sm.warp_hist[w][d];
@@ -555,38 +530,85 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_localsort(const uint64_t *__
         }
         __syncthreads();
         {
-            const uint32_t d = threadIdx.x;
+            const uint32_t d = threadIdx.x; // LS_THREADS == 256 digits
             uint32_t sum = 0;
-            if (d < 256) {
 #pragma unroll
-                for (int ww = 0; ww < LS_WARPS; ++ww) {
-                    uint32_t t = sm.warp_hist[ww][d];
-                    sm.warp_hist[ww][d] = sum;
-                    sum += t;
-                }
+            for (int ww = 0; ww < LS_WARPS; ++ww) {
+                const uint32_t x = sm.warp_hist[ww][d];
+                sm.warp_hist[ww][d] = sum;
+                sum += x;
             }
-            const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr); // threads >= 256 add 0 behind the digits
-            if (d < 256) sm.tile_base[d] = tb;
+            sm.tile_base[d] = block_excl_sum(sum, sm.scratch, nullptr);
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            if (li < m) {
-                uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
+            if (li < c) {
+                const uint32_t d = (uint32_t)(key[i] >> sh) & 0xffu;
                 sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
             }
         }
         __syncthreads();
     }
-    uint64_t *dp = dst + (uint64_t)b * stride + base + f;
-    for (uint32_t j = threadIdx.x; j < m; j += LS_THREADS) {
-        uint64_t x = sm.e[j];
-        dp[j] = ((uint64_t)sm.gpos_of[(uint32_t)(x >> gshift)] << gshift) | (x & lowmask);
+    // ---- regroup inside the region (positions relative to the tile)
+    const uint32_t a0 = threadIdx.x * RG_ITEMS;
+    uint64_t e[RG_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i) e[i] = a0 + i < c ? sm.e[a0 + i] : 0ull;
+    const uint64_t prev_e = (a0 > 0 && a0 < c) ? sm.e[a0 - 1] : 0ull;
+    const uint64_t next_e = a0 + RG_ITEMS < c ? sm.e[a0 + RG_ITEMS] : 0ull;
+    GroupView v;
+    group_view<false>(e, prev_e, next_e, a0, c, 0u, 0u, c - 1, sm.scr_i, v);
+    const uint32_t n = A.n_arr[b];
+    const bool done = A.sorted_len >= n;
+    const uint32_t tbase = t * RG_TILE;
+    uint32_t keep = 0;
+    unsigned kmask = 0;
+    if (a0 < c) {
+        const uint8_t *T = A.T + o;
+        uint8_t *L = A.L + o;
+        uint32_t *rank = A.rank + o;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            if (a0 + i < c) {
+                const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
+                rank[val] = tbase + v.P[i];
+                if (v.size[i] == 1 || done) L[tbase + v.p[i]] = T[val ? val - 1 : n - 1];
+                else { kmask |= 1u << i; ++keep; }
+            }
+        }
+    }
+    uint32_t total;
+    uint32_t off = block_excl_sum(keep, sm.scratch, &total);
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i)
+        if (kmask & (1u << i)) reg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
+    if (threadIdx.x == 0) {
+        *cnt_p = total;
+        if (total) atomicAdd(A.totals, (unsigned long long)total);
     }
 }
 
-// element |= rank[(i + h) mod n] << 20
+// local regions: element |= rank[(i + h) mod n] << 20
+__global__ void __launch_bounds__(256) k_bwt_gather_local(RoundArgs A, uint32_t h)
+{
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t c = A.loc_cnt[(uint64_t)b * A.tiles_per_block + t];
+    if (c == 0) return;
+    const uint32_t n = A.n_arr[b];
+    const uint64_t o = (uint64_t)b * A.stride;
+    uint64_t *reg = A.loc + o + (uint64_t)t * RG_TILE;
+    const uint32_t *rank = A.rank + o;
+    for (uint32_t j = threadIdx.x; j < c; j += 256) {
+        const uint64_t e = reg[j];
+        uint32_t p = (uint32_t)(e & VAL_MASK) + h; // h < n for every block that is still active
+        if (p >= n) p -= n;
+        reg[j] = e | ((uint64_t)rank[p] << VAL_BITS);
+    }
+}
+
+// bag: element |= rank[(i + h) mod n] << 20
 __global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ n_arr,
                                                      uint64_t stride, const uint32_t *__restrict__ rank, uint32_t h)
 {
@@ -602,18 +624,12 @@ __global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys,
     keys[o + a] = e | ((uint64_t)rank[o + p] << VAL_BITS);
 }
 
-// L[j] = T[(SA[j] - 1) mod n]; origPtr = rank[0]
-__global__ void __launch_bounds__(256) k_bwt_finish(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rank,
-                                                     const uint32_t *__restrict__ n_arr, uint64_t stride, uint8_t *__restrict__ L, uint32_t *__restrict__ orig)
+// origPtr = rank[0] = first position of rotation 0's tie group (kernel.cpp:3114-3116)
+__global__ void __launch_bounds__(128) k_bwt_finish(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ n_arr, uint64_t stride, uint32_t n_blocks,
+                                                     uint32_t *__restrict__ orig)
 {
-    const uint32_t b = blockIdx.y;
-    const uint32_t n = n_arr[b];
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t o = (uint64_t)b * stride;
-    if (j == 0 && n > 0) orig[b] = rank[o];
-    if (j >= n) return;
-    uint32_t i = sa[o + j];
-    L[o + j] = rle[o + (i ? i - 1 : n - 1)];
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_blocks) orig[b] = n_arr[b] ? rank[(uint64_t)b * stride] : 0u;
 }
 
 } // namespace bz

@@ -19,8 +19,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_flags, KID_k_bwt_tilescan, KID_k_bwt_regroup, KID_k_bwt_gather, KID_k_bwt_localsort, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_flags", "k_bwt_tilescan", "k_bwt_regroup", "k_bwt_gather", "k_bwt_localsort", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -51,7 +51,7 @@ struct bz2b200 {
     // per-call (grow only)
     DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     // per-batch, fixed size
-    DevBuf rle, L, ranks, kA, kB, sa, rank, pA, pB, mtf, hist, digit_base, tile_last, tile_keep_s, tile_keep_b, tile_carry, cnts, scalars,
+    DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, cnts, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
@@ -182,8 +182,7 @@ static int upload_constants(bz2b200 *h)
     CK(cudaMemcpyToSymbol(c_crc_pow8, pow8, sizeof(pow8)));
     CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-    CK(cudaFuncSetAttribute(k_bwt_localsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem)));
-    CK(cudaFuncSetAttribute(k_bwt_localsort, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -253,18 +252,13 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->ranks, G * S + 64);
     ENSURE(h->kA, G * S * 8);
     ENSURE(h->kB, G * S * 8);
-    ENSURE(h->sa, G * S * 4);
+    ENSURE(h->loc, G * S * 8);
+    ENSURE(h->loc_cnt, G * h->tilesG * 4);
     ENSURE(h->rank, G * S * 4);
-    ENSURE(h->pA, G * S * 4);
-    ENSURE(h->pB, G * S * 4);
     ENSURE(h->mtf, G * S * 2);
     ENSURE(h->hist, G * h->tilesR * 256 * 4);
     ENSURE(h->digit_base, G * 256 * 4);
-    ENSURE(h->tile_last, G * h->tilesG * 4);
-    ENSURE(h->tile_keep_s, G * h->tilesG * 4);
-    ENSURE(h->tile_keep_b, G * h->tilesG * 4);
-    ENSURE(h->tile_carry, G * h->tilesG * 4);
-    ENSURE(h->cnts, 6 * G * 4); // two sets of (total, small-group, other) active counts
+    ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
     ENSURE(h->scalars, 64 * 8);
     ENSURE(h->lists, G * h->tilesM * 256);
     ENSURE(h->dcount, G * h->tilesM * 4);
@@ -349,16 +343,16 @@ extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
     return n + n / 3 + blocks * (size_t)(2048 + h->bs / 50) + 4096;
 }
 
-static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const uint32_t *counts, const uint32_t *offs, int shift, int bits, uint32_t nb,
-                       uint32_t max_count, uint64_t total_elems)
+static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const uint32_t *counts, int shift, int bits, uint32_t nb, uint32_t max_count,
+                       uint64_t total_elems)
 {
     uint32_t tiles = (max_count + RS_TILE - 1) / RS_TILE;
     if (tiles == 0) return;
     dim3 grid(tiles, nb);
     uint32_t mask = (1u << bits) - 1u;
-    KL(KID_k_radix_hist, k_radix_hist<uint64_t><<<grid, RH_THREADS, 0, h->stream>>>(kin, counts, offs, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR));
+    KL(KID_k_radix_hist, k_radix_hist<uint64_t><<<grid, RH_THREADS, 0, h->stream>>>(kin, counts, nullptr, h->S, shift, mask, ptr<uint32_t>(h->hist), h->tilesR));
     KL(KID_k_radix_scan, k_radix_scan<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->hist), counts, h->tilesR, ptr<uint32_t>(h->digit_base)));
-    KL(KID_k_radix_scatter, k_radix_scatter<<<grid, RS_THREADS, sizeof(ScatterSmem), h->stream>>>(kin, kout, counts, offs, h->S, shift, mask, ptr<uint32_t>(h->hist),
+    KL(KID_k_radix_scatter, k_radix_scatter<<<grid, RS_THREADS, sizeof(ScatterSmem), h->stream>>>(kin, kout, counts, nullptr, h->S, shift, mask, ptr<uint32_t>(h->hist),
                                                                                                 h->tilesR, ptr<uint32_t>(h->digit_base)));
     h->stats.kernel_launches += 3;
     KBYTES(KID_k_radix_hist, total_elems * 8);
@@ -366,16 +360,15 @@ static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const ui
 }
 
 // sorts bits [VAL_BITS, VAL_BITS + total_bits) of the elements; returns 0 if the result is in k0, 1 if in k1
-static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *counts, const uint32_t *offs, int total_bits, uint32_t nb, uint32_t max_count,
-                      uint64_t total_elems)
+static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count, uint64_t total_elems)
 {
     int npass = (total_bits + 7) / 8;
     int basebits = total_bits / npass, extra = total_bits % npass;
     int shift = VAL_BITS, cur = 0;
     for (int p = 0; p < npass; ++p) {
         int bits = basebits + (p < extra ? 1 : 0);
-        if (cur == 0) radix_pass(h, k0, k1, counts, offs, shift, bits, nb, max_count, total_elems);
-        else radix_pass(h, k1, k0, counts, offs, shift, bits, nb, max_count, total_elems);
+        if (cur == 0) radix_pass(h, k0, k1, counts, shift, bits, nb, max_count, total_elems);
+        else radix_pass(h, k1, k0, counts, shift, bits, nb, max_count, total_elems);
         cur ^= 1;
         shift += bits;
     }
@@ -383,7 +376,7 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
 }
 
 struct Scalars { // layout of h->scalars (u64 each)
-    enum { TOTAL_ACTIVE = 0, BITPOS = 1, BATCH_BITS = 2, MAX_ACTIVE = 3, WALK_INFO = 4 /* 4 entries */, MAX_S = 8, MAX_B = 9, TOTAL_B = 10 };
+    enum { BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 4 entries */, ROUND = 8 /* kept rotations, max bag, sum of bags */ };
 };
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -558,95 +551,95 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         max_n = std::max(max_n, h->h_rle_len[b0 + i]);
         sum_n += h->h_rle_len[b0 + i];
     }
-    uint32_t *cset[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + 3 * (size_t)h->G}; // each: [total | small-group | other] x G
+    uint32_t *bag_cnt[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + (size_t)h->G};
     {
         dim3 g((max_n + 255) / 256, nb);
         KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint64_t>(h->kA)));
         stt.kernel_launches += 1;
     }
-    int res = radix_sort(h, ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_n, nullptr, 8 * h->key0_bytes, nb, max_n, sum_n);
+    int res = radix_sort(h, ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_n, 8 * h->key0_bytes, nb, max_n, sum_n);
     CK(cudaEventRecord(h->ev[4], st));
 
-    RegroupArgs A;
-    A.stride = S;
+    RoundArgs A;
     A.n_arr = d_n;
-    A.sa = ptr<uint32_t>(h->sa);
+    A.stride = S;
+    A.T = ptr<uint8_t>(h->rle);
+    A.L = ptr<uint8_t>(h->L);
     A.rank = ptr<uint32_t>(h->rank);
-    A.tile_last = ptr<int32_t>(h->tile_last);
-    A.tile_keep_s = ptr<uint32_t>(h->tile_keep_s);
-    A.tile_keep_b = ptr<uint32_t>(h->tile_keep_b);
-    A.tile_carry = ptr<int32_t>(h->tile_carry);
+    A.loc = ptr<uint64_t>(h->loc);
+    A.loc_cnt = ptr<uint32_t>(h->loc_cnt);
     A.tiles_per_block = h->tilesG;
-    A.nbits = h->nbits;
+    A.totals = reinterpret_cast<unsigned long long *>(d_scal + Scalars::ROUND);
     A.split = h->local_sort != 0;
-    A.totals = reinterpret_cast<unsigned long long *>(d_scal);
 
-    const int round_bits = 2 * h->nbits;
-    const int round_passes = (round_bits + 7) / 8;
+    const int round_bits = 2 * VAL_BITS;
+    const dim3 gtiles((max_n + RG_TILE - 1) / RG_TILE, nb);
     uint32_t sorted_len = (uint32_t)h->key0_bytes;
-    uint32_t max_count = max_n;
-    const uint32_t *counts = d_n;
-    int cs = 0; // count set written by the next regroup
-    uint32_t *pos_old = nullptr, *pos_new = ptr<uint32_t>(h->pA);
     uint64_t rounds = 0;
-    for (;;) {
-        // sorted elements are in buffer `res`; the next round's input goes to the other buffer
-        uint64_t *ks = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
-        uint64_t *kn = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
-        uint32_t *cT = cset[cs], *cS = cset[cs] + h->G, *cB = cset[cs] + 2 * (size_t)h->G;
-        A.counts = counts;
-        A.pos_old = pos_old;
-        A.cnt_t_new = cT;
-        A.cnt_s_new = cS;
-        A.cnt_b_new = cB;
-        A.pos_new = pos_new;
-        A.keys_new = kn;
+    CK(cudaMemsetAsync(h->loc_cnt.p, 0, (size_t)nb * h->tilesG * 4, st));
+    // round 0: regroup the whole block, sorted by its first key
+    {
+        uint64_t *sorted = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
+        uint64_t *bag = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
         A.sorted_len = sorted_len;
-        CK(cudaMemsetAsync(d_scal + Scalars::TOTAL_ACTIVE, 0, 8, st));
-        CK(cudaMemsetAsync(d_scal + Scalars::MAX_ACTIVE, 0, 8, st));
-        CK(cudaMemsetAsync(d_scal + Scalars::MAX_S, 0, 24, st));
-        dim3 g((max_count + RG_TILE - 1) / RG_TILE, nb);
-        KL(KID_k_bwt_flags, k_bwt_flags<<<g, RG_THREADS, 0, st>>>(ks, A));
-        KL(KID_k_bwt_tilescan, k_bwt_tilescan<<<(nb + 7) / 8, 256, 0, st>>>(A, nb));
-        KL(KID_k_bwt_regroup, k_bwt_regroup<<<g, RG_THREADS, 0, st>>>(ks, A));
-        stt.kernel_launches += 3;
-        CK(cudaMemcpyAsync(h->h_pinned, d_scal, 11 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
+        CK(cudaMemsetAsync(bag_cnt[0], 0, (size_t)nb * 4, st));
+        KL(KID_k_bwt_regroup, k_bwt_regroup<true><<<gtiles, RG_THREADS, 0, st>>>(sorted, d_n, A, bag, bag_cnt[0]));
+        KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[0], nb, A.totals));
+        stt.kernel_launches += 2;
+        KBYTES(KID_k_bwt_regroup, sum_n * 14);
+        res ^= 1; // the bag is in the other buffer
+    }
+    int cs = 0; // bag_cnt[cs] = sizes of the current bags
+    for (;;) {
+        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::ROUND, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h->profiling) prof_collect(h);
-        const uint64_t active = h->h_pinned[Scalars::TOTAL_ACTIVE];
+        const uint64_t active = h->h_pinned[0], total_b = h->h_pinned[2];
+        const uint32_t max_b = (uint32_t)h->h_pinned[1];
         if (active == 0) break;
-        const uint32_t max_s = (uint32_t)h->h_pinned[Scalars::MAX_S], max_b = (uint32_t)h->h_pinned[Scalars::MAX_B];
-        const uint64_t total_b = h->h_pinned[Scalars::TOTAL_B];
         stt.bwt_active_volume += active;
         ++rounds;
-        // next round: key = (group, rank of the rotation sorted_len further on); small groups are sorted in shared memory,
-        // the rest by the global radix sort; both land in the same buffer
-        counts = cT;
-        cs ^= 1;
-        pos_old = pos_new;
-        pos_new = (pos_new == ptr<uint32_t>(h->pA)) ? ptr<uint32_t>(h->pB) : ptr<uint32_t>(h->pA);
-        max_count = (uint32_t)std::min<uint64_t>(max_n, h->h_pinned[Scalars::MAX_ACTIVE]);
-        dim3 gg((max_count + 255) / 256, nb);
-        KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(kn, cT, d_n, S, ptr<uint32_t>(h->rank), sorted_len));
-        stt.kernel_launches += 1;
-        uint64_t *sorted = (round_passes & 1) ? ks : kn; // where an odd / even number of ping-pong passes ends
-        if (max_s && h->local_sort == 2) { // debug: small-group part through the global radix sort as well
-            radix_sort(h, kn, ks, cS, nullptr, round_bits, nb, max_s, active - total_b);
-        } else if (max_s) {
-            dim3 gl((max_s + LS_STRIDE - 1) / LS_STRIDE, nb);
-            KL(KID_k_bwt_localsort, k_bwt_localsort<<<gl, LS_THREADS, sizeof(LocalSmem), st>>>(kn, sorted, cS, S, h->nbits));
+        // next round: key = (group position, rank of the rotation sorted_len further on)
+        uint64_t *bag = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
+        uint64_t *other = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
+        const bool have_local = active > total_b;
+        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
+        if (have_local) {
+            KL(KID_k_bwt_gather_local, k_bwt_gather_local<<<gtiles, 256, 0, st>>>(A, sorted_len));
             stt.kernel_launches += 1;
-            KBYTES(KID_k_bwt_localsort, (active - total_b) * 16);
+            KBYTES(KID_k_bwt_gather_local, (active - total_b) * 20);
         }
-        if (max_b) radix_sort(h, kn, ks, cB, cS, round_bits, nb, max_b, total_b);
-        res = (sorted == ptr<uint64_t>(h->kB)) ? 1 : 0;
+        if (max_b) {
+            dim3 gg((max_b + 255) / 256, nb);
+            KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(bag, bag_cnt[cs], d_n, S, ptr<uint32_t>(h->rank), sorted_len));
+            stt.kernel_launches += 1;
+        }
+        A.sorted_len = sorted_len * 2;
+        if (have_local) {
+            KL(KID_k_bwt_local, k_bwt_local<<<gtiles, LS_THREADS, 0, st>>>(A));
+            stt.kernel_launches += 1;
+            KBYTES(KID_k_bwt_local, (active - total_b) * 22);
+        }
+        CK(cudaMemsetAsync(bag_cnt[cs ^ 1], 0, (size_t)nb * 4, st));
+        if (max_b) {
+            const int r = radix_sort(h, bag, other, bag_cnt[cs], round_bits, nb, max_b, total_b);
+            uint64_t *sorted = r ? other : bag, *newbag = r ? bag : other;
+            dim3 g((max_b + RG_TILE - 1) / RG_TILE, nb);
+            KL(KID_k_bwt_regroup, k_bwt_regroup<false><<<g, RG_THREADS, 0, st>>>(sorted, bag_cnt[cs], A, newbag, bag_cnt[cs ^ 1]));
+            stt.kernel_launches += 1;
+            KBYTES(KID_k_bwt_regroup, total_b * 14);
+            res = (newbag == ptr<uint64_t>(h->kB)) ? 1 : 0;
+        }
+        KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[cs ^ 1], nb, A.totals));
+        stt.kernel_launches += 1;
+        cs ^= 1;
         sorted_len *= 2;
     }
     stt.bwt_rounds = std::max<uint64_t>(stt.bwt_rounds, rounds);
     CK(cudaEventRecord(h->ev[5], st));
     {
-        dim3 g((max_n + 255) / 256, nb);
-        KL(KID_k_bwt_finish, k_bwt_finish<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), ptr<uint32_t>(h->sa), ptr<uint32_t>(h->rank), d_n, S, ptr<uint8_t>(h->L), ptr<uint32_t>(h->orig)));
+        KL(KID_k_bwt_finish, k_bwt_finish<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->rank), d_n, S, nb, ptr<uint32_t>(h->orig)));
         stt.kernel_launches += 1;
     }
     CK(cudaEventRecord(h->ev[6], st));
@@ -910,7 +903,7 @@ extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage,
     case BZ2B200_STAGE_MTF: src = ptr<uint16_t>(h->mtf) + bl * S; len = (size_t)hb.m * 2; break;
     case BZ2B200_STAGE_FREQ: src = ptr<uint32_t>(h->freq) + bl * 258; len = 258 * 4; break;
     case BZ2B200_STAGE_SELECTORS: src = ptr<uint8_t>(h->sel) + bl * h->sel_stride; len = hb.nsel; break;
-    case BZ2B200_STAGE_SA: src = ptr<uint32_t>(h->sa) + bl * S; len = (size_t)n * 4; break;
+    case BZ2B200_STAGE_RANK: src = ptr<uint32_t>(h->rank) + bl * S; len = (size_t)n * 4; break;
     case BZ2B200_STAGE_PRESENT: {
         uint32_t bm[8];
         CK(cudaMemcpy(bm, ptr<uint32_t>(h->present) + bl * 8, 32, cudaMemcpyDeviceToHost));

@@ -136,7 +136,7 @@ enum {
     BZ2B200_STAGE_FREQ = 6,      /* int32  [258]    mtfSymbolFrequencies        (kernel.cpp:2613,2641-2643) */
     BZ2B200_STAGE_SELECTORS = 7, /* uint8  [nsel]   final selectors             (kernel.cpp:2940-2943) */
     BZ2B200_STAGE_LENGTHS = 8,   /* uint8  [T*258]  final code lengths          (kernel.cpp:2947-2950) */
-    BZ2B200_STAGE_SA = 9         /* uint32 [n]      sorted rotation start indices (debug) */
+    BZ2B200_STAGE_RANK = 9       /* uint32 [n]      rank[i] = first SA position of rotation i's tie group (debug) */
 };
 int bz2b200_stage_dump(bz2b200_t *handle, uint64_t block_index, int stage, void *dst, size_t dst_capacity, size_t *len_bytes);
 
