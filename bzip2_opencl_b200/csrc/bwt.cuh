@@ -245,75 +245,90 @@ constexpr int SA_TILE_BITS = 11;
 static_assert((1 << SA_TILE_BITS) == RG_TILE, "SA tile = regroup tile");
 constexpr int INT_INF = 0x7fffffff;
 
-// kp[] is sorted non-decreasing by (e >> shift) and kp[pos] >> shift == key: first / last slot of the run of `key`
-// (galloping, so a short run costs a few probes).
-__device__ __forceinline__ uint32_t run_first(const uint64_t *kp, uint32_t pos, uint64_t key, int shift)
+// kp[] is sorted non-decreasing by (e >> shift) and kp[pos] >> shift == key: first / last slot of the run of `key`.
+// Called by a whole warp: 32 neighbouring slots in one round trip (a short run ends there), then a 32-ary search.
+__device__ __forceinline__ uint32_t warp_run_first(const uint64_t *kp, uint32_t pos, uint64_t key, int shift)
 {
-    uint32_t hi = pos, step = 1;
-    for (;;) {
-        if (hi == 0) return 0;
-        const uint32_t cand = hi >= step ? hi - step : 0u;
-        if ((kp[cand] >> shift) == key) { hi = cand; step <<= 1; continue; }
-        uint32_t lo = cand;
-        while (hi - lo > 1) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if ((kp[mid] >> shift) == key) hi = mid; else lo = mid;
-        }
-        return hi;
+    const uint32_t lane = (uint32_t)lane_id();
+    {
+        const bool eq = pos >= lane + 1 && (kp[pos - 1 - lane] >> shift) == key;
+        const unsigned ne = ~__ballot_sync(FULL, eq);
+        if (ne) return pos - (uint32_t)(__ffs((int)ne) - 1);
     }
+    uint32_t lo = 0, hi = pos - 32; // slot hi holds the key; the answer is in [lo, hi]
+    while (lo < hi) {
+        const uint32_t chunk = (hi - lo + 31) / 32;
+        const uint32_t x = lo + lane * chunk;
+        const bool t = x >= hi || (kp[x] >> shift) == key;
+        const unsigned tb = __ballot_sync(FULL, t);
+        if (tb == 0) { lo += 31 * chunk + 1; continue; }
+        const uint32_t f = (uint32_t)(__ffs((int)tb) - 1);
+        if (f == 0) return lo;
+        hi = min(hi, lo + f * chunk);
+        lo += (f - 1) * chunk + 1;
+    }
+    return hi;
 }
-__device__ __forceinline__ uint32_t run_last(const uint64_t *kp, uint32_t pos, uint32_t cnt, uint64_t key, int shift)
+__device__ __forceinline__ uint32_t warp_run_last(const uint64_t *kp, uint32_t pos, uint32_t cnt, uint64_t key, int shift)
 {
-    uint32_t lo = pos, step = 1;
-    for (;;) {
-        if (lo + 1 >= cnt) return lo;
-        const uint32_t cand = min(lo + step, cnt - 1);
-        if ((kp[cand] >> shift) == key) { lo = cand; step <<= 1; continue; }
-        uint32_t hi = cand;
-        while (hi - lo > 1) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if ((kp[mid] >> shift) == key) lo = mid; else hi = mid;
-        }
-        return lo;
+    const uint32_t lane = (uint32_t)lane_id();
+    {
+        const bool eq = pos + 1 + lane < cnt && (kp[pos + 1 + lane] >> shift) == key;
+        const unsigned ne = ~__ballot_sync(FULL, eq);
+        if (ne) return pos + (uint32_t)(__ffs((int)ne) - 1);
     }
+    uint32_t lo = pos + 32, hi = cnt - 1; // slot lo holds the key; the answer is in [lo, hi]
+    while (lo < hi) {
+        const uint32_t chunk = (hi - lo + 31) / 32;
+        const uint32_t x = hi - lane * chunk; // lo >= 32 keeps this from wrapping
+        const bool t = x <= lo || (kp[x] >> shift) == key;
+        const unsigned tb = __ballot_sync(FULL, t);
+        if (tb == 0) { hi -= 31 * chunk + 1; continue; }
+        const uint32_t f = (uint32_t)(__ffs((int)tb) - 1);
+        if (f == 0) return hi;
+        lo = max(lo, hi - f * chunk);
+        hi -= (f - 1) * chunk + 1;
+    }
+    return lo;
 }
 
-// What a thread knows about its RG_ITEMS consecutive slots a0 .. a0+RG_ITEMS-1 of a sorted list after the block-wide scans.
+// What a thread knows about its ITEMS consecutive slots a0 .. a0+ITEMS-1 of a sorted list after the block-wide scans.
+template <int ITEMS>
 struct GroupView {
-    uint32_t P[RG_ITEMS];    // SA position of the new group's first element (relative to the list's position base)
-    uint32_t p[RG_ITEMS];    // SA position of the element
-    uint32_t size[RG_ITEMS]; // elements in the new group
+    uint32_t P[ITEMS];    // SA position of the new group's first element (relative to the list's position base)
+    uint32_t p[ITEMS];    // SA position of the element
+    uint32_t size[ITEMS]; // elements in the new group
 };
 
-// e[i] = slot a0+i (0 past the end); prev_e = slot a0-1 (unused when a0 == 0); next_e = slot a0+RG_ITEMS (unused past the end).
+// e[i] = slot a0+i (0 past the end); prev_e = slot a0-1 (unused when a0 == 0); next_e = slot a0+ITEMS (unused past the end).
 // edge_s / edge_o: first slot of the new / old group that contains the tile's first slot; edge_e: last slot of the new group
 // that contains the tile's last slot.  ROUND0: the list is the whole block sorted by its first key (one old group at 0).
-template <bool ROUND0>
-__device__ __forceinline__ void group_view(const uint64_t (&e)[RG_ITEMS], uint64_t prev_e, uint64_t next_e, uint32_t a0, uint32_t cnt, uint32_t edge_s,
-                                           uint32_t edge_o, uint32_t edge_e, int *s_i, GroupView &v)
+template <bool ROUND0, int ITEMS>
+__device__ __forceinline__ void group_view(const uint64_t (&e)[ITEMS], uint64_t prev_e, uint64_t next_e, uint32_t a0, uint32_t cnt, uint32_t edge_s,
+                                           uint32_t edge_o, uint32_t edge_e, int *s_i, GroupView<ITEMS> &v)
 {
-    bool nf[RG_ITEMS], of[RG_ITEMS], nx[RG_ITEMS];
+    bool nf[ITEMS], of[ITEMS], nx[ITEMS];
     int last_n = -1, last_o = -1, first_end = INT_INF;
     if (a0 < cnt) {
         uint64_t prev = prev_e;
 #pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const uint32_t a = a0 + i;
             nf[i] = (a == 0) || ((e[i] >> VAL_BITS) != (prev >> VAL_BITS));
             of[i] = ROUND0 ? (a == 0) : ((a == 0) || ((e[i] >> GPOS_SHIFT) != (prev >> GPOS_SHIFT)));
             prev = e[i];
         }
 #pragma unroll
-        for (int i = 0; i < RG_ITEMS - 1; ++i) nx[i] = (a0 + i + 1 >= cnt) || nf[i + 1];
-        nx[RG_ITEMS - 1] = (a0 + RG_ITEMS >= cnt) || ((next_e >> VAL_BITS) != (e[RG_ITEMS - 1] >> VAL_BITS));
+        for (int i = 0; i < ITEMS - 1; ++i) nx[i] = (a0 + i + 1 >= cnt) || nf[i + 1];
+        nx[ITEMS - 1] = (a0 + ITEMS >= cnt) || ((next_e >> VAL_BITS) != (e[ITEMS - 1] >> VAL_BITS));
 #pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i)
+        for (int i = 0; i < ITEMS; ++i)
             if (a0 + i < cnt) {
                 if (nf[i]) last_n = (int)(a0 + i);
                 if (of[i]) last_o = (int)(a0 + i);
             }
 #pragma unroll
-        for (int i = RG_ITEMS - 1; i >= 0; --i)
+        for (int i = ITEMS - 1; i >= 0; --i)
             if (a0 + i < cnt && nx[i]) first_end = (int)(a0 + i);
     }
     const int prev_n = block_excl_max(last_n, s_i, nullptr);
@@ -321,16 +336,16 @@ __device__ __forceinline__ void group_view(const uint64_t (&e)[RG_ITEMS], uint64
     const int next_end = block_excl_min_suffix(first_end, s_i);
     if (a0 >= cnt) return;
     int e_run = next_end != INT_INF ? next_end : (int)edge_e;
-    int en[RG_ITEMS];
+    int en[ITEMS];
 #pragma unroll
-    for (int i = RG_ITEMS - 1; i >= 0; --i) {
+    for (int i = ITEMS - 1; i >= 0; --i) {
         if (a0 + i < cnt && nx[i]) e_run = (int)(a0 + i);
         en[i] = e_run;
     }
     int s_run = prev_n >= 0 ? prev_n : (int)edge_s;
     int o_run = ROUND0 ? 0 : (prev_o >= 0 ? prev_o : (int)edge_o);
 #pragma unroll
-    for (int i = 0; i < RG_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t a = a0 + i;
         if (a < cnt) {
             if (nf[i]) s_run = (int)a;
@@ -351,19 +366,20 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
     __shared__ int s_i[34];
     __shared__ uint32_t s_u[34];
     __shared__ uint32_t s_edge[3];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_base, s_tmain, s_lbase, s_lother;
     const uint32_t b = blockIdx.y, tile = blockIdx.x;
     const uint32_t cnt = counts[b];
     const uint32_t base = tile * RG_TILE;
     if (base >= cnt) return;
     const uint64_t *kp = keys + (uint64_t)b * A.stride;
     const uint32_t tile_last = min(base + (uint32_t)RG_TILE, cnt) - 1;
-    if (threadIdx.x < 3) {
-        uint32_t r = 0;
-        if (threadIdx.x == 0) r = run_first(kp, base, kp[base] >> VAL_BITS, VAL_BITS);
-        else if (threadIdx.x == 1) r = ROUND0 ? 0u : run_first(kp, base, kp[base] >> GPOS_SHIFT, GPOS_SHIFT);
-        else r = run_last(kp, tile_last, cnt, kp[tile_last] >> VAL_BITS, VAL_BITS);
-        s_edge[threadIdx.x] = r;
+    if (threadIdx.x == 0) { s_tmain = 0xffffffffu; s_lother = 0; }
+    if (warp_id() < 3) { // where do the groups that reach over the tile's edges start / end?
+        uint32_t r;
+        if (warp_id() == 0) r = warp_run_first(kp, base, kp[base] >> VAL_BITS, VAL_BITS);
+        else if (warp_id() == 1) r = ROUND0 ? 0u : warp_run_first(kp, base, kp[base] >> GPOS_SHIFT, GPOS_SHIFT);
+        else r = warp_run_last(kp, tile_last, cnt, kp[tile_last] >> VAL_BITS, VAL_BITS);
+        if (lane_id() == 0) s_edge[warp_id()] = r;
     }
     const uint32_t a0 = base + threadIdx.x * RG_ITEMS;
     uint64_t e[RG_ITEMS];
@@ -385,48 +401,58 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
         if (a0 + RG_ITEMS < cnt) next_e = kp[a0 + RG_ITEMS];
     }
     __syncthreads(); // s_edge
-    GroupView v;
-    group_view<ROUND0>(e, prev_e, next_e, a0, cnt, s_edge[0], s_edge[1], s_edge[2], s_i, v);
+    GroupView<RG_ITEMS> v;
+    group_view<ROUND0, RG_ITEMS>(e, prev_e, next_e, a0, cnt, s_edge[0], s_edge[1], s_edge[2], s_i, v);
     const uint32_t n = A.n_arr[b];
     const bool done = A.sorted_len >= n;
     const uint64_t o = (uint64_t)b * A.stride;
-    uint32_t kg = 0, kl = 0; // kept in the bag / in local regions
-    unsigned gmask = 0, lmask = 0;
+    uint32_t kg = 0; // kept in the bag
+    unsigned gmask = 0, lmask = 0, fmask = 0;
+    uint32_t tmin = 0xffffffffu;
     if (a0 < cnt) {
-        const uint8_t *T = A.T + o;
-        uint8_t *L = A.L + o;
         uint32_t *rank = A.rank + o;
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i) {
             if (a0 + i < cnt) {
-                const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
-                rank[val] = v.P[i];
-                if (v.size[i] == 1 || done) L[v.p[i]] = T[val ? val - 1 : n - 1];
-                else if (A.split && (v.P[i] >> SA_TILE_BITS) == ((v.P[i] + v.size[i] - 1) >> SA_TILE_BITS)) { lmask |= 1u << i; ++kl; }
+                rank[(uint32_t)(e[i] & VAL_MASK)] = v.P[i];
+                if (v.size[i] == 1 || done) fmask |= 1u << i;
+                else if (A.split && (v.P[i] >> SA_TILE_BITS) == ((v.P[i] + v.size[i] - 1) >> SA_TILE_BITS)) { lmask |= 1u << i; tmin = min(tmin, v.P[i] >> SA_TILE_BITS); }
                 else { gmask |= 1u << i; ++kg; }
             }
         }
-    }
-    uint32_t total_g, total_l;
-    uint32_t off = block_excl_sum(kg, s_u, &total_g);
-    (void)block_excl_sum(kl, s_u, &total_l);
-    if (threadIdx.x == 0) {
-        s_base = total_g ? atomicAdd(&bag_cnt[b], total_g) : 0u;
-        if (total_g + total_l) atomicAdd(A.totals, (unsigned long long)(total_g + total_l));
-    }
-    __syncthreads();
-    if (gmask) {
-        uint64_t *bg = bag + o + s_base;
+        // final rotations: L[position] = T[rotation - 1]; loads first, then stores
+        const uint8_t *T = A.T + o;
+        uint8_t *L = A.L + o;
+        uint8_t tb[RG_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i) {
+            const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
+            tb[i] = (fmask & (1u << i)) ? T[val ? val - 1 : n - 1] : (uint8_t)0;
+        }
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i)
-            if (gmask & (1u << i)) bg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
+            if (fmask & (1u << i)) L[v.p[i]] = tb[i];
     }
-    if (lmask) {
-        // one slot reservation per run of consecutive slots that go to the same SA tile
-        uint32_t *lc = A.loc_cnt + (uint64_t)b * A.tiles_per_block;
+    if (tmin != 0xffffffffu) atomicMin(&s_tmain, tmin);
+    uint32_t total_g, total_m;
+    uint32_t off = block_excl_sum(kg, s_u, &total_g); // its barriers also publish s_tmain
+    // local kept elements: those of the CTA's main SA tile get one reservation for the whole CTA, stragglers one per run
+    const uint32_t tmain = s_tmain;
+    unsigned mmask = 0;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; ++i)
+        if ((lmask & (1u << i)) && (v.P[i] >> SA_TILE_BITS) == tmain) mmask |= 1u << i;
+    uint32_t offm = block_excl_sum((uint32_t)__popc(mmask), s_u, &total_m);
+    uint32_t *lc = A.loc_cnt + (uint64_t)b * A.tiles_per_block;
+    if (threadIdx.x == 0) {
+        s_base = total_g ? atomicAdd(&bag_cnt[b], total_g) : 0u;
+        s_lbase = total_m ? atomicAdd(&lc[tmain], total_m) : 0u;
+    }
+    const unsigned omask = lmask & ~mmask;
+    if (omask) {
         uint32_t tl[RG_ITEMS], len[RG_ITEMS];
 #pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i) tl[i] = (lmask & (1u << i)) ? (v.P[i] >> SA_TILE_BITS) : 0xffffffffu;
+        for (int i = 0; i < RG_ITEMS; ++i) tl[i] = (omask & (1u << i)) ? (v.P[i] >> SA_TILE_BITS) : 0xffffffffu;
 #pragma unroll
         for (int i = RG_ITEMS - 1; i >= 0; --i)
             len[i] = tl[i] == 0xffffffffu ? 0u : 1u + ((i + 1 < RG_ITEMS && tl[(i + 1) % RG_ITEMS] == tl[i]) ? len[(i + 1) % RG_ITEMS] : 0u);
@@ -438,6 +464,24 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
                 *reg++ = ((uint64_t)(v.P[i] & (RG_TILE - 1)) << GPOS_SHIFT) | (e[i] & VAL_MASK);
             }
         }
+        atomicAdd(&s_lother, (uint32_t)__popc(omask));
+    }
+    __syncthreads();
+    if (gmask) {
+        uint64_t *bg = bag + o + s_base;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i)
+            if (gmask & (1u << i)) bg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
+    }
+    if (mmask) {
+        uint64_t *reg = A.loc + o + (uint64_t)tmain * RG_TILE + s_lbase;
+#pragma unroll
+        for (int i = 0; i < RG_ITEMS; ++i)
+            if (mmask & (1u << i)) reg[offm++] = ((uint64_t)(v.P[i] & (RG_TILE - 1)) << GPOS_SHIFT) | (e[i] & VAL_MASK);
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t kept = total_g + total_m + s_lother;
+        if (kept) atomicAdd(A.totals, (unsigned long long)kept);
     }
 }
 
@@ -457,8 +501,8 @@ __global__ void __launch_bounds__(256) k_bwt_roundstats(const uint32_t *__restri
 // One CTA per (SA tile, block): sort the region's elements by (group position, rank of the second half) in shared memory
 // (LSD radix, warp match_any multi-split, digits that are constant over the region skipped), regroup them exactly like
 // k_bwt_regroup does, and write the still-ambiguous ones back to the front of the same region.
-constexpr int LS_THREADS = RG_THREADS;
-constexpr int LS_ITEMS = RG_ITEMS;
+constexpr int LS_THREADS = 512;
+constexpr int LS_ITEMS = RG_TILE / LS_THREADS; // 4
 constexpr int LS_WARPS = LS_THREADS / 32;
 
 struct LocalSmem {
@@ -504,85 +548,94 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
         if (((diff >> shift) & 0xffu) == 0) continue; // uniform over the CTA
         const int sh = shift + VAL_BITS;
         uint64_t key[LS_ITEMS];
+        uint32_t dg[LS_ITEMS];
+        unsigned peers[LS_ITEMS];
         uint16_t rnk[LS_ITEMS];
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
             const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
             key[i] = li < c ? sm.e[li] : 0ull;
+            dg[i] = li < c ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
         }
         for (int i = threadIdx.x; i < LS_WARPS * 256; i += LS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i) peers[i] = __match_any_sync(FULL, dg[i]);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            const bool valid = li < c;
-            const uint32_t d = valid ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(FULL, d);
-            const int leader = __ffs(peers) - 1;
+            const uint32_t d = dg[i];
+            const int leader = __ffs(peers[i]) - 1;
             uint32_t old = 0;
-            if (valid && lane == leader) {
+            if (d != 0xffffffffu && lane == leader) {
                 old = sm.warp_hist[w][d];
-                sm.warp_hist[w][d] = old + __popc(peers);
+                sm.warp_hist[w][d] = old + __popc(peers[i]);
             }
             old = __shfl_sync(FULL, old, leader);
-            rnk[i] = (uint16_t)(old + __popc(peers & lt));
+            rnk[i] = (uint16_t)(old + __popc(peers[i] & lt));
             __syncwarp();
         }
         __syncthreads();
         {
-            const uint32_t d = threadIdx.x; // LS_THREADS == 256 digits
+            const uint32_t d = threadIdx.x;
             uint32_t sum = 0;
+            if (d < 256) {
 #pragma unroll
-            for (int ww = 0; ww < LS_WARPS; ++ww) {
-                const uint32_t x = sm.warp_hist[ww][d];
-                sm.warp_hist[ww][d] = sum;
-                sum += x;
+                for (int ww = 0; ww < LS_WARPS; ++ww) {
+                    const uint32_t x = sm.warp_hist[ww][d];
+                    sm.warp_hist[ww][d] = sum;
+                    sum += x;
+                }
             }
-            sm.tile_base[d] = block_excl_sum(sum, sm.scratch, nullptr);
+            const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr); // threads >= 256 add 0 behind the digits
+            if (d < 256) sm.tile_base[d] = tb;
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            if (li < c) {
-                const uint32_t d = (uint32_t)(key[i] >> sh) & 0xffu;
-                sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
-            }
+            const uint32_t d = dg[i];
+            if (d != 0xffffffffu) sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
         }
         __syncthreads();
     }
     // ---- regroup inside the region (positions relative to the tile)
-    const uint32_t a0 = threadIdx.x * RG_ITEMS;
-    uint64_t e[RG_ITEMS];
+    const uint32_t a0 = threadIdx.x * LS_ITEMS;
+    uint64_t e[LS_ITEMS];
 #pragma unroll
-    for (int i = 0; i < RG_ITEMS; ++i) e[i] = a0 + i < c ? sm.e[a0 + i] : 0ull;
+    for (int i = 0; i < LS_ITEMS; ++i) e[i] = a0 + i < c ? sm.e[a0 + i] : 0ull;
     const uint64_t prev_e = (a0 > 0 && a0 < c) ? sm.e[a0 - 1] : 0ull;
-    const uint64_t next_e = a0 + RG_ITEMS < c ? sm.e[a0 + RG_ITEMS] : 0ull;
-    GroupView v;
-    group_view<false>(e, prev_e, next_e, a0, c, 0u, 0u, c - 1, sm.scr_i, v);
+    const uint64_t next_e = a0 + LS_ITEMS < c ? sm.e[a0 + LS_ITEMS] : 0ull;
+    GroupView<LS_ITEMS> v;
+    group_view<false, LS_ITEMS>(e, prev_e, next_e, a0, c, 0u, 0u, c - 1, sm.scr_i, v);
     const uint32_t n = A.n_arr[b];
     const bool done = A.sorted_len >= n;
     const uint32_t tbase = t * RG_TILE;
-    uint32_t keep = 0;
-    unsigned kmask = 0;
+    unsigned kmask = 0, fmask = 0;
     if (a0 < c) {
         const uint8_t *T = A.T + o;
         uint8_t *L = A.L + o;
         uint32_t *rank = A.rank + o;
 #pragma unroll
-        for (int i = 0; i < RG_ITEMS; ++i) {
+        for (int i = 0; i < LS_ITEMS; ++i) {
             if (a0 + i < c) {
-                const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
-                rank[val] = tbase + v.P[i];
-                if (v.size[i] == 1 || done) L[tbase + v.p[i]] = T[val ? val - 1 : n - 1];
-                else { kmask |= 1u << i; ++keep; }
+                rank[(uint32_t)(e[i] & VAL_MASK)] = tbase + v.P[i];
+                if (v.size[i] == 1 || done) fmask |= 1u << i;
+                else kmask |= 1u << i;
             }
         }
+        uint8_t tb[LS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i) {
+            const uint32_t val = (uint32_t)(e[i] & VAL_MASK);
+            tb[i] = (fmask & (1u << i)) ? T[val ? val - 1 : n - 1] : (uint8_t)0;
+        }
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i)
+            if (fmask & (1u << i)) L[tbase + v.p[i]] = tb[i];
     }
     uint32_t total;
-    uint32_t off = block_excl_sum(keep, sm.scratch, &total);
+    uint32_t off = block_excl_sum((uint32_t)__popc(kmask), sm.scratch, &total);
 #pragma unroll
-    for (int i = 0; i < RG_ITEMS; ++i)
+    for (int i = 0; i < LS_ITEMS; ++i)
         if (kmask & (1u << i)) reg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
     if (threadIdx.x == 0) {
         *cnt_p = total;
