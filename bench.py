@@ -206,7 +206,6 @@ def main():
     res = None
     for _ in range(args.warmup):
         res = comp.compress_blocks_ptr(d_in.data_ptr(), n_in, d_out.data_ptr(), cap)
-    comp.set_profiling(True)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -221,8 +220,15 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    ktimes = comp.kernel_times()
     stats = comp.stats()
+    # per-kernel times (CUDA events around every launch) come from separate, untimed passes so that the event traffic stays
+    # out of the headline number
+    comp.set_profiling(True)
+    prof_steps = min(2, args.steps)
+    for _ in range(prof_steps):
+        comp.compress_blocks_ptr(d_in.data_ptr(), n_in, d_out.data_ptr(), cap)
+    torch.cuda.synchronize()
+    ktimes = comp.kernel_times()
     comp.set_profiling(False)
     value = total_bytes / 1e6 / (ms_dev / 1e3)
 
@@ -245,14 +251,16 @@ def main():
     top = max(ktimes.items(), key=lambda kv: kv[1][0])
     name, (k_ms, k_n, k_bytes) = top
     achieved = (k_bytes / 1e9) / (k_ms / 1e3) if k_ms > 0 and k_bytes else None
-    step_kernel_ms = sum(v[0] for v in ktimes.values()) / args.steps
+    step_kernel_ms = sum(v[0] for v in ktimes.values()) / prof_steps
     roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "launches_per_step": k_n // args.steps, "avg_launch_ms": round(k_ms / max(1, k_n), 4),
-                "share_of_step": round(k_ms / args.steps / ms_dev, 4),
+                "launches_per_step": k_n // prof_steps, "avg_launch_ms": round(k_ms / max(1, k_n), 4),
+                "share_of_step": round(k_ms / prof_steps / ms_dev, 4),
                 "algorithmic_bytes_per_launch": k_bytes // max(1, k_n),
-                "kernels_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:12]},
-                "sum_kernel_ms_per_step": round(step_kernel_ms, 3)}
+                "kernels_ms_per_step": {k: round(v[0] / prof_steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
+                "sum_kernel_ms_per_step": round(step_kernel_ms, 3),
+                "stage_ms_last_step": {k[3:]: round(float(stats[k]), 3) for k in ("ms_total", "ms_rle", "ms_bwt_sort0", "ms_bwt_rounds", "ms_bwt_finish", "ms_mtf",
+                                                                                  "ms_huffman", "ms_emit", "ms_walk")}}
     n_rle_total = sum_over_ranks(stats["n_rle"])
     rho = sum_over_ranks(stats["bwt_active_volume"]) / max(1.0, n_rle_total)
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbz2b200.so")
+LIB_PATH = os.environ.get("BZ2B200_LIB") or os.path.join(HERE, "libbz2b200.so")  # BZ2B200_LIB: development variants of the same library
 
 OK, E_BLOCKSIZE, E_PARALLEL, E_ARG, E_CUDA, E_NOMEM, E_OUTPUT, E_STATE = 0, -1, -2, -3, -4, -5, -6, -7
 

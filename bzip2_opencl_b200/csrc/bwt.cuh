@@ -331,9 +331,8 @@ __device__ __forceinline__ void group_view(const uint64_t (&e)[ITEMS], uint64_t 
         for (int i = ITEMS - 1; i >= 0; --i)
             if (a0 + i < cnt && nx[i]) first_end = (int)(a0 + i);
     }
-    const int prev_n = block_excl_max(last_n, s_i, nullptr);
-    const int prev_o = ROUND0 ? 0 : block_excl_max(last_o, s_i, nullptr);
-    const int next_end = block_excl_min_suffix(first_end, s_i);
+    int prev_n, prev_o, next_end;
+    block_scan_max2_minsuffix(last_n, last_o, first_end, s_i, prev_n, prev_o, next_end);
     if (a0 >= cnt) return;
     int e_run = next_end != INT_INF ? next_end : (int)edge_e;
     int en[ITEMS];
@@ -363,7 +362,7 @@ template <bool ROUND0>
 __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, RoundArgs A,
                                                              uint64_t *__restrict__ bag, uint32_t *__restrict__ bag_cnt)
 {
-    __shared__ int s_i[34];
+    __shared__ int s_i[96];
     __shared__ uint32_t s_u[34];
     __shared__ uint32_t s_edge[3];
     __shared__ uint32_t s_base, s_tmain, s_lbase, s_lother;
@@ -501,7 +500,13 @@ __global__ void __launch_bounds__(256) k_bwt_roundstats(const uint32_t *__restri
 // One CTA per (SA tile, block): sort the region's elements by (group position, rank of the second half) in shared memory
 // (LSD radix, warp match_any multi-split, digits that are constant over the region skipped), regroup them exactly like
 // k_bwt_regroup does, and write the still-ambiguous ones back to the front of the same region.
-constexpr int LS_THREADS = 512;
+#ifndef BZ_LS_THREADS
+#define BZ_LS_THREADS 256
+#endif
+#ifndef BZ_LS_MINB
+#define BZ_LS_MINB 4
+#endif
+constexpr int LS_THREADS = BZ_LS_THREADS;
 constexpr int LS_ITEMS = RG_TILE / LS_THREADS; // 4
 constexpr int LS_WARPS = LS_THREADS / 32;
 
@@ -510,11 +515,11 @@ struct LocalSmem {
     uint32_t warp_hist[LS_WARPS][256];
     uint32_t tile_base[256];
     uint32_t scratch[34];
-    int scr_i[34];
+    int scr_i[96];
     uint32_t red[2 * LS_WARPS];
 };
 
-__global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
+__global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs A)
 {
     __shared__ __align__(16) LocalSmem sm;
     const uint32_t b = blockIdx.y, t = blockIdx.x;
@@ -544,6 +549,11 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
         diff = x ^ y;
     }
     const unsigned lt = (1u << lane) - 1u;
+    // the sort uses as many warps as have at least two rows of 32 elements to rank; warp w owns elements [w*chunk, (w+1)*chunk)
+    const uint32_t nwu = min((uint32_t)LS_WARPS, (c + 63) / 64);
+    const uint32_t chunk = ((c + nwu - 1) / nwu + 31) & ~31u;
+    const uint32_t wbase = (uint32_t)w * chunk;
+    const uint32_t wcnt = ((uint32_t)w < nwu && wbase < c) ? min(chunk, c - wbase) : 0u;
     for (int shift = 0; shift < 32; shift += 8) {
         if (((diff >> shift) & 0xffu) == 0) continue; // uniform over the CTA
         const int sh = shift + VAL_BITS;
@@ -553,26 +563,29 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
         uint16_t rnk[LS_ITEMS];
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            const uint32_t li = w * (32 * LS_ITEMS) + i * 32 + lane;
-            key[i] = li < c ? sm.e[li] : 0ull;
-            dg[i] = li < c ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
+            const uint32_t q = i * 32 + lane;
+            key[i] = q < wcnt ? sm.e[wbase + q] : 0ull;
+            dg[i] = q < wcnt ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
         }
-        for (int i = threadIdx.x; i < LS_WARPS * 256; i += LS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+        for (uint32_t i = threadIdx.x; i < nwu * 256; i += LS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
 #pragma unroll
-        for (int i = 0; i < LS_ITEMS; ++i) peers[i] = __match_any_sync(FULL, dg[i]);
+        for (int i = 0; i < LS_ITEMS; ++i)
+            if ((uint32_t)i * 32 < wcnt) peers[i] = __match_any_sync(FULL, dg[i]);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
-            const uint32_t d = dg[i];
-            const int leader = __ffs(peers[i]) - 1;
-            uint32_t old = 0;
-            if (d != 0xffffffffu && lane == leader) {
-                old = sm.warp_hist[w][d];
-                sm.warp_hist[w][d] = old + __popc(peers[i]);
+            if ((uint32_t)i * 32 < wcnt) { // warp-uniform
+                const uint32_t d = dg[i];
+                const int leader = __ffs(peers[i]) - 1;
+                uint32_t old = 0;
+                if (d != 0xffffffffu && lane == leader) {
+                    old = sm.warp_hist[w][d];
+                    sm.warp_hist[w][d] = old + __popc(peers[i]);
+                }
+                old = __shfl_sync(FULL, old, leader);
+                rnk[i] = (uint16_t)(old + __popc(peers[i] & lt));
+                __syncwarp();
             }
-            old = __shfl_sync(FULL, old, leader);
-            rnk[i] = (uint16_t)(old + __popc(peers[i] & lt));
-            __syncwarp();
         }
         __syncthreads();
         {
@@ -581,9 +594,11 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
             if (d < 256) {
 #pragma unroll
                 for (int ww = 0; ww < LS_WARPS; ++ww) {
-                    const uint32_t x = sm.warp_hist[ww][d];
-                    sm.warp_hist[ww][d] = sum;
-                    sum += x;
+                    if ((uint32_t)ww < nwu) {
+                        const uint32_t x = sm.warp_hist[ww][d];
+                        sm.warp_hist[ww][d] = sum;
+                        sum += x;
+                    }
                 }
             }
             const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr); // threads >= 256 add 0 behind the digits
@@ -593,7 +608,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_bwt_local(RoundArgs A)
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
             const uint32_t d = dg[i];
-            if (d != 0xffffffffu) sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
+            if ((uint32_t)i * 32 < wcnt && d != 0xffffffffu) sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
         }
         __syncthreads();
     }

@@ -788,10 +788,11 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->drain_dev = out ? is_device_ptr(out) != 0 : false;
     {
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
+        // (the walk finds ~4 blocks in the time the kernels compress one, so every chunk may be 4x the batch that hides it)
         bool pending = false;
-        uint64_t b0 = 0;
+        uint64_t b0 = 0, chunk = std::min<uint64_t>(h->G, 48);
         if (!h->w_finished) {
-            rc = walk_launch(h, std::min<uint64_t>(h->G, 48));
+            rc = walk_launch(h, chunk);
             if (rc) return rc;
             pending = true;
         }
@@ -802,7 +803,8 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 pending = false;
             }
             if (!h->w_finished) {
-                rc = walk_launch(h, h->G);
+                chunk = std::min<uint64_t>(h->G, chunk * 4);
+                rc = walk_launch(h, chunk);
                 if (rc) return rc;
                 pending = true;
             }

@@ -140,4 +140,43 @@ __device__ __forceinline__ int block_excl_min_suffix(int v, int *scratch)
     return res;
 }
 
+// Three block-wide scans in one set of barriers: exclusive prefix maxima of a and b (-1 if no earlier thread) and the
+// exclusive suffix minimum of c (INT_MAX if no later thread).  `scratch` needs 3 * 32 ints; blockDim.x <= 1024, multiple of 32.
+__device__ __forceinline__ void block_scan_max2_minsuffix(int a, int b, int c, int *scratch, int &prev_a, int &prev_b, int &next_c)
+{
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    int ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int oa = __shfl_up_sync(FULL, ia, d), ob = __shfl_up_sync(FULL, ib, d), oc = __shfl_down_sync(FULL, ic, d);
+        if (lane >= d) { ia = max(ia, oa); ib = max(ib, ob); }
+        if (lane + d < 32) ic = min(ic, oc);
+    }
+    if (lane == 31) { scratch[w] = ia; scratch[32 + w] = ib; }
+    if (lane == 0) scratch[64 + w] = ic;
+    __syncthreads();
+    if (w == 0) { // exclusive scans over the warp totals
+        int xa = lane < nw ? scratch[lane] : -1, xb = lane < nw ? scratch[32 + lane] : -1, xc = lane < nw ? scratch[64 + lane] : 0x7fffffff;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int oa = __shfl_up_sync(FULL, xa, d), ob = __shfl_up_sync(FULL, xb, d), oc = __shfl_down_sync(FULL, xc, d);
+            if (lane >= d) { xa = max(xa, oa); xb = max(xb, ob); }
+            if (lane + d < 32) xc = min(xc, oc);
+        }
+        int ea = __shfl_up_sync(FULL, xa, 1), eb = __shfl_up_sync(FULL, xb, 1), ec = __shfl_down_sync(FULL, xc, 1);
+        if (lane == 0) { ea = -1; eb = -1; }
+        if (lane == 31) ec = 0x7fffffff;
+        scratch[lane] = ea; scratch[32 + lane] = eb; scratch[64 + lane] = ec;
+    }
+    __syncthreads();
+    const int wa = scratch[w], wb = scratch[32 + w], wc = scratch[64 + w];
+    int pa = __shfl_up_sync(FULL, ia, 1), pb = __shfl_up_sync(FULL, ib, 1), nc = __shfl_down_sync(FULL, ic, 1);
+    if (lane == 0) { pa = -1; pb = -1; }
+    if (lane == 31) nc = 0x7fffffff;
+    prev_a = max(wa, pa);
+    prev_b = max(wb, pb);
+    next_c = min(wc, nc);
+    __syncthreads();
+}
+
 } // namespace bz
