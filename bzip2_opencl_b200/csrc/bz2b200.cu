@@ -68,6 +68,18 @@ struct bz2b200 {
     uint32_t *pin_len = nullptr;    // G + 2
     uint64_t *pin_info = nullptr;   // 4
     WalkLevels wl{};
+    // input arrives in segments (host input: chunked H2D on its own stream, overlapped with the kernels); the tree of
+    // summaries and the walk are extended segment by segment on the side stream
+    cudaStream_t h2d = nullptr;
+    std::vector<cudaEvent_t> ev_seg;
+    std::vector<uint64_t> seg_end;
+    size_t seg_avail = 0, seg_copied = 0;
+    const uint8_t *host_src = nullptr; // non-null: segments still have to be copied from here
+    bool host_pinned = false;
+    uint64_t tiles_done = 0;
+    bool tree_pending = false; // ev_t0/ev_t1 hold a tree update that walk_collect has not accounted yet
+    int caller_final = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     const uint8_t *w_in = nullptr;
     uint64_t w_n = 0, w_cap = 0, w_req = 0, w_found = 0;
     int w_final = 0;
@@ -228,6 +240,10 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
     if (h->pin_info) cudaFreeHost(h->pin_info);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->copy) cudaStreamDestroy(h->copy);
+    if (h->h2d) cudaStreamDestroy(h->h2d);
+    for (cudaEvent_t e : h->ev_seg) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_t0, h->ev_t1})
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {h->ev_tree, h->ev_walk, h->ev_w0, h->ev_w1})
         if (e) cudaEventDestroy(e);
     for (auto &e : h->ev)
@@ -292,6 +308,9 @@ static int create_impl(bz2b200 *h)
     CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_t1));
     CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev_w0));
@@ -394,37 +413,78 @@ static int is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// Stage A over the whole input, part 1: the tree of summaries (main stream).  The sequential walk over blocks then runs in
-// chunks on a side stream (walk_launch / walk_collect), one batch ahead of the compression kernels.
+// Stage A over the whole input, part 1: the tree of summaries.  The input becomes available in segments (seg_end[]); the
+// tree is extended and the sequential walk over blocks runs in chunks on a side stream (walk_extend / walk_launch /
+// walk_collect), ahead of the compression kernels on the main stream.
 static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
 {
     h->h_starts.assign(1, 0);
     h->h_rle_len.clear();
     h->w_in = d_in;
-    h->w_n = n;
-    h->w_final = is_final;
+    h->w_n = 0;
+    h->caller_final = is_final;
+    h->w_final = 0;
     h->w_found = 0;
-    h->w_finished = (n == 0);
-    if (n == 0) return BZ2B200_OK;
-    uint64_t cnt[RLE_MAX_LEVELS];
-    int nl = 1;
-    cnt[0] = (n + RLE_TILE - 1) / RLE_TILE;
-    while (cnt[nl - 1] > 1 && nl < RLE_MAX_LEVELS) { cnt[nl] = (cnt[nl - 1] + RLE_FANOUT - 1) / RLE_FANOUT; ++nl; }
-    for (int l = 0; l < nl; ++l) ENSURE(h->seg[l], cnt[l] * sizeof(Seg));
+    h->w_finished = true; // nothing available yet: walk_extend brings the first segment in
+    h->seg_avail = 0;
+    h->tiles_done = 0;
+    if (n == 0) { h->seg_end.clear(); return BZ2B200_OK; }
+    uint64_t c = (n + RLE_TILE - 1) / RLE_TILE;
+    for (int l = 0; l < RLE_MAX_LEVELS; ++l) {
+        ENSURE(h->seg[l], c * sizeof(Seg));
+        if (c <= 1) break;
+        c = (c + RLE_FANOUT - 1) / RLE_FANOUT;
+    }
     h->w_cap = n / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
     ENSURE(h->starts, (h->w_cap + 2) * 8);
     ENSURE(h->rle_len, (h->w_cap + 2) * 4);
-    KL(KID_k_rle_tile_seg, k_rle_tile_seg<<<(unsigned)((cnt[0] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(d_in, n, ptr<Seg>(h->seg[0]), cnt[0]));
-    for (int l = 1; l < nl; ++l)
-        KL(KID_k_rle_reduce, k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->stream>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]),
-                                                                                                           cnt[l]));
-    h->stats.kernel_launches += nl;
-    for (int l = 0; l < RLE_MAX_LEVELS; ++l) { h->wl.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; h->wl.cnt[l] = l < nl ? cnt[l] : 0; }
-    h->wl.n_levels = nl;
     uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
     CK(cudaMemsetAsync(d_info, 0, 32, h->stream));
     CK(cudaEventRecord(h->ev_tree, h->stream));
     CK(cudaStreamWaitEvent(h->side, h->ev_tree, 0));
+    return BZ2B200_OK;
+}
+
+static bool walk_more_input(const bz2b200 *h) { return h->seg_avail < h->seg_end.size(); }
+
+// the next input segment: (host input) its copy, then level-0 summaries of the new tiles and the upper tree levels
+static int walk_extend(bz2b200 *h)
+{
+    size_t k = h->seg_avail;
+    if (h->host_src) {
+        // pinned memory: every copy was queued up front; pageable memory: cudaMemcpyAsync blocks the host, so copy one segment ahead only
+        const size_t upto = h->host_pinned ? h->seg_end.size() : std::min(h->seg_end.size(), k + 2);
+        for (; h->seg_copied < upto; ++h->seg_copied) {
+            const uint64_t lo = h->seg_copied ? h->seg_end[h->seg_copied - 1] : 0, hi = h->seg_end[h->seg_copied];
+            if (h->seg_copied == 0) CK(cudaEventRecord(h->ev[0], h->h2d));
+            CK(cudaMemcpyAsync(ptr<uint8_t>(h->in) + lo, h->host_src + lo, hi - lo, cudaMemcpyHostToDevice, h->h2d));
+            CK(cudaEventRecord(h->ev_seg[h->seg_copied], h->h2d));
+            if (h->seg_copied + 1 == h->seg_end.size()) CK(cudaEventRecord(h->ev[1], h->h2d));
+        }
+        while (k + 1 < h->seg_copied && cudaEventQuery(h->ev_seg[k + 1]) == cudaSuccess) ++k; // take everything that has already arrived
+        (void)cudaGetLastError();
+        CK(cudaStreamWaitEvent(h->side, h->ev_seg[k], 0));
+    }
+    const uint64_t n = h->seg_end[k];
+    uint64_t cnt[RLE_MAX_LEVELS];
+    int nl = 1;
+    cnt[0] = (n + RLE_TILE - 1) / RLE_TILE;
+    while (cnt[nl - 1] > 1 && nl < RLE_MAX_LEVELS) { cnt[nl] = (cnt[nl - 1] + RLE_FANOUT - 1) / RLE_FANOUT; ++nl; }
+    const uint64_t t0 = h->tiles_done, nt = cnt[0] - t0;
+    CK(cudaEventRecord(h->ev_t0, h->side));
+    k_rle_tile_seg<<<(unsigned)((nt + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(h->w_in, n, ptr<Seg>(h->seg[0]), t0, cnt[0]);
+    for (int l = 1; l < nl; ++l)
+        k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]), cnt[l]);
+    CK(cudaEventRecord(h->ev_t1, h->side));
+    h->stats.kernel_launches += nl;
+    for (int l = 0; l < RLE_MAX_LEVELS; ++l) { h->wl.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; h->wl.cnt[l] = l < nl ? cnt[l] : 0; }
+    h->wl.n_levels = nl;
+    h->tiles_done = n / RLE_TILE; // a partial last tile is summarised again when more bytes arrive
+    h->w_n = n;
+    h->seg_avail = k + 1;
+    h->w_final = (h->caller_final && h->seg_avail == h->seg_end.size()) ? 1 : 0;
+    h->w_finished = false;
+    h->tree_pending = true;
     return BZ2B200_OK;
 }
 
@@ -465,21 +525,50 @@ static int walk_collect(bz2b200 *h)
     cudaEventElapsedTime(&ms, h->ev_w0, h->ev_w1);
     h->stats.ms_walk += ms;
     if (h->profiling) { h->k_ms[KID_k_rle_walk] += ms; h->k_launches[KID_k_rle_walk] += 1; }
+    if (h->tree_pending) { // the walk ran behind the tree update on the same stream, so that has completed as well
+        float tms = 0;
+        cudaEventElapsedTime(&tms, h->ev_t0, h->ev_t1);
+        h->stats.ms_walk += tms;
+        if (h->profiling) { h->k_ms[KID_k_rle_tile_seg] += tms; h->k_launches[KID_k_rle_tile_seg] += 1; }
+        h->tree_pending = false;
+    }
     return BZ2B200_OK;
 }
 
-// resolves `input` to a 16-byte aligned device pointer (copying when it is host memory or misaligned)
+// resolves `input` to a 16-byte aligned device pointer and cuts it into segments.  Device input is one segment (copied once
+// if misaligned); host input is copied segment by segment on the H2D stream while earlier segments are being compressed.
 static int stage_input(bz2b200 *h, const uint8_t *input, size_t n, const uint8_t **d_in)
 {
+    h->seg_end.clear();
+    h->host_src = nullptr;
+    h->seg_copied = 0;
     if (n == 0) { *d_in = nullptr; return BZ2B200_OK; }
-    const bool dev = is_device_ptr(input);
-    if (dev && (reinterpret_cast<uintptr_t>(input) & 15u) == 0) { *d_in = input; return BZ2B200_OK; }
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, input);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+    const bool dev = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (dev) {
+        h->seg_end.push_back(n);
+        if ((reinterpret_cast<uintptr_t>(input) & 15u) == 0) { *d_in = input; return BZ2B200_OK; }
+        ENSURE(h->in, n + 64);
+        CK(cudaMemcpyAsync(h->in.p, input, n, cudaMemcpyDeviceToDevice, h->stream));
+        *d_in = ptr<uint8_t>(h->in);
+        return BZ2B200_OK;
+    }
     ENSURE(h->in, n + 64);
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    CK(cudaMemcpyAsync(h->in.p, input, n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->stats.ms_h2d = ev_ms(h->ev[0], h->ev[1]);
+    // a short first segment lets the kernels start early; later segments are long enough to amortise a tree update
+    const uint64_t first = 16ull << 20, rest = 128ull << 20;
+    for (uint64_t pos = 0; pos < n;) {
+        pos = std::min<uint64_t>(n, pos + (pos == 0 ? first : rest));
+        h->seg_end.push_back(pos);
+    }
+    while (h->ev_seg.size() < h->seg_end.size()) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_seg.push_back(ev);
+    }
+    h->host_src = input;
+    h->host_pinned = at.type == cudaMemoryTypeHost;
     *d_in = ptr<uint8_t>(h->in);
     return BZ2B200_OK;
 }
@@ -494,12 +583,17 @@ extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_
     if (rc) return rc;
     rc = walk_setup(h, d_in, n_bytes, 1);
     if (rc) return rc;
-    while (!h->w_finished) {
+    while (!h->w_finished || walk_more_input(h)) {
+        if (h->w_finished) {
+            rc = walk_extend(h);
+            if (rc) return rc;
+        }
         rc = walk_launch(h, h->G);
         if (rc) return rc;
         rc = walk_collect(h);
         if (rc) return rc;
     }
+    CK(cudaStreamSynchronize(h->h2d));
     if (h->profiling) { CK(cudaStreamSynchronize(h->stream)); prof_collect(h); }
     const uint64_t nb = h->w_found;
     *n_blocks = nb;
@@ -587,16 +681,27 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_bwt_regroup, k_bwt_regroup<true><<<gtiles, RG_THREADS, 0, st>>>(sorted, d_n, A, bag, bag_cnt[0]));
         KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[0], nb, A.totals));
         stt.kernel_launches += 2;
-        KBYTES(KID_k_bwt_regroup, sum_n * 14);
         res ^= 1; // the bag is in the other buffer
     }
     int cs = 0; // bag_cnt[cs] = sizes of the current bags
+    // algorithmic bytes of the regroup kernels: element in (8) + rank out (4) + T in / L out for final rotations (2) or the
+    // kept element out (8); known once the next round's counts are back
+    uint64_t prev_regroup_in = sum_n, prev_local_in = 0, prev_active = sum_n;
     for (;;) {
         CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::ROUND, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h->profiling) prof_collect(h);
         const uint64_t active = h->h_pinned[0], total_b = h->h_pinned[2];
         const uint32_t max_b = (uint32_t)h->h_pinned[1];
+        if (h->profiling) {
+            const uint64_t in = prev_regroup_in + prev_local_in, fin = prev_active > active ? prev_active - active : 0; // final this round
+            const uint64_t kept_r = in ? (uint64_t)((double)active * prev_regroup_in / in) : 0;
+            KBYTES(KID_k_bwt_regroup, 12 * prev_regroup_in + 2 * (in ? (uint64_t)((double)fin * prev_regroup_in / in) : 0) + 8 * kept_r);
+            KBYTES(KID_k_bwt_local, 12 * prev_local_in + 2 * (in ? (uint64_t)((double)fin * prev_local_in / in) : 0) + 8 * (active - kept_r));
+        }
+        prev_active = active;
+        prev_regroup_in = total_b;
+        prev_local_in = active - total_b;
         if (active == 0) break;
         stt.bwt_active_volume += active;
         ++rounds;
@@ -619,7 +724,6 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         if (have_local) {
             KL(KID_k_bwt_local, k_bwt_local<<<gtiles, LS_THREADS, 0, st>>>(A));
             stt.kernel_launches += 1;
-            KBYTES(KID_k_bwt_local, (active - total_b) * 22);
         }
         CK(cudaMemsetAsync(bag_cnt[cs ^ 1], 0, (size_t)nb * 4, st));
         if (max_b) {
@@ -628,7 +732,6 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
             dim3 g((max_b + RG_TILE - 1) / RG_TILE, nb);
             KL(KID_k_bwt_regroup, k_bwt_regroup<false><<<g, RG_THREADS, 0, st>>>(sorted, bag_cnt[cs], A, newbag, bag_cnt[cs ^ 1]));
             stt.kernel_launches += 1;
-            KBYTES(KID_k_bwt_regroup, total_b * 14);
             res = (newbag == ptr<uint64_t>(h->kB)) ? 1 : 0;
         }
         KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[cs ^ 1], nb, A.totals));
@@ -745,7 +848,9 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
         // never leave copies into the caller's buffer or a walk in flight, whatever the outcome
         cudaStreamSynchronize(h->copy);
         cudaStreamSynchronize(h->side);
+        cudaStreamSynchronize(h->h2d);
         h->drain_dst = nullptr;
+        h->host_src = nullptr;
         if (rc != BZ2B200_OK) (void)cudaGetLastError();
     }
     return rc;
@@ -790,17 +895,16 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
         // (the walk finds ~4 blocks in the time the kernels compress one, so every chunk may be 4x the batch that hides it)
         bool pending = false;
-        uint64_t b0 = 0, chunk = std::min<uint64_t>(h->G, 48);
-        if (!h->w_finished) {
-            rc = walk_launch(h, chunk);
-            if (rc) return rc;
-            pending = true;
-        }
-        while (pending || b0 < h->w_found) {
+        uint64_t b0 = 0, chunk = std::min<uint64_t>(h->G, 12);
+        while (pending || b0 < h->w_found || !h->w_finished || walk_more_input(h)) {
             if (pending) {
                 rc = walk_collect(h);
                 if (rc) return rc;
                 pending = false;
+            }
+            if (h->w_finished && walk_more_input(h)) { // the walk ran out of bytes: bring the next input segment in
+                rc = walk_extend(h);
+                if (rc) return rc;
             }
             if (!h->w_finished) {
                 chunk = std::min<uint64_t>(h->G, chunk * 4);
@@ -846,6 +950,10 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         h->stats.ms_d2h = ev_ms(h->ev[12], h->ev[13]);
     }
     h->drain_dst = nullptr;
+    if (h->host_src && h->seg_copied == h->seg_end.size() && !h->seg_end.empty()) {
+        CK(cudaStreamSynchronize(h->h2d));
+        h->stats.ms_h2d = ev_ms(h->ev[0], h->ev[1]);
+    }
     if (block_crcs && nb) CK(cudaMemcpy(block_crcs, h->all_crc.p, nb * 4, cudaMemcpyDeviceToHost));
     if (block_nbits && nb) CK(cudaMemcpy(block_nbits, h->all_nbits.p, nb * 8, cudaMemcpyDeviceToHost));
     {

@@ -97,10 +97,11 @@ __device__ __forceinline__ Seg lane_seg(const uint8_t *sm, uint32_t cnt)
 }
 
 // ---------------------------------------------------------------- level 0 summaries of the raw input
-__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_tile_seg(const uint8_t *__restrict__ in, uint64_t n_bytes, Seg *__restrict__ seg0, uint64_t n_tiles)
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_tile_seg(const uint8_t *__restrict__ in, uint64_t n_bytes, Seg *__restrict__ seg0, uint64_t tile0,
+                                                                   uint64_t n_tiles)
 {
     __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
-    uint64_t tile = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    uint64_t tile = tile0 + (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
     if (tile >= n_tiles) return;
     uint8_t *sm = sm_all[warp_id()];
     uint64_t lo = tile * RLE_TILE;
