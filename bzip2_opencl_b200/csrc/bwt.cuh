@@ -198,6 +198,168 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ radix: one sweep per digit
+// The same stable LSD pass without the per-tile histogram kernel and the per-block scan: the digit totals of ALL passes come
+// from one counting kernel up front (k_radix_count + k_radix_bases), and each pass resolves "how many keys with my digit sit
+// in earlier tiles of my block" with a decoupled look-back over per-tile status words (tile aggregate / inclusive prefix), as
+// in single-pass prefix scans.  A pass then reads and writes every key exactly once.
+constexpr int RC_TILES = 16;                 // radix tiles per counting CTA
+constexpr int RC_MAXPASS = 5;
+constexpr uint32_t LB_AGG = 1u << 30, LB_PREFIX = 2u << 30, LB_VALUE = (1u << 30) - 1u;
+
+// partial[(b * ctas_per_block + cta) * npass * 256 + p * 256 + d] = keys of the CTA's tiles whose pass-p digit is d (8-bit digits
+// at VAL_BITS + 8p)
+__global__ void __launch_bounds__(RH_THREADS) k_radix_count(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t stride, int npass,
+                                                             uint32_t *__restrict__ partial, int ctas_per_block)
+{
+    __shared__ uint32_t h[RC_MAXPASS][256];
+    const uint32_t b = blockIdx.y;
+    const uint32_t cnt = counts[b];
+    const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
+    if (base0 >= cnt) return;
+    for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += RH_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t *kp = keys + (uint64_t)b * stride;
+    const uint32_t end = min(cnt, base0 + RC_TILES * RS_TILE);
+    for (uint32_t base = base0; base < end; base += RS_TILE) {
+        const uint32_t i0 = base + threadIdx.x * RH_ITEMS;
+        if (i0 >= end) continue;
+        uint64_t kk[RH_ITEMS];
+        if (i0 + RH_ITEMS <= end) {
+            const uint4 *vp = reinterpret_cast<const uint4 *>(kp + i0);
+#pragma unroll
+            for (int v = 0; v < RH_ITEMS / 2; ++v) {
+                const uint4 q = __ldg(vp + v);
+                kk[2 * v] = ((uint64_t)q.y << 32) | q.x;
+                kk[2 * v + 1] = ((uint64_t)q.w << 32) | q.z;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RH_ITEMS; ++j) kk[j] = i0 + j < end ? kp[i0 + j] : ~0ull;
+        }
+        const int nvalid = (int)min((uint32_t)RH_ITEMS, end - i0);
+        for (int p = 0; p < npass; ++p) { // consecutive keys: run-length encode the digit before touching shared memory
+            const int sh = VAL_BITS + 8 * p;
+            uint32_t prev = 0xffffffffu, run = 0;
+#pragma unroll
+            for (int j = 0; j < RH_ITEMS; ++j) {
+                if (j < nvalid) {
+                    const uint32_t d = (uint32_t)(kk[j] >> sh) & 0xffu;
+                    if (d != prev) { if (run) atomicAdd(&h[p][prev], run); prev = d; run = 0; }
+                    ++run;
+                }
+            }
+            if (run) atomicAdd(&h[p][prev], run);
+        }
+    }
+    __syncthreads();
+    uint32_t *out = partial + ((uint64_t)b * ctas_per_block + blockIdx.x) * npass * 256;
+    for (int i = threadIdx.x; i < npass * 256; i += RH_THREADS) out[i] = (&h[0][0])[i];
+}
+
+// digit_base[(p * n_blocks + b) * 256 + d] = keys of block b whose pass-p digit is < d
+__global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ counts, int npass, int ctas_per_block,
+                                                      uint32_t n_blocks, uint32_t *__restrict__ digit_base)
+{
+    __shared__ uint32_t scratch[33];
+    const uint32_t b = blockIdx.x, d = threadIdx.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t nc = (cnt + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
+    for (int p = 0; p < npass; ++p) {
+        uint32_t tot = 0;
+        for (uint32_t c = 0; c < nc; ++c) tot += partial[(((uint64_t)b * ctas_per_block + c) * npass + p) * 256 + d];
+        digit_base[((uint64_t)p * n_blocks + b) * 256 + d] = block_excl_sum(tot, scratch, nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_onesweep(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+                                                                const uint32_t *__restrict__ counts, uint64_t stride, int shift,
+                                                                const uint32_t *__restrict__ digit_base, uint32_t *__restrict__ tile_state,
+                                                                int tiles_per_block, uint32_t *__restrict__ ticket)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    // tiles are taken in ticket order, so the tiles a CTA looks back at are always held by CTAs that are already running
+    if (threadIdx.x == 0) sm.scratch[33] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tk = sm.scratch[33];
+    const uint32_t b = tk / gridDim.x, tile = tk % gridDim.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t base = tile * RS_TILE;
+    if (base >= cnt) return;
+    const uint32_t tcnt = min((uint32_t)RS_TILE, cnt - base);
+    const int lane = lane_id(), w = warp_id();
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    const uint64_t *kp = keys_in + (uint64_t)b * stride + base;
+    uint64_t key[RS_ITEMS];
+    uint16_t rnk[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        key[i] = li < tcnt ? kp[li] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        const bool valid = li < tcnt;
+        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 0xffu) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(FULL, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = sm.warp_hist[w][d];
+            sm.warp_hist[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rnk[i] = (uint16_t)(old + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x; // RS_THREADS == 256: one digit per thread
+        uint32_t sum = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            const uint32_t t = sm.warp_hist[ww][d];
+            sm.warp_hist[ww][d] = sum;
+            sum += t;
+        }
+        volatile uint32_t *st = tile_state + ((uint64_t)b * tiles_per_block) * 256 + d;
+        // publish this tile's count, then add up the tiles in front of it
+        st[(uint64_t)tile * 256] = (tile == 0 ? LB_PREFIX : LB_AGG) | sum;
+        const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr);
+        uint32_t before = 0;
+        if (tile > 0) {
+            for (int t = (int)tile - 1;; --t) {
+                uint32_t v;
+                do { v = st[(uint64_t)t * 256]; } while ((v & ~LB_VALUE) == 0);
+                before += v & LB_VALUE;
+                if (v & LB_PREFIX) break;
+            }
+            st[(uint64_t)tile * 256] = LB_PREFIX | (before + sum);
+        }
+        sm.tile_base[d] = tb;
+        sm.gofs[d] = digit_base[b * 256 + d] + before - tb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        if (li < tcnt) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+            sm.keys[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
+        }
+    }
+    __syncthreads();
+    uint64_t *ko = keys_out + (uint64_t)b * stride;
+    for (uint32_t p = threadIdx.x; p < tcnt; p += RS_THREADS) {
+        const uint64_t k = sm.keys[p];
+        ko[sm.gofs[(uint32_t)(k >> shift) & 0xffu] + p] = k;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ round 0 keys
 // element = (first `nbytes` (<= 4) bytes of rotation i, big-endian) << 20 | i
 __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride, int nbytes,
@@ -242,6 +404,7 @@ struct RoundArgs {
 
 constexpr int GPOS_SHIFT = 2 * VAL_BITS;  // element = group position << 40 | rank of the second half << 20 | rotation index
 constexpr int SA_TILE_BITS = 11;
+static_assert(RS_THREADS == 256, "one thread per digit in k_radix_onesweep");
 static_assert((1 << SA_TILE_BITS) == RG_TILE, "SA tile = regroup tile");
 constexpr int INT_INF = 0x7fffffff;
 
@@ -510,10 +673,12 @@ constexpr int LS_THREADS = BZ_LS_THREADS;
 constexpr int LS_ITEMS = RG_TILE / LS_THREADS; // 4
 constexpr int LS_WARPS = LS_THREADS / 32;
 
+static_assert(LS_THREADS == 256, "one thread per digit in the scan of k_bwt_local");
 struct LocalSmem {
     uint64_t e[RG_TILE];
-    uint32_t warp_hist[LS_WARPS][256];
+    uint32_t warp_hist[2][LS_WARPS][256]; // double buffered: the next pass's counters are cleared while this pass runs
     uint32_t tile_base[256];
+    uint32_t wtot[LS_WARPS];
     uint32_t scratch[34];
     int scr_i[96];
     uint32_t red[2 * LS_WARPS];
@@ -554,9 +719,13 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     const uint32_t chunk = ((c + nwu - 1) / nwu + 31) & ~31u;
     const uint32_t wbase = (uint32_t)w * chunk;
     const uint32_t wcnt = ((uint32_t)w < nwu && wbase < c) ? min(chunk, c - wbase) : 0u;
+    for (uint32_t i = threadIdx.x; i < nwu * 256; i += LS_THREADS) (&sm.warp_hist[0][0][0])[i] = 0;
+    __syncthreads();
+    int hb = 0;
     for (int shift = 0; shift < 32; shift += 8) {
         if (((diff >> shift) & 0xffu) == 0) continue; // uniform over the CTA
         const int sh = shift + VAL_BITS;
+        uint32_t(*hist)[256] = sm.warp_hist[hb];
         uint64_t key[LS_ITEMS];
         uint32_t dg[LS_ITEMS];
         unsigned peers[LS_ITEMS];
@@ -567,11 +736,10 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
             key[i] = q < wcnt ? sm.e[wbase + q] : 0ull;
             dg[i] = q < wcnt ? ((uint32_t)(key[i] >> sh) & 0xffu) : 0xffffffffu;
         }
-        for (uint32_t i = threadIdx.x; i < nwu * 256; i += LS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i)
             if ((uint32_t)i * 32 < wcnt) peers[i] = __match_any_sync(FULL, dg[i]);
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nwu * 256; i += LS_THREADS) (&sm.warp_hist[hb ^ 1][0][0])[i] = 0;
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
             if ((uint32_t)i * 32 < wcnt) { // warp-uniform
@@ -579,8 +747,8 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
                 const int leader = __ffs(peers[i]) - 1;
                 uint32_t old = 0;
                 if (d != 0xffffffffu && lane == leader) {
-                    old = sm.warp_hist[w][d];
-                    sm.warp_hist[w][d] = old + __popc(peers[i]);
+                    old = hist[w][d];
+                    hist[w][d] = old + __popc(peers[i]);
                 }
                 old = __shfl_sync(FULL, old, leader);
                 rnk[i] = (uint16_t)(old + __popc(peers[i] & lt));
@@ -588,29 +756,36 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
             }
         }
         __syncthreads();
+        uint32_t sum = 0, incl;
         {
             const uint32_t d = threadIdx.x;
-            uint32_t sum = 0;
-            if (d < 256) {
 #pragma unroll
-                for (int ww = 0; ww < LS_WARPS; ++ww) {
-                    if ((uint32_t)ww < nwu) {
-                        const uint32_t x = sm.warp_hist[ww][d];
-                        sm.warp_hist[ww][d] = sum;
-                        sum += x;
-                    }
+            for (int ww = 0; ww < LS_WARPS; ++ww) {
+                if ((uint32_t)ww < nwu) {
+                    const uint32_t x = hist[ww][d];
+                    hist[ww][d] = sum;
+                    sum += x;
                 }
             }
-            const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr); // threads >= 256 add 0 behind the digits
-            if (d < 256) sm.tile_base[d] = tb;
+            incl = warp_incl_sum(sum);
+            if (lane == 31) sm.wtot[w] = incl;
+        }
+        __syncthreads();
+        {
+            uint32_t before = 0;
+#pragma unroll
+            for (int ww = 0; ww < LS_WARPS; ++ww)
+                if (ww < w) before += sm.wtot[ww];
+            sm.tile_base[threadIdx.x] = before + incl - sum;
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < LS_ITEMS; ++i) {
             const uint32_t d = dg[i];
-            if ((uint32_t)i * 32 < wcnt && d != 0xffffffffu) sm.e[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
+            if ((uint32_t)i * 32 < wcnt && d != 0xffffffffu) sm.e[sm.tile_base[d] + hist[w][d] + rnk[i]] = key[i];
         }
         __syncthreads();
+        hb ^= 1;
     }
     // ---- regroup inside the region (positions relative to the tile)
     const uint32_t a0 = threadIdx.x * LS_ITEMS;

@@ -19,8 +19,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -43,6 +43,7 @@ struct bz2b200 {
     uint64_t S = 0;       // element stride per block
     int nbits = 0;        // bits needed for a position inside a block
     int key0_bytes = 4;
+    int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
     cudaStream_t stream = 0;
     std::string err;
@@ -51,9 +52,10 @@ struct bz2b200 {
     // per-call (grow only)
     DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     // per-batch, fixed size
-    DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, cnts, scalars,
+    DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
+    int ctasC = 0;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
     uint64_t sel_stride = 0;
     uint64_t *h_pinned = nullptr; // small pinned scratch (64 u64)
@@ -194,6 +196,8 @@ static int upload_constants(bz2b200 *h)
     CK(cudaMemcpyToSymbol(c_crc_pow8, pow8, sizeof(pow8)));
     CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -273,7 +277,9 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->rank, G * S * 4);
     ENSURE(h->mtf, G * S * 2);
     ENSURE(h->hist, G * h->tilesR * 256 * 4);
-    ENSURE(h->digit_base, G * 256 * 4);
+    ENSURE(h->digit_base, G * 256 * 4 * RC_MAXPASS);
+    h->ctasC = (int)((S + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE));
+    ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
     ENSURE(h->scalars, 64 * 8);
     ENSURE(h->lists, G * h->tilesM * 256);
@@ -340,6 +346,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
         if (k >= 1 && k <= 4) h->key0_bytes = k;
     }
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
+    if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     int rc = create_impl(h);
     if (rc != BZ2B200_OK) {
         // keep the message reachable through a static for the failing create
@@ -362,6 +369,10 @@ extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
     return n + n / 3 + blocks * (size_t)(2048 + h->bs / 50) + 4096;
 }
 
+struct Scalars { // layout of h->scalars (u64 each)
+    enum { BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 4 entries */, ROUND = 8 /* kept rotations, max bag, sum of bags */, TICKET = 12 };
+};
+
 static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const uint32_t *counts, int shift, int bits, uint32_t nb, uint32_t max_count,
                        uint64_t total_elems)
 {
@@ -382,6 +393,27 @@ static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const ui
 static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *counts, int total_bits, uint32_t nb, uint32_t max_count, uint64_t total_elems)
 {
     int npass = (total_bits + 7) / 8;
+    if (h->onesweep && total_bits % 8 == 0 && npass <= RC_MAXPASS && max_count > 0) {
+        // digit totals of every pass in one read, then one sweep (read + write of every key) per digit
+        const uint32_t nc = (max_count + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_count + RS_TILE - 1) / RS_TILE;
+        uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
+        KL(KID_k_radix_count, k_radix_count<<<dim3(nc, nb), RH_THREADS, 0, h->stream>>>(k0, counts, h->S, npass, ptr<uint32_t>(h->rc_partial), h->ctasC));
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), counts, npass, h->ctasC, nb, ptr<uint32_t>(h->digit_base)));
+        h->stats.kernel_launches += 2;
+        KBYTES(KID_k_radix_count, total_elems * 8);
+        int cur = 0;
+        for (int p = 0; p < npass; ++p) {
+            cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, h->stream);
+            cudaMemsetAsync(ticket, 0, 4, h->stream);
+            KL(KID_k_radix_onesweep, k_radix_onesweep<<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
+                                         cur ? k1 : k0, cur ? k0 : k1, counts, h->S, VAL_BITS + 8 * p, ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256,
+                                         ptr<uint32_t>(h->hist), h->tilesR, ticket));
+            h->stats.kernel_launches += 1;
+            KBYTES(KID_k_radix_onesweep, total_elems * 16);
+            cur ^= 1;
+        }
+        return cur;
+    }
     int basebits = total_bits / npass, extra = total_bits % npass;
     int shift = VAL_BITS, cur = 0;
     for (int p = 0; p < npass; ++p) {
@@ -393,10 +425,6 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
     }
     return cur;
 }
-
-struct Scalars { // layout of h->scalars (u64 each)
-    enum { BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 4 entries */, ROUND = 8 /* kept rotations, max bag, sum of bags */ };
-};
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 {
