@@ -115,7 +115,7 @@ struct ScatterSmem {
     uint32_t tile_base[256];
     uint32_t gofs[256];
     uint32_t scratch[34];
-    uint64_t keys[RS_TILE];
+    alignas(16) uint64_t keys[RS_TILE];
 };
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__
 // from one counting kernel up front (k_radix_count + k_radix_bases), and each pass resolves "how many keys with my digit sit
 // in earlier tiles of my block" with a decoupled look-back over per-tile status words (tile aggregate / inclusive prefix), as
 // in single-pass prefix scans.  A pass then reads and writes every key exactly once.
+#ifndef BZ_OS_MINB
+#define BZ_OS_MINB 3
+#endif
 constexpr int RC_TILES = 16;                 // radix tiles per counting CTA
 constexpr int RC_MAXPASS = 5;
 constexpr uint32_t LB_AGG = 1u << 30, LB_PREFIX = 2u << 30, LB_VALUE = (1u << 30) - 1u;
@@ -258,8 +261,9 @@ __global__ void __launch_bounds__(RH_THREADS) k_radix_count(const uint64_t *__re
 }
 
 // digit_base[(p * n_blocks + b) * 256 + d] = keys of block b whose pass-p digit is < d
+// (nrep > 1: the totals of pass 0 are valid for nrep passes -- round 0, where every pass's digit is a byte of the same cyclic text)
 __global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ counts, int npass, int ctas_per_block,
-                                                      uint32_t n_blocks, uint32_t *__restrict__ digit_base)
+                                                      uint32_t n_blocks, uint32_t *__restrict__ digit_base, int nrep)
 {
     __shared__ uint32_t scratch[33];
     const uint32_t b = blockIdx.x, d = threadIdx.x;
@@ -268,14 +272,46 @@ __global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict_
     for (int p = 0; p < npass; ++p) {
         uint32_t tot = 0;
         for (uint32_t c = 0; c < nc; ++c) tot += partial[(((uint64_t)b * ctas_per_block + c) * npass + p) * 256 + d];
-        digit_base[((uint64_t)p * n_blocks + b) * 256 + d] = block_excl_sum(tot, scratch, nullptr);
+        const uint32_t ex = block_excl_sum(tot, scratch, nullptr);
+        for (int r = 0; r < (npass == 1 ? nrep : 1); ++r) digit_base[((uint64_t)(p + r) * n_blocks + b) * 256 + d] = ex;
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_onesweep(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+// byte histogram of the RLE1 block (same partial[] layout as k_radix_count with npass = 1)
+__global__ void __launch_bounds__(256) k_bwt_bytehist(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                       uint32_t *__restrict__ partial, int ctas_per_block)
+{
+    __shared__ uint32_t h[8][256];
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = n_arr[b];
+    const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
+    if (base0 >= n) return;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint8_t *T = rle + (uint64_t)b * stride;
+    const uint32_t end = min(n, base0 + RC_TILES * RS_TILE);
+    uint32_t *wh = h[warp_id()];
+    for (uint32_t i = base0 + threadIdx.x * 16; i < end; i += 256 * 16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T + i)); // the slot is padded past n
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (i + j < end) atomicAdd(&wh[(w4[j >> 2] >> (8 * (j & 3))) & 0xffu], 1u);
+    }
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += h[w][threadIdx.x];
+    partial[((uint64_t)b * ctas_per_block + blockIdx.x) * 256 + threadIdx.x] = s;
+}
+
+// FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first 4 bytes of rotation i, big-endian) << 20 | i, from
+// the RLE1 block `text` instead of reading them from keys_in.
+template <bool FROM_TEXT>
+__global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                 const uint32_t *__restrict__ counts, uint64_t stride, int shift,
                                                                 const uint32_t *__restrict__ digit_base, uint32_t *__restrict__ tile_state,
-                                                                int tiles_per_block, uint32_t *__restrict__ ticket)
+                                                                int tiles_per_block, uint32_t *__restrict__ ticket, const uint8_t *__restrict__ text)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
@@ -283,7 +319,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_onesweep(const uint64_t *_
     if (threadIdx.x == 0) sm.scratch[33] = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tk = sm.scratch[33];
-    const uint32_t b = tk / gridDim.x, tile = tk % gridDim.x;
+    // tile-major over the batch: the previous tile of the same block is gridDim.y tickets back, i.e. normally finished already,
+    // so the look-back below is one step deep instead of walking through every tile that is still in flight
+    const uint32_t b = tk % gridDim.y, tile = tk / gridDim.y;
     const uint32_t cnt = counts[b];
     const uint32_t base = tile * RS_TILE;
     if (base >= cnt) return;
@@ -291,13 +329,31 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_onesweep(const uint64_t *_
     const int lane = lane_id(), w = warp_id();
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
-    const uint64_t *kp = keys_in + (uint64_t)b * stride + base;
     uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
+    if (FROM_TEXT) {
+        // stage the tile's bytes (+3 for the last key, wrapping around the block) in the output staging area
+        uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
+        const uint8_t *T = text + (uint64_t)b * stride;
+        for (uint32_t j = threadIdx.x * 16; j < tcnt + 3; j += RS_THREADS * 16) {
+            if (base + j + 16 <= cnt) *reinterpret_cast<uint4 *>(tb + j) = __ldg(reinterpret_cast<const uint4 *>(T + base + j));
+            else
+                for (uint32_t k = j; k < min(j + 16, tcnt + 3); ++k) { uint32_t p = base + k; tb[k] = T[p >= cnt ? (p - cnt) % cnt : p]; }
+        }
+        __syncthreads();
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-        key[i] = li < tcnt ? kp[li] : 0ull;
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            const uint32_t k4 = ((uint32_t)tb[li] << 24) | ((uint32_t)tb[li + 1] << 16) | ((uint32_t)tb[li + 2] << 8) | (uint32_t)tb[li + 3];
+            key[i] = li < tcnt ? (((uint64_t)k4 << VAL_BITS) | (base + li)) : 0ull;
+        }
+    } else {
+        const uint64_t *kp = keys_in + (uint64_t)b * stride + base;
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            key[i] = li < tcnt ? kp[li] : 0ull;
+        }
     }
     __syncthreads();
 #pragma unroll

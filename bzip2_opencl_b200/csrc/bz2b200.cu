@@ -19,8 +19,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -196,8 +196,10 @@ static int upload_constants(bz2b200 *h)
     CK(cudaMemcpyToSymbol(c_crc_pow8, pow8, sizeof(pow8)));
     CK(cudaMemcpyToSymbol(c_crc_lane_shift, lane_shift, sizeof(lane_shift)));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-    CK(cudaFuncSetAttribute(k_radix_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-    CK(cudaFuncSetAttribute(k_radix_onesweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -398,16 +400,16 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
         const uint32_t nc = (max_count + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_count + RS_TILE - 1) / RS_TILE;
         uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
         KL(KID_k_radix_count, k_radix_count<<<dim3(nc, nb), RH_THREADS, 0, h->stream>>>(k0, counts, h->S, npass, ptr<uint32_t>(h->rc_partial), h->ctasC));
-        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), counts, npass, h->ctasC, nb, ptr<uint32_t>(h->digit_base)));
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), counts, npass, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1));
         h->stats.kernel_launches += 2;
         KBYTES(KID_k_radix_count, total_elems * 8);
         int cur = 0;
         for (int p = 0; p < npass; ++p) {
             cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, h->stream);
             cudaMemsetAsync(ticket, 0, 4, h->stream);
-            KL(KID_k_radix_onesweep, k_radix_onesweep<<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
+            KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
                                          cur ? k1 : k0, cur ? k0 : k1, counts, h->S, VAL_BITS + 8 * p, ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256,
-                                         ptr<uint32_t>(h->hist), h->tilesR, ticket));
+                                         ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr));
             h->stats.kernel_launches += 1;
             KBYTES(KID_k_radix_onesweep, total_elems * 16);
             cur ^= 1;
@@ -424,6 +426,32 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
         shift += bits;
     }
     return cur;
+}
+
+// Round 0: all rotations by their first 4 bytes.  Every pass's digit is one byte of the same cyclic text, so one byte histogram
+// gives the digit totals of all four passes, and the first pass builds its elements straight from the text.  Result in kA.
+static void radix_sort_round0(bz2b200 *h, const uint32_t *d_n, uint32_t nb, uint32_t max_n, uint64_t sum_n)
+{
+    const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_n + RS_TILE - 1) / RS_TILE;
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
+    KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, h->stream>>>(ptr<uint8_t>(h->rle), d_n, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
+    KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 4));
+    h->stats.kernel_launches += 2;
+    KBYTES(KID_k_bwt_bytehist, sum_n);
+    uint64_t *kA = ptr<uint64_t>(h->kA), *kB = ptr<uint64_t>(h->kB);
+    for (int p = 0; p < 4; ++p) {
+        cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, h->stream);
+        cudaMemsetAsync(ticket, 0, 4, h->stream);
+        uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
+        if (p == 0)
+            KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
+                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle)));
+        else
+            KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
+                                         (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr));
+        h->stats.kernel_launches += 1;
+        KBYTES(KID_k_radix_onesweep, sum_n * (p == 0 ? 9 : 16));
+    }
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -674,12 +702,15 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         sum_n += h->h_rle_len[b0 + i];
     }
     uint32_t *bag_cnt[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + (size_t)h->G};
-    {
+    int res = 0;
+    if (h->onesweep && h->key0_bytes == 4) {
+        radix_sort_round0(h, d_n, nb, max_n, sum_n);
+    } else {
         dim3 g((max_n + 255) / 256, nb);
         KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint64_t>(h->kA)));
         stt.kernel_launches += 1;
+        res = radix_sort(h, ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_n, 8 * h->key0_bytes, nb, max_n, sum_n);
     }
-    int res = radix_sort(h, ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_n, 8 * h->key0_bytes, nb, max_n, sum_n);
     CK(cudaEventRecord(h->ev[4], st));
 
     RoundArgs A;
