@@ -22,8 +22,20 @@ namespace bz {
 
 // encoded size of a pending run of r (0..254) bytes when it is flushed: writeRun(value, r)
 BZ_HD uint32_t rle_enc_small(uint32_t r) { return r < 4u ? r : 5u; }
+// x = 255 q + r.  Runs are almost always shorter than 255 bytes: keep the 64-bit division off the common path.
+BZ_HD void divmod255(uint64_t x, uint64_t &q, uint32_t &r)
+{
+    if (x < 255ull) { q = 0; r = (uint32_t)x; }
+    else if (x <= 0xffffffffull) { const uint32_t x32 = (uint32_t)x; q = x32 / 255u; r = x32 % 255u; }
+    else { q = x / 255ull; r = (uint32_t)(x % 255ull); }
+}
 // encoded size of a maximal run of `len` equal bytes chunked from its first byte: full 255-chunks (4+1 bytes) + rest
-BZ_HD uint64_t rle_enc_run(uint64_t len) { return 5ull * (len / 255ull) + rle_enc_small((uint32_t)(len % 255ull)); }
+BZ_HD uint64_t rle_enc_run(uint64_t len)
+{
+    uint64_t q; uint32_t r;
+    divmod255(len, q, r);
+    return 5ull * q + rle_enc_small(r);
+}
 
 struct Seg {
     uint64_t len;   // bytes covered (0 = empty segment, the identity)
@@ -131,15 +143,19 @@ BZ_HD RleState state_apply(const Seg &S, RleState s)
         uint64_t tot;
         if (s.run > 0 && s.cur == S.first) tot = s.run + S.len;
         else { s.bl += rle_enc_small(s.run); tot = S.len; }
-        s.bl += 5ull * (tot / 255ull);
-        s.run = (uint32_t)(tot % 255ull);
+        uint64_t q; uint32_t r;
+        divmod255(tot, q, r);
+        s.bl += 5ull * q;
+        s.run = r;
         s.cur = S.first;
     } else {
         uint64_t tot;
         if (s.run > 0 && s.cur == S.first) tot = s.run + S.lead;
         else { s.bl += rle_enc_small(s.run); tot = S.lead; }
-        s.bl += rle_enc_run(tot) + S.mid + 5ull * (S.trail / 255ull);
-        s.run = (uint32_t)(S.trail % 255ull);
+        uint64_t q; uint32_t r;
+        divmod255(S.trail, q, r);
+        s.bl += rle_enc_run(tot) + S.mid + 5ull * q;
+        s.run = r;
         s.cur = S.last;
     }
     return s;

@@ -199,6 +199,42 @@ def test_sharded_block_ranges_reassemble_bit_exactly():
         assert api.stream_from_blocks(mult, parts) == whole
 
 
+def test_host_input_arrives_in_segments():
+    # host input above the first 16 MiB segment: H2D copies, the tree of summaries and the walk are extended segment by
+    # segment while earlier blocks are already being compressed (pinned and pageable memory take different copy schedules);
+    # a run crossing the segment edge and a block boundary near it must not show
+    import torch
+    head = corpus.word_text((16 << 20) - 1000, 61)
+    d = head + bytes(5000) + corpus.mixed_corpus(20 << 20, 4 << 20) + b"z" * 700
+    c = comp(9, 100000, 16)
+    exp = refimpl.compress(d, 9, 100000, threads=os.cpu_count() or 8) if have_ref(100000) else oracle.compress(d, 9, 100000)
+    assert c.compress(d) == exp                                  # pageable host memory
+    t = torch.empty(len(d), dtype=torch.uint8, pin_memory=True)
+    t.numpy()[:] = np.frombuffer(d, dtype=np.uint8)
+    cap = c.max_output_bytes(len(d)) + 64
+    out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    r = c.compress_blocks_ptr(t.data_ptr(), len(d), out.data_ptr(), cap)   # pinned: every copy queued up front
+    bits = out[:(r["nbits"] + 7) // 8].numpy().tobytes()
+    assert api.stream_from_blocks(9, [(bits, r["nbits"], r["crcs"])]) == exp
+    assert (c.scan_blocks(d) == oracle.rle1_blocks(d, 9, 100000)[0]).all()
+
+
+def test_alternative_sort_paths_give_the_same_bits(monkeypatch):
+    # development switches: three-kernel radix passes instead of the single sweep; every group through the global sort
+    d = corpus.mixed_corpus(3 << 20, 1 << 20) + b"ab" * 300000 + bytes(100000)
+    exp = oracle.compress(d, 9, 100000)
+    for env in ({"BZ2B200_ONESWEEP": "0"}, {"BZ2B200_LOCALSORT": "0"}, {"BZ2B200_ONESWEEP": "0", "BZ2B200_LOCALSORT": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = api.Compressor(9, 8, 100000)
+        try:
+            assert c.compress(d) == exp, env
+        finally:
+            c.close()
+            for k in env:
+                monkeypatch.delenv(k)
+
+
 @pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
 def test_config1_64mb_markov_text_vs_real_reference():
     # BASELINE configs[0]: 64 MiB English-like Markov text, -9 (900k), against the reference's own code (oracle/_ref)

@@ -1,3 +1,1 @@
-timeout 900 python tools/gpu_debug.py > gpurun_out/debug30.log 2>&1; echo exit=$?; grep -v "^   -> OK\|^==" gpurun_out/debug30.log | head -40
-python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench29.json 2> gpurun_out/bench29.err; echo bench_exit=$?; python -c "
-import json; d=json.load(open('gpurun_out/bench29.json')); print(d['value'], d['e2e']['value'], d['ms_per_step']); print(list(d['roofline']['kernels_ms_per_step'].items())[:12]); print(d['roofline']['stage_ms_last_step'])"
+timeout 1500 python -m pytest tests -m gpu -x -q -k "segments or alternative or stage_dumps or streaming" > gpurun_out/pytest_gpu8.log 2>&1; echo pytest_exit=$?; tail -5 gpurun_out/pytest_gpu8.log
