@@ -19,8 +19,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_tiles, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_tiles", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -814,15 +814,14 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
                                                                           ptr<uint32_t>(h->dcount), h->tilesM));
         KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
         KL(KID_k_mtf_ranks, k_mtf_ranks<<<gm, MW_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), h->tilesM,
-                                                                   ptr<uint8_t>(h->ranks)));
+                                                                   ptr<uint8_t>(h->ranks), ptr<R2Tile>(h->r2tiles)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
-        KL(KID_k_rle2_tiles, k_rle2_tiles<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<R2Tile>(h->r2tiles), h->tilesR2));
         KL(KID_k_rle2_scan, k_rle2_scan<<<(nb + 127) / 128, 128, 0, st>>>(ptr<R2Tile>(h->r2tiles), d_n, h->tilesR2, nb, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase),
                                                        ptr<uint32_t>(h->present), ptr<uint16_t>(h->mtf), S, ptr<uint32_t>(h->freq), ptr<uint32_t>(h->m_arr),
                                                        ptr<uint32_t>(h->alpha_arr)));
         KL(KID_k_rle2_emit, k_rle2_emit<<<gr, R2_THREADS, 0, st>>>(ptr<uint8_t>(h->ranks), d_n, S, ptr<uint32_t>(h->zin), ptr<uint32_t>(h->obase), h->tilesR2, ptr<uint16_t>(h->mtf), S,
                                                 ptr<uint32_t>(h->freq)));
-        stt.kernel_launches += 6;
+        stt.kernel_launches += 5;
         KBYTES(KID_k_mtf_recency, sum_n);
         KBYTES(KID_k_mtf_ranks, 2 * sum_n);
     }

@@ -8,7 +8,7 @@
 //   k_mtf_ranks       one WARP per tile re-runs MTF from its true start list, 32 symbols per step: ranks come from a
 //                     branch-free dominance count over the step's previous-occurrence times, then the list is rebuilt in
 //                     shared memory (recent symbols first, stable compaction of the rest).
-//   k_rle2_tiles / k_rle2_scan / k_rle2_emit  turn ranks into the RUNA/RUNB/rank+1/EOB symbol stream with an
+//   k_rle2_scan / k_rle2_emit  (tile summaries come from k_mtf_ranks) turn ranks into the RUNA/RUNB/rank+1/EOB symbol stream with an
 //                     exclusive scan of emission counts, and histogram the symbols (mtfSymbolFrequencies).
 #pragma once
 #include "util.cuh"
@@ -28,6 +28,15 @@ __device__ __forceinline__ void build_symbol_map(const uint32_t *present8, uint8
         map[v] = (uint8_t)c;
     }
 }
+
+__device__ __forceinline__ uint32_t run_digits(uint32_t r) { return r ? 31u - __clz(r + 1u) : 0u; } // bijective base-2 digits of r
+
+struct R2Tile {
+    uint32_t lead;   // zeros before the first non-zero rank (== len when all zero)
+    uint32_t trail;  // zeros after the last non-zero rank
+    uint32_t inner;  // symbols emitted by the non-zero ranks after the first one (run digits + the rank symbol)
+    uint32_t allzero;
+};
 
 // ---- pass 1: the tile's distinct symbols ordered by recency (most recent first).  Fully parallel: last occurrence of every
 // symbol with shared-memory atomicMax (only run ends write), then a counting rank over the <= 256 present symbols.
@@ -107,7 +116,7 @@ struct MtfWarpSmem {
 
 __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
                                                               const uint32_t *__restrict__ present, const uint64_t *__restrict__ lists,
-                                                              int tiles_per_block, uint8_t *__restrict__ ranks)
+                                                              int tiles_per_block, uint8_t *__restrict__ ranks, R2Tile *__restrict__ r2tiles)
 {
     __shared__ __align__(16) MtfWarpSmem sm_all[MW_WARPS];
     __shared__ uint8_t map[256];
@@ -147,6 +156,10 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__re
     }
     __syncwarp();
     const unsigned lt = (1u << lane) - 1u, gt = 0xfffffffeu << lane;
+    // zero-run summary of the tile for the RLE2 stage (what k_rle2_scan composes): first / last non-zero rank, symbols
+    // emitted by the non-zero ranks after the first one
+    int firstnz = -1, lastnz = -1;
+    uint32_t inner = 0;
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
         const bool valid = c0 + lane < cnt;
         const uint32_t sym = S.stage[c0 + lane];
@@ -164,6 +177,18 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__re
         }
         const uint32_t rank = __popc(acc & W) + (first ? v : 0u);
         if (valid) S.stage[c0 + lane] = (uint8_t)rank;
+        {
+            const unsigned nz = __ballot_sync(FULL, valid && rank != 0);
+            if (valid && rank != 0) {
+                const unsigned below = nz & lt;
+                const int p = below ? (int)c0 + 31 - __clz((int)below) : lastnz;
+                if (p >= 0) inner += run_digits(c0 + lane - 1 - (uint32_t)p) + 1;
+            }
+            if (nz) {
+                if (firstnz < 0) firstnz = (int)c0 + __ffs((int)nz) - 1;
+                lastnz = (int)c0 + 31 - __clz((int)nz);
+            }
+        }
         // ---- rebuild the list
         const bool is_last = valid && (peers & gt) == 0;
         const unsigned Bl = __ballot_sync(FULL, is_last);
@@ -195,6 +220,15 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__re
     for (int q = 0; q < MTF_TILE / 512; ++q) {
         const uint32_t off = (q * 32 + lane) * 16;
         if (off < cnt) *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(S.stage + off);
+    }
+    inner = __reduce_add_sync(FULL, inner);
+    if (lane == 0) {
+        R2Tile t;
+        t.allzero = lastnz < 0;
+        t.lead = t.allzero ? cnt : (uint32_t)firstnz;
+        t.trail = t.allzero ? cnt : cnt - 1 - (uint32_t)lastnz;
+        t.inner = inner;
+        r2tiles[(uint64_t)b * tiles_per_block + tile] = t;
     }
 }
 
@@ -241,15 +275,9 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_compose(const uint32_t *
 constexpr int R2_THREADS = 256;
 constexpr int R2_ITEMS = 8;
 constexpr int R2_TILE = R2_THREADS * R2_ITEMS; // 2048
+static_assert(R2_TILE == MTF_TILE, "k_mtf_ranks writes the RLE2 tile summaries");
 
-__device__ __forceinline__ uint32_t run_digits(uint32_t r) { return r ? 31u - __clz(r + 1u) : 0u; } // bijective base-2 digits of r
 
-struct R2Tile {
-    uint32_t lead;   // zeros before the first non-zero rank (== len when all zero)
-    uint32_t trail;  // zeros after the last non-zero rank
-    uint32_t inner;  // symbols emitted by the non-zero ranks after the first one (run digits + the rank symbol)
-    uint32_t allzero;
-};
 
 // per-element view of a tile: for a non-zero rank at a, zeros immediately before it inside the tile
 __device__ __forceinline__ void r2_load(const uint8_t *rp, uint32_t a0, uint32_t cnt, uint32_t (&r)[R2_ITEMS], int &lastnz)
@@ -260,54 +288,6 @@ __device__ __forceinline__ void r2_load(const uint8_t *rp, uint32_t a0, uint32_t
         uint32_t a = a0 + i;
         r[i] = a < cnt ? rp[a] : 0u;
         if (a < cnt && r[i]) lastnz = (int)a;
-    }
-}
-
-__global__ void __launch_bounds__(R2_THREADS) k_rle2_tiles(const uint8_t *__restrict__ ranks, const uint32_t *__restrict__ n_arr, uint64_t stride,
-                                                            R2Tile *__restrict__ tiles, int tiles_per_block)
-{
-    __shared__ int s_i[34];
-    __shared__ uint32_t s_red[R2_THREADS / 32];
-    __shared__ int s_first[R2_THREADS / 32];
-    const uint32_t b = blockIdx.y, tile = blockIdx.x;
-    const uint32_t n = n_arr[b];
-    const uint32_t base = tile * R2_TILE;
-    if (base >= n) return;
-    const uint32_t cnt = min((uint32_t)R2_TILE, n - base); // tile-local indexing below
-    const uint8_t *rp = ranks + (uint64_t)b * stride + base;
-    const uint32_t a0 = threadIdx.x * R2_ITEMS;
-    uint32_t r[R2_ITEMS];
-    int lastnz;
-    r2_load(rp, a0, cnt, r, lastnz);
-    int total_last;
-    int prev = block_excl_max(lastnz, s_i, &total_last);
-    // first non-zero of the tile
-    int firstnz = 0x7fffffff;
-#pragma unroll
-    for (int i = R2_ITEMS - 1; i >= 0; --i) if (a0 + i < cnt && r[i]) firstnz = (int)(a0 + i);
-    firstnz = __reduce_min_sync(FULL, firstnz);
-    uint32_t inner = 0;
-    int p = prev;
-#pragma unroll
-    for (int i = 0; i < R2_ITEMS; ++i) {
-        uint32_t a = a0 + i;
-        if (a < cnt && r[i]) {
-            if (p >= 0) inner += run_digits(a - 1 - (uint32_t)p) + 1; // not the first non-zero of the tile
-            p = (int)a;
-        }
-    }
-    inner = __reduce_add_sync(FULL, inner);
-    if (lane_id() == 0) { s_red[warp_id()] = inner; s_first[warp_id()] = firstnz; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0; int f = 0x7fffffff;
-        for (int w = 0; w < R2_THREADS / 32; ++w) { s += s_red[w]; f = min(f, s_first[w]); }
-        R2Tile t;
-        t.allzero = total_last < 0;
-        t.lead = t.allzero ? cnt : (uint32_t)f;
-        t.trail = t.allzero ? cnt : cnt - 1 - (uint32_t)total_last;
-        t.inner = s;
-        tiles[(uint64_t)b * tiles_per_block + tile] = t;
     }
 }
 
