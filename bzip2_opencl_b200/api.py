@@ -13,12 +13,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BZ2B200_LIB") or os.path.join(HERE, "libbz2b200.so")  # BZ2B200_LIB: development variants of the same library
 
-OK, E_BLOCKSIZE, E_PARALLEL, E_ARG, E_CUDA, E_NOMEM, E_OUTPUT, E_STATE = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_BLOCKSIZE, E_PARALLEL, E_ARG, E_CUDA, E_NOMEM, E_OUTPUT, E_STATE, E_FORMAT = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAGE_SELECTORS, STAGE_LENGTHS, STAGE_RANK = range(1, 10)
 
 EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200_max_output_bytes", "bz2b200_scan_blocks",
-           "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
+           "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_decompress_stream", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
            "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times"]
 
 
@@ -58,6 +58,8 @@ def load_library() -> C.CDLL:
     L.bz2b200_compress_blocks.argtypes = [vp, vp, sz, C.c_int, C.c_uint, vp, sz, u64p, C.POINTER(sz), vp, vp, sz, u64p]
     L.bz2b200_compress_stream.restype = C.c_int
     L.bz2b200_compress_stream.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
+    L.bz2b200_decompress_stream.restype = C.c_int
+    L.bz2b200_decompress_stream.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
     L.bz2b200_get_stats.restype = C.c_int
     L.bz2b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bz2b200_stage_dump.restype = C.c_int
@@ -133,6 +135,28 @@ class Compressor:
         n = C.c_size_t(0)
         self._check(self.lib.bz2b200_compress_stream(self.h, _np_ptr(src), len(data), _np_ptr(out), cap, C.byref(n)))
         return out[:n.value].tobytes()
+
+    # ---- decompress side ---------------------------------------------------------------------------
+    def decompress(self, stream, out_capacity: int | None = None) -> bytes:
+        """Whole .bz2 stream -> original bytes (host buffers).  Raises Bz2Error(E_FORMAT, <the reference's exception text>) on a
+        bad stream.  Without out_capacity the buffer grows until the output fits."""
+        src = np.frombuffer(stream, dtype=np.uint8) if len(stream) else np.zeros(1, dtype=np.uint8)
+        cap = out_capacity if out_capacity is not None else max(1 << 16, 6 * len(stream))
+        while True:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            n = C.c_size_t(0)
+            rc = self.lib.bz2b200_decompress_stream(self.h, _np_ptr(src), len(stream), _np_ptr(out), cap, C.byref(n))
+            if rc == E_OUTPUT and out_capacity is None:
+                cap = max(2 * cap, int(n.value) * 2)
+                continue
+            self._check(rc)
+            return out[:n.value].tobytes()
+
+    def decompress_ptr(self, in_ptr: int, nbytes: int, out_ptr: int, out_cap: int) -> int:
+        """Raw-pointer variant (host or device pointers); returns the number of bytes written."""
+        n = C.c_size_t(0)
+        self._check(self.lib.bz2b200_decompress_stream(self.h, C.c_void_p(in_ptr), nbytes, C.c_void_p(out_ptr), out_cap, C.byref(n)))
+        return int(n.value)
 
     def scan_blocks(self, data=None, *, ptr: int = 0, nbytes: int = 0) -> np.ndarray:
         if data is not None:

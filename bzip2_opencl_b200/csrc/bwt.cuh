@@ -305,13 +305,14 @@ __global__ void __launch_bounds__(256) k_bwt_bytehist(const uint8_t *__restrict_
     partial[((uint64_t)b * ctas_per_block + blockIdx.x) * 256 + threadIdx.x] = s;
 }
 
-// FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first 4 bytes of rotation i, big-endian) << 20 | i, from
-// the RLE1 block `text` instead of reading them from keys_in.
+// FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first text_bytes bytes of rotation i, big-endian) << 20 | i,
+// from the block `text` instead of reading them from keys_in.
 template <bool FROM_TEXT>
 __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                 const uint32_t *__restrict__ counts, uint64_t stride, int shift,
                                                                 const uint32_t *__restrict__ digit_base, uint32_t *__restrict__ tile_state,
-                                                                int tiles_per_block, uint32_t *__restrict__ ticket, const uint8_t *__restrict__ text)
+                                                                int tiles_per_block, uint32_t *__restrict__ ticket, const uint8_t *__restrict__ text,
+                                                                int text_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
@@ -344,7 +345,9 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-            const uint32_t k4 = ((uint32_t)tb[li] << 24) | ((uint32_t)tb[li + 1] << 16) | ((uint32_t)tb[li + 2] << 8) | (uint32_t)tb[li + 3];
+            // (text_bytes == 1: the key is the byte itself -- the decompressor's counting sort of the BWT column, dec.cuh)
+            const uint32_t k4 = text_bytes == 1 ? (uint32_t)tb[li]
+                                                : ((uint32_t)tb[li] << 24) | ((uint32_t)tb[li + 1] << 16) | ((uint32_t)tb[li + 2] << 8) | (uint32_t)tb[li + 3];
             key[i] = li < tcnt ? (((uint64_t)k4 << VAL_BITS) | (base + li)) : 0ull;
         }
     } else {

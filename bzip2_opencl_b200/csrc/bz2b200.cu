@@ -16,11 +16,12 @@
 #include "mtf.cuh"
 #include "huff.cuh"
 #include "emit.cuh"
+#include "dec.cuh"
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_dec_scan, KID_k_dec_block, KID_k_dec_bases, KID_k_dec_double, KID_k_dec_chase, KID_k_dec_expand, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_dec_scan", "k_dec_block", "k_dec_counts", "k_dec_double", "k_dec_chase", "k_dec_expand", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -51,6 +52,7 @@ struct bz2b200 {
 
     // per-call (grow only)
     DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
+    DevBuf dec_cand, dec_info, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
@@ -201,6 +203,7 @@ static int upload_constants(bz2b200 *h)
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_dec_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DB_WARPS * sizeof(DecTables))));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -228,6 +231,7 @@ extern "C" const char *bz2b200_strerror(int code)
     case BZ2B200_E_NOMEM: return "out of device memory";
     case BZ2B200_E_OUTPUT: return "output buffer too small";
     case BZ2B200_E_STATE: return "requested block is not resident";
+    case BZ2B200_E_FORMAT: return "not a valid bzip2 stream";
     default: return "unknown error";
     }
 }
@@ -409,7 +413,7 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
             cudaMemsetAsync(ticket, 0, 4, h->stream);
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
                                          cur ? k1 : k0, cur ? k0 : k1, counts, h->S, VAL_BITS + 8 * p, ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256,
-                                         ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr));
+                                         ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0));
             h->stats.kernel_launches += 1;
             KBYTES(KID_k_radix_onesweep, total_elems * 16);
             cur ^= 1;
@@ -445,10 +449,10 @@ static void radix_sort_round0(bz2b200 *h, const uint32_t *d_n, uint32_t nb, uint
         uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
         if (p == 0)
             KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
-                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle)));
+                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), 4));
         else
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
-                                         (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr));
+                                         (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0));
         h->stats.kernel_launches += 1;
         KBYTES(KID_k_radix_onesweep, sum_n * (p == 0 ? 9 : 16));
     }
@@ -1050,6 +1054,210 @@ extern "C" int bz2b200_compress_stream(bz2b200_t *h, const uint8_t *input, size_
     put(24, 0x177245); put(24, 0x385090); put(32, scrc);
     *out_bytes = (size_t)((bitpos + 7) / 8);
     return BZ2B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- decompress
+static const char *dec_err_text(uint32_t e)
+{
+    switch (e) { // the reference's exception messages (BlockDecompressor.hpp, HuffmanStageDecoder.hpp, BitInputStream.hpp)
+    case DEC_E_TABLES: return "block Huffman tables invalid";
+    case DEC_E_BLOCKSIZE: return "BZip2 block exceeds declared block size";
+    case DEC_E_DECODE: return "Error decoding  block";
+    case DEC_E_STARTPTR: return "BZip2 start pointer invalid";
+    case DEC_E_DATA: return "Insufficient data";
+    case DEC_E_RANDOMISED: return "BZip2 randomised blocks not implemented";
+    default: return "BZip2 stream format error";
+    }
+}
+
+static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint8_t *out, size_t out_capacity, size_t *out_bytes)
+{
+    cudaStream_t st = h->stream;
+    h->stats = bz2b200_stats_t{};
+    *out_bytes = 0;
+    auto fail = [&](const char *msg) { h->err = msg; return BZ2B200_E_FORMAT; };
+    // ---- stream header (InputStream::initializeStream, InputStream.hpp:104-128)
+    if (n_in < 4) return fail(n_in == 0 ? "Insufficient data" : "Invalid BZip2 header");
+    uint8_t hdr[4];
+    CK(cudaMemcpy(hdr, input, 4, cudaMemcpyDefault));
+    if (hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h' || hdr[3] < '1' || hdr[3] > '9') return fail("Invalid BZip2 header");
+    const uint32_t stream_bs = (uint32_t)(hdr[3] - '0') * (uint32_t)h->base;
+    if (stream_bs > (uint32_t)h->bs) { h->err = "stream block size exceeds the handle's block size"; return BZ2B200_E_BLOCKSIZE; }
+    const uint32_t max_selectors = (uint32_t)h->base * 9 / 50 + 1; // HUFFMAN_MAXIMUM_SELECTORS, Config.hpp:41
+    // ---- input to the device, zero padded (the bit reader fetches whole 32-bit windows)
+    ENSURE(h->in, n_in + 64);
+    CK(cudaMemsetAsync(ptr<uint8_t>(h->in) + n_in, 0, 64, st));
+    CK(cudaEventRecord(h->ev[0], st));
+    CK(cudaMemcpyAsync(h->in.p, input, n_in, cudaMemcpyDefault, st));
+    CK(cudaEventRecord(h->ev[1], st));
+    const uint8_t *d_in = ptr<uint8_t>(h->in);
+    const uint64_t n_bits = (uint64_t)n_in * 8;
+    const bool out_dev = out && is_device_ptr(out);
+    uint8_t *d_out = out;
+    if (!out_dev) { ENSURE(h->out, out_capacity + 64); d_out = ptr<uint8_t>(h->out); }
+    // ---- block candidates: both magics at every bit position
+    const uint32_t cap_c = (uint32_t)std::min<uint64_t>(n_in / 16 + 1024, 1u << 28);
+    const uint32_t G = h->G;
+    ENSURE(h->dec_cand, (size_t)cap_c * 8);
+    ENSURE(h->dec_info, (size_t)G * sizeof(DecInfo));
+    ENSURE(h->dec_len, (size_t)G * 8);
+    ENSURE(h->dec_off, (size_t)G * 8);
+    ENSURE(h->dec_starts, (size_t)(G + 1) * 8);
+    ENSURE(h->dec_crc, (size_t)G * 4);
+    uint32_t *d_count = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET) + 1;
+    CK(cudaEventRecord(h->ev[10], st));
+    CK(cudaMemsetAsync(d_count, 0, 4, st));
+    KL(KID_k_dec_scan, k_dec_scan<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(d_in, n_in, ptr<uint64_t>(h->dec_cand), cap_c, d_count));
+    h->stats.kernel_launches += 1;
+    uint32_t n_cand = 0;
+    CK(cudaMemcpyAsync(&n_cand, d_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->stats.ms_h2d = ev_ms(h->ev[0], h->ev[1]);
+    if (n_cand > cap_c) return fail("BZip2 stream format error");
+    std::vector<uint64_t> cand(n_cand);
+    if (n_cand) CK(cudaMemcpy(cand.data(), h->dec_cand.p, (size_t)n_cand * 8, cudaMemcpyDeviceToHost));
+    std::sort(cand.begin(), cand.end());
+    if (n_cand) CK(cudaMemcpy(h->dec_cand.p, cand.data(), (size_t)n_cand * 8, cudaMemcpyHostToDevice));
+    // ---- batches of candidates; the chain walk (InputStream::initializeNextBlock, :130-158) accepts a candidate only where the
+    // previous block ended, so a magic that occurs inside coded data is never used
+    std::vector<DecInfo> info(G);
+    std::vector<uint64_t> len(G), off(G), starts(G + 1);
+    std::vector<uint32_t> crc(G);
+    uint64_t expected = 32, total_out = 0;
+    uint32_t stream_crc = 0;
+    bool ended = false;
+    size_t ci = 0;
+    uint64_t nblocks = 0;
+    while (!ended) {
+        // next batch: block candidates at or behind `expected`; stop at an end marker sitting exactly there
+        while (ci < cand.size() && (cand[ci] >> 1) < expected) ++ci;
+        if (ci >= cand.size()) return fail((expected + 48 > n_bits) ? "Insufficient data" : "BZip2 stream format error");
+        if ((cand[ci] >> 1) != expected) return fail("BZip2 stream format error");
+        if (cand[ci] & 1) { ended = true; break; }
+        const size_t c0 = ci;
+        uint32_t nb = 0;
+        while (ci < cand.size() && nb < G && !(cand[ci] & 1)) { ++ci; ++nb; } // block candidates only; an end marker closes the batch
+        // (sorted candidates: block candidates between c0 and ci are contiguous in the list, false positives included)
+        KL(KID_k_dec_block, k_dec_block<<<(nb + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, DB_WARPS * sizeof(DecTables), st>>>(d_in, n_bits, ptr<uint64_t>(h->dec_cand), (uint32_t)c0, nb, stream_bs,
+                                                                  ptr<uint8_t>(h->L), h->S, ptr<uint8_t>(h->sel), h->sel_stride, max_selectors, ptr<DecInfo>(h->dec_info)));
+        uint32_t *d_counts = ptr<uint32_t>(h->cnts);
+        KL(KID_k_dec_bases, k_dec_counts<<<(nb + 255) / 256, 256, 0, st>>>(ptr<DecInfo>(h->dec_info), nb, d_counts));
+        CK(cudaMemcpyAsync(info.data(), h->dec_info.p, (size_t)nb * sizeof(DecInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h->profiling) prof_collect(h);
+        uint32_t max_n = 0;
+        for (uint32_t i = 0; i < nb; ++i) max_n = std::max(max_n, info[i].n);
+        if (max_n) {
+            // inverse BWT: stable counting sort of L by byte value (one single-sweep radix pass), then the pointer chase
+            uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
+            const uint32_t tiles = (max_n + RS_TILE - 1) / RS_TILE;
+            const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
+            KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->L), d_counts, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
+            KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_counts, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1));
+            CK(cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, st));
+            CK(cudaMemsetAsync(ticket, 0, 4, st));
+            KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                         nullptr, ptr<uint64_t>(h->kA), d_counts, h->S, VAL_BITS, ptr<uint32_t>(h->digit_base), ptr<uint32_t>(h->hist), h->tilesR,
+                                         ticket, ptr<uint8_t>(h->L), 1));
+            dim3 gd((max_n + 255) / 256, nb);
+            KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_counts, h->S, 1));
+            KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kB), ptr<uint64_t>(h->kA), d_counts, h->S, 2));
+            KL(KID_k_dec_chase, k_dec_chase<<<(nb + 31) / 32, 32, 0, st>>>(ptr<uint64_t>(h->kA), h->S, ptr<DecInfo>(h->dec_info), nb, ptr<uint8_t>(h->rle), ptr<uint64_t>(h->dec_len)));
+            h->stats.kernel_launches += 6;
+        } else {
+            CK(cudaMemsetAsync(h->dec_len.p, 0, (size_t)nb * 8, st));
+        }
+        h->stats.kernel_launches += 2;
+        CK(cudaMemcpyAsync(len.data(), h->dec_len.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h->profiling) prof_collect(h);
+        // chain walk over the batch
+        uint32_t n_acc = 0;
+        const uint64_t batch_out0 = total_out;
+        bool stop_batch = false;
+        for (uint32_t i = 0; i < nb; ++i) {
+            off[i] = ~0ull;
+            if (stop_batch) continue;
+            const uint64_t pos = cand[c0 + i] >> 1;
+            if (pos < expected) continue;                 // a magic inside the previous block's bits
+            if (pos > expected) { stop_batch = true; continue; } // resolved by the outer loop (end marker or format error)
+            if (info[i].err != DEC_OK) return fail(dec_err_text(info[i].err));
+            if (total_out + len[i] > out_capacity) {
+                *out_bytes = (size_t)(total_out + len[i]);
+                h->err = "output buffer too small";
+                return BZ2B200_E_OUTPUT;
+            }
+            off[i] = total_out;
+            starts[n_acc] = total_out;
+            crc[n_acc] = info[i].crc;
+            ++n_acc;
+            total_out += len[i];
+            expected = info[i].end_bit;
+            ++nblocks;
+        }
+        if (n_acc == 0) return fail("BZip2 stream format error");
+        starts[n_acc] = total_out;
+        CK(cudaMemcpyAsync(h->dec_off.p, off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->dec_starts.p, starts.data(), (size_t)(n_acc + 1) * 8, cudaMemcpyHostToDevice, st));
+        KL(KID_k_dec_expand, k_dec_expand<<<(nb + DX_WARPS - 1) / DX_WARPS, DX_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->rle), h->S, ptr<DecInfo>(h->dec_info), nb, ptr<uint64_t>(h->dec_off), d_out));
+        // block CRCs over the decoded bytes (BlockDecompressor::checkCRC, :99-106)
+        uint64_t max_len = 0;
+        for (uint32_t i = 0; i < n_acc; ++i) max_len = std::max(max_len, starts[i + 1] - starts[i]);
+        CK(cudaMemsetAsync(h->dec_crc.p, 0, (size_t)n_acc * 4, st));
+        if (max_len) {
+            dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), n_acc);
+            KL(KID_k_crc_chunks, k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_out, ptr<uint64_t>(h->dec_starts), 0u, ptr<uint32_t>(h->dec_crc)));
+        }
+        KL(KID_k_crc_finish, k_crc_finish<<<(n_acc + 127) / 128, 128, 0, st>>>(ptr<uint64_t>(h->dec_starts), 0u, n_acc, ptr<uint32_t>(h->dec_crc)));
+        h->stats.kernel_launches += 3;
+        std::vector<uint32_t> got(n_acc);
+        CK(cudaMemcpyAsync(got.data(), h->dec_crc.p, (size_t)n_acc * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h->profiling) prof_collect(h);
+        for (uint32_t i = 0; i < n_acc; ++i) {
+            if (got[i] != crc[i]) return fail("BZip2 block CRC error");
+            stream_crc = ((stream_crc << 1) | (stream_crc >> 31)) ^ crc[i]; // InputStream.hpp:136-137
+        }
+        (void)batch_out0;
+        // candidates of this batch that were not reached stay for the next one
+        size_t back = c0;
+        while (back < ci && (cand[back] >> 1) < expected) ++back;
+        ci = back;
+    }
+    // ---- end of stream: stored combined CRC (InputStream.hpp:146-153)
+    if (expected + 48 + 32 > n_bits) return fail("Insufficient data");
+    uint8_t tail[8] = {0};
+    const uint64_t tb = (expected + 48) >> 3;
+    CK(cudaMemcpy(tail, d_in + tb, std::min<uint64_t>(8, n_in + 64 - tb), cudaMemcpyDeviceToHost));
+    uint64_t w = 0;
+    for (int k = 0; k < 8; ++k) w = (w << 8) | tail[k];
+    const uint32_t stored = (uint32_t)((w << ((expected + 48) & 7)) >> 32);
+    if (stored != stream_crc) return fail("BZip2 stream CRC error");
+    CK(cudaEventRecord(h->ev[11], st));
+    if (!out_dev && total_out) {
+        CK(cudaEventRecord(h->ev[12], st));
+        CK(cudaMemcpyAsync(out, d_out, total_out, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->ev[13], st));
+    }
+    CK(cudaStreamSynchronize(st));
+    h->stats.ms_total = ev_ms(h->ev[10], h->ev[11]);
+    if (!out_dev && total_out) h->stats.ms_d2h = ev_ms(h->ev[12], h->ev[13]);
+    h->stats.n_input = n_in;
+    h->stats.n_blocks = nblocks;
+    *out_bytes = (size_t)total_out;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_decompress_stream(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes)
+{
+    if (!h) return BZ2B200_E_ARG;
+    if ((!input && n_bytes) || !out_bytes || (!out && out_capacity)) { h->err = "bad argument"; return BZ2B200_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    h->err.clear();
+    int rc = decompress_impl(h, input, n_bytes, out, out_capacity, out_bytes);
+    cudaStreamSynchronize(h->stream);
+    if (rc != BZ2B200_OK) (void)cudaGetLastError();
+    return rc;
 }
 
 extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage, void *dst, size_t cap, size_t *len_bytes)

@@ -1,0 +1,410 @@
+// dec.cuh -- the decompress side: InputStream / BlockDecompressor / HuffmanStageDecoder / MoveToFront /
+// BitInputStream of the reference (include/InputStream.hpp:36-159, BlockDecompressor.hpp:37-283, HuffmanStageDecoder.hpp:33-137,
+// MoveToFront.hpp:31-75, BitInputStream.hpp:30-85 -- one sequential CPU loop there) as device kernels:
+//   k_dec_scan        every bit position of the stream is tested for the 48-bit block / end-of-stream magics (blocks are
+//                     independent once their start is known; false positives are dropped by the host's chain check)
+//   k_dec_block       one warp per block: header, symbol map, selectors, delta-coded tables -> canonical decode tables in
+//                     shared memory; Huffman + inverse MTF (list spread over the lanes) + RUNA/RUNB expansion -> BWT column L
+//   (k_bwt_bytehist + k_radix_bases + k_radix_onesweep with 1-byte keys from bwt.cuh: stable counting sort of L = the
+//                     reference's bwtMergedPointers, BlockDecompressor.hpp:244-263)
+//   k_dec_double      two rounds of pointer doubling: every merged pointer carries four bytes and the pointer four steps on
+//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, a word per load
+//   k_dec_rle_len / k_dec_expand   RLE1 decode (:56-84): decoded length of every block, then the bytes at their final offset
+//   (k_crc_chunks / k_crc_finish from rle.cuh verify the block CRCs over the decoded output.)
+#pragma once
+#include "util.cuh"
+#include "bwt.cuh"
+
+namespace bz {
+
+constexpr uint64_t DEC_BLOCK_MAGIC = 0x314159265359ull; // Config.hpp: BLOCK_HEADER_MARKER_1/2
+constexpr uint64_t DEC_END_MAGIC = 0x177245385090ull;   // Config.hpp: STREAM_END_MARKER_1/2
+constexpr int DEC_MAXLEN = 23;                          // HUFFMAN_DECODE_MAXIMUM_CODE_LENGTH (Config.hpp)
+
+enum DecErr { // the reference's exception texts, by number (bz2b200.cu maps them back)
+    DEC_OK = 0, DEC_E_TABLES = 1, DEC_E_BLOCKSIZE = 2, DEC_E_DECODE = 3, DEC_E_STARTPTR = 4, DEC_E_DATA = 5, DEC_E_RANDOMISED = 6
+};
+
+struct DecInfo {
+    uint64_t end_bit;   // first bit after the block's end-of-block symbol
+    uint32_t crc;       // stored block CRC
+    uint32_t orig;      // origPtr
+    uint32_t n;         // BWT block length
+    uint32_t err;       // DecErr
+};
+
+// ---- candidates: every bit position holding one of the two magics
+__global__ void __launch_bounds__(256) k_dec_scan(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t *__restrict__ cand, uint32_t cap,
+                                                   uint32_t *__restrict__ count)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_bytes) return;
+    uint64_t w = 0; // bytes p .. p+6, big-endian, in bits 55..0
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w = (w << 8) | (p + k < n_bytes ? (uint64_t)__ldg(in + p + k) : 0ull);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const uint64_t v = (w >> (8 - o)) & 0xffffffffffffull;
+        if (v == DEC_BLOCK_MAGIC || v == DEC_END_MAGIC) {
+            const uint32_t k = atomicAdd(count, 1u);
+            if (k < cap) cand[k] = ((p * 8 + o) << 1) | (v == DEC_END_MAGIC ? 1ull : 0ull);
+        }
+    }
+}
+
+// ---- sequential MSB-first bit reader (BitInputStream.hpp:30-85).  Every lane of the decoding warp keeps the same copy, so
+// the loads are broadcasts and the control flow stays uniform.  A 64-bit window is refilled 32 bits at a time.
+struct BitReader {
+    const uint8_t *in;
+    uint64_t win;      // next bits, MSB first, left aligned
+    uint32_t have;     // valid bits in win
+    uint32_t ahead;    // the word after the window, loaded one refill early so its latency is off the decode chain
+    uint64_t next;     // byte offset of the word after `ahead` (multiple of 4)
+    uint64_t pos, end; // bit position, total bits
+    bool overrun;
+    __device__ __forceinline__ uint32_t word(uint64_t byte) const
+    {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(in + byte)); // the buffer is 16-byte aligned and zero padded
+        return __byte_perm(w, 0, 0x0123);
+    }
+    __device__ void init(const uint8_t *p, uint64_t bitpos, uint64_t nbits, uint64_t nbytes_padded)
+    {
+        in = p; pos = bitpos; end = nbits; overrun = false;
+        limit_byte = nbytes_padded - 4;
+        const uint64_t b0 = (bitpos >> 3) & ~3ull;
+        win = ((uint64_t)word(b0) << 32) | word(min(b0 + 4, limit_byte));
+        const uint32_t skip = (uint32_t)(bitpos - b0 * 8);
+        win <<= skip;
+        have = 64 - skip;
+        ahead = word(min(b0 + 8, limit_byte));
+        next = b0 + 12;
+    }
+    uint64_t limit_byte; // last word offset that may be loaded
+    __device__ __forceinline__ uint32_t peek(int count) // 1..24 bits without consuming
+    {
+        if (have < 32) {
+            win |= (uint64_t)ahead << (32 - have);
+            have += 32;
+            ahead = word(min(next, limit_byte));
+            next += 4;
+        }
+        return (uint32_t)(win >> (64 - count));
+    }
+    __device__ __forceinline__ void skip(int count)
+    {
+        win <<= count;
+        have -= count;
+        pos += count;
+        if (pos > end) overrun = true;
+    }
+    __device__ __forceinline__ uint32_t bits(int count) // 0..24
+    {
+        if (count == 0) return 0;
+        const uint32_t v = peek(count);
+        skip(count);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t bit() { return bits(1); }
+};
+
+// canonical decode tables of one block (HuffmanStageDecoder.hpp:77-134), in the decoding warp's shared memory
+constexpr int DEC_LUT_BITS = 10;
+struct DecTables {
+    int32_t limit[6][DEC_MAXLEN + 2];
+    int32_t base[6][DEC_MAXLEN + 2];
+    uint16_t perm[6][258];
+    uint16_t lut[6][1 << DEC_LUT_BITS]; // next DEC_LUT_BITS bits -> (symbol << 5) | code length, 0 = code longer than the window
+    uint8_t len[258];
+    uint8_t minlen[6];
+};
+
+constexpr int DB_WARPS = 4; // blocks per CTA of k_dec_block
+
+// One WARP per candidate block.  The bit stream is sequential, so all lanes decode the same symbols redundantly (uniform control
+// flow, broadcast loads); the lanes share the work that has width: the 256-entry move-to-front list lives in one 64-bit register
+// per lane (entries 8*lane .. 8*lane+7, shifted with shuffles), runs are stored 32 bytes at a time.
+__global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__restrict__ in, uint64_t n_bits, const uint64_t *__restrict__ cand, uint32_t c0,
+                                                              uint32_t nb, uint32_t block_size, uint8_t *__restrict__ L, uint64_t stride,
+                                                              uint8_t *__restrict__ sel_scratch, uint64_t sel_stride, uint32_t max_selectors,
+                                                              DecInfo *__restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char dec_smem[];
+    DecTables *s_tab = reinterpret_cast<DecTables *>(dec_smem);
+    const uint32_t bl = blockIdx.x * DB_WARPS + warp_id();
+    if (bl >= nb) return;
+    const int lane = lane_id();
+    DecTables &T = s_tab[warp_id()];
+    DecInfo I;
+    I.end_bit = 0; I.crc = 0; I.orig = 0; I.n = 0; I.err = DEC_OK;
+    BitReader br;
+    br.init(in, (cand[c0 + bl] >> 1) + 48, n_bits, (n_bits >> 3) + 64);
+    // BlockDecompressor ctor (BlockDecompressor.hpp:40-52)
+    I.crc = (br.bits(16) << 16) | br.bits(16);
+    const uint32_t randomised = br.bit();
+    I.orig = br.bits(24);
+    uint8_t *sel = sel_scratch + (uint64_t)bl * sel_stride;
+    // readHuffmanTables (:137-187).  The move-to-front list starts as the used byte values in order (huffmanSymbolMap composed
+    // with the identity list of MoveToFront), so its entries are output bytes directly.
+    uint64_t list = 0; // entries 8*lane .. 8*lane+7, entry k in byte k
+    int nsym = 0;
+    const uint32_t ranges = br.bits(16);
+    for (int i = 0; i < 16; ++i)
+        if (ranges & (0x8000u >> i)) {
+            const uint32_t m = br.bits(16);
+            for (int j = 0; j < 16; ++j)
+                if (m & (0x8000u >> j)) {
+                    if ((nsym >> 3) == lane) list |= (uint64_t)(i * 16 + j) << (8 * (nsym & 7));
+                    ++nsym;
+                }
+        }
+    const int eob = nsym + 1, alpha = nsym + 2;
+    const uint32_t ntab = br.bits(3), nsel = br.bits(15);
+    if (br.overrun) I.err = DEC_E_DATA;
+    else if (ntab < 2 || ntab > 6 || nsel < 1 || nsel > max_selectors) I.err = DEC_E_TABLES;
+    else if (randomised) I.err = DEC_E_RANDOMISED;
+    if (I.err == DEC_OK) {
+        uint32_t tmtf = 0x543210u; // six 4-bit entries
+        for (uint32_t i = 0; i < nsel && !br.overrun; ++i) { // selectors: unary MTF index (:164-167)
+            uint32_t u = 0;
+            while (br.bit()) { if (++u > 5 || br.overrun) break; }
+            if (u > 5) { I.err = DEC_E_TABLES; break; } // (the reference indexes past its table list here; a 2..6-table stream never does)
+            const uint32_t v = (tmtf >> (4 * u)) & 15u;
+            const uint32_t lowmask = (1u << (4 * u)) - 1u;
+            tmtf = (tmtf & ~((lowmask << 4) | 15u)) | ((tmtf & lowmask) << 4) | v;
+            if (lane == 0) sel[i] = (uint8_t)v;
+        }
+    }
+    if (I.err == DEC_OK) {
+        for (uint32_t t = 0; t < ntab && I.err == DEC_OK; ++t) { // delta-coded lengths (:169-183), then createHuffmanDecodingTables
+            int cur = (int)br.bits(5);
+            int mn = DEC_MAXLEN, mx = 0;
+            for (int j = 0; j <= eob; ++j) {
+                while (br.bit()) { cur += br.bit() ? -1 : 1; if (br.overrun) break; }
+                if (cur < 1 || cur > DEC_MAXLEN) { I.err = DEC_E_TABLES; break; } // outside what the decode tables can hold
+                if (lane == 0) T.len[j] = (uint8_t)cur;
+                mn = min(mn, cur); mx = max(mx, cur);
+            }
+            if (I.err != DEC_OK) break;
+            __syncwarp();
+            if (lane == 0) {
+                int32_t *bases = T.base[t], *limits = T.limit[t];
+                for (int i = 0; i < DEC_MAXLEN + 2; ++i) { bases[i] = 0; limits[i] = -1; }
+                for (int i = 0; i < alpha; ++i) bases[T.len[i] + 1]++;
+                for (int i = 1; i < DEC_MAXLEN + 2; ++i) bases[i] += bases[i - 1];
+                int code = 0;
+                for (int i = mn; i <= mx; ++i) {
+                    const int b0 = code;
+                    code += bases[i + 1] - bases[i];
+                    bases[i] = b0 - bases[i];
+                    limits[i] = code - 1;
+                    code <<= 1;
+                }
+                int ci = 0;
+                for (int bits = mn; bits <= mx; ++bits)
+                    for (int s = 0; s < alpha; ++s)
+                        if (T.len[s] == bits) T.perm[t][ci++] = (uint16_t)s;
+                T.minlen[t] = (uint8_t)mn;
+            }
+            __syncwarp();
+            // lookup window: every symbol with a code of at most DEC_LUT_BITS bits fills its 2^(window - length) slots
+            for (int k = lane; k < (1 << DEC_LUT_BITS); k += 32) T.lut[t][k] = 0;
+            __syncwarp();
+            {
+                const int32_t *bases = T.base[t], *limits = T.limit[t];
+                for (int ci = lane; ci < alpha; ci += 32) { // canonical order: ci-th code
+                    const int sym = T.perm[t][ci];
+                    const int l = T.len[sym];
+                    if (l <= DEC_LUT_BITS) {
+                        const int code = ci + bases[l]; // inverse of  symbol = perm[code - base[len]]
+                        const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
+                        for (int k = 0; k < cnt; ++k) T.lut[t][lo + k] = (uint16_t)((sym << 5) | l);
+                    }
+                    (void)limits;
+                }
+            }
+            __syncwarp();
+        }
+        if (br.overrun && I.err == DEC_OK) I.err = DEC_E_DATA;
+    }
+    // decodeHuffmanData (:189-241): Huffman symbol -> RUNA/RUNB run or inverse MTF -> L
+    uint32_t n = 0;
+    if (I.err == DEC_OK) {
+        __syncwarp();
+        uint8_t *out = L + (uint64_t)bl * stride;
+        uint32_t group = 0, in_group = 0, tbl = sel[0];
+        uint32_t repeat = 0, inc = 1;
+        uint32_t front = (uint32_t)__shfl_sync(FULL, (uint32_t)list, 0) & 0xffu; // byte value at the head of the list
+        uint64_t acc = 0; // lane 0: bytes waiting for an aligned 8-byte store
+        for (;;) {
+            if (in_group == 50) { // HuffmanStageDecoder::nextSymbol group switch (:51-60)
+                in_group = 0;
+                if (++group == nsel) { I.err = DEC_E_DECODE; break; }
+                tbl = sel[group];
+            }
+            ++in_group;
+            int sym = -1;
+            const uint32_t e = T.lut[tbl][br.peek(DEC_LUT_BITS)];
+            if (e) { sym = (int)(e >> 5); br.skip((int)(e & 31u)); }
+            else { // long code: the reference's limit search (HuffmanStageDecoder.hpp:62-74)
+                int clen = T.minlen[tbl];
+                int32_t code = (int32_t)br.bits(clen);
+                while (clen <= DEC_MAXLEN) {
+                    if (code <= T.limit[tbl][clen]) { sym = T.perm[tbl][code - T.base[tbl][clen]]; break; }
+                    code = (code << 1) | (int32_t)br.bit();
+                    ++clen;
+                }
+            }
+            if (sym < 0 || br.overrun) { I.err = br.overrun ? DEC_E_DATA : DEC_E_DECODE; break; }
+            if (sym == 0) { repeat += inc; inc <<= 1; if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; } continue; }
+            if (sym == 1) { repeat += inc << 1; inc <<= 1; if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; } continue; }
+            if (repeat > 0) {
+                if (n + repeat > block_size) { I.err = DEC_E_BLOCKSIZE; break; }
+                // flush lane 0's partial word, then the run
+                if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) out[k] = (uint8_t)(acc >> (8 * (k & 7)));
+                for (uint32_t k = lane; k < repeat; k += 32) out[n + k] = (uint8_t)front;
+                n += repeat;
+                repeat = 0; inc = 1;
+                acc = 0;
+                if (n & 7u) { // re-load the bytes of the current 8-byte word that are already final
+                    __syncwarp();
+                    if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) acc |= (uint64_t)out[k] << (8 * (k & 7));
+                }
+            }
+            if (sym == eob) break;
+            if (n >= block_size) { I.err = DEC_E_BLOCKSIZE; break; }
+            // MoveToFront::indexToFront (MoveToFront.hpp:62-72) on the distributed list
+            const uint32_t idx = (uint32_t)sym - 1;
+            const int src = (int)(idx >> 3), bi = (int)(idx & 7);
+            const uint64_t srcw = shfl_u64(list, src);
+            const uint32_t v = (uint32_t)(srcw >> (8 * bi)) & 0xffu;
+            const uint64_t up = shfl_up_u64(list, 1); // previous lane's entries
+            if (lane < src) list = (list << 8) | (lane == 0 ? (uint64_t)v : (up >> 56));
+            else if (lane == src) {
+                const uint64_t lowmask = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull); // entries 0..bi of this lane change
+                const uint64_t shifted = (list << 8) | (lane == 0 ? (uint64_t)v : (up >> 56));
+                list = (list & ~lowmask) | (shifted & lowmask);
+            }
+            front = v;
+            if (lane == 0) {
+                acc |= (uint64_t)v << (8 * (n & 7));
+                if ((n & 7) == 7) { *reinterpret_cast<uint64_t *>(out + (n & ~7u)) = acc; acc = 0; }
+            }
+            ++n;
+        }
+        if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) out[k] = (uint8_t)(acc >> (8 * (k & 7)));
+    }
+    if (I.err == DEC_OK && I.orig >= n) I.err = DEC_E_STARTPTR; // initialiseInverseBWT (:244-248)
+    I.n = I.err == DEC_OK ? n : 0u;
+    I.end_bit = br.pos;
+    if (lane == 0) info[bl] = I;
+}
+
+// counts[bl] = block length (0 for a failed block)
+__global__ void __launch_bounds__(256) k_dec_counts(const DecInfo *__restrict__ info, uint32_t nb, uint32_t *__restrict__ counts)
+{
+    const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bl < nb) counts[bl] = info[bl].n;
+}
+
+// Merged pointers (BlockDecompressor.hpp:256-262) = the sort elements of bwt.cuh after a stable sort of L by byte value:
+// element j = (L[i] << 20) | i for the j-th smallest byte.  The chase (:265-282) is one dependent load per byte; two rounds of
+// pointer doubling (fully parallel gathers) make every element carry FOUR bytes and the pointer four steps on:
+//   bits 0..19 pointer, bits 20..27 / 28..35 / 36..43 / 44..51 the bytes at hops 0..3.
+__global__ void __launch_bounds__(256) k_dec_double(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, const uint32_t *__restrict__ counts,
+                                                     uint64_t stride, int have_bytes)
+{
+    const uint32_t bl = blockIdx.y;
+    const uint32_t n = counts[bl];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t *m = src + (uint64_t)bl * stride;
+    const uint64_t x = m[j];
+    const uint64_t y = m[x & VAL_MASK];
+    const uint64_t mask = (1ull << (8 * have_bytes)) - 1ull;
+    dst[(uint64_t)bl * stride + j] = (y & VAL_MASK) | (((x >> VAL_BITS) & mask) << VAL_BITS) | (((y >> VAL_BITS) & mask) << (VAL_BITS + 8 * have_bytes));
+}
+
+// one thread per block follows the four-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
+// (BlockDecompressor::read, :56-84) runs along to give the decoded length (its cost hides behind the dependent loads)
+__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ merged4, uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb,
+                                                   uint8_t *__restrict__ rle, uint64_t *__restrict__ out_len)
+{
+    const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bl >= nb) return;
+    const uint32_t n = info[bl].n;
+    if (n == 0) { out_len[bl] = 0; return; }
+    const uint64_t *m = merged4 + (uint64_t)bl * stride;
+    uint8_t *out = rle + (uint64_t)bl * stride;
+    uint64_t cur = m[info[bl].orig];
+    uint64_t o = 0;
+    int last = -1;
+    uint32_t acc = 0;
+    bool count_next = false;
+    auto step = [&](uint32_t v) {
+        if (count_next) { o += v; count_next = false; acc = 0; }
+        else if ((int)v != last) { last = (int)v; acc = 1; ++o; }
+        else { ++o; if (++acc == 4) count_next = true; }
+    };
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t w = (uint32_t)(cur >> VAL_BITS);
+        cur = m[cur & VAL_MASK];
+        *reinterpret_cast<uint32_t *>(out + i) = w;
+        step(w & 0xffu); step((w >> 8) & 0xffu); step((w >> 16) & 0xffu); step(w >> 24);
+    }
+    for (uint32_t k = 0; i < n; ++i, ++k) {
+        const uint32_t v = (uint32_t)(cur >> (VAL_BITS + 8 * k)) & 0xffu;
+        out[i] = (uint8_t)v;
+        step(v);
+    }
+    out_len[bl] = o;
+}
+
+// RLE1 decode (BlockDecompressor::read, :56-84) of one block at its final offset, one WARP per block: 1 KiB of coded bytes at a
+// time is loaded by the warp, a ballot marks where the value changes, and every maximal piece of equal bytes between two
+// "parse events" is written by all lanes together.  The parse itself (which byte is a count?) stays sequential but runs on
+// the per-chunk change mask, not on single bytes.
+constexpr int DX_WARPS = 4;
+constexpr int DX_CHUNK = 1024;
+
+__global__ void __launch_bounds__(DX_WARPS * 32) k_dec_expand(const uint8_t *__restrict__ rle, uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb,
+                                                               const uint64_t *__restrict__ out_off, uint8_t *__restrict__ out)
+{
+    __shared__ __align__(16) uint8_t s_buf[DX_WARPS][DX_CHUNK];
+    const uint32_t bl = blockIdx.x * DX_WARPS + warp_id();
+    if (bl >= nb || out_off[bl] == ~0ull) return;
+    const int lane = lane_id();
+    const uint32_t n = info[bl].n;
+    const uint8_t *src = rle + (uint64_t)bl * stride;
+    uint8_t *dst = out + out_off[bl];
+    uint8_t *buf = s_buf[warp_id()];
+    uint64_t o = 0;
+    int last = -1;
+    uint32_t acc = 0;
+    bool count_next = false;
+    for (uint32_t c0 = 0; c0 < n; c0 += DX_CHUNK) {
+        const uint32_t cn = min((uint32_t)DX_CHUNK, n - c0);
+        __syncwarp();
+        for (uint32_t k = lane * 16; k < cn; k += 32 * 16) *reinterpret_cast<uint4 *>(buf + k) = __ldg(reinterpret_cast<const uint4 *>(src + c0 + k)); // slot padded
+        __syncwarp();
+        // sequential parse over the chunk in pieces: a piece = consecutive literal bytes of one value (at most until acc hits 4)
+        uint32_t i = 0;
+        while (i < cn) {
+            const uint32_t v = buf[i];
+            if (count_next) { // v is a repeat count: v more copies of `last`
+                for (uint32_t k = lane; k < v; k += 32) dst[o + k] = (uint8_t)last;
+                o += v; count_next = false; acc = 0; ++i;
+                continue;
+            }
+            if ((int)v != last) { last = (int)v; acc = 0; }
+            // literals of value v from i on: up to (4 - acc) of them, inside the chunk
+            uint32_t want = 4 - acc, got = 0;
+            while (got < want && i + got < cn && buf[i + got] == v) ++got;
+            if (lane < (int)got) dst[o + lane] = (uint8_t)v;
+            o += got; i += got; acc += got;
+            if (acc == 4) count_next = true;
+        }
+    }
+}
+
+} // namespace bz

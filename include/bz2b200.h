@@ -37,7 +37,8 @@ enum {
     BZ2B200_E_CUDA = -4,      /* no device / CUDA runtime error (text in bz2b200_last_error) */
     BZ2B200_E_NOMEM = -5,     /* device or pinned allocation failed */
     BZ2B200_E_OUTPUT = -6,    /* out_capacity / block_capacity too small; nothing useful was written */
-    BZ2B200_E_STATE = -7      /* stage dump asked for a block that is not in the last batch */
+    BZ2B200_E_STATE = -7,     /* stage dump asked for a block that is not in the last batch */
+    BZ2B200_E_FORMAT = -8     /* decompress: the input is not a valid stream; bz2b200_last_error holds the reference's exception text */
 };
 
 /* Number of CUDA devices visible (0 when there is none or the driver is unusable). */
@@ -101,6 +102,19 @@ int bz2b200_compress_blocks(bz2b200_t *handle, const uint8_t *input, size_t n_by
  */
 int bz2b200_compress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity,
                             size_t *out_bytes);
+
+/*
+ * The decompress side: one whole .bz2 stream in, the original bytes out.  == InputStream ctor + read* until -1
+ * (InputStream.hpp:36-159) with everything it drives: BlockDecompressor (BlockDecompressor.hpp:37-283), HuffmanStageDecoder
+ * (HuffmanStageDecoder.hpp:33-137), MoveToFront::indexToFront (MoveToFront.hpp:62-72), BitInputStream (BitInputStream.hpp:30-85).
+ * Blocks are found by scanning for the 48-bit block magic at every bit position and decoded independently on the device; block CRCs
+ * and the stream CRC are verified.  The stream's block size (header digit x base_block_size of the handle) must not exceed the
+ * handle's.  Errors: BZ2B200_E_FORMAT with the reference's exception text in bz2b200_last_error ("Invalid BZip2 header",
+ * "BZip2 stream format error", "BZip2 stream CRC error", "BZip2 block CRC error", "block Huffman tables invalid",
+ * "BZip2 block exceeds declared block size", "Error decoding  block", "BZip2 start pointer invalid", "Insufficient data");
+ * BZ2B200_E_OUTPUT when out_capacity is too small (*out_bytes = bytes decoded so far + the block that did not fit).
+ */
+int bz2b200_decompress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes);
 
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the LAST compress call. */
 typedef struct {
