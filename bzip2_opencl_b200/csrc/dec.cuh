@@ -7,9 +7,12 @@
 //                     shared memory; Huffman + inverse MTF (list spread over the lanes) + RUNA/RUNB expansion -> BWT column L
 //   (k_bwt_bytehist + k_radix_bases + k_radix_onesweep with 1-byte keys from bwt.cuh: stable counting sort of L = the
 //                     reference's bwtMergedPointers, BlockDecompressor.hpp:244-263)
-//   k_dec_double      two rounds of pointer doubling: every merged pointer carries four bytes and the pointer four steps on
-//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, a word per load
-//   k_dec_rle_len / k_dec_expand   RLE1 decode (:56-84): decoded length of every block, then the bytes at their final offset
+//   k_dec_double / k_dec_double8   three rounds of pointer doubling: every merged pointer carries eight bytes and the pointer
+//                     eight steps on
+//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, 8 bytes per dependent load,
+//                     and the RLE1 decoded length on the way
+//   k_dec_expand      RLE1 decode (:56-84) at the final offset: literal stretches copied by whole warps, only the four-equal
+//                     triggers parsed in order
 //   (k_crc_chunks / k_crc_finish from rle.cuh verify the block CRCs over the decoded output.)
 #pragma once
 #include "util.cuh"
@@ -324,18 +327,34 @@ __global__ void __launch_bounds__(256) k_dec_double(const uint64_t *__restrict__
     dst[(uint64_t)bl * stride + j] = (y & VAL_MASK) | (((x >> VAL_BITS) & mask) << VAL_BITS) | (((y >> VAL_BITS) & mask) << (VAL_BITS + 8 * have_bytes));
 }
 
-// one thread per block follows the four-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
+// third doubling round: eight bytes per element, split over two arrays (bytes8[j], ptr8[j]) that the chase loads side by side
+__global__ void __launch_bounds__(256) k_dec_double8(const uint64_t *__restrict__ src4, uint64_t *__restrict__ bytes8, uint32_t *__restrict__ ptr8,
+                                                      const uint32_t *__restrict__ counts, uint64_t stride)
+{
+    const uint32_t bl = blockIdx.y;
+    const uint32_t n = counts[bl];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t *m = src4 + (uint64_t)bl * stride;
+    const uint64_t x = m[j];
+    const uint64_t y = m[x & VAL_MASK];
+    bytes8[(uint64_t)bl * stride + j] = ((x >> VAL_BITS) & 0xffffffffull) | ((y >> VAL_BITS) << 32);
+    ptr8[(uint64_t)bl * stride + j] = (uint32_t)(y & VAL_MASK);
+}
+
+// one thread per block follows the eight-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
 // (BlockDecompressor::read, :56-84) runs along to give the decoded length (its cost hides behind the dependent loads)
-__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ merged4, uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb,
-                                                   uint8_t *__restrict__ rle, uint64_t *__restrict__ out_len)
+__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ bytes8, const uint32_t *__restrict__ ptr8, uint64_t stride,
+                                                   const DecInfo *__restrict__ info, uint32_t nb, uint8_t *__restrict__ rle, uint64_t *__restrict__ out_len)
 {
     const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
     if (bl >= nb) return;
     const uint32_t n = info[bl].n;
     if (n == 0) { out_len[bl] = 0; return; }
-    const uint64_t *m = merged4 + (uint64_t)bl * stride;
+    const uint64_t *mb = bytes8 + (uint64_t)bl * stride;
+    const uint32_t *mp = ptr8 + (uint64_t)bl * stride;
     uint8_t *out = rle + (uint64_t)bl * stride;
-    uint64_t cur = m[info[bl].orig];
+    uint32_t p = info[bl].orig;
     uint64_t o = 0;
     int last = -1;
     uint32_t acc = 0;
@@ -346,63 +365,93 @@ __global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ m
         else { ++o; if (++acc == 4) count_next = true; }
     };
     uint32_t i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t w = (uint32_t)(cur >> VAL_BITS);
-        cur = m[cur & VAL_MASK];
-        *reinterpret_cast<uint32_t *>(out + i) = w;
-        step(w & 0xffu); step((w >> 8) & 0xffu); step((w >> 16) & 0xffu); step(w >> 24);
+    for (; i + 8 <= n; i += 8) {
+        const uint64_t w = mb[p];
+        p = mp[p];
+        *reinterpret_cast<uint64_t *>(out + i) = w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) step((uint32_t)(w >> (8 * k)) & 0xffu);
     }
-    for (uint32_t k = 0; i < n; ++i, ++k) {
-        const uint32_t v = (uint32_t)(cur >> (VAL_BITS + 8 * k)) & 0xffu;
-        out[i] = (uint8_t)v;
-        step(v);
+    if (i < n) {
+        const uint64_t w = mb[p];
+        for (uint32_t k = 0; i < n; ++i, ++k) {
+            const uint32_t v = (uint32_t)(w >> (8 * k)) & 0xffu;
+            out[i] = (uint8_t)v;
+            step(v);
+        }
     }
     out_len[bl] = o;
 }
 
-// RLE1 decode (BlockDecompressor::read, :56-84) of one block at its final offset, one WARP per block: 1 KiB of coded bytes at a
-// time is loaded by the warp, a ballot marks where the value changes, and every maximal piece of equal bytes between two
-// "parse events" is written by all lanes together.  The parse itself (which byte is a count?) stays sequential but runs on
-// the per-chunk change mask, not on single bytes.
+// RLE1 decode (BlockDecompressor::read, :56-84) of one block at its final offset, one WARP per block.  A count byte exists only
+// behind four equal literals, so the warp works on 1 KiB chunks: every lane marks, for its 32 bytes, where a byte completes three
+// consecutive "equal to its predecessor" steps (a possible fourth literal); between such triggers everything is a literal and is
+// copied by all lanes at once, and only the triggers themselves are parsed in order.
 constexpr int DX_WARPS = 4;
 constexpr int DX_CHUNK = 1024;
 
 __global__ void __launch_bounds__(DX_WARPS * 32) k_dec_expand(const uint8_t *__restrict__ rle, uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb,
                                                                const uint64_t *__restrict__ out_off, uint8_t *__restrict__ out)
 {
-    __shared__ __align__(16) uint8_t s_buf[DX_WARPS][DX_CHUNK];
+    __shared__ __align__(16) uint8_t s_buf[DX_WARPS][DX_CHUNK + 16];
     const uint32_t bl = blockIdx.x * DX_WARPS + warp_id();
     if (bl >= nb || out_off[bl] == ~0ull) return;
     const int lane = lane_id();
     const uint32_t n = info[bl].n;
     const uint8_t *src = rle + (uint64_t)bl * stride;
     uint8_t *dst = out + out_off[bl];
-    uint8_t *buf = s_buf[warp_id()];
+    uint8_t *buf = s_buf[warp_id()] + 16; // buf[-3..-1] = last three bytes of the previous chunk
     uint64_t o = 0;
-    int last = -1;
-    uint32_t acc = 0;
-    bool count_next = false;
+    bool count_next = false;   // the next byte is a repeat count for `runval`
+    uint32_t runval = 0;
+    uint32_t lit_start = 0;    // absolute index of the first byte that may belong to the current run of literals
     for (uint32_t c0 = 0; c0 < n; c0 += DX_CHUNK) {
         const uint32_t cn = min((uint32_t)DX_CHUNK, n - c0);
         __syncwarp();
+        if (c0 > 0 && lane < 3) buf[-3 + lane] = buf[DX_CHUNK - 3 + lane];
+        __syncwarp();
         for (uint32_t k = lane * 16; k < cn; k += 32 * 16) *reinterpret_cast<uint4 *>(buf + k) = __ldg(reinterpret_cast<const uint4 *>(src + c0 + k)); // slot padded
         __syncwarp();
-        // sequential parse over the chunk in pieces: a piece = consecutive literal bytes of one value (at most until acc hits 4)
-        uint32_t i = 0;
+        // trig bit j of lane l: bytes (32l+j-3 .. 32l+j) of the chunk are equal (indices relative to the chunk, -3.. allowed)
+        uint32_t trig = 0;
+        for (int j = 0; j < 32; ++j) {
+            const int q = lane * 32 + j;
+            if ((uint32_t)q < cn && (int64_t)c0 + q - 3 >= 0) {
+                const uint8_t v = buf[q];
+                if (buf[q - 1] == v && buf[q - 2] == v && buf[q - 3] == v) trig |= 1u << j;
+            }
+        }
+        uint32_t i = 0; // next chunk byte to handle
         while (i < cn) {
-            const uint32_t v = buf[i];
-            if (count_next) { // v is a repeat count: v more copies of `last`
-                for (uint32_t k = lane; k < v; k += 32) dst[o + k] = (uint8_t)last;
-                o += v; count_next = false; acc = 0; ++i;
+            if (count_next) { // buf[i] more copies of the run value
+                const uint32_t rep = buf[i];
+                for (uint32_t k = lane; k < rep; k += 32) dst[o + k] = (uint8_t)runval;
+                o += rep;
+                count_next = false;
+                ++i;
+                lit_start = c0 + i;
                 continue;
             }
-            if ((int)v != last) { last = (int)v; acc = 0; }
-            // literals of value v from i on: up to (4 - acc) of them, inside the chunk
-            uint32_t want = 4 - acc, got = 0;
-            while (got < want && i + got < cn && buf[i + got] == v) ++got;
-            if (lane < (int)got) dst[o + lane] = (uint8_t)v;
-            o += got; i += got; acc += got;
-            if (acc == 4) count_next = true;
+            // first trigger at or after max(i, lit_start + 3): its four bytes are literals of the current parse
+            const uint32_t from = max(c0 + i, lit_start + 3) - c0; // chunk-relative, may be >= cn
+            uint32_t e = cn; // chunk-relative position of the trigger, cn = none in this chunk
+            {
+                const int fl = (int)(from >> 5);
+                uint32_t m = trig;
+                if (lane < fl) m = 0;
+                else if (lane == fl) m &= ~0u << (from & 31);
+                const unsigned any = __ballot_sync(FULL, m != 0 && from < cn);
+                if (any) {
+                    const int l = __ffs((int)any) - 1;
+                    const uint32_t mm = __shfl_sync(FULL, m, l);
+                    e = (uint32_t)l * 32 + (uint32_t)(__ffs((int)mm) - 1);
+                }
+            }
+            const uint32_t upto = e < cn ? e + 1 : cn; // literals [i, upto)
+            for (uint32_t k = i + lane; k < upto; k += 32) dst[o + (k - i)] = buf[k];
+            o += upto - i;
+            if (e < cn) { count_next = true; runval = buf[e]; }
+            i = upto;
         }
     }
 }

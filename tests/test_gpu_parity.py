@@ -305,3 +305,85 @@ def test_cpp_facade_end_to_end(tmp_path):
         dst = tmp_path / f"out_{mult}_{par}.bz2"
         subprocess.check_call([exe, str(src), str(dst), str(mult), str(par)] + (["bulk"] if bulk else []), env=env)
         assert dst.read_bytes() == oracle.compress(d, mult, 100000)
+
+
+# ---------------------------------------------------------------------------------------------------- decompress side (8f N1)
+def test_decompress_matches_libbzip2_and_reference_decoder():
+    # streams made by the CUDA compressor, by libbzip2 (17-bit codes, its own tables) and of every block size
+    c = comp(9, 100000, 16)
+    cases = [b"", b"x", corpus.g_runs(), corpus.word_text(2_500_000, 71), corpus.rand_bytes(1_000_003, 72), bytes(3_000_000),
+             b"ab" * 500_000 + b"x", corpus.mixed_corpus(5 << 20, 1 << 20)]
+    for d in cases:
+        for s in (c.compress(d), bz2.compress(d, 9), bz2.compress(d, 1)):
+            assert c.decompress(s) == d
+            assert c.decompress(s, out_capacity=len(d)) == d      # exact capacity
+    d = corpus.word_text(3_000_000, 73)
+    for mult in (1, 4, 9):
+        s = comp(mult, 100000, 16).compress(d)
+        assert comp(mult, 100000, 16).decompress(s) == d
+        if have_ref(100000):
+            assert refimpl.decompress(s, len(d) + 16, 100000) == d   # and the reference decoder agrees on the same stream
+    # stock base 10000 (-9 = 90 kB blocks)
+    s = comp(9, 10000, 16).compress(d)
+    assert comp(9, 10000, 16).decompress(s) == d
+
+
+def test_decompress_device_pointers_and_batches():
+    import torch
+    d = corpus.mixed_corpus(12 << 20, 2 << 20)
+    c = comp(9, 100000, 4)                     # 13+ blocks through batches of 4
+    s = c.compress(d)
+    t_in = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+    t_out = torch.zeros(len(d) + 64, dtype=torch.uint8, device="cuda")
+    n = c.decompress_ptr(t_in.data_ptr(), len(s), t_out.data_ptr(), len(d) + 64)
+    assert n == len(d) and t_out[:n].cpu().numpy().tobytes() == d
+    assert c.stats()["n_blocks"] == len(c.scan_blocks(d))
+
+
+def test_decompress_error_texts_are_the_references():
+    c = comp(9, 100000, 16)
+    d = corpus.word_text(400_000, 74)
+    s = bytearray(c.compress(d))
+
+    def err(b):
+        with pytest.raises(api.Bz2Error) as e:
+            c.decompress(bytes(b))
+        assert e.value.code == api.E_FORMAT
+        return str(e.value)
+
+    b = bytearray(s); b[2] = ord("x")
+    assert "Invalid BZip2 header" in err(b)
+    b = bytearray(s); b[len(b) // 2] ^= 0x04
+    assert any(t in err(b) for t in ("BZip2 block CRC error", "Error decoding  block", "block Huffman tables invalid",
+                                     "BZip2 block exceeds declared block size", "BZip2 stream format error", "BZip2 start pointer invalid"))
+    b = bytearray(s); b[-1] ^= 0x80; b[-3] ^= 1
+    assert "BZip2 stream CRC error" in err(b)
+    assert "Insufficient data" in err(s[:len(s) - 30])
+    assert "BZip2 stream format error" in err(bytes(s[:4]) + b"\x00" * 40)
+    with pytest.raises(api.Bz2Error) as e:       # output too small is not a format error
+        c.decompress(bytes(s), out_capacity=1000)
+    assert e.value.code == api.E_OUTPUT
+    # a stream of a larger block size than the handle's
+    with pytest.raises(api.Bz2Error) as e:
+        comp(1, 100000, 16).decompress(bytes(s))
+    assert e.value.code == api.E_BLOCKSIZE
+
+
+def test_cpp_input_stream_facade(tmp_path):
+    exe = str(tmp_path / "facade_dec")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "host", "facade_decompress.cpp"), "-o", exe,
+                           "-DBZ2B200_BLOCKSIZE_DEFAULT=100000", "-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    d = corpus.word_text(1_200_000, 75) + bytes(400_000) + corpus.rand_bytes(300_000, 76)
+    src = tmp_path / "in.bz2"
+    src.write_bytes(bz2.compress(d, 9))
+    for bulk in (False, True):
+        dst = tmp_path / f"out_{bulk}"
+        subprocess.check_call([exe, str(src), str(dst)] + (["bulk"] if bulk else []), env=env)
+        assert dst.read_bytes() == d
+    bad = tmp_path / "bad.bz2"
+    b = bytearray(src.read_bytes()); b[-2] ^= 1
+    bad.write_bytes(b)
+    r = subprocess.run([exe, str(bad), str(tmp_path / "x")], env=env, capture_output=True)
+    assert r.returncode == 4 and b"BZip2 stream CRC error" in r.stderr

@@ -1,2 +1,1 @@
-timeout 600 python tools/dec_debug.py > gpurun_out/dec2.log 2>&1; echo exit=$?; grep -v " OK " gpurun_out/dec2.log | tail -12
-python tools/dec_probe.py 256 600 mixed 2>&1 | tail -4
+timeout 1500 python -m pytest tests -m gpu -x -q -k "decompress or input_stream" > gpurun_out/pytest_gpu9.log 2>&1; echo pytest_exit=$?; tail -15 gpurun_out/pytest_gpu9.log
