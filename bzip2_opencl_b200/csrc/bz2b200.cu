@@ -20,8 +20,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_dec_scan, KID_k_dec_block, KID_k_dec_bases, KID_k_dec_double, KID_k_dec_chase, KID_k_dec_expand, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_dec_scan", "k_dec_block", "k_dec_counts", "k_dec_double", "k_dec_chase", "k_dec_expand", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_dec_scan, KID_k_dec_block, KID_k_imtf_tiles, KID_k_imtf_compose, KID_k_dec_bases, KID_k_dec_double, KID_k_dec_chase, KID_k_dec_expand, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_dec_scan", "k_dec_block", "k_imtf_tiles", "k_imtf_compose", "k_dec_counts", "k_dec_double", "k_dec_chase", "k_dec_expand", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -52,7 +52,7 @@ struct bz2b200 {
 
     // per-call (grow only)
     DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
-    DevBuf dec_cand, dec_info, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
+    DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
         lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
@@ -1100,6 +1100,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     const uint32_t G = h->G;
     ENSURE(h->dec_cand, (size_t)cap_c * 8);
     ENSURE(h->dec_info, (size_t)G * sizeof(DecInfo));
+    ENSURE(h->dec_list0, (size_t)G * 256);
     ENSURE(h->dec_len, (size_t)G * 8);
     ENSURE(h->dec_off, (size_t)G * 8);
     ENSURE(h->dec_starts, (size_t)(G + 1) * 8);
@@ -1138,8 +1139,10 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
         uint32_t nb = 0;
         while (ci < cand.size() && nb < G && !(cand[ci] & 1)) { ++ci; ++nb; } // block candidates only; an end marker closes the batch
         // (sorted candidates: block candidates between c0 and ci are contiguous in the list, false positives included)
-        KL(KID_k_dec_block, k_dec_block<<<(nb + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, DB_WARPS * sizeof(DecTables), st>>>(d_in, n_bits, ptr<uint64_t>(h->dec_cand), (uint32_t)c0, nb, stream_bs,
-                                                                  ptr<uint8_t>(h->L), h->S, ptr<uint8_t>(h->sel), h->sel_stride, max_selectors, ptr<DecInfo>(h->dec_info)));
+        CK(cudaMemsetAsync(h->ranks.p, 0, (size_t)nb * h->S, st)); // rank 0 everywhere: runs are not stored
+        KL(KID_k_dec_block, k_dec_block<<<(nb + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, DB_WARPS * sizeof(DecTables), st>>>(
+                                d_in, n_bits, ptr<uint64_t>(h->dec_cand), (uint32_t)c0, nb, stream_bs, ptr<uint8_t>(h->ranks), h->S, ptr<uint8_t>(h->sel), h->sel_stride,
+                                max_selectors, ptr<uint64_t>(h->dec_list0), ptr<DecInfo>(h->dec_info)));
         uint32_t *d_counts = ptr<uint32_t>(h->cnts);
         KL(KID_k_dec_bases, k_dec_counts<<<(nb + 255) / 256, 256, 0, st>>>(ptr<DecInfo>(h->dec_info), nb, d_counts));
         CK(cudaMemcpyAsync(info.data(), h->dec_info.p, (size_t)nb * sizeof(DecInfo), cudaMemcpyDeviceToHost, st));
@@ -1151,6 +1154,15 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             // inverse BWT: stable counting sort of L by byte value (one single-sweep radix pass), then the pointer chase
             uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
             const uint32_t tiles = (max_n + RS_TILE - 1) / RS_TILE;
+            // inverse move-to-front, tile-parallel: ranks -> L
+            {
+                dim3 gi((max_n + IM_WARPS * IM_TILE - 1) / (IM_WARPS * IM_TILE), nb);
+                KL(KID_k_imtf_tiles, k_imtf_tiles<false><<<gi, IM_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->ranks), d_counts, h->S, ptr<uint64_t>(h->lists), h->tilesM, ptr<uint8_t>(h->L)));
+                KL(KID_k_imtf_compose, k_imtf_compose<<<(nb + IM_WARPS - 1) / IM_WARPS, IM_WARPS * 32, 0, st>>>(d_counts, ptr<uint64_t>(h->lists), h->tilesM,
+                                                                                                          ptr<uint64_t>(h->dec_list0), nb));
+                KL(KID_k_imtf_tiles, k_imtf_tiles<true><<<gi, IM_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->ranks), d_counts, h->S, ptr<uint64_t>(h->lists), h->tilesM, ptr<uint8_t>(h->L)));
+                h->stats.kernel_launches += 3;
+            }
             const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
             KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->L), d_counts, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
             KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_counts, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1));
@@ -1163,7 +1175,8 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_counts, h->S, 1));
             KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kB), ptr<uint64_t>(h->kA), d_counts, h->S, 2));
             KL(KID_k_dec_double, k_dec_double8<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kA), ptr<uint64_t>(h->loc), ptr<uint32_t>(h->rank), d_counts, h->S));
-            KL(KID_k_dec_chase, k_dec_chase<<<(nb + 31) / 32, 32, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint32_t>(h->rank), h->S, ptr<DecInfo>(h->dec_info), nb,
+            KL(KID_k_dec_double, k_dec_double16<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint32_t>(h->rank), ptr<uint64_t>(h->kB), ptr<uint32_t>(h->kA), d_counts, h->S));
+            KL(KID_k_dec_chase, k_dec_chase<<<(nb + 31) / 32, 32, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint64_t>(h->kB), ptr<uint32_t>(h->kA), h->S, ptr<DecInfo>(h->dec_info), nb,
                                                                       ptr<uint8_t>(h->rle), ptr<uint64_t>(h->dec_len)));
             h->stats.kernel_launches += 6;
         } else {

@@ -3,13 +3,14 @@
 // MoveToFront.hpp:31-75, BitInputStream.hpp:30-85 -- one sequential CPU loop there) as device kernels:
 //   k_dec_scan        every bit position of the stream is tested for the 48-bit block / end-of-stream magics (blocks are
 //                     independent once their start is known; false positives are dropped by the host's chain check)
-//   k_dec_block       one warp per block: header, symbol map, selectors, delta-coded tables -> canonical decode tables in
-//                     shared memory; Huffman + inverse MTF (list spread over the lanes) + RUNA/RUNB expansion -> BWT column L
+//   k_dec_block       one warp per block: header, symbol map, selectors, delta-coded tables -> canonical decode tables + a 10-bit
+//                     lookup window in shared memory; Huffman symbols -> move-to-front ranks (RUNA/RUNB runs = rank 0 stretches)
+//   k_imtf_tiles<0> / k_imtf_compose / k_imtf_tiles<1>   inverse move-to-front, tile-parallel -> BWT column L
 //   (k_bwt_bytehist + k_radix_bases + k_radix_onesweep with 1-byte keys from bwt.cuh: stable counting sort of L = the
 //                     reference's bwtMergedPointers, BlockDecompressor.hpp:244-263)
-//   k_dec_double / k_dec_double8   three rounds of pointer doubling: every merged pointer carries eight bytes and the pointer
-//                     eight steps on
-//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, 8 bytes per dependent load,
+//   k_dec_double / k_dec_double8 / k_dec_double16   four rounds of pointer doubling: every merged pointer carries sixteen bytes
+//                     and the pointer sixteen steps on
+//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, 16 bytes per dependent load,
 //                     and the RLE1 decoded length on the way
 //   k_dec_expand      RLE1 decode (:56-84) at the final offset: literal stretches copied by whole warps, only the four-equal
 //                     triggers parsed in order
@@ -98,13 +99,15 @@ struct BitReader {
         win <<= count;
         have -= count;
         pos += count;
-        if (pos > end) overrun = true;
     }
+    // reading past the end only yields the zero padding; callers test this at their own pace (per field / per 50-symbol group)
+    __device__ __forceinline__ bool past_end() { if (pos > end) overrun = true; return overrun; }
     __device__ __forceinline__ uint32_t bits(int count) // 0..24
     {
         if (count == 0) return 0;
         const uint32_t v = peek(count);
         skip(count);
+        if (pos > end) overrun = true;
         return v;
     }
     __device__ __forceinline__ uint32_t bit() { return bits(1); }
@@ -124,12 +127,13 @@ struct DecTables {
 constexpr int DB_WARPS = 4; // blocks per CTA of k_dec_block
 
 // One WARP per candidate block.  The bit stream is sequential, so all lanes decode the same symbols redundantly (uniform control
-// flow, broadcast loads); the lanes share the work that has width: the 256-entry move-to-front list lives in one 64-bit register
-// per lane (entries 8*lane .. 8*lane+7, shifted with shuffles), runs are stored 32 bytes at a time.
+// flow, broadcast loads).  Output: the move-to-front RANKS of the block (RUNA/RUNB runs = stretches of rank 0, which the
+// pre-zeroed buffer already holds) and the initial list (the used byte values in order); the inverse MTF itself runs tile-parallel
+// afterwards (k_imtf_*).
 __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__restrict__ in, uint64_t n_bits, const uint64_t *__restrict__ cand, uint32_t c0,
-                                                              uint32_t nb, uint32_t block_size, uint8_t *__restrict__ L, uint64_t stride,
+                                                              uint32_t nb, uint32_t block_size, uint8_t *__restrict__ ranks, uint64_t stride,
                                                               uint8_t *__restrict__ sel_scratch, uint64_t sel_stride, uint32_t max_selectors,
-                                                              DecInfo *__restrict__ info)
+                                                              uint64_t *__restrict__ list0, DecInfo *__restrict__ info)
 {
     extern __shared__ __align__(16) unsigned char dec_smem[];
     DecTables *s_tab = reinterpret_cast<DecTables *>(dec_smem);
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
                     ++nsym;
                 }
         }
+    list0[(uint64_t)bl * 32 + lane] = list;
     const int eob = nsym + 1, alpha = nsym + 2;
     const uint32_t ntab = br.bits(3), nsel = br.bits(15);
     if (br.overrun) I.err = DEC_E_DATA;
@@ -212,41 +217,38 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
             // lookup window: every symbol with a code of at most DEC_LUT_BITS bits fills its 2^(window - length) slots
             for (int k = lane; k < (1 << DEC_LUT_BITS); k += 32) T.lut[t][k] = 0;
             __syncwarp();
-            {
-                const int32_t *bases = T.base[t], *limits = T.limit[t];
-                for (int ci = lane; ci < alpha; ci += 32) { // canonical order: ci-th code
-                    const int sym = T.perm[t][ci];
-                    const int l = T.len[sym];
-                    if (l <= DEC_LUT_BITS) {
-                        const int code = ci + bases[l]; // inverse of  symbol = perm[code - base[len]]
-                        const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
-                        for (int k = 0; k < cnt; ++k) T.lut[t][lo + k] = (uint16_t)((sym << 5) | l);
-                    }
-                    (void)limits;
+            for (int ci = lane; ci < alpha; ci += 32) { // canonical order: ci-th code
+                const int sym = T.perm[t][ci];
+                const int l = T.len[sym];
+                if (l <= DEC_LUT_BITS) {
+                    const int code = ci + T.base[t][l]; // inverse of  symbol = perm[code - base[len]]
+                    const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
+                    for (int k = 0; k < cnt; ++k) T.lut[t][lo + k] = (uint16_t)((sym << 5) | l);
                 }
             }
             __syncwarp();
         }
         if (br.overrun && I.err == DEC_OK) I.err = DEC_E_DATA;
     }
-    // decodeHuffmanData (:189-241): Huffman symbol -> RUNA/RUNB run or inverse MTF -> L
+    // decodeHuffmanData (:189-241): Huffman symbol -> RUNA/RUNB run (rank 0 repeated) or rank = symbol - 1
     uint32_t n = 0;
     if (I.err == DEC_OK) {
         __syncwarp();
-        uint8_t *out = L + (uint64_t)bl * stride;
+        uint8_t *out = ranks + (uint64_t)bl * stride;
         uint32_t group = 0, in_group = 0, tbl = sel[0];
+        const uint16_t *lutp = T.lut[tbl];
         uint32_t repeat = 0, inc = 1;
-        uint32_t front = (uint32_t)__shfl_sync(FULL, (uint32_t)list, 0) & 0xffu; // byte value at the head of the list
-        uint64_t acc = 0; // lane 0: bytes waiting for an aligned 8-byte store
         for (;;) {
             if (in_group == 50) { // HuffmanStageDecoder::nextSymbol group switch (:51-60)
                 in_group = 0;
                 if (++group == nsel) { I.err = DEC_E_DECODE; break; }
                 tbl = sel[group];
+                lutp = T.lut[tbl];
+                if (br.past_end()) { I.err = DEC_E_DATA; break; }
             }
             ++in_group;
             int sym = -1;
-            const uint32_t e = T.lut[tbl][br.peek(DEC_LUT_BITS)];
+            const uint32_t e = lutp[br.peek(DEC_LUT_BITS)];
             if (e) { sym = (int)(e >> 5); br.skip((int)(e & 31u)); }
             else { // long code: the reference's limit search (HuffmanStageDecoder.hpp:62-74)
                 int clen = T.minlen[tbl];
@@ -257,49 +259,117 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
                     ++clen;
                 }
             }
-            if (sym < 0 || br.overrun) { I.err = br.overrun ? DEC_E_DATA : DEC_E_DECODE; break; }
-            if (sym == 0) { repeat += inc; inc <<= 1; if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; } continue; }
-            if (sym == 1) { repeat += inc << 1; inc <<= 1; if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; } continue; }
+            if (sym < 0) { I.err = br.past_end() ? DEC_E_DATA : DEC_E_DECODE; break; }
+            if (sym <= 1) { // RUNA / RUNB
+                repeat += inc << sym; inc <<= 1;
+                if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; }
+                continue;
+            }
             if (repeat > 0) {
                 if (n + repeat > block_size) { I.err = DEC_E_BLOCKSIZE; break; }
-                // flush lane 0's partial word, then the run
-                if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) out[k] = (uint8_t)(acc >> (8 * (k & 7)));
-                for (uint32_t k = lane; k < repeat; k += 32) out[n + k] = (uint8_t)front;
-                n += repeat;
+                n += repeat; // rank 0 x repeat: already in the zeroed buffer
                 repeat = 0; inc = 1;
-                acc = 0;
-                if (n & 7u) { // re-load the bytes of the current 8-byte word that are already final
-                    __syncwarp();
-                    if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) acc |= (uint64_t)out[k] << (8 * (k & 7));
-                }
             }
-            if (sym == eob) break;
+            if (sym == eob) { if (br.past_end()) I.err = DEC_E_DATA; break; }
             if (n >= block_size) { I.err = DEC_E_BLOCKSIZE; break; }
-            // MoveToFront::indexToFront (MoveToFront.hpp:62-72) on the distributed list
-            const uint32_t idx = (uint32_t)sym - 1;
-            const int src = (int)(idx >> 3), bi = (int)(idx & 7);
-            const uint64_t srcw = shfl_u64(list, src);
-            const uint32_t v = (uint32_t)(srcw >> (8 * bi)) & 0xffu;
-            const uint64_t up = shfl_up_u64(list, 1); // previous lane's entries
-            if (lane < src) list = (list << 8) | (lane == 0 ? (uint64_t)v : (up >> 56));
-            else if (lane == src) {
-                const uint64_t lowmask = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull); // entries 0..bi of this lane change
-                const uint64_t shifted = (list << 8) | (lane == 0 ? (uint64_t)v : (up >> 56));
-                list = (list & ~lowmask) | (shifted & lowmask);
-            }
-            front = v;
-            if (lane == 0) {
-                acc |= (uint64_t)v << (8 * (n & 7));
-                if ((n & 7) == 7) { *reinterpret_cast<uint64_t *>(out + (n & ~7u)) = acc; acc = 0; }
-            }
+            if (lane == 0) out[n] = (uint8_t)(sym - 1);
             ++n;
         }
-        if (lane == 0) for (uint32_t k = n & ~7u; k < n; ++k) out[k] = (uint8_t)(acc >> (8 * (k & 7)));
     }
     if (I.err == DEC_OK && I.orig >= n) I.err = DEC_E_STARTPTR; // initialiseInverseBWT (:244-248)
     I.n = I.err == DEC_OK ? n : 0u;
     I.end_bit = br.pos;
     if (lane == 0) info[bl] = I;
+}
+
+// ---- inverse move-to-front, tile-parallel (the mirror of mtf.cuh): applying a tile's ranks to ANY list permutes its POSITIONS
+// the same way, so (1) every tile's position permutation comes from running its ranks on the identity, (2) one warp per block
+// composes them into the list at every tile start, (3) every tile re-runs from its true start list and writes the bytes.
+// The 256-entry list lives in one 64-bit register per lane (entries 8*lane .. 8*lane+7), moved with shuffles
+// (MoveToFront::indexToFront, MoveToFront.hpp:62-72).
+constexpr int IM_TILE = 2048;
+constexpr int IM_WARPS = 8;
+
+__device__ __forceinline__ uint32_t list_index_to_front(uint64_t &list, uint32_t idx, int lane)
+{
+    const int src = (int)(idx >> 3), bi = (int)(idx & 7);
+    const uint64_t srcw = shfl_u64(list, src);
+    const uint32_t v = (uint32_t)(srcw >> (8 * bi)) & 0xffu;
+    const uint64_t up = shfl_up_u64(list, 1); // previous lane's entries
+    const uint64_t shifted = (list << 8) | (lane == 0 ? (uint64_t)v : (up >> 56));
+    if (lane < src) list = shifted;
+    else if (lane == src) {
+        const uint64_t lowmask = bi == 7 ? ~0ull : ((1ull << (8 * (bi + 1))) - 1ull); // entries 0..bi of this lane change
+        list = (list & ~lowmask) | (shifted & lowmask);
+    }
+    return v;
+}
+
+// APPLY = false: perm[tile] = positions after the tile's ranks, from the identity.  APPLY = true: lists[tile] is the true start
+// list; write the bytes.
+template <bool APPLY>
+__global__ void __launch_bounds__(IM_WARPS * 32) k_imtf_tiles(const uint8_t *__restrict__ ranks, const uint32_t *__restrict__ counts, uint64_t stride,
+                                                               uint64_t *__restrict__ lists, int tiles_per_block, uint8_t *__restrict__ L)
+{
+    const uint32_t bl = blockIdx.y;
+    const uint32_t n = counts[bl];
+    const uint32_t tile = blockIdx.x * IM_WARPS + warp_id();
+    const uint32_t base = tile * IM_TILE;
+    if (base >= n) return;
+    const int lane = lane_id();
+    const uint32_t cnt = min((uint32_t)IM_TILE, n - base);
+    uint64_t *lp = lists + ((uint64_t)bl * tiles_per_block + tile) * 32 + lane;
+    uint64_t list;
+    if (APPLY) list = *lp;
+    else {
+        list = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) list |= (uint64_t)(lane * 8 + k) << (8 * k);
+    }
+    const uint8_t *rp = ranks + (uint64_t)bl * stride + base;
+    uint8_t *op = L + (uint64_t)bl * stride + base;
+    uint32_t front = (uint32_t)__shfl_sync(FULL, (uint32_t)list, 0) & 0xffu;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const bool valid = c0 + lane < cnt;
+        const uint32_t r = valid ? rp[c0 + lane] : 0u;
+        unsigned nz = __ballot_sync(FULL, r != 0);
+        uint32_t mine = front; // rank 0: the value at the head when this position is reached
+        while (nz) {
+            const int q = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            const uint32_t v = list_index_to_front(list, __shfl_sync(FULL, r, q), lane);
+            if (lane >= q) mine = v;
+            front = v;
+        }
+        if (APPLY && valid) op[c0 + lane] = (uint8_t)mine;
+    }
+    if (!APPLY) *lp = list;
+}
+
+// one warp per block: lists[t] (position permutation of tile t) -> lists[t] = list at the start of tile t
+__global__ void __launch_bounds__(IM_WARPS * 32) k_imtf_compose(const uint32_t *__restrict__ counts, uint64_t *__restrict__ lists, int tiles_per_block,
+                                                                 const uint64_t *__restrict__ list0, uint32_t nb)
+{
+    __shared__ __align__(8) uint8_t s_cur[IM_WARPS][256];
+    const uint32_t bl = blockIdx.x * IM_WARPS + warp_id();
+    if (bl >= nb) return;
+    const int lane = lane_id();
+    const uint32_t n = counts[bl];
+    const uint32_t nt = (n + IM_TILE - 1) / IM_TILE;
+    uint8_t *cur = s_cur[warp_id()];
+    uint64_t c8 = list0[(uint64_t)bl * 32 + lane];
+    for (uint32_t t = 0; t < nt; ++t) {
+        uint64_t *lp = lists + ((uint64_t)bl * tiles_per_block + t) * 32 + lane;
+        const uint64_t p8 = *lp; // positions: new entry k = old entry p[k]
+        *lp = c8;
+        *reinterpret_cast<uint64_t *>(cur + lane * 8) = c8;
+        __syncwarp();
+        uint64_t nx = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nx |= (uint64_t)cur[(uint32_t)(p8 >> (8 * k)) & 0xffu] << (8 * k);
+        __syncwarp();
+        c8 = nx;
+    }
 }
 
 // counts[bl] = block length (0 for a failed block)
@@ -342,18 +412,34 @@ __global__ void __launch_bounds__(256) k_dec_double8(const uint64_t *__restrict_
     ptr8[(uint64_t)bl * stride + j] = (uint32_t)(y & VAL_MASK);
 }
 
-// one thread per block follows the eight-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
+// fourth doubling round: sixteen bytes per element: lo8[j] stays, hi8[j] = bytes8[ptr8[j]], ptr16[j] = ptr8[ptr8[j]]
+__global__ void __launch_bounds__(256) k_dec_double16(const uint64_t *__restrict__ bytes8, const uint32_t *__restrict__ ptr8, uint64_t *__restrict__ hi8,
+                                                       uint32_t *__restrict__ ptr16, const uint32_t *__restrict__ counts, uint64_t stride)
+{
+    const uint32_t bl = blockIdx.y;
+    const uint32_t n = counts[bl];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t o = (uint64_t)bl * stride;
+    const uint32_t q = ptr8[o + j];
+    hi8[o + j] = bytes8[o + q];
+    ptr16[o + j] = ptr8[o + q];
+}
+
+// one thread per block follows the sixteen-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
 // (BlockDecompressor::read, :56-84) runs along to give the decoded length (its cost hides behind the dependent loads)
-__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ bytes8, const uint32_t *__restrict__ ptr8, uint64_t stride,
-                                                   const DecInfo *__restrict__ info, uint32_t nb, uint8_t *__restrict__ rle, uint64_t *__restrict__ out_len)
+__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ lo8, const uint64_t *__restrict__ hi8, const uint32_t *__restrict__ ptr16,
+                                                   uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb, uint8_t *__restrict__ rle,
+                                                   uint64_t *__restrict__ out_len)
 {
     const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
     if (bl >= nb) return;
     const uint32_t n = info[bl].n;
     if (n == 0) { out_len[bl] = 0; return; }
-    const uint64_t *mb = bytes8 + (uint64_t)bl * stride;
-    const uint32_t *mp = ptr8 + (uint64_t)bl * stride;
-    uint8_t *out = rle + (uint64_t)bl * stride;
+    const uint64_t base = (uint64_t)bl * stride;
+    const uint64_t *ml = lo8 + base, *mh = hi8 + base;
+    const uint32_t *mp = ptr16 + base;
+    uint8_t *out = rle + base;
     uint32_t p = info[bl].orig;
     uint64_t o = 0;
     int last = -1;
@@ -365,17 +451,19 @@ __global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ b
         else { ++o; if (++acc == 4) count_next = true; }
     };
     uint32_t i = 0;
-    for (; i + 8 <= n; i += 8) {
-        const uint64_t w = mb[p];
+    for (; i + 16 <= n; i += 16) {
+        const uint64_t w0 = ml[p], w1 = mh[p];
         p = mp[p];
-        *reinterpret_cast<uint64_t *>(out + i) = w;
+        *reinterpret_cast<uint4 *>(out + i) = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) step((uint32_t)(w >> (8 * k)) & 0xffu);
+        for (int k = 0; k < 8; ++k) step((uint32_t)(w0 >> (8 * k)) & 0xffu);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) step((uint32_t)(w1 >> (8 * k)) & 0xffu);
     }
     if (i < n) {
-        const uint64_t w = mb[p];
+        const uint64_t w0 = ml[p], w1 = mh[p];
         for (uint32_t k = 0; i < n; ++i, ++k) {
-            const uint32_t v = (uint32_t)(w >> (8 * k)) & 0xffu;
+            const uint32_t v = (uint32_t)((k < 8 ? w0 >> (8 * k) : w1 >> (8 * (k - 8))) & 0xffu);
             out[i] = (uint8_t)v;
             step(v);
         }
