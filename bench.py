@@ -281,6 +281,30 @@ def main():
         ours = comp.compress(sample)
         parity = "bit-identical to oracle/_ref on the sample" if ours == ref_out else "MISMATCH vs oracle/_ref on the sample"
 
+    # ---- the decompress side, reported next to the headline: the stream just produced, back to bytes on the device
+    decompress = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            stream = comp.compress(data)
+            comp.close()
+            dcomp = api.Compressor(MULT, max(args.parallel, int(stats["n_blocks"]) + 8), BASE, device=local_rank)  # every block in one batch
+            d_s = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+            d_o = torch.empty(n1 + 64, dtype=torch.uint8, device="cuda")
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                nout = dcomp.decompress_ptr(d_s.data_ptr(), len(stream), d_o.data_ptr(), n1 + 64)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t
+                best = dt if best is None else min(best, dt)
+            ok = nout == n1 and bool(torch.equal(d_o[:n1], d_unit))
+            decompress = {"value": round(n1 / 1e6 / best, 2), "unit": "output MB/s", "ms": round(1e3 * best, 2), "blocks": int(dcomp.stats()["n_blocks"]),
+                          "roundtrip_equals_input": ok, "what": "bz2b200_decompress_stream, device-resident, best of 3"}
+            dcomp.close()
+        except Exception as e:  # the headline number must not depend on this
+            decompress = {"error": str(e)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -293,7 +317,7 @@ def main():
                         "d2h_bytes_per_step": int(out_bytes),
                         "last_step": {k: round(float(e2e_stats[k]), 3) for k in ("ms_total", "ms_h2d", "ms_d2h")}},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "decompress": decompress, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
