@@ -254,8 +254,16 @@ def main():
     name, (k_ms, k_n, k_bytes) = top
     achieved = (k_bytes / 1e9) / (k_ms / 1e3) if k_ms > 0 and k_bytes else None
     step_kernel_ms = sum(v[0] for v in ktimes.values()) / prof_steps
+    # DRAM traffic of that kernel per launch from the committed ncu capture of this same command (profiles/), if there is one
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if name in tj["kernels"]:
+            traffic, traffic_src = int(tj["kernels"][name]["dram_bytes_per_launch"]), tj.get("source")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "launches_per_step": k_n // prof_steps, "avg_launch_ms": round(k_ms / max(1, k_n), 4),
                 "share_of_step": round(k_ms / prof_steps / ms_dev, 4),
                 "algorithmic_bytes_per_launch": k_bytes // max(1, k_n),

@@ -33,4 +33,5 @@ if len(sys.argv) > 2:
 else:
     print(text)
 if len(sys.argv) > 3 and traffic:
-    json.dump(traffic, open(sys.argv[3], "w"), indent=1)
+    json.dump({"source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over the bench command ({src})",
+               "kernels": traffic}, open(sys.argv[3], "w"), indent=1)
