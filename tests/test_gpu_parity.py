@@ -387,3 +387,32 @@ def test_cpp_input_stream_facade(tmp_path):
     bad.write_bytes(b)
     r = subprocess.run([exe, str(bad), str(tmp_path / "x")], env=env, capture_output=True)
     assert r.returncode == 4 and b"BZip2 stream CRC error" in r.stderr
+
+
+def test_cli_front_end_round_trip(tmp_path):
+    # app.cpp's flags and file rules -- compress removes the input unless -k, -d strips ".bz2" (".out" if taken), -c checks
+    exe = str(tmp_path / "bzip2_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "bzip2_opencl_b200", "cli", "bzip2_b200.cpp"), "-o", exe,
+                           "-DBZ2B200_BLOCKSIZE_DEFAULT=100000", "-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    d = corpus.word_text(1_300_000, 81) + bytes(200_000) + corpus.rand_bytes(100_000, 82)
+    f = tmp_path / "data.bin"
+    f.write_bytes(d)
+    subprocess.check_call([exe, str(f), "-s", "5", "-p", "4", "-k"], env=env)
+    z = tmp_path / "data.bin.bz2"
+    assert f.exists() and z.read_bytes() == oracle.compress(d, 5, 100000)
+    r = subprocess.run([exe, str(z), "--check"], env=env, capture_output=True)
+    assert r.returncode == 0 and b"Integrity check passed!" in r.stdout and z.exists()
+    r = subprocess.run([exe, str(z), "-d", "-k"], env=env, capture_output=True)      # data.bin exists -> data.bin.out
+    assert r.returncode == 0 and b"Warning: Output file exists" in r.stderr
+    assert (tmp_path / "data.bin.out").read_bytes() == d and z.exists()
+    f.unlink()
+    subprocess.check_call([exe, str(z), "--dec"], env=env)                            # input removed, name restored
+    assert f.read_bytes() == d and not z.exists()
+    subprocess.check_call([exe, str(f)], env=env)                                     # default -9, input removed
+    assert not f.exists() and bz2.decompress(z.read_bytes()) == d
+    b = bytearray(z.read_bytes()); b[len(b) // 2] ^= 1
+    z.write_bytes(b)
+    r = subprocess.run([exe, str(z), "-c"], env=env, capture_output=True)
+    assert r.returncode == 2 and b"BZip2" in r.stderr or b"block" in r.stderr

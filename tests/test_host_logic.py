@@ -167,3 +167,24 @@ def test_world_size_2_sharding_over_gloo(tmp_path):
                           "--master-port", "29531", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "SHARDED-OK" in out.stdout
+
+
+def test_cli_front_end_argument_handling(tmp_path):
+    # the reference's flags and messages (app.cpp:31-92); nothing here reaches the device
+    exe = str(tmp_path / "bzip2_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "bzip2_opencl_b200", "cli", "bzip2_b200.cpp"), "-o", exe,
+                           "-DBZ2B200_BLOCKSIZE_DEFAULT=100000", "-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], env=env, capture_output=True)
+    assert r.returncode == 1 and b"Usage" in r.stderr
+    r = subprocess.run([exe, "-h"], env=env, capture_output=True)
+    assert r.returncode == 0 and b"--parallel" in r.stdout
+    r = subprocess.run([exe, "file", "--bogus"], env=env, capture_output=True)
+    assert r.returncode == 1 and b"Unknown flag!" in r.stderr
+    r = subprocess.run([exe, str(tmp_path / "missing")], env=env, capture_output=True)
+    assert r.returncode == 1 and b"Failed to open input file." in r.stderr
+    f = tmp_path / "plain.txt"
+    f.write_bytes(b"x")
+    r = subprocess.run([exe, str(f), "-d"], env=env, capture_output=True)
+    assert r.returncode == 1 and b".bz2 extenstion" in r.stderr and f.exists()
