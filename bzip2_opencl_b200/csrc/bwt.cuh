@@ -781,7 +781,44 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     for (uint32_t i = threadIdx.x; i < nwu * 256; i += LS_THREADS) (&sm.warp_hist[0][0][0])[i] = 0;
     __syncthreads();
     int hb = 0;
-    for (int shift = 0; shift < 32; shift += 8) {
+    // The first digit that differs has no earlier order to preserve: its pass need not be stable, so elements take their slots
+    // with one shared-memory atomic each (no warp match, no per-warp counters).
+    int shift_first = 0;
+    while (shift_first < 32 && ((diff >> shift_first) & 0xffu) == 0) shift_first += 8;
+    if (shift_first < 32) {
+        const int sh = shift_first + VAL_BITS;
+        uint32_t *h0 = sm.warp_hist[1][0];
+        h0[threadIdx.x] = 0;
+        uint64_t key[LS_ITEMS];
+        uint16_t rnk[LS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i) {
+            const uint32_t q = i * 32 + lane;
+            key[i] = q < wcnt ? sm.e[wbase + q] : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i)
+            if ((uint32_t)i * 32 + lane < wcnt) rnk[i] = (uint16_t)atomicAdd(&h0[(uint32_t)(key[i] >> sh) & 0xffu], 1u);
+        __syncthreads();
+        const uint32_t sum = h0[threadIdx.x];
+        const uint32_t incl = warp_incl_sum(sum);
+        if (lane == 31) sm.wtot[w] = incl;
+        __syncthreads();
+        {
+            uint32_t before = 0;
+#pragma unroll
+            for (int ww = 0; ww < LS_WARPS; ++ww)
+                if (ww < w) before += sm.wtot[ww];
+            sm.tile_base[threadIdx.x] = before + incl - sum;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LS_ITEMS; ++i)
+            if ((uint32_t)i * 32 + lane < wcnt) sm.e[sm.tile_base[(uint32_t)(key[i] >> sh) & 0xffu] + rnk[i]] = key[i];
+        __syncthreads();
+    }
+    for (int shift = shift_first + 8; shift < 32; shift += 8) {
         if (((diff >> shift) & 0xffu) == 0) continue; // uniform over the CTA
         const int sh = shift + VAL_BITS;
         uint32_t(*hist)[256] = sm.warp_hist[hb];
