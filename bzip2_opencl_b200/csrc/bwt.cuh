@@ -359,21 +359,33 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
         }
     }
     __syncthreads();
+    // Round 0's first pass has no earlier order to preserve: inside the tile its keys take their slots with one shared-memory
+    // atomic each instead of the stable warp multi-split (the decompressor's 1-byte counting sort must stay stable).
+    // (Not used for the bag sorts: their low digits can be nearly constant, and 32 lanes on one counter serialise.)
+    const bool unstable = FROM_TEXT && text_bytes == 4;
+    if (unstable) {
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-        const bool valid = li < tcnt;
-        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 0xffu) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(FULL, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = sm.warp_hist[w][d];
-            sm.warp_hist[w][d] = old + __popc(peers);
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            if (li < tcnt) rnk[i] = (uint16_t)atomicAdd(&sm.warp_hist[0][(uint32_t)(key[i] >> shift) & 0xffu], 1u);
         }
-        old = __shfl_sync(FULL, old, leader);
-        rnk[i] = (uint16_t)(old + __popc(peers & lt));
-        __syncwarp();
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            const bool valid = li < tcnt;
+            const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 0xffu) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(FULL, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = sm.warp_hist[w][d];
+                sm.warp_hist[w][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(FULL, old, leader);
+            rnk[i] = (uint16_t)(old + __popc(peers & lt));
+            __syncwarp();
+        }
     }
     __syncthreads();
     {
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
         const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
         if (li < tcnt) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
-            sm.keys[sm.tile_base[d] + sm.warp_hist[w][d] + rnk[i]] = key[i];
+            sm.keys[sm.tile_base[d] + (unstable ? 0u : sm.warp_hist[w][d]) + rnk[i]] = key[i];
         }
     }
     __syncthreads();
