@@ -743,6 +743,8 @@ __global__ void __launch_bounds__(256) k_bwt_roundstats(const uint32_t *__restri
 constexpr int LS_THREADS = BZ_LS_THREADS;
 constexpr int LS_ITEMS = RG_TILE / LS_THREADS; // 4
 constexpr int LS_WARPS = LS_THREADS / 32;
+constexpr uint32_t LS_SMALL_FROM = 32;  // try the counting path once rotations are ordered by at least this many bytes
+constexpr int LS_SMALL_MAX = 32;        // ... and no group of the region is larger than this
 
 static_assert(LS_THREADS == 256, "one thread per digit in the scan of k_bwt_local");
 struct LocalSmem {
@@ -784,6 +786,76 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
         for (int ww = 0; ww < LS_WARPS; ++ww) { x |= sm.red[ww]; y &= sm.red[LS_WARPS + ww]; }
         diff = x ^ y;
     }
+    // ---- deep rounds: groups are mostly a handful of rotations (long repeats keep many groups of 2..9 alive for ~log n rounds).
+    // If the region is still in group order (kept elements are; appended ones may not be) and no group is larger than
+    // LS_SMALL_MAX, every element finds its place by counting the smaller keys inside its own group: no radix passes at all.
+    bool sorted_small = false;
+    if (A.sorted_len >= LS_SMALL_FROM) {
+        const uint32_t a0 = threadIdx.x * LS_ITEMS;
+        uint64_t e[LS_ITEMS];
+        int last_s = -1, first_s = INT_INF;
+        bool bad = false;
+        unsigned gf = 0;
+        if (a0 < c) {
+            uint32_t pg = a0 > 0 ? (uint32_t)(sm.e[a0 - 1] >> GPOS_SHIFT) : 0u;
+#pragma unroll
+            for (int i = 0; i < LS_ITEMS; ++i) {
+                const uint32_t a = a0 + i;
+                e[i] = a < c ? sm.e[a] : 0ull;
+                if (a < c) {
+                    const uint32_t g = (uint32_t)(e[i] >> GPOS_SHIFT);
+                    if (a == 0 || g != pg) { gf |= 1u << i; last_s = (int)a; if (first_s == INT_INF) first_s = (int)a; }
+                    bad |= a > 0 && g < pg;
+                    pg = g;
+                }
+            }
+        }
+        int prev_s, unused, next_s;
+        block_scan_max2_minsuffix(last_s, -1, first_s, sm.scr_i, prev_s, unused, next_s);
+        int gs[LS_ITEMS], ge[LS_ITEMS];
+        int mx = 0;
+        if (a0 < c) {
+            int nxt = next_s == INT_INF ? (int)c : next_s;
+#pragma unroll
+            for (int i = LS_ITEMS - 1; i >= 0; --i) {
+                ge[i] = nxt - 1;
+                if (gf & (1u << i)) nxt = (int)(a0 + i);
+            }
+            int run = prev_s;
+#pragma unroll
+            for (int i = 0; i < LS_ITEMS; ++i) {
+                if (gf & (1u << i)) run = (int)(a0 + i);
+                gs[i] = run;
+                if (a0 + i < c) mx = max(mx, ge[i] - gs[i] + 1);
+            }
+        }
+        if (!__syncthreads_or((bad || mx > LS_SMALL_MAX) ? 1 : 0)) {
+            uint32_t np[LS_ITEMS];
+            if (a0 < c) {
+#pragma unroll
+                for (int i = 0; i < LS_ITEMS; ++i) {
+                    const int j = (int)(a0 + i);
+                    if (j < (int)c) {
+                        const uint32_t kj = (uint32_t)(e[i] >> VAL_BITS);
+                        uint32_t r = 0;
+                        for (int q = gs[i]; q <= ge[i]; ++q) {
+                            const uint32_t kq = (uint32_t)(sm.e[q] >> VAL_BITS);
+                            r += (kq < kj || (kq == kj && q < j)) ? 1u : 0u;
+                        }
+                        np[i] = (uint32_t)gs[i] + r;
+                    }
+                }
+            }
+            __syncthreads();
+            if (a0 < c) {
+#pragma unroll
+                for (int i = 0; i < LS_ITEMS; ++i)
+                    if (a0 + i < c) sm.e[np[i]] = e[i];
+            }
+            __syncthreads();
+            sorted_small = true;
+        }
+    }
     const unsigned lt = (1u << lane) - 1u;
     // the sort uses as many warps as have at least two rows of 32 elements to rank; warp w owns elements [w*chunk, (w+1)*chunk)
     const uint32_t nwu = min((uint32_t)LS_WARPS, (c + 63) / 64);
@@ -795,7 +867,7 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     int hb = 0;
     // The first digit that differs has no earlier order to preserve: its pass need not be stable, so elements take their slots
     // with one shared-memory atomic each (no warp match, no per-warp counters).
-    int shift_first = 0;
+    int shift_first = sorted_small ? 32 : 0;
     while (shift_first < 32 && ((diff >> shift_first) & 0xffu) == 0) shift_first += 8;
     if (shift_first < 32) {
         const int sh = shift_first + VAL_BITS;

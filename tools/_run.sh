@@ -1,3 +1,1 @@
-python bench.py > gpurun_out/bench35.json 2> gpurun_out/bench35.err; echo bench_exit=$?
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_r01_v5.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu11.log 2>&1; echo ncu_exit=$?
-ncu --set full --clock-control none --import-source on -k regex:'k_bwt_local|k_radix_onesweep|k_bwt_regroup|k_mtf_ranks' --launch-skip 3 --launch-count 10 -o gpurun_out/prof_r01_v5_top -f python tools/ncu_probe.py 256 320 > gpurun_out/ncu12.log 2>&1; echo ncu_exit=$?
+python tools/kprobe.py rep 256 300 2>&1 | tail -2
