@@ -44,6 +44,7 @@ struct bz2b200 {
     uint64_t S = 0;       // element stride per block
     int nbits = 0;        // bits needed for a position inside a block
     int key0_bytes = 4;
+    int prefix_walk = 1;  // BZ2B200_WALK=0: the tree-descent walk (k_rle_walk) instead of the prefix-state walk (k_rle_walk_prefix)
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
     cudaStream_t stream = 0;
@@ -51,7 +52,7 @@ struct bz2b200 {
     std::vector<DevBuf *> all;
 
     // per-call (grow only)
-    DevBuf in, seg[RLE_MAX_LEVELS], starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
+    DevBuf in, seg[RLE_MAX_LEVELS], segP[RLE_MAX_LEVELS], pstate, starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
@@ -353,6 +354,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     }
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
+    if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
     int rc = create_impl(h);
     if (rc != BZ2B200_OK) {
         // keep the message reachable through a static for the failing create
@@ -490,8 +492,10 @@ static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
     h->tiles_done = 0;
     if (n == 0) { h->seg_end.clear(); return BZ2B200_OK; }
     uint64_t c = (n + RLE_TILE - 1) / RLE_TILE;
+    ENSURE(h->pstate, (c + 1) * sizeof(PState));
     for (int l = 0; l < RLE_MAX_LEVELS; ++l) {
         ENSURE(h->seg[l], c * sizeof(Seg));
+        if (l > 0) ENSURE(h->segP[l], c * sizeof(Seg));
         if (c <= 1) break;
         c = (c + RLE_FANOUT - 1) / RLE_FANOUT;
     }
@@ -500,6 +504,7 @@ static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
     ENSURE(h->rle_len, (h->w_cap + 2) * 4);
     uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
     CK(cudaMemsetAsync(d_info, 0, 32, h->stream));
+    CK(cudaMemsetAsync(d_info + 12, 0, 16, h->stream)); // the global machine's state at the walk position (fresh)
     CK(cudaEventRecord(h->ev_tree, h->stream));
     CK(cudaStreamWaitEvent(h->side, h->ev_tree, 0));
     return BZ2B200_OK;
@@ -535,6 +540,16 @@ static int walk_extend(bz2b200 *h)
     k_rle_tile_seg<<<(unsigned)((nt + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(h->w_in, n, ptr<Seg>(h->seg[0]), t0, cnt[0]);
     for (int l = 1; l < nl; ++l)
         k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]), cnt[l]);
+    if (h->prefix_walk) {
+        // top-down: summaries of everything in front of every node; level 0 as machine states
+        for (int l = nl - 2; l >= 0; --l)
+            k_rle_prefix<<<(unsigned)((cnt[l + 1] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(
+                ptr<Seg>(h->seg[l]), cnt[l], l + 1 == nl - 1 ? nullptr : ptr<Seg>(h->segP[l + 1]), cnt[l + 1], l == 0 ? nullptr : ptr<Seg>(h->segP[l]),
+                l == 0 ? ptr<PState>(h->pstate) : nullptr);
+        if (nl == 1)
+            k_rle_prefix<<<1, RLE_WARPS * 32, 0, h->side>>>(ptr<Seg>(h->seg[0]), cnt[0], nullptr, 1, nullptr, ptr<PState>(h->pstate));
+        h->stats.kernel_launches += nl > 1 ? nl - 1 : 1;
+    }
     CK(cudaEventRecord(h->ev_t1, h->side));
     h->stats.kernel_launches += nl;
     for (int l = 0; l < RLE_MAX_LEVELS; ++l) { h->wl.seg[l] = l < nl ? ptr<Seg>(h->seg[l]) : nullptr; h->wl.cnt[l] = l < nl ? cnt[l] : 0; }
@@ -555,8 +570,12 @@ static int walk_launch(bz2b200 *h, uint64_t max_new)
     const uint64_t b0 = h->w_found;
     h->w_req = max_new;
     CK(cudaEventRecord(h->ev_w0, h->side));
-    k_rle_walk<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), h->w_cap,
-                                       d_info, max_new);
+    if (h->prefix_walk)
+        k_rle_walk_prefix<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<PState>(h->pstate), ptr<uint64_t>(h->starts),
+                                                  ptr<uint32_t>(h->rle_len), h->w_cap, d_info, max_new);
+    else
+        k_rle_walk<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), h->w_cap,
+                                           d_info, max_new);
     CK(cudaEventRecord(h->ev_w1, h->side));
     h->stats.kernel_launches += 1;
     CK(cudaMemcpyAsync(h->pin_info, d_info, 32, cudaMemcpyDeviceToHost, h->side));

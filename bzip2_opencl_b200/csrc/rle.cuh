@@ -231,6 +231,167 @@ __global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in,
     }
 }
 
+// ---------------------------------------------------------------- prefix states + the walk on them
+// pre[l][i] = summary of everything in front of node i of level l.  One warp per parent: exclusive scan of its <= 64 children
+// on top of the parent's own prefix.  Level 0 stores the global machine's STATE at the tile start instead (16 bytes),
+// pstate[n_tiles] = state at the end of the available input.
+struct PState { uint64_t bl; uint32_t cur, run; };
+
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_prefix(const Seg *__restrict__ child, uint64_t n_child, const Seg *__restrict__ parent_pre,
+                                                                uint64_t n_parent, Seg *__restrict__ child_pre, PState *__restrict__ pstate)
+{
+    uint64_t p = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
+    if (p >= n_parent) return;
+    const int lane = lane_id();
+    uint64_t c0 = p * RLE_FANOUT + 2 * lane;
+    Seg a = c0 < n_child ? child[c0] : seg_empty();
+    Seg b = c0 + 1 < n_child ? child[c0 + 1] : seg_empty();
+    Seg incl = warp_seg_incl_scan(seg_combine(a, b));
+    Seg excl = shfl_up_seg(incl, 1);
+    if (lane == 0) excl = seg_empty();
+    const Seg base = parent_pre ? parent_pre[p] : seg_empty();
+    const Seg pa = seg_combine(base, excl), pb = seg_combine(pa, a);
+    if (pstate) {
+        if (c0 < n_child) { RleState st = state_apply(pa, state_fresh()); PState o{st.bl, st.cur, st.run}; pstate[c0] = o; }
+        if (c0 + 1 < n_child) { RleState st = state_apply(pb, state_fresh()); PState o{st.bl, st.cur, st.run}; pstate[c0 + 1] = o; }
+        // the state behind the last tile
+        if (c0 + 1 == n_child - 1 || c0 == n_child - 1) {
+            RleState st = state_apply(seg_combine(pb, b), state_fresh());
+            PState o{st.bl, st.cur, st.run};
+            pstate[n_child] = o;
+        }
+    } else {
+        if (c0 < n_child) child_pre[c0] = pa;
+        if (c0 + 1 < n_child) child_pre[c0 + 1] = pb;
+    }
+}
+
+struct DevRunEnd {
+    const uint8_t *in;
+    uint64_t n;
+    WalkLevels lv;
+    // first q > s with in[q] != in[s], or n.  32 bytes per step inside the tile of s, then whole uniform nodes of the tree.
+    __device__ uint64_t operator()(uint64_t s) const
+    {
+        const int lane = lane_id();
+        const uint32_t v = __ldg(in + s);
+        const uint64_t tile_end = min(n, (s / RLE_TILE + 1) * RLE_TILE);
+        for (uint64_t q0 = s + 1; q0 < tile_end; q0 += 32) {
+            const uint64_t q = q0 + lane;
+            const bool diff = q < tile_end && __ldg(in + q) != v;
+            const unsigned m = __ballot_sync(FULL, diff);
+            if (m) return q0 + (uint64_t)(__ffs((int)m) - 1);
+        }
+        uint64_t t = tile_end / RLE_TILE; // first tile not yet looked at (tile_end is a tile boundary unless it is n)
+        if (tile_end >= n) return n;
+        for (;;) {
+            if (t >= lv.cnt[0]) return n;
+            // the largest aligned node starting at tile t that is one run of v
+            int level = 0;
+            uint64_t idx = t, span = 1;
+            for (;;) {
+                const Seg sg = lv.seg[level][idx];
+                const bool ok = sg.uniform && sg.first == v;
+                if (!ok) {
+                    if (level == 0) { // the run ends inside (or right at the start of) this tile
+                        if (sg.first != v) return t * RLE_TILE;
+                        return min(n, t * RLE_TILE + sg.lead);
+                    }
+                    break; // fall back to the child level result found before
+                }
+                if (level + 1 < lv.n_levels && idx % RLE_FANOUT == 0 && idx / RLE_FANOUT < lv.cnt[level + 1]) {
+                    const Seg up = lv.seg[level + 1][idx / RLE_FANOUT];
+                    if (up.uniform && up.first == v) { ++level; idx /= RLE_FANOUT; span *= RLE_FANOUT; continue; }
+                }
+                break;
+            }
+            t += span;
+        }
+    }
+};
+
+struct DevByte {
+    const uint8_t *in;
+    __device__ uint32_t operator()(uint64_t q) const { return __ldg(in + q); }
+};
+
+struct DevPState {
+    const PState *ps;
+    __device__ RleState operator()(uint64_t t) const
+    {
+        const PState p = ps[t];
+        RleState r;
+        r.bl = p.bl; r.cur = p.cur; r.run = p.run;
+        return r;
+    }
+};
+
+struct DevFirstOver {
+    const PState *ps;
+    uint64_t n_tiles;
+    // smallest t > t_lo with ps[t].bl > lim (ps[].bl is non-decreasing), n_tiles + 1 if none: 32 probes 16 tiles apart, then 16 in a row
+    __device__ uint64_t operator()(uint64_t t_lo, uint64_t lim) const
+    {
+        const int lane = lane_id();
+        for (;;) {
+            if (t_lo >= n_tiles) return n_tiles + 1;
+            const uint64_t t = min(n_tiles, (uint64_t)(t_lo + 16u * (uint64_t)(lane + 1)));
+            const unsigned m = __ballot_sync(FULL, ps[t].bl > lim);
+            if (m) {
+                const int f = __ffs((int)m) - 1;
+                const uint64_t base = t_lo + 16ull * (uint64_t)f; // ps[base].bl <= lim
+                const uint64_t t2 = min(n_tiles, (uint64_t)(base + 1 + (uint64_t)(lane & 15)));
+                const unsigned m2 = __ballot_sync(FULL, ps[t2].bl > lim) & 0xffffu;
+                return base + 1 + (uint64_t)(__ffs((int)m2) - 1); // m2 != 0: the probe 16 further on was over the limit
+            }
+            t_lo = min(n_tiles, (uint64_t)(t_lo + 512ull));
+        }
+    }
+};
+
+// Resumable like k_rle_walk (same info[] protocol); info[12], info[13] carry the global machine's state at info[1].
+__global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t limit, int is_final, WalkLevels lv,
+                                                         const PState *__restrict__ pstate, uint64_t *__restrict__ starts, uint32_t *__restrict__ rle_len,
+                                                         uint64_t cap, uint64_t *__restrict__ info, uint64_t max_new)
+{
+    __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
+    DevTileScan scan{in, sm};
+    DevRunEnd run_end{in, n_bytes, lv};
+    DevByte byte{in};
+    DevPState ps{pstate};
+    DevFirstOver first_over{pstate, (n_bytes + RLE_TILE - 1) / RLE_TILE};
+    uint64_t nb = info[0], s = info[1];
+    RleState g;
+    g.bl = info[12]; g.cur = (uint32_t)(info[13] >> 32); g.run = (uint32_t)info[13];
+    const uint64_t target = nb + max_new;
+    uint64_t finished = 0;
+    __syncwarp();
+    while (nb < target) {
+        if (s >= n_bytes) { finished = 1; break; }
+        RleState st, g2 = g;
+        const uint64_t e = walk_block_prefix(s, n_bytes, limit, g2, run_end, byte, ps, first_over, scan, st);
+        const bool complete = (e < n_bytes) || is_final; // e == n_bytes without a refusal: flushed only when the stream ends
+        if (!complete) { finished = 1; break; }
+        if (lane_id() == 0 && nb < cap) {
+            starts[nb] = s;
+            rle_len[nb] = (uint32_t)state_final_length(st);
+        }
+        ++nb;
+        s = e;
+        g = g2;
+    }
+    if (s >= n_bytes) finished = 1;
+    __syncwarp();
+    if (lane_id() == 0) {
+        if (nb <= cap) starts[nb] = s;
+        info[0] = nb;
+        info[1] = s;
+        info[2] = finished;
+        info[12] = g.bl;
+        info[13] = ((uint64_t)g.cur << 32) | g.run;
+    }
+}
+
 // ---------------------------------------------------------------- block-relative tiles
 // Tile k of block b covers input [starts[b] + k*RLE_TILE, min(.., starts[b+1])).
 __device__ __forceinline__ bool btile_range(const uint64_t *starts, uint32_t b, uint64_t k, uint64_t &lo, uint32_t &n)

@@ -324,4 +324,76 @@ BZ_HD uint64_t walk_block_wide(uint64_t start, uint64_t n_bytes, uint64_t limit,
     return r.pos;
 }
 
+// ---- the same walk on PREFIX states: one tile simulation per block instead of a tree descent ----
+// Let the GLOBAL machine be the one that never starts a new block (it runs from byte 0), and pstate(t) its state at the first
+// byte of tile t (a parallel scan of the tile summaries).  A block's fresh machine, started at s, and the global machine agree
+// on (cur, run) as soon as the run that contains s has ended (both flush it when the next different byte arrives), and from
+// then on their blockLengths differ by a constant D.  So "first byte refused by the fresh machine" = "first byte where the
+// global blockLength exceeds limit + D": a search in the monotone pstate[].bl plus one exact tile simulation.
+//   gstate       in: global state at s; out: global state at the returned position
+//   run_end(s)   first q > s with in[q] != in[s], or n_bytes
+//   byte(q)      in[q]
+//   pstate(t)    global state at byte t * RLE_TILE for t <= n_tiles (pstate(n_tiles) = state at n_bytes)
+//   first_over(t_lo, lim)  smallest t > t_lo with pstate(t).bl > lim, or n_tiles + 1 if none
+//   scan(lo, hi, state, lim) as above (any state / limit)
+// Returns the end position; st_end = FRESH machine state there (for the block's RLE1 length).
+template <typename RunEnd, typename Byte, typename PState, typename FirstOver, typename Scan>
+BZ_HD uint64_t walk_block_prefix(uint64_t s, uint64_t n_bytes, uint64_t limit, RleState &gstate, RunEnd run_end, Byte byte, PState pstate,
+                                 FirstOver first_over, Scan scan, RleState &st_end)
+{
+    const uint64_t n_tiles = (n_bytes + RLE_TILE - 1) / RLE_TILE;
+    const uint32_t v = byte(s);
+    const uint64_t r = run_end(s);
+    const uint64_t L1 = r - s;
+    // the block ends inside its first run: 255-byte chunks of 5 encoded bytes each
+    const uint64_t k = limit / 5 + 1;
+    if (255ull * k <= L1) {
+        const uint64_t e = s + 255ull * k;
+        st_end = state_apply(seg_byte_run(v, 255ull * k), state_fresh());
+        gstate = state_apply(seg_byte_run(v, 255ull * k), gstate);
+        return e;
+    }
+    const Seg first_run = seg_byte_run(v, L1);
+    RleState f = state_apply(first_run, state_fresh());
+    RleState g = state_apply(first_run, gstate);
+    if (r >= n_bytes) { st_end = f; gstate = g; return n_bytes; }
+    // both machines take byte r: the first run is flushed in both, (cur, run) agree from here on
+    state_step(f, byte(r));
+    state_step(g, byte(r));
+    const uint64_t D = g.bl - f.bl;
+    const uint64_t limD = limit + D;
+    uint64_t pos = r + 1; // next byte to enter, global state g
+    if (g.bl > limD) { st_end = f; gstate = g; return pos; }
+    if (pos >= n_bytes) { st_end = f; gstate = g; return n_bytes; }
+    uint64_t t = pos / RLE_TILE; // tile of pos
+    // rest of the current tile, only if the refusal can be inside it
+    {
+        const uint64_t t_next = t + 1;
+        const RleState pn = pstate(t_next <= n_tiles ? t_next : n_tiles);
+        const uint64_t hi = t_next * RLE_TILE < n_bytes ? t_next * RLE_TILE : n_bytes;
+        if (pn.bl > limD) {
+            if (pos < hi) {
+                TileScanResult res = scan(pos, hi, g, limD);
+                gstate = res.st;
+                st_end = res.st; st_end.bl -= D;
+                return res.pos; // refusal inside [pos, hi) or exactly at hi (then res.st.bl > limD)
+            }
+            gstate = pn; st_end = pn; st_end.bl -= D;
+            return hi;
+        }
+    }
+    // whole tiles: first tile boundary whose global blockLength is over the limit
+    const uint64_t ts = first_over(t + 1, limD); // > t + 1 by the test above
+    if (ts > n_tiles) { // never: the block runs to the end of the input
+        const RleState pe = pstate(n_tiles);
+        gstate = pe; st_end = pe; st_end.bl -= D;
+        return n_bytes;
+    }
+    const uint64_t lo = (ts - 1) * RLE_TILE, hi = ts * RLE_TILE < n_bytes ? ts * RLE_TILE : n_bytes;
+    TileScanResult res = scan(lo, hi, pstate(ts - 1), limD);
+    gstate = res.st;
+    st_end = res.st; st_end.bl -= D;
+    return res.pos;
+}
+
 } // namespace bz

@@ -110,6 +110,47 @@ static Blocks tree_walk(const std::vector<uint8_t> &in, uint64_t limit)
     return b;
 }
 
+// the prefix-state walk (walk_block_prefix) with literal host callbacks
+static Blocks prefix_walk(const std::vector<uint8_t> &in, uint64_t limit)
+{
+    const uint64_t n = in.size();
+    const uint64_t nt = (n + RLE_TILE - 1) / RLE_TILE;
+    std::vector<Seg> l0 = level0(in);
+    std::vector<RleState> ps(nt + 1);
+    {
+        Seg acc = seg_empty();
+        for (uint64_t t = 0; t <= nt; ++t) {
+            ps[t] = state_apply(acc, state_fresh());
+            if (t < nt) acc = seg_combine(acc, l0[t]);
+        }
+    }
+    auto run_end = [&](uint64_t s) { uint64_t q = s + 1; while (q < n && in[q] == in[s]) ++q; return q; };
+    auto byte = [&](uint64_t q) { return (uint32_t)in[q]; };
+    auto pstate = [&](uint64_t t) { return ps[t]; };
+    auto first_over = [&](uint64_t t_lo, uint64_t lim) { uint64_t t = t_lo + 1; while (t <= nt && ps[t].bl <= lim) ++t; return t; };
+    auto scan = [&](uint64_t lo, uint64_t hi, RleState st, uint64_t lim) {
+        TileScanResult res; res.pos = hi;
+        RleState s = st;
+        for (uint64_t q = lo; q < hi; ++q) {
+            if (s.bl > lim) { res.pos = q; break; }
+            state_step(s, in[q]);
+        }
+        res.st = s;
+        return res;
+    };
+    Blocks b;
+    uint64_t s = 0;
+    RleState g = state_fresh();
+    while (s < n) {
+        RleState st;
+        uint64_t e = walk_block_prefix(s, n, limit, g, run_end, byte, pstate, first_over, scan, st);
+        b.starts.push_back(s); b.lens.push_back(state_final_length(st));
+        if (e <= s) { printf("prefix walk made no progress at %llu\n", (unsigned long long)s); exit(4); }
+        s = e;
+    }
+    return b;
+}
+
 static uint64_t rng = 88172645463325252ull;
 static uint32_t rnd() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 11); }
 
@@ -140,7 +181,13 @@ int main()
         uint64_t bss[] = {20, 100, 1000, 10000, 90000, 300000};
         for (uint64_t bs : bss) {
             uint64_t limit = bs - 6;
-            Blocks a = reference_walk(in, limit), b = tree_walk(in, limit);
+            Blocks a = reference_walk(in, limit), b = tree_walk(in, limit), p = prefix_walk(in, limit);
+            if (a.starts != p.starts || a.lens != p.lens) {
+                printf("PREFIX MISMATCH iter %d mode %d n %zu bs %llu: ref %zu blocks, prefix %zu blocks\n", iter, mode, n, (unsigned long long)bs, a.starts.size(), p.starts.size());
+                for (size_t k = 0; k < a.starts.size() && k < p.starts.size(); ++k)
+                    if (a.starts[k] != p.starts[k] || a.lens[k] != p.lens[k]) { printf(" first diff at block %zu: ref (%llu,%llu) prefix (%llu,%llu)\n", k, (unsigned long long)a.starts[k], (unsigned long long)a.lens[k], (unsigned long long)p.starts[k], (unsigned long long)p.lens[k]); break; }
+                return 1;
+            }
             if (a.starts != b.starts || a.lens != b.lens) {
                 printf("MISMATCH iter %d mode %d n %zu bs %llu: ref %zu blocks, tree %zu blocks\n", iter, mode, n, (unsigned long long)bs, a.starts.size(), b.starts.size());
                 for (size_t k = 0; k < a.starts.size() && k < b.starts.size(); ++k)
