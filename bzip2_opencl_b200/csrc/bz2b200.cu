@@ -44,6 +44,8 @@ struct bz2b200 {
     uint64_t S = 0;       // element stride per block
     int nbits = 0;        // bits needed for a position inside a block
     int key0_bytes = 4;
+    int walk_growth = 6;  // each walk chunk may be this many times the batch that hides it (the walk finds ~7 blocks while one is compressed)
+    int walk_first = 48;  // blocks of the first chunk: its latency is exposed
     int prefix_walk = 1;  // BZ2B200_WALK=0: the tree-descent walk (k_rle_walk) instead of the prefix-state walk (k_rle_walk_prefix)
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
@@ -355,6 +357,9 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
+    if (const char *e = getenv("BZ2B200_WALK_GROWTH")) h->walk_growth = std::max(1, atoi(e));
+    if (const char *e = getenv("BZ2B200_WALK_FIRST")) h->walk_first = std::max(1, atoi(e));
+    if (!h->prefix_walk) h->walk_growth = std::min(h->walk_growth, 4);
     int rc = create_impl(h);
     if (rc != BZ2B200_OK) {
         // keep the message reachable through a static for the failing create
@@ -974,9 +979,8 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->drain_dev = out ? is_device_ptr(out) != 0 : false;
     {
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
-        // (the walk finds ~4 blocks in the time the kernels compress one, so every chunk may be 4x the batch that hides it)
         bool pending = false;
-        uint64_t b0 = 0, chunk = std::min<uint64_t>(h->G, 12);
+        uint64_t b0 = 0, chunk = std::max<uint64_t>(1, std::min<uint64_t>(h->G, (uint64_t)h->walk_first) / (uint64_t)h->walk_growth);
         while (pending || b0 < h->w_found || !h->w_finished || walk_more_input(h)) {
             if (pending) {
                 rc = walk_collect(h);
@@ -988,7 +992,7 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 if (rc) return rc;
             }
             if (!h->w_finished) {
-                chunk = std::min<uint64_t>(h->G, chunk * 4);
+                chunk = std::min<uint64_t>(h->G, chunk * (uint64_t)h->walk_growth);
                 rc = walk_launch(h, chunk);
                 if (rc) return rc;
                 pending = true;
