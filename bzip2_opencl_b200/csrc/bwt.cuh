@@ -262,8 +262,10 @@ __global__ void __launch_bounds__(RH_THREADS) k_radix_count(const uint64_t *__re
 
 // digit_base[(p * n_blocks + b) * 256 + d] = keys of block b whose pass-p digit is < d
 // (nrep > 1: the totals of pass 0 are valid for nrep passes -- round 0, where every pass's digit is a byte of the same cyclic text)
+// present != nullptr: also the block's symbol-presence bitmap (value v <-> bit v & 31 of word v >> 5) from the pass-0 totals -- for
+// round 0 those are the byte counts of the RLE1 block, which is exactly blockValuesPresent (BlockCompressor.hpp:136,148).
 __global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ counts, int npass, int ctas_per_block,
-                                                      uint32_t n_blocks, uint32_t *__restrict__ digit_base, int nrep)
+                                                      uint32_t n_blocks, uint32_t *__restrict__ digit_base, int nrep, uint32_t *__restrict__ present)
 {
     __shared__ uint32_t scratch[33];
     const uint32_t b = blockIdx.x, d = threadIdx.x;
@@ -272,6 +274,10 @@ __global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict_
     for (int p = 0; p < npass; ++p) {
         uint32_t tot = 0;
         for (uint32_t c = 0; c < nc; ++c) tot += partial[(((uint64_t)b * ctas_per_block + c) * npass + p) * 256 + d];
+        if (present && p == 0) {
+            const unsigned m = __ballot_sync(FULL, tot != 0);
+            if (lane_id() == 0) present[b * 8 + warp_id()] = m;
+        }
         const uint32_t ex = block_excl_sum(tot, scratch, nullptr);
         for (int r = 0; r < (npass == 1 ? nrep : 1); ++r) digit_base[((uint64_t)(p + r) * n_blocks + b) * 256 + d] = ex;
     }

@@ -411,7 +411,7 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
         const uint32_t nc = (max_count + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_count + RS_TILE - 1) / RS_TILE;
         uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
         KL(KID_k_radix_count, k_radix_count<<<dim3(nc, nb), RH_THREADS, 0, h->stream>>>(k0, counts, h->S, npass, ptr<uint32_t>(h->rc_partial), h->ctasC));
-        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), counts, npass, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1));
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), counts, npass, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, nullptr));
         h->stats.kernel_launches += 2;
         KBYTES(KID_k_radix_count, total_elems * 8);
         int cur = 0;
@@ -446,7 +446,7 @@ static void radix_sort_round0(bz2b200 *h, const uint32_t *d_n, uint32_t nb, uint
     const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_n + RS_TILE - 1) / RS_TILE;
     uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
     KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, h->stream>>>(ptr<uint8_t>(h->rle), d_n, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
-    KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 4));
+    KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 4, ptr<uint32_t>(h->present)));
     h->stats.kernel_launches += 2;
     KBYTES(KID_k_bwt_bytehist, sum_n);
     uint64_t *kA = ptr<uint64_t>(h->kA), *kB = ptr<uint64_t>(h->kB);
@@ -699,7 +699,6 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     const uint32_t *d_n = ptr<uint32_t>(h->rle_len) + b0;
     auto &stt = h->stats;
 
-    CK(cudaMemsetAsync(h->present.p, 0, (size_t)nb * 32, st));
     CK(cudaMemsetAsync(h->crc.p, 0, (size_t)nb * 4, st));
     CK(cudaMemsetAsync(h->freq.p, 0, (size_t)nb * 258 * 4, st));
     CK(cudaMemsetAsync(h->tf.p, 0, (size_t)nb * HUFF_MAXTABLES * HUFF_MAXALPHA * 4, st));
@@ -713,8 +712,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_rle_btile_seg, k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles));
         KL(KID_k_rle_btile_scan, k_rle_btile_scan<<<(nb + RLE_WARPS - 1) / RLE_WARPS, RLE_WARPS * 32, 0, st>>>(ptr<Seg>(h->segB), d_starts, (uint32_t)b0, nb, ptr<uint64_t>(h->tstate),
                                                                                        max_tiles));
-        KL(KID_k_rle_emit, k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S,
-                                                     ptr<uint32_t>(h->present)));
+        KL(KID_k_rle_emit, k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S));
         dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), nb);
         KL(KID_k_crc_chunks, k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint32_t>(h->crc)));
         KL(KID_k_crc_finish, k_crc_finish<<<(nb + 127) / 128, 128, 0, st>>>(d_starts, (uint32_t)b0, nb, ptr<uint32_t>(h->crc)));
@@ -734,6 +732,10 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     if (h->onesweep && h->key0_bytes == 4) {
         radix_sort_round0(h, d_n, nb, max_n, sum_n);
     } else {
+        // (development paths) the byte histogram is still what gives the presence bitmap
+        const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
+        KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->rc_partial), h->ctasC));
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, ptr<uint32_t>(h->present)));
         dim3 g((max_n + 255) / 256, nb);
         KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint64_t>(h->kA)));
         stt.kernel_launches += 1;
@@ -1188,7 +1190,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             }
             const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
             KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->L), d_counts, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
-            KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_counts, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1));
+            KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_counts, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, nullptr));
             CK(cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, st));
             CK(cudaMemsetAsync(ticket, 0, 4, st));
             KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(

@@ -90,9 +90,43 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t n)
     return c < 0 ? 0u : (c > (int)RLE_LANE_BYTES ? RLE_LANE_BYTES : (uint32_t)c);
 }
 
+// Bit i (1..63) of the result: byte i of the lane's 64 staged bytes equals byte i-1 (bit 0 is 0).  Four bytes per step:
+// per-byte SIMD compare of a word with itself shifted by one byte, the four result bytes gathered with one multiply.
+__device__ __forceinline__ uint64_t lane_eq_mask(const uint8_t *p)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p); // lane offsets are multiples of 4
+    uint64_t eq = 0;
+    uint32_t prev = ~w[0] << 24; // byte "-1" differs from byte 0
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t x = w[k];
+        const uint32_t d = __vcmpeq4(x, __funnelshift_l(prev, x, 8)); // 0xff where byte j == byte j-1
+        eq |= (uint64_t)(((d & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+        prev = x;
+    }
+    return eq;
+}
+// no run of four or more equal bytes inside a full lane
+__device__ __forceinline__ bool lane_short_runs(uint64_t eq) { return (eq & (eq >> 1) & (eq >> 2)) == 0; }
+
 __device__ __forceinline__ Seg lane_seg(const uint8_t *sm, uint32_t cnt)
 {
     const uint8_t *p = sm + lane_id() * RLE_SM_STRIDE;
+    if (cnt == RLE_LANE_BYTES) {
+        const uint64_t eq = lane_eq_mask(p);
+        if (lane_short_runs(eq)) { // every run is shorter than 4: it is encoded as itself (BlockCompressor.hpp:134-154)
+            Seg s;
+            s.pad = 0;
+            s.len = RLE_LANE_BYTES;
+            s.lead = (uint64_t)__ffsll((long long)~(eq >> 1));
+            s.trail = 1ull + (uint64_t)__clzll((long long)~eq);
+            s.mid = RLE_LANE_BYTES - s.lead - s.trail;
+            s.first = p[0];
+            s.last = p[RLE_LANE_BYTES - 1];
+            s.uniform = 0;
+            return s;
+        }
+    }
     return seg_from_bytes([p](uint32_t i) { return (uint32_t)p[i]; }, cnt);
 }
 
@@ -454,26 +488,27 @@ __device__ __forceinline__ void bm_set(uint32_t (&bm)[8], uint32_t v)
     for (int w = 0; w < 8; ++w) bm[w] |= (w == (int)(v >> 5)) ? (1u << (v & 31)) : 0u;
 }
 
-__device__ __forceinline__ void emit_run(uint8_t *dst, uint32_t v, uint32_t len, uint32_t (&bm)[8])
+__device__ __forceinline__ void emit_run(uint8_t *dst, uint32_t v, uint32_t len, uint32_t (&)[8])
 {
     // writeRun, BlockCompressor.hpp:134-154
-    bm_set(bm, v);
     dst[0] = (uint8_t)v;
     if (len > 1) dst[1] = (uint8_t)v;
     if (len > 2) dst[2] = (uint8_t)v;
     if (len > 3) {
         dst[3] = (uint8_t)v;
         dst[4] = (uint8_t)(len - 4);
-        bm_set(bm, len - 4);
     }
 }
 
-// one warp per block-relative tile: RLE1 bytes into rle[bl*stride ...], presence bitmap into present[bl*8 ...]
+// one warp per block-relative tile: RLE1 bytes into rle[bl*stride ...]
+constexpr int RLE_OUT_STAGE = 2640; // bytes a tile can emit (2048 * 5/4 + carried run) + 16 of alignment slack, multiple of 16
+
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
                                                                const uint64_t *__restrict__ tstate, uint64_t max_tiles, uint8_t *__restrict__ rle,
-                                                               uint64_t stride, uint32_t *__restrict__ present)
+                                                               uint64_t stride)
 {
     __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
+    __shared__ __align__(16) uint8_t so_all[RLE_WARPS][RLE_OUT_STAGE];
     uint64_t k = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
     uint32_t bl = blockIdx.y;
     uint64_t lo; uint32_t n;
@@ -486,28 +521,58 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_emit(const uint8_t *__re
     Seg excl = shfl_up_seg(incl, 1);
     if (lane == 0) excl = seg_empty();
     RleState s = state_apply(excl, unpack_state(tstate[(uint64_t)bl * max_tiles + k]));
-    uint8_t *out = rle + (uint64_t)bl * stride;
-    uint32_t bm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t *p = sm + lane * RLE_SM_STRIDE;
     uint32_t blen = (uint32_t)s.bl, cur = s.cur, run = s.run;
-    for (uint32_t i = 0; i < cnt; ++i) {
-        uint32_t v = p[i];
-        if (run == 0) { cur = v; run = 1; }
-        else if (cur == v) {
-            if (++run > 254) { emit_run(out + blen, cur, 255, bm); blen += 5; run = 0; }
-        } else {
-            emit_run(out + blen, cur, run, bm);
-            blen += rle_enc_small(run);
-            cur = v; run = 1;
+    // The tile writes the runs that END inside it: output bytes [base, end) of the block.  They are assembled in shared memory
+    // at the same offset mod 16 as their final address, then stored with aligned 16-byte stores.
+    const uint32_t base = __shfl_sync(FULL, blen, 0);
+    uint8_t *so = so_all[warp_id()] + (base & 15u) - base; // so[x] <-> output byte x of the block
+    // finishRLE (BlockCompressor.hpp:112-118): the lane holding the block's last byte flushes the pending run
+    const bool last_lane = cnt > 0 && (lo + (uint64_t)lane * RLE_LANE_BYTES + cnt == starts[b0 + bl + 1]);
+    bool done = false;
+    if (cnt == RLE_LANE_BYTES && !last_lane && run < 4) {
+        // no run of 4+ inside the lane and none completed by the bytes carried in: the RLE1 output of the runs that end in this
+        // lane is the carried run followed by the lane's bytes up to its own (still pending) trailing run -- a plain copy
+        const uint64_t eq = lane_eq_mask(p);
+        const uint32_t lead = (uint32_t)__ffsll((long long)~(eq >> 1));
+        if (lane_short_runs(eq) && (run == 0 || cur != p[0] || run + lead < 4)) {
+            const uint32_t trail = 1u + (uint32_t)__clzll((long long)~eq);
+            uint8_t *o = so + blen;
+            for (uint32_t i = 0; i < run; ++i) o[i] = (uint8_t)cur;
+            o += run;
+            const uint32_t m = RLE_LANE_BYTES - trail;
+            for (uint32_t i = 0; i < m; ++i) o[i] = p[i];
+            blen += run + m;
+            done = true;
         }
     }
-    // finishRLE (BlockCompressor.hpp:112-118): the lane holding the block's last byte flushes the pending run
-    bool last_lane = cnt > 0 && (lo + (uint64_t)lane * RLE_LANE_BYTES + cnt == starts[b0 + bl + 1]);
-    if (last_lane && run > 0) emit_run(out + blen, cur, run, bm);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        uint32_t r = __reduce_or_sync(FULL, bm[w]);
-        if (lane == 0 && r) atomicOr(&present[bl * 8 + w], r);
+    if (!done) {
+        uint32_t bm[8]; // (presence comes from the byte histogram of the RLE1 block, k_radix_bases)
+        for (uint32_t i = 0; i < cnt; ++i) {
+            uint32_t v = p[i];
+            if (run == 0) { cur = v; run = 1; }
+            else if (cur == v) {
+                if (++run > 254) { emit_run(so + blen, cur, 255, bm); blen += 5; run = 0; }
+            } else {
+                emit_run(so + blen, cur, run, bm);
+                blen += rle_enc_small(run);
+                cur = v; run = 1;
+            }
+        }
+        if (last_lane && run > 0) { emit_run(so + blen, cur, run, bm); blen += rle_enc_small(run); }
+    }
+    // end of the tile's output = where the last lane with bytes stopped
+    const unsigned have = __ballot_sync(FULL, cnt > 0);
+    const uint32_t end = __shfl_sync(FULL, blen, 31 - __clz((int)have));
+    __syncwarp();
+    uint8_t *out = rle + (uint64_t)bl * stride;
+    const uint8_t *sb = so_all[warp_id()];
+    const uint32_t a0 = base & ~15u;                     // first 16-byte chunk of the block's output this tile touches
+    for (uint32_t c = a0 + lane * 16; c < end; c += 32 * 16) {
+        const uint8_t *src = sb + (c - a0);
+        if (c >= base && c + 16 <= end) *reinterpret_cast<uint4 *>(out + c) = *reinterpret_cast<const uint4 *>(src);
+        else
+            for (uint32_t x = max(c, base); x < min(c + 16, end); ++x) out[x] = src[x - c];
     }
 }
 
