@@ -18,7 +18,7 @@ OK, E_BLOCKSIZE, E_PARALLEL, E_ARG, E_CUDA, E_NOMEM, E_OUTPUT, E_STATE, E_FORMAT
 STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAGE_SELECTORS, STAGE_LENGTHS, STAGE_RANK = range(1, 10)
 
 EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200_max_output_bytes", "bz2b200_scan_blocks",
-           "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_decompress_stream", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
+           "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_decompress_stream", "bz2b200_decompress_concat", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
            "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times"]
 
 
@@ -60,6 +60,8 @@ def load_library() -> C.CDLL:
     L.bz2b200_compress_stream.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
     L.bz2b200_decompress_stream.restype = C.c_int
     L.bz2b200_decompress_stream.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
+    L.bz2b200_decompress_concat.restype = C.c_int
+    L.bz2b200_decompress_concat.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_uint64)]
     L.bz2b200_get_stats.restype = C.c_int
     L.bz2b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bz2b200_stage_dump.restype = C.c_int
@@ -137,15 +139,21 @@ class Compressor:
         return out[:n.value].tobytes()
 
     # ---- decompress side ---------------------------------------------------------------------------
-    def decompress(self, stream, out_capacity: int | None = None) -> bytes:
+    def decompress(self, stream, out_capacity: int | None = None, multi: bool = False) -> bytes:
         """Whole .bz2 stream -> original bytes (host buffers).  Raises Bz2Error(E_FORMAT, <the reference's exception text>) on a
-        bad stream.  Without out_capacity the buffer grows until the output fits."""
+        bad stream.  Without out_capacity the buffer grows until the output fits.  multi=True decodes every concatenated stream
+        (bz2b200_decompress_concat); self.last_streams is then the number of streams decoded."""
         src = np.frombuffer(stream, dtype=np.uint8) if len(stream) else np.zeros(1, dtype=np.uint8)
         cap = out_capacity if out_capacity is not None else max(1 << 16, 6 * len(stream))
         while True:
             out = np.empty(max(cap, 1), dtype=np.uint8)
             n = C.c_size_t(0)
-            rc = self.lib.bz2b200_decompress_stream(self.h, _np_ptr(src), len(stream), _np_ptr(out), cap, C.byref(n))
+            if multi:
+                ns = C.c_uint64(0)
+                rc = self.lib.bz2b200_decompress_concat(self.h, _np_ptr(src), len(stream), _np_ptr(out), cap, C.byref(n), C.byref(ns))
+                self.last_streams = int(ns.value)
+            else:
+                rc = self.lib.bz2b200_decompress_stream(self.h, _np_ptr(src), len(stream), _np_ptr(out), cap, C.byref(n))
             if rc == E_OUTPUT and out_capacity is None:
                 cap = max(2 * cap, int(n.value) * 2)
                 continue

@@ -749,7 +749,13 @@ __global__ void __launch_bounds__(256) k_bwt_roundstats(const uint32_t *__restri
 constexpr int LS_THREADS = BZ_LS_THREADS;
 constexpr int LS_ITEMS = RG_TILE / LS_THREADS; // 4
 constexpr int LS_WARPS = LS_THREADS / 32;
-constexpr uint32_t LS_SMALL_FROM = 32;  // try the counting path once rotations are ordered by at least this many bytes
+#ifndef BZ_LS_SMALL_FROM
+#define BZ_LS_SMALL_FROM 32
+#endif
+#ifndef BZ_LS_WARP_MIN
+#define BZ_LS_WARP_MIN 64
+#endif
+constexpr uint32_t LS_SMALL_FROM = BZ_LS_SMALL_FROM;  // try the counting path once rotations are ordered by at least this many bytes
 constexpr int LS_SMALL_MAX = 32;        // ... and no group of the region is larger than this
 
 static_assert(LS_THREADS == 256, "one thread per digit in the scan of k_bwt_local");
@@ -864,7 +870,7 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     }
     const unsigned lt = (1u << lane) - 1u;
     // the sort uses as many warps as have at least two rows of 32 elements to rank; warp w owns elements [w*chunk, (w+1)*chunk)
-    const uint32_t nwu = min((uint32_t)LS_WARPS, (c + 63) / 64);
+    const uint32_t nwu = min((uint32_t)LS_WARPS, (c + BZ_LS_WARP_MIN - 1) / BZ_LS_WARP_MIN);
     const uint32_t chunk = ((c + nwu - 1) / nwu + 31) & ~31u;
     const uint32_t wbase = (uint32_t)w * chunk;
     const uint32_t wcnt = ((uint32_t)w < nwu && wbase < c) ? min(chunk, c - wbase) : 0u;

@@ -1095,7 +1095,10 @@ static const char *dec_err_text(uint32_t e)
     }
 }
 
-static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint8_t *out, size_t out_capacity, size_t *out_bytes)
+// multi: after a complete stream keep decoding while another "BZh1".."BZh9" header follows at the next byte (concatenated .bz2
+// files, what bzip2 -d and libbzip2 front ends do); anything else behind a complete stream is ignored, as the
+// reference's InputStream ignores everything behind its first stream (InputStream.hpp:146-153).
+static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint8_t *out, size_t out_capacity, size_t *out_bytes, bool multi, uint64_t *n_streams)
 {
     cudaStream_t st = h->stream;
     h->stats = bz2b200_stats_t{};
@@ -1106,7 +1109,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     uint8_t hdr[4];
     CK(cudaMemcpy(hdr, input, 4, cudaMemcpyDefault));
     if (hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h' || hdr[3] < '1' || hdr[3] > '9') return fail("Invalid BZip2 header");
-    const uint32_t stream_bs = (uint32_t)(hdr[3] - '0') * (uint32_t)h->base;
+    uint32_t stream_bs = (uint32_t)(hdr[3] - '0') * (uint32_t)h->base;
     if (stream_bs > (uint32_t)h->bs) { h->err = "stream block size exceeds the handle's block size"; return BZ2B200_E_BLOCKSIZE; }
     const uint32_t max_selectors = (uint32_t)h->base * 9 / 50 + 1; // HUFFMAN_MAXIMUM_SELECTORS, Config.hpp:41
     // ---- input to the device, zero padded (the bit reader fetches whole 32-bit windows)
@@ -1153,7 +1156,10 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     uint32_t stream_crc = 0;
     bool ended = false;
     size_t ci = 0;
-    uint64_t nblocks = 0;
+    uint64_t nblocks = 0, nstreams = 0;
+    for (;;) { // one iteration per stream
+    ended = false;
+    stream_crc = 0;
     while (!ended) {
         // next batch: block candidates at or behind `expected`; stop at an end marker sitting exactly there
         while (ci < cand.size() && (cand[ci] >> 1) < expected) ++ci;
@@ -1273,6 +1279,17 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     for (int k = 0; k < 8; ++k) w = (w << 8) | tail[k];
     const uint32_t stored = (uint32_t)((w << ((expected + 48) & 7)) >> 32);
     if (stored != stream_crc) return fail("BZip2 stream CRC error");
+    ++nstreams;
+    if (!multi) break;
+    const uint64_t nxt = (expected + 48 + 32 + 7) >> 3; // the padding ends the stream on a byte boundary (OutputStream.hpp:172)
+    if (nxt + 4 > n_in) break;
+    CK(cudaMemcpy(hdr, d_in + nxt, 4, cudaMemcpyDeviceToHost));
+    if (hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h' || hdr[3] < '1' || hdr[3] > '9') break; // trailing bytes that are no stream
+    stream_bs = (uint32_t)(hdr[3] - '0') * (uint32_t)h->base;
+    if (stream_bs > (uint32_t)h->bs) { h->err = "stream block size exceeds the handle's block size"; return BZ2B200_E_BLOCKSIZE; }
+    expected = nxt * 8 + 32;
+    } // streams
+    if (n_streams) *n_streams = nstreams;
     CK(cudaEventRecord(h->ev[11], st));
     if (!out_dev && total_out) {
         CK(cudaEventRecord(h->ev[12], st));
@@ -1294,7 +1311,20 @@ extern "C" int bz2b200_decompress_stream(bz2b200_t *h, const uint8_t *input, siz
     if ((!input && n_bytes) || !out_bytes || (!out && out_capacity)) { h->err = "bad argument"; return BZ2B200_E_ARG; }
     CK(cudaSetDevice(h->device));
     h->err.clear();
-    int rc = decompress_impl(h, input, n_bytes, out, out_capacity, out_bytes);
+    int rc = decompress_impl(h, input, n_bytes, out, out_capacity, out_bytes, false, nullptr);
+    cudaStreamSynchronize(h->stream);
+    if (rc != BZ2B200_OK) (void)cudaGetLastError();
+    return rc;
+}
+
+extern "C" int bz2b200_decompress_concat(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes,
+                                         uint64_t *n_streams)
+{
+    if (!h) return BZ2B200_E_ARG;
+    if ((!input && n_bytes) || !out_bytes || (!out && out_capacity)) { h->err = "bad argument"; return BZ2B200_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    h->err.clear();
+    int rc = decompress_impl(h, input, n_bytes, out, out_capacity, out_bytes, true, n_streams);
     cudaStreamSynchronize(h->stream);
     if (rc != BZ2B200_OK) (void)cudaGetLastError();
     return rc;

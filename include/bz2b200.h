@@ -116,6 +116,17 @@ int bz2b200_compress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_by
  */
 int bz2b200_decompress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes);
 
+/*
+ * Concatenated streams (interoperability beyond the reference's decoder): like bz2b200_decompress_stream, but
+ * after a complete stream decoding goes on while another "BZh1".."BZh9" header starts at the next byte -- what `bzip2 -d` / `cat a.bz2
+ * b.bz2 | bzip2 -d` accept.  The reference reads exactly one stream and never looks behind its CRC (InputStream.hpp:146-153);
+ * bytes behind the last complete stream that do not start a stream are ignored here in the same way.  Every stream has its own
+ * block-size digit and combined CRC.  *n_streams (may be NULL) = streams decoded.  Errors as for bz2b200_decompress_stream; an
+ * error in a later stream fails the call.
+ */
+int bz2b200_decompress_concat(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes,
+                              uint64_t *n_streams);
+
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the LAST compress call. */
 typedef struct {
     float ms_total;       /* first kernel to last kernel, device side, excludes host<->device copies */

@@ -416,3 +416,47 @@ def test_cli_front_end_round_trip(tmp_path):
     z.write_bytes(b)
     r = subprocess.run([exe, str(z), "-c"], env=env, capture_output=True)
     assert r.returncode == 2 and b"BZip2" in r.stderr or b"block" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------- on-disk framing extras (8f N4)
+def test_concatenated_streams_decode_like_bzip2():
+    # `cat a.bz2 b.bz2 | bzip2 -d`: streams of different block sizes and makers, an empty stream in between, trailing bytes ignored
+    c = comp(9, 100000, 8)
+    a, b, e = corpus.word_text(1_900_000, 91), corpus.rand_bytes(950_000, 92) + bytes(70_000), corpus.mixed_corpus(3 << 20, 1 << 20)
+    parts = [c.compress(a), bz2.compress(b, 3), c.compress(b""), comp(2, 100000, 8).compress(e), bz2.compress(a[:10], 1)]
+    cat = b"".join(parts)
+    want = a + b + e + a[:10]
+    assert bz2.decompress(cat) == want                      # libbzip2's own multi-stream reading agrees on what the file means
+    assert c.decompress(cat, multi=True) == want and c.last_streams == 5
+    assert c.decompress(cat) == a                            # the reference's InputStream stops behind the first stream (InputStream.hpp:146-153)
+    assert c.decompress(cat + b"\x00garbage", multi=True) == want and c.last_streams == 5
+    assert c.decompress(parts[0], multi=True) == a and c.last_streams == 1
+    bad = bytearray(cat); bad[len(parts[0]) + len(parts[1]) // 2] ^= 0x10      # damage inside the second stream fails the call
+    with pytest.raises(api.Bz2Error) as ex:
+        c.decompress(bytes(bad), multi=True)
+    assert ex.value.code == api.E_FORMAT
+    with pytest.raises(api.Bz2Error) as ex:                  # a later stream with larger blocks than the handle allows
+        comp(2, 100000, 8).decompress(parts[3] + parts[0], multi=True)
+    assert ex.value.code == api.E_BLOCKSIZE
+
+
+def test_bzip2_cli_accepts_every_block_size(tmp_path):
+    # `bzip2 -t` / `bzip2 -dc` sweep: header digit '0'+mult (OutputStream.hpp:128) with blocks of mult x base bytes.  With the stock
+    # base 10000 the digit promises ten times the real block size, which every decoder accepts (blocks may be shorter than declared).
+    import shutil
+    exe = shutil.which("bzip2")
+    if exe is None:
+        pytest.skip("no bzip2 binary in this image")
+    d = corpus.word_text(700_000, 93) + bytes(300_000) + corpus.rand_bytes(250_000, 94) + b"ab" * 200_000
+    for base in (100000, 10000):
+        for mult in range(1, 10):
+            s = comp(mult, base, 16).compress(d)
+            assert s[:4] == b"BZh" + bytes([ord("0") + mult])
+            f = tmp_path / f"s_{base}_{mult}.bz2"
+            f.write_bytes(s)
+            assert subprocess.run([exe, "-t", str(f)], capture_output=True).returncode == 0
+            if mult in (1, 9):
+                assert subprocess.run([exe, "-dc", str(f)], capture_output=True, check=True).stdout == d
+    cat = tmp_path / "cat.bz2"                               # multi-stream file written by two compressors
+    cat.write_bytes(comp(9, 100000, 16).compress(d) + comp(1, 100000, 16).compress(d[::-1]))
+    assert subprocess.run([exe, "-dc", str(cat)], capture_output=True, check=True).stdout == d + d[::-1]
