@@ -339,22 +339,24 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
     if (FROM_TEXT) {
-        // stage the tile's bytes (+3 for the last key, wrapping around the block) in the output staging area
+        // stage the tile's bytes (+ text_bytes - 1 for the last key, wrapping around the block) in the output staging area
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
         const uint8_t *T = text + (uint64_t)b * stride;
-        for (uint32_t j = threadIdx.x * 16; j < tcnt + 3; j += RS_THREADS * 16) {
+        const uint32_t extra = (uint32_t)text_bytes - 1u;
+        for (uint32_t j = threadIdx.x * 16; j < tcnt + extra; j += RS_THREADS * 16) {
             if (base + j + 16 <= cnt) *reinterpret_cast<uint4 *>(tb + j) = __ldg(reinterpret_cast<const uint4 *>(T + base + j));
             else
-                for (uint32_t k = j; k < min(j + 16, tcnt + 3); ++k) { uint32_t p = base + k; tb[k] = T[p >= cnt ? (p - cnt) % cnt : p]; }
+                for (uint32_t k = j; k < min(j + 16, tcnt + extra); ++k) { uint32_t p = base + k; tb[k] = T[p >= cnt ? (p - cnt) % cnt : p]; }
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
             // (text_bytes == 1: the key is the byte itself -- the decompressor's counting sort of the BWT column, dec.cuh)
-            const uint32_t k4 = text_bytes == 1 ? (uint32_t)tb[li]
-                                                : ((uint32_t)tb[li] << 24) | ((uint32_t)tb[li + 1] << 16) | ((uint32_t)tb[li + 2] << 8) | (uint32_t)tb[li + 3];
-            key[i] = li < tcnt ? (((uint64_t)k4 << VAL_BITS) | (base + li)) : 0ull;
+            uint64_t k4 = text_bytes == 1 ? (uint64_t)tb[li]
+                                          : (uint64_t)(((uint32_t)tb[li] << 24) | ((uint32_t)tb[li + 1] << 16) | ((uint32_t)tb[li + 2] << 8) | (uint32_t)tb[li + 3]);
+            if (text_bytes == 5) k4 = (k4 << 8) | tb[li + 4]; // 40 key bits + 20 index bits still fit the element
+            key[i] = li < tcnt ? ((k4 << VAL_BITS) | (base + li)) : 0ull;
         }
     } else {
         const uint64_t *kp = keys_in + (uint64_t)b * stride + base;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     // Round 0's first pass has no earlier order to preserve: inside the tile its keys take their slots with one shared-memory
     // atomic each instead of the stable warp multi-split (the decompressor's 1-byte counting sort must stay stable).
     // (Not used for the bag sorts: their low digits can be nearly constant, and 32 lanes on one counter serialise.)
-    const bool unstable = FROM_TEXT && text_bytes == 4;
+    const bool unstable = FROM_TEXT && text_bytes >= 4;
     if (unstable) {
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
@@ -447,12 +449,13 @@ __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ r
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t *T = rle + (uint64_t)b * stride;
-    uint32_t key = 0, p = i;
-    for (int k = 0; k < nbytes; ++k) {
+    uint64_t key = 0;
+    uint32_t p = i;
+    for (int k = 0; k < nbytes; ++k) { // nbytes <= 5: 40 key bits above the 20 index bits
         key = (key << 8) | T[p];
         if (++p == n) p = 0;
     }
-    keys[(uint64_t)b * stride + i] = ((uint64_t)key << VAL_BITS) | i;
+    keys[(uint64_t)b * stride + i] = (key << VAL_BITS) | i;
 }
 
 // ------------------------------------------------------------------------------------------------ regroup

@@ -9,6 +9,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <chrono>
 
 #include "../../include/bz2b200.h"
 #include "rle.cuh"
@@ -37,13 +41,45 @@ struct CudaErr {
 
 } // namespace
 
+// Lanes: a handle compresses its batches on `n_lanes` lanes.  A lane is a handle of its own (per-batch buffers for G / n_lanes
+// blocks, its own stream) driven by its own host thread, so the kernels of one batch that keep few SMs busy (one warp per block:
+// list composition, code-length allocation, selector coding, headers) and the host round trips of the prefix-doubling rounds
+// overlap with the wide kernels of the other batch.  What the batches share lives in the parent: input, block table, output
+// stream and its bit position (handed from batch to batch in order, LaneCtl).
+struct LaneCtl {
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t bits_issued = 0; // batches whose bit offsets have been queued (events ev_bits recorded)
+    uint64_t done = 0;        // batches completed and drained, in order
+    int rc = 0;               // first failure of any lane
+    std::string err;
+    cudaEvent_t ev_bits[4] = {};
+    cudaEvent_t ev_setup = nullptr;
+};
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct bz2b200 {
+    int trace = 0;        // BZ2B200_TRACE=1: host-clock timeline of walk chunks and batches on stderr (development aid)
+    double t_call = 0;
+    bz2b200 *parent = nullptr;      // lane: the handle it works for
+    std::vector<bz2b200 *> lanes;   // parent: its lanes (empty: batches run on the handle itself)
+    std::vector<std::thread> lane_thr;
+    std::vector<char> lane_busy;
+    LaneCtl *ctl = nullptr;
+    int n_lanes = 2, last_lane = 0;
+    bool batch_ready = false;       // per-batch buffers allocated (a parent with lanes needs them for the decompress side only)
+    uint64_t call_id = 0, lane_call = 0; // lane_call != parent's call_id: first batch of this call on the lane
     int device = 0;
     int base = 0, mult = 0, bs = 0;
     uint32_t G = 0;       // blocks per batch
     uint64_t S = 0;       // element stride per block
     int nbits = 0;        // bits needed for a position inside a block
-    int key0_bytes = 4;
+    int key0_bytes = 5;   // bytes of the round-0 key (BZ2B200_KEY0_BYTES=1..5): 5 bytes = 40 key bits + 20 index bits in one element; one more
+                          // radix pass than 4 bytes, but the doubling rounds then see 5, 10, 20 ... sorted bytes and ~25 % fewer rotations
     int walk_growth = 6;  // each walk chunk may be this many times the batch that hides it (the walk finds ~7 blocks while one is compressed)
     int walk_first = 48;  // blocks of the first chunk: its latency is exposed
     int prefix_walk = 1;  // BZ2B200_WALK=0: the tree-descent walk (k_rle_walk) instead of the prefix-state walk (k_rle_walk_prefix)
@@ -245,6 +281,16 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    for (std::thread &t : h->lane_thr)
+        if (t.joinable()) t.join();
+    for (bz2b200 *l : h->lanes) bz2b200_destroy(l);
+    if (h->parent && h->stream) cudaStreamDestroy(h->stream);
+    if (h->ctl) {
+        for (cudaEvent_t e : h->ctl->ev_bits)
+            if (e) cudaEventDestroy(e);
+        if (h->ctl->ev_setup) cudaEventDestroy(h->ctl->ev_setup);
+        delete h->ctl;
+    }
     for (DevBuf *b : h->all)
         if (b->p) cudaFree(b->p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -264,7 +310,9 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
     delete h;
 }
 
-static int create_impl(bz2b200 *h)
+static int alloc_batch(bz2b200 *h);
+
+static int create_impl(bz2b200 *h, bool with_batch)
 {
     CK(cudaSetDevice(h->device));
     int rc = upload_constants(h);
@@ -276,6 +324,33 @@ static int create_impl(bz2b200 *h)
     h->tilesR2 = (int)((S + R2_TILE - 1) / R2_TILE);
     h->tilesD = (int)((S + HP_SYMS - 1) / HP_SYMS);
     h->sel_stride = ((uint64_t)h->tilesD * HP_THREADS + 63) / 64 * 64;
+    h->ctasC = (int)((S + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE));
+    ENSURE(h->scalars, 64 * 8);
+    if (with_batch) {
+        rc = alloc_batch(h);
+        if (rc) return rc;
+    }
+    CK(cudaMallocHost(&h->h_pinned, 64 * sizeof(uint64_t)));
+    CK(cudaMallocHost(&h->pin_starts, (G + 2) * sizeof(uint64_t)));
+    CK(cudaMallocHost(&h->pin_len, (G + 2) * sizeof(uint32_t)));
+    CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_t1));
+    CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h->ev_w0));
+    CK(cudaEventCreate(&h->ev_w1));
+    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    return BZ2B200_OK;
+}
+
+// the per-batch buffers (fixed size: G blocks of stride S)
+static int alloc_batch(bz2b200 *h)
+{
+    const uint64_t G = h->G, S = h->S;
     ENSURE(h->rle, G * S + 64);
     ENSURE(h->L, G * S + 64);
     ENSURE(h->ranks, G * S + 64);
@@ -287,10 +362,8 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->mtf, G * S * 2);
     ENSURE(h->hist, G * h->tilesR * 256 * 4);
     ENSURE(h->digit_base, G * 256 * 4 * RC_MAXPASS);
-    h->ctasC = (int)((S + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE));
     ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
-    ENSURE(h->scalars, 64 * 8);
     ENSURE(h->lists, G * h->tilesM * 256);
     ENSURE(h->dcount, G * h->tilesM * 4);
     ENSURE(h->r2tiles, G * h->tilesR2 * sizeof(R2Tile));
@@ -317,20 +390,31 @@ static int create_impl(bz2b200 *h)
     ENSURE(h->bitoff, G * 8);
     ENSURE(h->datastart, G * 8);
     ENSURE(h->tilebits, G * h->tilesD * 4);
-    CK(cudaMallocHost(&h->h_pinned, 64 * sizeof(uint64_t)));
-    CK(cudaMallocHost(&h->pin_starts, (G + 2) * sizeof(uint64_t)));
-    CK(cudaMallocHost(&h->pin_len, (G + 2) * sizeof(uint32_t)));
-    CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
-    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&h->ev_t0));
-    CK(cudaEventCreate(&h->ev_t1));
-    CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming));
-    CK(cudaEventCreate(&h->ev_w0));
-    CK(cudaEventCreate(&h->ev_w1));
-    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    h->batch_ready = true;
+    return BZ2B200_OK;
+}
+
+// lanes of a fresh parent: G / n_lanes blocks each, on their own streams
+static int create_lanes(bz2b200 *h)
+{
+    const uint32_t nl = (uint32_t)std::min<uint64_t>((uint64_t)h->n_lanes, h->G);
+    if (nl < 2) return BZ2B200_OK;
+    h->ctl = new LaneCtl();
+    for (auto &e : h->ctl->ev_bits) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ctl->ev_setup, cudaEventDisableTiming));
+    for (uint32_t i = 0; i < nl; ++i) {
+        bz2b200 *l = new bz2b200();
+        h->lanes.push_back(l);
+        l->parent = h;
+        l->device = h->device; l->base = h->base; l->mult = h->mult; l->bs = h->bs; l->S = h->S; l->nbits = h->nbits;
+        l->key0_bytes = h->key0_bytes; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->n_lanes = 1;
+        l->G = (h->G + nl - 1) / nl;
+        int rc = create_impl(l, true);
+        if (rc == BZ2B200_OK && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) rc = BZ2B200_E_CUDA;
+        if (rc) { h->err = l->err; return rc; }
+    }
+    h->lane_thr.resize(nl);
+    h->lane_busy.assign(nl, 0);
     return BZ2B200_OK;
 }
 
@@ -352,7 +436,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     h->nbits = ilog2_ceil((uint64_t)h->bs + 1);
     if (const char *e = getenv("BZ2B200_KEY0_BYTES")) {
         int k = atoi(e);
-        if (k >= 1 && k <= 4) h->key0_bytes = k;
+        if (k >= 1 && k <= 5) h->key0_bytes = k;
     }
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
@@ -360,7 +444,11 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (const char *e = getenv("BZ2B200_WALK_GROWTH")) h->walk_growth = std::max(1, atoi(e));
     if (const char *e = getenv("BZ2B200_WALK_FIRST")) h->walk_first = std::max(1, atoi(e));
     if (!h->prefix_walk) h->walk_growth = std::min(h->walk_growth, 4);
-    int rc = create_impl(h);
+    if (const char *e = getenv("BZ2B200_TRACE")) h->trace = atoi(e);
+    if (const char *e = getenv("BZ2B200_LANES")) h->n_lanes = std::max(1, std::min(4, atoi(e)));
+    const bool laned = h->n_lanes > 1 && h->G > 1;
+    int rc = create_impl(h, !laned);
+    if (rc == BZ2B200_OK && laned) rc = create_lanes(h);
     if (rc != BZ2B200_OK) {
         // keep the message reachable through a static for the failing create
         static thread_local std::string last;
@@ -446,17 +534,17 @@ static void radix_sort_round0(bz2b200 *h, const uint32_t *d_n, uint32_t nb, uint
     const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE), tiles = (max_n + RS_TILE - 1) / RS_TILE;
     uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
     KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, h->stream>>>(ptr<uint8_t>(h->rle), d_n, h->S, ptr<uint32_t>(h->rc_partial), h->ctasC));
-    KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 4, ptr<uint32_t>(h->present)));
+    KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, h->stream>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), h->key0_bytes, ptr<uint32_t>(h->present)));
     h->stats.kernel_launches += 2;
     KBYTES(KID_k_bwt_bytehist, sum_n);
     uint64_t *kA = ptr<uint64_t>(h->kA), *kB = ptr<uint64_t>(h->kB);
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < h->key0_bytes; ++p) {
         cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, h->stream);
         cudaMemsetAsync(ticket, 0, 4, h->stream);
         uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
         if (p == 0)
             KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
-                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), 4));
+                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), h->key0_bytes));
         else
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
                                          (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0));
@@ -605,6 +693,7 @@ static int walk_collect(bz2b200 *h)
     for (uint64_t i = 0; i < fresh; ++i) h->h_rle_len[h->w_found + i] = h->pin_len[i];
     h->w_found = nb;
     h->w_finished = h->pin_info[2] != 0;
+    if (h->trace) fprintf(stderr, "[trace %8.2f] walk: %llu blocks known (input to %llu MiB)%s\n", now_ms() - h->t_call, (unsigned long long)nb, (unsigned long long)(h->w_n >> 20), h->w_finished ? " chunk ran out of input" : "");
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_w0, h->ev_w1);
     h->stats.ms_walk += ms;
@@ -685,18 +774,27 @@ extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_
     return nb > capacity ? BZ2B200_E_OUTPUT : BZ2B200_OK;
 }
 
-static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words)
+// One batch: blocks [b0, b0 + nb) of the call, `seq` = number of the batch inside the call.  h is the handle itself or one of its
+// lanes; P owns what the batches share.
+static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq)
 {
+    bz2b200 *P = h->parent ? h->parent : h;
+    LaneCtl *ctl = h->parent ? P->ctl : nullptr;
     cudaStream_t st = h->stream;
     const uint64_t S = h->S;
+    if (P->trace) fprintf(stderr, "[trace %8.2f] batch %llu start: blocks %llu..%llu\n", now_ms() - P->t_call, (unsigned long long)seq, (unsigned long long)b0, (unsigned long long)(b0 + nb));
+    if (ctl && h->lane_call != P->call_id) { // first batch of this call on the lane: behind the parent's set-up work
+        CK(cudaStreamWaitEvent(st, ctl->ev_setup, 0));
+        h->lane_call = P->call_id;
+    }
     uint64_t max_len = 0;
-    for (uint32_t i = 0; i < nb; ++i) max_len = std::max(max_len, h->h_starts[b0 + i + 1] - h->h_starts[b0 + i]);
+    for (uint32_t i = 0; i < nb; ++i) max_len = std::max(max_len, P->h_starts[b0 + i + 1] - P->h_starts[b0 + i]);
     const uint64_t max_tiles = (max_len + RLE_TILE - 1) / RLE_TILE;
     ENSURE(h->segB, (uint64_t)nb * max_tiles * sizeof(Seg));
     ENSURE(h->tstate, (uint64_t)nb * max_tiles * 8);
     uint64_t *d_scal = ptr<uint64_t>(h->scalars);
-    const uint64_t *d_starts = ptr<uint64_t>(h->starts);
-    const uint32_t *d_n = ptr<uint32_t>(h->rle_len) + b0;
+    const uint64_t *d_starts = ptr<uint64_t>(P->starts);
+    const uint32_t *d_n = ptr<uint32_t>(P->rle_len) + b0;
     auto &stt = h->stats;
 
     CK(cudaMemsetAsync(h->crc.p, 0, (size_t)nb * 4, st));
@@ -724,13 +822,14 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     uint32_t max_n = 0;
     uint64_t sum_n = 0;
     for (uint32_t i = 0; i < nb; ++i) {
-        max_n = std::max(max_n, h->h_rle_len[b0 + i]);
-        sum_n += h->h_rle_len[b0 + i];
+        max_n = std::max(max_n, P->h_rle_len[b0 + i]);
+        sum_n += P->h_rle_len[b0 + i];
     }
     uint32_t *bag_cnt[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + (size_t)h->G};
     int res = 0;
-    if (h->onesweep && h->key0_bytes == 4) {
+    if (h->onesweep && h->key0_bytes >= 4) {
         radix_sort_round0(h, d_n, nb, max_n, sum_n);
+        res = h->key0_bytes & 1; // pass p writes kB for even p: four passes end in kA (res 0), five in kB (res 1)
     } else {
         // (development paths) the byte histogram is still what gives the presence bitmap
         const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
@@ -881,7 +980,20 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     {
         KL(KID_k_block_bits, k_block_bits<<<(nb + 127) / 128, 128, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->selbits), ptr<uint32_t>(h->tabbits),
                                                         ptr<uint32_t>(h->databits), nb, ptr<uint64_t>(h->nbits_b)));
-        KL(KID_k_bit_offsets, k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, d_scal + Scalars::BITPOS, ptr<uint64_t>(h->bitoff)));
+        if (ctl) { // the stream's bit position passes from batch to batch in order
+            std::unique_lock<std::mutex> lk(ctl->mu);
+            ctl->cv.wait(lk, [&] { return ctl->bits_issued == seq || ctl->rc != 0; });
+            if (ctl->rc) return ctl->rc;
+            if (seq) CK(cudaStreamWaitEvent(st, ctl->ev_bits[(seq - 1) & 3], 0));
+        }
+        KL(KID_k_bit_offsets, k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, ptr<uint64_t>(P->scalars) + Scalars::BITPOS, ptr<uint64_t>(h->bitoff),
+                                                                d_scal + Scalars::BATCH_BITS));
+        if (ctl) {
+            CK(cudaEventRecord(ctl->ev_bits[seq & 3], st));
+            std::lock_guard<std::mutex> lk(ctl->mu);
+            ctl->bits_issued = seq + 1;
+            ctl->cv.notify_all();
+        }
         KL(KID_k_emit_header, k_emit_header<<<(nb + 7) / 8, 256, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
                                                                        ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbitoff), h->sel_stride, ptr<uint32_t>(h->selbits),
                                                                        ptr<uint32_t>(h->pertab), ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
@@ -892,23 +1004,34 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_emit_data, k_emit_data<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->codes), ptr<uint8_t>(h->sel), h->sel_stride,
                                                 ptr<uint32_t>(h->tilebits), h->tilesD, ptr<uint64_t>(h->datastart), d_out_words));
         stt.kernel_launches += 6;
-        CK(cudaMemcpyAsync(ptr<uint32_t>(h->all_crc) + b0, h->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(ptr<uint64_t>(h->all_nbits) + b0, h->nbits_b.p, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ptr<uint32_t>(P->all_crc) + b0, h->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ptr<uint64_t>(P->all_nbits) + b0, h->nbits_b.p, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
     }
     CK(cudaEventRecord(h->ev[9], st));
-    CK(cudaMemcpyAsync(h->h_pinned + 16, d_scal + Scalars::BITPOS, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_pinned + 16, d_scal + Scalars::BATCH_BITS, 8, cudaMemcpyDeviceToHost, st)); // bit position behind this batch
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (h->profiling) prof_collect(h);
-    if (h->drain_dst) {
+    if (P->trace) fprintf(stderr, "[trace %8.2f] batch %llu done\n", now_ms() - P->t_call, (unsigned long long)seq);
+    if (ctl) { // batches finish in order: everything in front of this one has been written (and drained)
+        std::unique_lock<std::mutex> lk(ctl->mu);
+        ctl->cv.wait(lk, [&] { return ctl->done == seq || ctl->rc != 0; });
+        if (ctl->rc) return ctl->rc;
+    }
+    if (P->drain_dst) {
         // every byte below the current bit position is final: ship it now, overlapped with the next batch
         const size_t done = (size_t)(h->h_pinned[16] >> 3);
-        if (done > h->drain_cap) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
-        if (done > h->drained) {
-            CK(cudaMemcpyAsync(h->drain_dst + h->drained, ptr<uint8_t>(h->out) + h->drained, done - h->drained,
-                               h->drain_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->copy));
-            h->drained = done;
+        if (done > P->drain_cap) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+        if (done > P->drained) {
+            CK(cudaMemcpyAsync(P->drain_dst + P->drained, ptr<uint8_t>(P->out) + P->drained, done - P->drained,
+                               P->drain_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, P->copy));
+            P->drained = done;
         }
+    }
+    if (ctl) {
+        std::lock_guard<std::mutex> lk(ctl->mu);
+        ctl->done = seq + 1;
+        ctl->cv.notify_all();
     }
     stt.ms_rle += ev_ms(h->ev[2], h->ev[3]);
     stt.ms_bwt_sort0 += ev_ms(h->ev[3], h->ev[4]);
@@ -926,6 +1049,73 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                                 size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
                                 size_t block_capacity, uint64_t *n_blocks);
 
+// ---- lanes: one host thread per batch in flight
+static void lane_main(bz2b200 *l, int idx, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq)
+{
+    bz2b200 *P = l->parent;
+    int rc = cudaSetDevice(l->device) == cudaSuccess ? BZ2B200_OK : BZ2B200_E_CUDA;
+    if (rc == BZ2B200_OK) rc = run_batch(l, d_in, b0, nb, d_out_words, seq);
+    std::lock_guard<std::mutex> lk(P->ctl->mu);
+    if (rc && !P->ctl->rc) { P->ctl->rc = rc; P->ctl->err = l->err; }
+    P->lane_busy[idx] = 0;
+    P->ctl->cv.notify_all();
+}
+
+// hands the batch to a free lane (waits for one); with profiling on, batches run one at a time so that per-kernel times are clean
+static int lane_dispatch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq)
+{
+    LaneCtl *ctl = h->ctl;
+    int idx = -1;
+    {
+        std::unique_lock<std::mutex> lk(ctl->mu);
+        ctl->cv.wait(lk, [&] {
+            if (ctl->rc) return true;
+            size_t busy = 0;
+            for (char b : h->lane_busy) busy += b ? 1 : 0;
+            return h->profiling ? busy == 0 : busy < h->lane_busy.size();
+        });
+        if (ctl->rc) { h->err = ctl->err; return ctl->rc; }
+        for (size_t i = 0; i < h->lane_busy.size(); ++i) {
+            const size_t k = (seq + i) % h->lane_busy.size(); // alternate, so that a profiled pass uses every lane too
+            if (!h->lane_busy[k]) { idx = (int)k; break; }
+        }
+        h->lane_busy[idx] = 1;
+    }
+    if (h->lane_thr[idx].joinable()) h->lane_thr[idx].join();
+    bz2b200 *l = h->lanes[idx];
+    l->profiling = h->profiling;
+    h->last_lane = idx;
+    h->lane_thr[idx] = std::thread(lane_main, l, idx, d_in, b0, nb, d_out_words, seq);
+    return BZ2B200_OK;
+}
+
+// waits for every batch in flight, folds the lanes' counters into the parent's
+static int lanes_finish(bz2b200 *h)
+{
+    if (h->lanes.empty()) return BZ2B200_OK;
+    for (std::thread &t : h->lane_thr)
+        if (t.joinable()) t.join();
+    auto &s = h->stats;
+    for (bz2b200 *l : h->lanes) {
+        auto &q = l->stats;
+        s.ms_rle += q.ms_rle; s.ms_bwt_sort0 += q.ms_bwt_sort0; s.ms_bwt_rounds += q.ms_bwt_rounds; s.ms_bwt_finish += q.ms_bwt_finish;
+        s.ms_mtf += q.ms_mtf; s.ms_huffman += q.ms_huffman; s.ms_emit += q.ms_emit;
+        s.bwt_rounds = std::max(s.bwt_rounds, q.bwt_rounds);
+        s.bwt_active_volume += q.bwt_active_volume;
+        s.kernel_launches += q.kernel_launches;
+        q = bz2b200_stats_t{};
+        for (int i = 0; i < KID_COUNT; ++i) {
+            h->k_ms[i] += l->k_ms[i]; h->k_launches[i] += l->k_launches[i]; h->k_bytes[i] += l->k_bytes[i];
+            l->k_ms[i] = 0; l->k_launches[i] = 0; l->k_bytes[i] = 0;
+        }
+    }
+    bz2b200 *last = h->lanes[h->last_lane];
+    h->last_b0 = last->last_b0;
+    h->last_nb = last->last_nb;
+    if (h->ctl->rc) { h->err = h->ctl->err; return h->ctl->rc; }
+    return BZ2B200_OK;
+}
+
 extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                        size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
                                        size_t block_capacity, uint64_t *n_blocks)
@@ -933,7 +1123,8 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
     int rc = compress_blocks_impl(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits,
                                   block_capacity, n_blocks);
     if (h) {
-        // never leave copies into the caller's buffer or a walk in flight, whatever the outcome
+        // never leave batches, copies into the caller's buffer or a walk in flight, whatever the outcome
+        (void)lanes_finish(h);
         cudaStreamSynchronize(h->copy);
         cudaStreamSynchronize(h->side);
         cudaStreamSynchronize(h->h2d);
@@ -957,6 +1148,7 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->err.clear();
     h->stats = bz2b200_stats_t{};
     h->last_nb = 0;
+    h->t_call = now_ms();
     *out_nbits = 0; *consumed = 0; *n_blocks = 0;
     cudaStream_t st = h->stream;
     const uint8_t *d_in = nullptr;
@@ -979,6 +1171,17 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->drain_cap = out_capacity;
     h->drained = 0;
     h->drain_dev = out ? is_device_ptr(out) != 0 : false;
+    const bool laned = !h->lanes.empty();
+    uint64_t seq = 0;
+    if (laned) {
+        h->h_starts.reserve(h->w_cap + 2); // the lanes read the block table while the walk appends to it: no reallocation
+        h->h_rle_len.reserve(h->w_cap + 2);
+        ++h->call_id;
+        h->ctl->bits_issued = 0; h->ctl->done = 0; h->ctl->rc = 0; h->ctl->err.clear();
+        for (bz2b200 *l : h->lanes) l->stats = bz2b200_stats_t{};
+        CK(cudaEventRecord(h->ctl->ev_setup, st));
+    }
+    const uint64_t Gb = laned ? h->lanes[0]->G : h->G; // blocks per batch
     {
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
         bool pending = false;
@@ -1000,13 +1203,16 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 pending = true;
             }
             if (b0 < h->w_found) {
-                uint32_t cnt = (uint32_t)std::min<uint64_t>(h->G, h->w_found - b0);
-                rc = run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out));
+                uint32_t cnt = (uint32_t)std::min<uint64_t>(Gb, h->w_found - b0);
+                rc = laned ? lane_dispatch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq) : run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq);
                 if (rc) return rc;
                 b0 += cnt;
+                ++seq;
             }
         }
     }
+    rc = lanes_finish(h);
+    if (rc) return rc;
     const uint64_t nb = h->w_found, used = h->h_starts[nb];
     h->last_total_blocks = nb;
     *n_blocks = nb;
@@ -1103,6 +1309,10 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     cudaStream_t st = h->stream;
     h->stats = bz2b200_stats_t{};
     *out_bytes = 0;
+    if (!h->batch_ready) { // a handle whose compress batches run on lanes gets its own per-batch buffers at the first decompress call
+        int rc = alloc_batch(h);
+        if (rc) return rc;
+    }
     auto fail = [&](const char *msg) { h->err = msg; return BZ2B200_E_FORMAT; };
     // ---- stream header (InputStream::initializeStream, InputStream.hpp:104-128)
     if (n_in < 4) return fail(n_in == 0 ? "Insufficient data" : "Invalid BZip2 header");
@@ -1338,6 +1548,7 @@ extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage,
     const uint64_t bl = block_index - h->last_b0, S = h->S;
     uint32_t n = 0;
     CK(cudaMemcpy(&n, ptr<uint32_t>(h->rle_len) + block_index, 4, cudaMemcpyDeviceToHost));
+    if (!h->lanes.empty()) h = h->lanes[h->last_lane]; // the batch's buffers belong to the lane that ran it
     HuffBlock hb;
     CK(cudaMemcpy(&hb, ptr<HuffBlock>(h->hb) + bl, sizeof(hb), cudaMemcpyDeviceToHost));
     const void *src = nullptr;

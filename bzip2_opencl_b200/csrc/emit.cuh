@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) k_block_bits(const HuffBlock *__restrict_
 
 // single CTA: bitoff[b] = *bitpos + exclusive sum; *bitpos advances by the batch total (so batches chain without a host sync)
 __global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict__ nbits, uint32_t n_blocks, uint64_t *__restrict__ bitpos,
-                                                       uint64_t *__restrict__ bitoff)
+                                                       uint64_t *__restrict__ bitoff, uint64_t *__restrict__ batch_end)
 {
     __shared__ uint64_t s_w[33];
     __shared__ uint64_t s_carry;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict
         if (threadIdx.x == 0) s_carry += s_w[32];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *bitpos = s_carry;
+    if (threadIdx.x == 0) { *bitpos = s_carry; *batch_end = s_carry; } // batch_end: this batch's own copy (bitpos moves on with the next batch)
 }
 
 // OR `len` (1..32) bits of `value` into the stream at absolute bit position `pos`

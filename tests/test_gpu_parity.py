@@ -235,6 +235,37 @@ def test_alternative_sort_paths_give_the_same_bits(monkeypatch):
                 monkeypatch.delenv(k)
 
 
+def test_lanes_never_change_the_stream(monkeypatch):
+    # batches of a call run on 1..3 lanes (own stream + host thread each); the bit position passes from batch to batch in order,
+    # so the stream, the per-block tables and the bytes drained so far are the same whatever the lane count or batch size
+    d = corpus.mixed_corpus(9 << 20, 3 << 20) + bytes(1_200_000) + corpus.rand_bytes(2_000_000, 97) + b"ab" * 700_000
+    exp = oracle.compress(d, 2, 100000)                       # 200k blocks: ~70 blocks through batches of 1..12
+    ref_crcs = None
+    for lanes, par in (("1", 5), ("2", 5), ("2", 2), ("3", 7), ("4", 24), ("2", 1)):
+        monkeypatch.setenv("BZ2B200_LANES", lanes)
+        c = api.Compressor(2, par, 100000)
+        try:
+            assert c.compress(d) == exp, (lanes, par)
+            r = c.compress_blocks(d, True)
+            if ref_crcs is None:
+                ref_crcs, ref_nbits = r["crcs"], r["block_nbits"]
+            assert (r["crcs"] == ref_crcs).all() and (r["block_nbits"] == ref_nbits).all()
+            assert c.stats()["n_blocks"] == len(ref_crcs)
+            last = len(ref_crcs) - 1                             # the last batch stays resident for the stage dumps, on whichever lane ran it
+            o = oracle.block_stages(d, last, 2, 100000)
+            assert (c.stage(last, api.STAGE_BWT) == o["L"]).all() and c.stage(last, api.STAGE_ORIGPTR)[0] == o["orig_ptr"]
+            assert c.decompress(exp) == d                        # the handle's own per-batch buffers (decompress side) appear on first use
+            src = np.frombuffer(d, dtype=np.uint8)               # a failure in the middle of the batches comes back as a code, nothing hangs
+            out = np.zeros(200_000, dtype=np.uint8)
+            n = C.c_size_t(0)
+            rc = c.lib.bz2b200_compress_stream(c.h, src.ctypes.data_as(C.c_void_p), len(d), out.ctypes.data_as(C.c_void_p), out.size, C.byref(n))
+            assert rc == api.E_OUTPUT
+            assert c.compress(d[:3_000_000]) == oracle.compress(d[:3_000_000], 2, 100000)   # and the handle works afterwards
+        finally:
+            c.close()
+    monkeypatch.delenv("BZ2B200_LANES")
+
+
 @pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
 def test_config1_64mb_markov_text_vs_real_reference():
     # BASELINE configs[0]: 64 MiB English-like Markov text, -9 (900k), against the reference's own code (oracle/_ref)
