@@ -230,51 +230,122 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
         }
         if (br.overrun && I.err == DEC_OK) I.err = DEC_E_DATA;
     }
-    // decodeHuffmanData (:189-241): Huffman symbol -> RUNA/RUNB run (rank 0 repeated) or rank = symbol - 1
+    // decodeHuffmanData (:189-241): Huffman symbol -> RUNA/RUNB run (rank 0 repeated) or rank = symbol - 1.
+    // The reference reads one symbol after the other; here the warp decodes a WINDOW per step.  Lane k decodes the code that would
+    // start at bit pos + k (lookup window, canonical search for the rare long codes); which of the 32 candidates are real symbol
+    // starts follows from pointer doubling over "start + length" from bit 0 (log2(#symbols) rounds of one shuffle and one warp
+    // OR-reduction); the real ones, in lane order, are the next symbols.  A step ends at the group's 50th symbol (the table
+    // changes there, HuffmanStageDecoder.hpp:51-60), at the end-of-block symbol or at the first undecodable position.  Run
+    // digits are weighted by their place inside their stretch of RUNA/RUNB symbols (carried across steps), so a prefix sum over
+    // the window gives every literal its output index; zero runs are never written (the buffer is pre-zeroed).
     uint32_t n = 0;
     if (I.err == DEC_OK) {
         __syncwarp();
         uint8_t *out = ranks + (uint64_t)bl * stride;
-        uint32_t group = 0, in_group = 0, tbl = sel[0];
+        const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in);
+        const uint64_t limit_word = ((n_bits >> 3) + 64) / 4 - 1; // last word of the zero-padded buffer
+        const uint64_t end = n_bits;
+        uint64_t pos = br.pos;
+        // the stream around pos: 3 chunks of 32 big-endian words, one word per lane; the third is loaded a chunk ahead of its use
+        uint64_t chunk = pos >> 10;
+        uint32_t cur, nxt, nn;
+        {
+            const uint64_t w0 = chunk * 32 + lane;
+            cur = __byte_perm(__ldg(in32 + min(w0, limit_word)), 0, 0x0123);
+            nxt = __byte_perm(__ldg(in32 + min(w0 + 32, limit_word)), 0, 0x0123);
+            nn = __byte_perm(__ldg(in32 + min(w0 + 64, limit_word)), 0, 0x0123);
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        uint32_t group = 0, in_group = 0, runk = 0; // runk: RUNA/RUNB symbols at the tail of what has been decoded (open stretch)
+        uint32_t tbl = sel[0], tbl_next = sel[nsel > 1 ? 1 : 0];
         const uint16_t *lutp = T.lut[tbl];
-        uint32_t repeat = 0, inc = 1;
         for (;;) {
             if (in_group == 50) { // HuffmanStageDecoder::nextSymbol group switch (:51-60)
                 in_group = 0;
                 if (++group == nsel) { I.err = DEC_E_DECODE; break; }
-                tbl = sel[group];
+                tbl = tbl_next;
+                tbl_next = sel[min(group + 1, nsel - 1)];
                 lutp = T.lut[tbl];
-                if (br.past_end()) { I.err = DEC_E_DATA; break; }
+                if (pos > end) { I.err = DEC_E_DATA; break; }
             }
-            ++in_group;
+            const uint64_t c2 = pos >> 10;
+            if (c2 != chunk) { // a step moves pos by less than two words: at most one chunk further
+                chunk = c2;
+                cur = nxt; nxt = nn;
+                nn = __byte_perm(__ldg(in32 + min(chunk * 32 + 64 + lane, limit_word)), 0, 0x0123);
+            }
+            const uint32_t wi = (uint32_t)(pos >> 5) & 31u, off = (uint32_t)pos & 31u;
+            const uint32_t W0 = __shfl_sync(FULL, cur, wi);
+            const uint32_t W1 = wi + 1 < 32 ? __shfl_sync(FULL, cur, wi + 1) : __shfl_sync(FULL, nxt, wi + 1 - 32);
+            const uint32_t W2 = wi + 2 < 32 ? __shfl_sync(FULL, cur, wi + 2) : __shfl_sync(FULL, nxt, wi + 2 - 32);
+            const uint32_t hi = __funnelshift_l(W1, W0, off), lo = __funnelshift_l(W2, W1, off);
+            const uint32_t v = __funnelshift_l(lo, hi, lane); // bits [pos + lane, pos + lane + 32)
+            // ---- the code starting at this lane's bit
             int sym = -1;
-            const uint32_t e = lutp[br.peek(DEC_LUT_BITS)];
-            if (e) { sym = (int)(e >> 5); br.skip((int)(e & 31u)); }
-            else { // long code: the reference's limit search (HuffmanStageDecoder.hpp:62-74)
-                int clen = T.minlen[tbl];
-                int32_t code = (int32_t)br.bits(clen);
-                while (clen <= DEC_MAXLEN) {
-                    if (code <= T.limit[tbl][clen]) { sym = T.perm[tbl][code - T.base[tbl][clen]]; break; }
-                    code = (code << 1) | (int32_t)br.bit();
-                    ++clen;
+            uint32_t len = 32;
+            const uint32_t e = lutp[v >> (32 - DEC_LUT_BITS)];
+            if (e) { sym = (int)(e >> 5); len = e & 31u; }
+            else { // longer than the lookup window: the reference's limit search (HuffmanStageDecoder.hpp:62-74)
+                for (int clen = max((int)T.minlen[tbl], DEC_LUT_BITS + 1); clen <= DEC_MAXLEN; ++clen) {
+                    const int32_t code = (int32_t)(v >> (32 - clen));
+                    if (code <= T.limit[tbl][clen]) {
+                        const int32_t idx = code - T.base[tbl][clen];
+                        if ((uint32_t)idx < (uint32_t)alpha) { sym = T.perm[tbl][idx]; len = (uint32_t)clen; }
+                        break;
+                    }
                 }
             }
-            if (sym < 0) { I.err = br.past_end() ? DEC_E_DATA : DEC_E_DECODE; break; }
-            if (sym <= 1) { // RUNA / RUNB
-                repeat += inc << sym; inc <<= 1;
-                if (inc > (1u << 24)) { I.err = DEC_E_BLOCKSIZE; break; }
-                continue;
+            const uint32_t nx1 = (uint32_t)lane + len; // where the next symbol starts (relative to pos)
+            // ---- which lanes are symbol starts: reachable from bit 0
+            uint32_t jump = min(nx1, 32u), mask = 1u;
+            for (;;) {
+                const bool mem = (mask >> lane) & 1u;
+                const uint32_t add = __reduce_or_sync(FULL, (mem && jump < 32u) ? (1u << jump) : 0u);
+                if ((add & ~mask) == 0u) break;
+                mask |= add;
+                const uint32_t j2 = __shfl_sync(FULL, jump, jump & 31u);
+                jump = jump < 32u ? j2 : 32u;
             }
-            if (repeat > 0) {
-                if (n + repeat > block_size) { I.err = DEC_E_BLOCKSIZE; break; }
-                n += repeat; // rank 0 x repeat: already in the zeroed buffer
-                repeat = 0; inc = 1;
+            bool acc = ((mask >> lane) & 1u) && (uint32_t)__popc(mask & lt) < 50u - in_group;
+            const unsigned eobm = __ballot_sync(FULL, acc && sym == eob);
+            if (eobm) acc = acc && lane < __ffs(eobm);
+            const unsigned A = __ballot_sync(FULL, acc);
+            const bool isrun = acc && (uint32_t)sym <= 1u;
+            const unsigned RUN = __ballot_sync(FULL, isrun);
+            uint32_t c = 0, lerr = DEC_OK, place = 0;
+            if (isrun) { // digit number `place` of its stretch: weight (sym + 1) << place  (:203-214)
+                const unsigned nr = A & ~RUN & lt, below = RUN & lt;
+                place = nr == 0u ? (uint32_t)__popc(below) + runk : (uint32_t)__popc(below >> (32 - __clz(nr)));
+                if (place >= 24u) lerr = DEC_E_BLOCKSIZE;
+                else c = (uint32_t)(sym + 1) << place;
+            } else if (acc && sym >= 0 && sym != eob) c = 1;
+            uint32_t incl;
+            if (RUN == 0u) incl = (uint32_t)__popc(__ballot_sync(FULL, c != 0u) & (lt | (1u << lane))); // literals only: count them
+            else {
+                incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
             }
-            if (sym == eob) { if (br.past_end()) I.err = DEC_E_DATA; break; }
-            if (n >= block_size) { I.err = DEC_E_BLOCKSIZE; break; }
-            if (lane == 0) out[n] = (uint8_t)(sym - 1);
-            ++n;
+            const uint32_t at = n + incl - c; // ranks in front of this symbol
+            if (acc && !isrun) {
+                if (sym < 0) lerr = (pos + (uint32_t)lane + DEC_MAXLEN > end) ? DEC_E_DATA : DEC_E_DECODE;
+                else if (sym == eob ? at > block_size : at >= block_size) lerr = DEC_E_BLOCKSIZE;
+            }
+            const unsigned errm = __ballot_sync(FULL, acc && lerr != DEC_OK);
+            if (errm) { I.err = __shfl_sync(FULL, lerr, __ffs(errm) - 1); break; }
+            if (acc && !isrun && sym != eob) out[at] = (uint8_t)(sym - 1);
+            const int klast = 31 - __clz(A); // lane 0 always is a symbol start
+            n += __shfl_sync(FULL, incl, 31);
+            pos += __shfl_sync(FULL, nx1, klast);
+            const uint32_t lplace = __shfl_sync(FULL, place, klast);
+            runk = ((RUN >> klast) & 1u) ? lplace + 1u : 0u;
+            in_group += (uint32_t)__popc(A);
+            if (eobm) { if (pos > end) I.err = DEC_E_DATA; break; }
         }
+        br.pos = pos;
     }
     if (I.err == DEC_OK && I.orig >= n) I.err = DEC_E_STARTPTR; // initialiseInverseBWT (:244-248)
     I.n = I.err == DEC_OK ? n : 0u;
