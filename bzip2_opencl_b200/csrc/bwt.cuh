@@ -311,6 +311,49 @@ __global__ void __launch_bounds__(256) k_bwt_bytehist(const uint8_t *__restrict_
     partial[((uint64_t)b * ctas_per_block + blockIdx.x) * 256 + threadIdx.x] = s;
 }
 
+// Packed round-0 keys (see k_bwt_count_packed): thread v < 256 fills map[v] = rank of byte value v among the block's used values;
+// bits per symbol, symbols per key and their total width come back in every thread.
+__device__ __forceinline__ void packed_setup(const uint32_t *__restrict__ present, uint32_t b, uint8_t *map, int &bits, int &hc, int &width)
+{
+    const uint32_t v = threadIdx.x;
+    uint32_t alpha = 0, below = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t m = present[b * 8 + w];
+        alpha += __popc(m);
+        if ((uint32_t)w < (v >> 5)) below += __popc(m);
+        else if ((uint32_t)w == (v >> 5)) below += __popc(m & ((1u << (v & 31u)) - 1u));
+    }
+    if (v < 256) map[v] = (uint8_t)below;
+    bits = alpha <= 2u ? 1 : 32 - __clz((int)alpha - 1);
+    hc = min(16, (40 + bits - 1) / bits);
+    width = hc * bits;
+}
+// mapped symbols of positions [base, base + need) of the block (wrapping) into sym[], 16 per thread, all threads of the CTA
+__device__ __forceinline__ void packed_stage(const uint8_t *__restrict__ T, uint32_t n, uint32_t base, uint32_t need, const uint8_t *map, uint8_t *sym)
+{
+    for (uint32_t j = threadIdx.x * 16; j < need; j += blockDim.x * 16) {
+        if (base + j + 16 <= n) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T + base + j));
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o4[k] = (uint32_t)map[w4[k] & 0xffu] | ((uint32_t)map[(w4[k] >> 8) & 0xffu] << 8) | ((uint32_t)map[(w4[k] >> 16) & 0xffu] << 16) |
+                        ((uint32_t)map[w4[k] >> 24] << 24);
+            *reinterpret_cast<uint4 *>(sym + j) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+            for (uint32_t k = j; k < min(j + 16, need); ++k) { uint32_t p = base + k; sym[k] = map[T[p >= n ? (p - n) % n : p]]; }
+        }
+    }
+}
+__device__ __forceinline__ uint64_t packed_key(const uint8_t *sym, uint32_t li, int bits, int hc, int width)
+{
+    uint64_t c = 0;
+    for (int j = 0; j < hc; ++j) c = (c << bits) | sym[li + j];
+    return width >= 40 ? c >> (width - 40) : c << (40 - width);
+}
+
 // FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first text_bytes bytes of rotation i, big-endian) << 20 | i,
 // from the block `text` instead of reading them from keys_in.
 template <bool FROM_TEXT>
@@ -318,10 +361,11 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
                                                                 const uint32_t *__restrict__ counts, uint64_t stride, int shift,
                                                                 const uint32_t *__restrict__ digit_base, uint32_t *__restrict__ tile_state,
                                                                 int tiles_per_block, uint32_t *__restrict__ ticket, const uint8_t *__restrict__ text,
-                                                                int text_bytes)
+                                                                int text_bytes, const uint32_t *__restrict__ present)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    __shared__ uint8_t s_map[256]; // text_bytes == 0: keys over the block's own alphabet
     // tiles are taken in ticket order, so the tiles a CTA looks back at are always held by CTAs that are already running
     if (threadIdx.x == 0) sm.scratch[33] = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -338,7 +382,19 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
     uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
-    if (FROM_TEXT) {
+    if (FROM_TEXT && text_bytes == 0) {
+        int bits, hc, width;
+        packed_setup(present, b, s_map, bits, hc, width);
+        __syncthreads();
+        uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
+        packed_stage(text + (uint64_t)b * stride, cnt, base, tcnt + (uint32_t)hc - 1u, s_map, tb);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            key[i] = li < tcnt ? ((packed_key(tb, li, bits, hc, width) << VAL_BITS) | (base + li)) : 0ull;
+        }
+    } else if (FROM_TEXT) {
         // stage the tile's bytes (+ text_bytes - 1 for the last key, wrapping around the block) in the output staging area
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
         const uint8_t *T = text + (uint64_t)b * stride;
@@ -370,7 +426,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     // Round 0's first pass has no earlier order to preserve: inside the tile its keys take their slots with one shared-memory
     // atomic each instead of the stable warp multi-split (the decompressor's 1-byte counting sort must stay stable).
     // (Not used for the bag sorts: their low digits can be nearly constant, and 32 lanes on one counter serialise.)
-    const bool unstable = FROM_TEXT && text_bytes >= 4;
+    const bool unstable = FROM_TEXT && text_bytes != 1;
     if (unstable) {
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
@@ -458,6 +514,57 @@ __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ r
     keys[(uint64_t)b * stride + i] = (key << VAL_BITS) | i;
 }
 
+// Round-0 keys over the block's own alphabet.  The block uses `alpha` of the 256 byte values (the presence bitmap); mapped to
+// 0..alpha-1 in byte order a symbol needs bits = ceil(log2 alpha) bits, and the 40 key bits of an element hold the first
+// floor(40 / bits) symbols of the rotation (capped at 16) plus the leading bits of the next one -- 8 symbols for lower-case text,
+// 6 for program text, 5 for binary data.  Mapping and truncation are monotone, so the order of the keys is the order of the
+// rotations on h0 = floor(40 / bits) bytes, refined further by the partial symbol (a refinement consistent with the final order
+// is all prefix doubling needs).  h0 goes to h0_out[b]: every block of a batch doubles from its own depth.
+constexpr int KP_TILE = 4096;
+// digit histograms of the packed keys for all five passes, straight from the text (the keys themselves are built again by the first
+// sweep): partial[] in k_radix_count's layout, one CTA per RC_TILES radix tiles
+__global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                           const uint32_t *__restrict__ present, uint32_t *__restrict__ partial, int ctas_per_block,
+                                                           uint32_t *__restrict__ h0_out)
+{
+    __shared__ uint8_t map[256];
+    __shared__ __align__(16) uint8_t sym[KP_TILE + 32];
+    __shared__ uint32_t h[RC_MAXPASS][256];
+    const uint32_t b = blockIdx.y, n = n_arr[b];
+    const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
+    int bits, hc, width;
+    packed_setup(present, b, map, bits, hc, width);
+    if (blockIdx.x == 0 && threadIdx.x == 0) h0_out[b] = (uint32_t)min(16, 40 / bits);
+    if (base0 >= n) return;
+    for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += 256) (&h[0][0])[i] = 0;
+    const uint8_t *T = rle + (uint64_t)b * stride;
+    const uint32_t end = min(n, base0 + RC_TILES * RS_TILE);
+    for (uint32_t base = base0; base < end; base += KP_TILE) {
+        const uint32_t tcnt = min((uint32_t)KP_TILE, end - base);
+        __syncthreads();
+        packed_stage(T, n, base, tcnt + (uint32_t)hc - 1u, map, sym);
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < KP_TILE / 256; ++k) {
+            const uint32_t li = threadIdx.x + 256u * k;
+            if (li < tcnt) {
+                const uint64_t key = packed_key(sym, li, bits, hc, width);
+#pragma unroll
+                for (int p = 0; p < RC_MAXPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (8 * p)) & 0xffu], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t *out = partial + ((uint64_t)b * ctas_per_block + blockIdx.x) * RC_MAXPASS * 256;
+    for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += 256) out[i] = (&h[0][0])[i];
+}
+
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ p, uint32_t n, uint32_t v)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------ regroup
 // After a sort, equal keys form the new groups.  For every element: rank[rotation] = SA position of its group's first element;
 // a rotation alone in its group (or any rotation once 2h >= n) is final and its BWT byte goes straight to L[position].
@@ -478,9 +585,11 @@ struct RoundArgs {
     uint32_t *loc_cnt;          // [G*tiles] elements in each local region
     int tiles_per_block;
     unsigned long long *totals; // [0] rotations kept for the next round (all blocks)
-    uint32_t sorted_len;        // rotations are now ordered by their first sorted_len bytes
+    const uint32_t *h0;         // [G] bytes the round-0 key of each block orders its rotations by (differs per block with packed keys)
+    uint32_t round;             // rotations of block b are now ordered by their first h0[b] << round bytes
     int split;                  // 0: keep every group in the bag (debug)
 };
+__device__ __forceinline__ uint32_t sorted_len_of(const RoundArgs &A, uint32_t b) { return A.h0[b] << A.round; } // h0 <= 16, round <= 20
 
 constexpr int GPOS_SHIFT = 2 * VAL_BITS;  // element = group position << 40 | rank of the second half << 20 | rotation index
 constexpr int SA_TILE_BITS = 11;
@@ -646,7 +755,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
     GroupView<RG_ITEMS> v;
     group_view<ROUND0, RG_ITEMS>(e, prev_e, next_e, a0, cnt, s_edge[0], s_edge[1], s_edge[2], s_i, v);
     const uint32_t n = A.n_arr[b];
-    const bool done = A.sorted_len >= n;
+    const bool done = sorted_len_of(A, b) >= n;
     const uint64_t o = (uint64_t)b * A.stride;
     uint32_t kg = 0; // kept in the bag
     unsigned gmask = 0, lmask = 0, fmask = 0;
@@ -805,7 +914,7 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     // If the region is still in group order (kept elements are; appended ones may not be) and no group is larger than
     // LS_SMALL_MAX, every element finds its place by counting the smaller keys inside its own group: no radix passes at all.
     bool sorted_small = false;
-    if (A.sorted_len >= LS_SMALL_FROM) {
+    if (sorted_len_of(A, b) >= LS_SMALL_FROM) {
         const uint32_t a0 = threadIdx.x * LS_ITEMS;
         uint64_t e[LS_ITEMS];
         int last_s = -1, first_s = INT_INF;
@@ -992,7 +1101,7 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
     GroupView<LS_ITEMS> v;
     group_view<false, LS_ITEMS>(e, prev_e, next_e, a0, c, 0u, 0u, c - 1, sm.scr_i, v);
     const uint32_t n = A.n_arr[b];
-    const bool done = A.sorted_len >= n;
+    const bool done = sorted_len_of(A, b) >= n;
     const uint32_t tbase = t * RG_TILE;
     unsigned kmask = 0, fmask = 0;
     if (a0 < c) {
@@ -1029,12 +1138,12 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
 }
 
 // local regions: element |= rank[(i + h) mod n] << 20
-__global__ void __launch_bounds__(256) k_bwt_gather_local(RoundArgs A, uint32_t h)
+__global__ void __launch_bounds__(256) k_bwt_gather_local(RoundArgs A)
 {
     const uint32_t b = blockIdx.y, t = blockIdx.x;
     const uint32_t c = A.loc_cnt[(uint64_t)b * A.tiles_per_block + t];
     if (c == 0) return;
-    const uint32_t n = A.n_arr[b];
+    const uint32_t n = A.n_arr[b], h = sorted_len_of(A, b);
     const uint64_t o = (uint64_t)b * A.stride;
     uint64_t *reg = A.loc + o + (uint64_t)t * RG_TILE;
     const uint32_t *rank = A.rank + o;
@@ -1048,13 +1157,13 @@ __global__ void __launch_bounds__(256) k_bwt_gather_local(RoundArgs A, uint32_t 
 
 // bag: element |= rank[(i + h) mod n] << 20
 __global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ n_arr,
-                                                     uint64_t stride, const uint32_t *__restrict__ rank, uint32_t h)
+                                                     uint64_t stride, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ h0, uint32_t round)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t cnt = counts[b];
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= cnt) return;
-    const uint32_t n = n_arr[b];
+    const uint32_t n = n_arr[b], h = h0[b] << round;
     const uint64_t o = (uint64_t)b * stride;
     const uint64_t e = keys[o + a];
     uint32_t p = (uint32_t)(e & VAL_MASK) + h; // h < n for every block that is still active

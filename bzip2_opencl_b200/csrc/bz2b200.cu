@@ -83,6 +83,7 @@ struct bz2b200 {
     int walk_growth = 6;  // each walk chunk may be this many times the batch that hides it (the walk finds ~7 blocks while one is compressed)
     int walk_first = 48;  // blocks of the first chunk: its latency is exposed
     int prefix_walk = 1;  // BZ2B200_WALK=0: the tree-descent walk (k_rle_walk) instead of the prefix-state walk (k_rle_walk_prefix)
+    int pack_keys = 1;    // round-0 keys over the block's own alphabet (k_bwt_keys_packed); BZ2B200_PACK=0: the first key0_bytes bytes
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
     cudaStream_t stream = 0;
@@ -94,7 +95,7 @@ struct bz2b200 {
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
-        lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
+        h0, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int ctasC = 0;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
@@ -364,6 +365,7 @@ static int alloc_batch(bz2b200 *h)
     ENSURE(h->digit_base, G * 256 * 4 * RC_MAXPASS);
     ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
+    ENSURE(h->h0, G * 4);
     ENSURE(h->lists, G * h->tilesM * 256);
     ENSURE(h->dcount, G * h->tilesM * 4);
     ENSURE(h->r2tiles, G * h->tilesR2 * sizeof(R2Tile));
@@ -407,7 +409,7 @@ static int create_lanes(bz2b200 *h)
         h->lanes.push_back(l);
         l->parent = h;
         l->device = h->device; l->base = h->base; l->mult = h->mult; l->bs = h->bs; l->S = h->S; l->nbits = h->nbits;
-        l->key0_bytes = h->key0_bytes; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->n_lanes = 1;
+        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->n_lanes = 1;
         l->G = (h->G + nl - 1) / nl;
         int rc = create_impl(l, true);
         if (rc == BZ2B200_OK && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) rc = BZ2B200_E_CUDA;
@@ -438,6 +440,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
         int k = atoi(e);
         if (k >= 1 && k <= 5) h->key0_bytes = k;
     }
+    if (const char *e = getenv("BZ2B200_PACK")) h->pack_keys = atoi(e);
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
@@ -508,7 +511,7 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
             cudaMemsetAsync(ticket, 0, 4, h->stream);
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
                                          cur ? k1 : k0, cur ? k0 : k1, counts, h->S, VAL_BITS + 8 * p, ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256,
-                                         ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0));
+                                         ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0, nullptr));
             h->stats.kernel_launches += 1;
             KBYTES(KID_k_radix_onesweep, total_elems * 16);
             cur ^= 1;
@@ -544,10 +547,10 @@ static void radix_sort_round0(bz2b200 *h, const uint32_t *d_n, uint32_t nb, uint
         uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
         if (p == 0)
             KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
-                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), h->key0_bytes));
+                                         nullptr, kB, d_n, h->S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), h->key0_bytes, nullptr));
         else
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
-                                         (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0));
+                                         (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, h->S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0, nullptr));
         h->stats.kernel_launches += 1;
         KBYTES(KID_k_radix_onesweep, sum_n * (p == 0 ? 9 : 16));
     }
@@ -827,7 +830,37 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     }
     uint32_t *bag_cnt[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + (size_t)h->G};
     int res = 0;
-    if (h->onesweep && h->key0_bytes >= 4) {
+    uint32_t *d_h0 = ptr<uint32_t>(h->h0);
+    if (h->onesweep && h->pack_keys) {
+        // keys over each block's own alphabet: byte histogram -> presence bitmap -> packed keys (+ the depth h0 they order by)
+        const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
+        KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->rc_partial), h->ctasC));
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, ptr<uint32_t>(h->present)));
+        const uint32_t tiles = (max_n + RS_TILE - 1) / RS_TILE;
+        KL(KID_k_bwt_keys0, k_bwt_count_packed<<<dim3(std::max(nc, 1u), nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->present), ptr<uint32_t>(h->rc_partial),
+                                                                                          h->ctasC, d_h0)); // (h0 is written by the first CTA of every block, empty or not)
+        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, RC_MAXPASS, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, nullptr));
+        stt.kernel_launches += 4;
+        KBYTES(KID_k_bwt_bytehist, sum_n);
+        KBYTES(KID_k_bwt_keys0, sum_n);
+        uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
+        uint64_t *kA = ptr<uint64_t>(h->kA), *kB = ptr<uint64_t>(h->kB);
+        for (int p = 0; p < RC_MAXPASS && tiles; ++p) { // five sweeps; the first builds its elements from the text
+            CK(cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, st));
+            CK(cudaMemsetAsync(ticket, 0, 4, st));
+            uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
+            if (p == 0)
+                KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                             nullptr, kB, d_n, S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), 0, ptr<uint32_t>(h->present)));
+            else
+                KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                             (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0, nullptr));
+            stt.kernel_launches += 1;
+            KBYTES(KID_k_radix_onesweep, sum_n * (p == 0 ? 9 : 16));
+        }
+        res = 1; // five sweeps end in kB
+    } else if (h->onesweep && h->key0_bytes >= 4) {
+        k_fill_u32<<<(nb + 255) / 256, 256, 0, st>>>(d_h0, nb, (uint32_t)h->key0_bytes);
         radix_sort_round0(h, d_n, nb, max_n, sum_n);
         res = h->key0_bytes & 1; // pass p writes kB for even p: four passes end in kA (res 0), five in kB (res 1)
     } else {
@@ -835,6 +868,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
         KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->rc_partial), h->ctasC));
         KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, ptr<uint32_t>(h->present)));
+        k_fill_u32<<<(nb + 255) / 256, 256, 0, st>>>(d_h0, nb, (uint32_t)h->key0_bytes);
         dim3 g((max_n + 255) / 256, nb);
         KL(KID_k_bwt_keys0, k_bwt_keys0<<<g, 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, h->key0_bytes, ptr<uint64_t>(h->kA)));
         stt.kernel_launches += 1;
@@ -856,14 +890,15 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
 
     const int round_bits = 2 * VAL_BITS;
     const dim3 gtiles((max_n + RG_TILE - 1) / RG_TILE, nb);
-    uint32_t sorted_len = (uint32_t)h->key0_bytes;
+    A.h0 = d_h0;
+    uint32_t round_no = 0; // rotations of block b are ordered by h0[b] << round_no bytes
     uint64_t rounds = 0;
     CK(cudaMemsetAsync(h->loc_cnt.p, 0, (size_t)nb * h->tilesG * 4, st));
     // round 0: regroup the whole block, sorted by its first key
     {
         uint64_t *sorted = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
         uint64_t *bag = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
-        A.sorted_len = sorted_len;
+        A.round = round_no;
         CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
         CK(cudaMemsetAsync(bag_cnt[0], 0, (size_t)nb * 4, st));
         KL(KID_k_bwt_regroup, k_bwt_regroup<true><<<gtiles, RG_THREADS, 0, st>>>(sorted, d_n, A, bag, bag_cnt[0]));
@@ -899,16 +934,16 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         const bool have_local = active > total_b;
         CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
         if (have_local) {
-            KL(KID_k_bwt_gather_local, k_bwt_gather_local<<<gtiles, 256, 0, st>>>(A, sorted_len));
+            KL(KID_k_bwt_gather_local, k_bwt_gather_local<<<gtiles, 256, 0, st>>>(A));
             stt.kernel_launches += 1;
             KBYTES(KID_k_bwt_gather_local, (active - total_b) * 20);
         }
         if (max_b) {
             dim3 gg((max_b + 255) / 256, nb);
-            KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(bag, bag_cnt[cs], d_n, S, ptr<uint32_t>(h->rank), sorted_len));
+            KL(KID_k_bwt_gather, k_bwt_gather<<<gg, 256, 0, st>>>(bag, bag_cnt[cs], d_n, S, ptr<uint32_t>(h->rank), d_h0, round_no));
             stt.kernel_launches += 1;
         }
-        A.sorted_len = sorted_len * 2;
+        A.round = round_no + 1;
         if (have_local) {
             KL(KID_k_bwt_local, k_bwt_local<<<gtiles, LS_THREADS, 0, st>>>(A));
             stt.kernel_launches += 1;
@@ -925,7 +960,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[cs ^ 1], nb, A.totals));
         stt.kernel_launches += 1;
         cs ^= 1;
-        sorted_len *= 2;
+        ++round_no;
     }
     stt.bwt_rounds = std::max<uint64_t>(stt.bwt_rounds, rounds);
     CK(cudaEventRecord(h->ev[5], st));
@@ -1411,7 +1446,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             CK(cudaMemsetAsync(ticket, 0, 4, st));
             KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
                                          nullptr, ptr<uint64_t>(h->kA), d_counts, h->S, VAL_BITS, ptr<uint32_t>(h->digit_base), ptr<uint32_t>(h->hist), h->tilesR,
-                                         ticket, ptr<uint8_t>(h->L), 1));
+                                         ticket, ptr<uint8_t>(h->L), 1, nullptr));
             dim3 gd((max_n + 255) / 256, nb);
             KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kA), ptr<uint64_t>(h->kB), d_counts, h->S, 1));
             KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kB), ptr<uint64_t>(h->kA), d_counts, h->S, 2));

@@ -223,7 +223,9 @@ def test_alternative_sort_paths_give_the_same_bits(monkeypatch):
     # development switches: three-kernel radix passes instead of the single sweep; every group through the global sort
     d = corpus.mixed_corpus(3 << 20, 1 << 20) + b"ab" * 300000 + bytes(100000)
     exp = oracle.compress(d, 9, 100000)
-    for env in ({"BZ2B200_ONESWEEP": "0"}, {"BZ2B200_LOCALSORT": "0"}, {"BZ2B200_ONESWEEP": "0", "BZ2B200_LOCALSORT": "0"}):
+    # byte keys instead of keys over the block's alphabet (5 and 4 bytes)
+    for env in ({"BZ2B200_ONESWEEP": "0"}, {"BZ2B200_LOCALSORT": "0"}, {"BZ2B200_ONESWEEP": "0", "BZ2B200_LOCALSORT": "0"},
+                {"BZ2B200_PACK": "0"}, {"BZ2B200_PACK": "0", "BZ2B200_KEY0_BYTES": "4"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         c = api.Compressor(9, 8, 100000)
