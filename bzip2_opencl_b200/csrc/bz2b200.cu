@@ -83,6 +83,7 @@ struct bz2b200 {
     int walk_growth = 6;  // each walk chunk may be this many times the batch that hides it (the walk finds ~7 blocks while one is compressed)
     int walk_first = 48;  // blocks of the first chunk: its latency is exposed
     int prefix_walk = 1;  // BZ2B200_WALK=0: the tree-descent walk (k_rle_walk) instead of the prefix-state walk (k_rle_walk_prefix)
+    uint64_t seg_first = 16ull << 20, seg_rest = 64ull << 20; // host input: bytes per H2D segment (BZ2B200_SEG_MB=first,rest)
     int pack_keys = 1;    // round-0 keys over the block's own alphabet (k_bwt_keys_packed); BZ2B200_PACK=0: the first key0_bytes bytes
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
@@ -440,6 +441,10 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
         int k = atoi(e);
         if (k >= 1 && k <= 5) h->key0_bytes = k;
     }
+    if (const char *e = getenv("BZ2B200_SEG_MB")) {
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { h->seg_first = (uint64_t)a << 20; h->seg_rest = (uint64_t)b << 20; }
+    }
     if (const char *e = getenv("BZ2B200_PACK")) h->pack_keys = atoi(e);
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
@@ -732,8 +737,9 @@ static int stage_input(bz2b200 *h, const uint8_t *input, size_t n, const uint8_t
         return BZ2B200_OK;
     }
     ENSURE(h->in, n + 64);
-    // a short first segment lets the kernels start early; later segments are long enough to amortise a tree update
-    const uint64_t first = 16ull << 20, rest = 128ull << 20;
+    // a short first segment lets the kernels start early; the later ones are short enough that blocks become known at a steady
+    // pace (a batch is cut from what the walk has found so far) and long enough to amortise a tree update
+    const uint64_t first = h->seg_first, rest = h->seg_rest;
     for (uint64_t pos = 0; pos < n;) {
         pos = std::min<uint64_t>(n, pos + (pos == 0 ? first : rest));
         h->seg_end.push_back(pos);
@@ -1237,7 +1243,20 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 if (rc) return rc;
                 pending = true;
             }
-            if (b0 < h->w_found) {
+            bool go = b0 < h->w_found;
+            if (go && laned) {
+                // A batch costs about the same wall time whatever its size (its one-warp-per-block kernels), so a lane is not spent
+                // on a few blocks while the other one is busy: wait until half a batch is known -- unless nothing more will come.
+                const uint64_t undis = h->w_found - b0;
+                const bool nothing_more = !pending && h->w_finished && !walk_more_input(h);
+                if (undis < (Gb + 1) / 2 && !nothing_more) {
+                    std::lock_guard<std::mutex> lk(h->ctl->mu);
+                    bool busy = false;
+                    for (char c : h->lane_busy) busy |= c != 0;
+                    go = !busy;
+                }
+            }
+            if (go) {
                 uint32_t cnt = (uint32_t)std::min<uint64_t>(Gb, h->w_found - b0);
                 rc = laned ? lane_dispatch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq) : run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq);
                 if (rc) return rc;
