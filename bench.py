@@ -318,7 +318,8 @@ def main():
                 "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
                 "config": {"workload": workload_name(world, args.size_mb), "input_bytes_total": total_bytes, "blocks_per_rank": int(stats["n_blocks"]),
-                           "blocks_in_flight": args.parallel, "l2": "inputs (>= 1 GiB per rank) and sort state are larger than the 126 MB L2; no flush needed",
+                           "blocks_in_flight": args.parallel, "lanes": int(os.environ.get("BZ2B200_LANES", "2")),
+                           "stage_ms_note": "stage_ms_last_step sums the lanes (batches overlap), ms_per_step is the wall-clock of the step", "l2": "inputs (>= 1 GiB per rank) and sort state are larger than the 126 MB L2; no flush needed",
                            "rho_prefix_doubling": round(rho, 3), "bwt_rounds": int(stats["bwt_rounds"]),
                            "compressed_bytes_rank0": int(out_bytes), "parity_check": parity},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": int(n_in),

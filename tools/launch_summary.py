@@ -11,6 +11,7 @@ per = collections.defaultdict(lambda: collections.defaultdict(float))
 launches = collections.defaultdict(set)
 for r in rows[1:]:
     name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "").replace("bz::", "")
+    name = re.sub(r"<[^>]*>", "", name)   # template variants together, as bz2b200_kernel_times reports them
     metric, unit, val = r[ix["Metric Name"]], r[ix["Metric Unit"]], float(r[ix["Metric Value"]].replace(",", ""))
     scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
     per[name][metric] += val * scale
