@@ -329,29 +329,41 @@ __device__ __forceinline__ void packed_setup(const uint32_t *__restrict__ presen
     hc = min(16, (40 + bits - 1) / bits);
     width = hc * bits;
 }
-// mapped symbols of positions [base, base + need) of the block (wrapping) into sym[], 16 per thread, all threads of the CTA
+// Mapped symbols of positions [base, base + need) of the block (wrapping) into sym[], 16 per thread, all threads of the CTA.
+// Layout: symbol p lives at byte p + 4 * (p >> 4) (one pad word after every 16 symbols), so that threads walking 16 consecutive
+// symbols each (a 20-byte stride between lanes) never meet in a shared-memory bank.
+constexpr int PK_STAGE_BYTES = (4096 + 32) / 16 * 20;
+__device__ __forceinline__ uint32_t pk_addr(uint32_t p) { return p + ((p >> 4) << 2); }
 __device__ __forceinline__ void packed_stage(const uint8_t *__restrict__ T, uint32_t n, uint32_t base, uint32_t need, const uint8_t *map, uint8_t *sym)
 {
     for (uint32_t j = threadIdx.x * 16; j < need; j += blockDim.x * 16) {
         if (base + j + 16 <= n) {
             const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T + base + j));
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-            uint32_t o4[4];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sym + pk_addr(j));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                o4[k] = (uint32_t)map[w4[k] & 0xffu] | ((uint32_t)map[(w4[k] >> 8) & 0xffu] << 8) | ((uint32_t)map[(w4[k] >> 16) & 0xffu] << 16) |
-                        ((uint32_t)map[w4[k] >> 24] << 24);
-            *reinterpret_cast<uint4 *>(sym + j) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                dst[k] = (uint32_t)map[w4[k] & 0xffu] | ((uint32_t)map[(w4[k] >> 8) & 0xffu] << 8) | ((uint32_t)map[(w4[k] >> 16) & 0xffu] << 16) |
+                         ((uint32_t)map[w4[k] >> 24] << 24);
         } else {
-            for (uint32_t k = j; k < min(j + 16, need); ++k) { uint32_t p = base + k; sym[k] = map[T[p >= n ? (p - n) % n : p]]; }
+            for (uint32_t k = j; k < min(j + 16, need); ++k) { uint32_t p = base + k; sym[pk_addr(k)] = map[T[p >= n ? (p - n) % n : p]]; }
         }
     }
 }
-__device__ __forceinline__ uint64_t packed_key(const uint8_t *sym, uint32_t li, int bits, int hc, int width)
+// the packed keys of the 16 consecutive rotations starting at tile position p0 (a multiple of 16): a sliding window of hc symbols
+template <typename F>
+__device__ __forceinline__ void packed_keys16(const uint8_t *sym, uint32_t p0, int bits, int hc, int width, F &&emit)
 {
     uint64_t c = 0;
-    for (int j = 0; j < hc; ++j) c = (c << bits) | sym[li + j];
-    return width >= 40 ? c >> (width - 40) : c << (40 - width);
+    for (int j = 0; j + 1 < hc; ++j) c = (c << bits) | sym[pk_addr(p0 + (uint32_t)j)];
+    const uint64_t m = (1ull << width) - 1ull; // width <= 47
+    const int down = width >= 40 ? width - 40 : 0, up = width >= 40 ? 0 : 40 - width;
+    const uint32_t tail = p0 + (uint32_t)hc - 1u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        c = ((c << bits) | sym[pk_addr(tail + (uint32_t)i)]) & m;
+        emit(i, (c >> down) << up);
+    }
 }
 
 // FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first text_bytes bytes of rotation i, big-endian) << 20 | i,
@@ -389,11 +401,9 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
         packed_stage(text + (uint64_t)b * stride, cnt, base, tcnt + (uint32_t)hc - 1u, s_map, tb);
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-            key[i] = li < tcnt ? ((packed_key(tb, li, bits, hc, width) << VAL_BITS) | (base + li)) : 0ull;
-        }
+        // (this sweep ranks with atomics, so which thread holds which element does not matter: 16 consecutive rotations per thread)
+        const uint32_t p0 = threadIdx.x * RS_ITEMS;
+        packed_keys16(tb, p0, bits, hc, width, [&](int i, uint64_t k) { key[i] = p0 + i < tcnt ? ((k << VAL_BITS) | (base + p0 + i)) : 0ull; });
     } else if (FROM_TEXT) {
         // stage the tile's bytes (+ text_bytes - 1 for the last key, wrapping around the block) in the output staging area
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
@@ -427,10 +437,11 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     // atomic each instead of the stable warp multi-split (the decompressor's 1-byte counting sort must stay stable).
     // (Not used for the bag sorts: their low digits can be nearly constant, and 32 lanes on one counter serialise.)
     const bool unstable = FROM_TEXT && text_bytes != 1;
+    const bool contig = FROM_TEXT && text_bytes == 0; // packed keys: thread t holds tile positions 16 t .. 16 t + 15
     if (unstable) {
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
-            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+            const uint32_t li = contig ? threadIdx.x * RS_ITEMS + i : w * RS_WARP_ELEMS + i * 32 + lane;
             if (li < tcnt) rnk[i] = (uint16_t)atomicAdd(&sm.warp_hist[0][(uint32_t)(key[i] >> shift) & 0xffu], 1u);
         }
     } else {
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
+        const uint32_t li = contig ? threadIdx.x * RS_ITEMS + i : w * RS_WARP_ELEMS + i * 32 + lane;
         if (li < tcnt) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
             sm.keys[sm.tile_base[d] + (unstable ? 0u : sm.warp_hist[w][d]) + rnk[i]] = key[i];
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restr
                                                            uint32_t *__restrict__ h0_out)
 {
     __shared__ uint8_t map[256];
-    __shared__ __align__(16) uint8_t sym[KP_TILE + 32];
+    __shared__ __align__(16) uint8_t sym[PK_STAGE_BYTES];
     __shared__ uint32_t h[RC_MAXPASS][256];
     const uint32_t b = blockIdx.y, n = n_arr[b];
     const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
@@ -544,15 +555,14 @@ __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restr
         __syncthreads();
         packed_stage(T, n, base, tcnt + (uint32_t)hc - 1u, map, sym);
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < KP_TILE / 256; ++k) {
-            const uint32_t li = threadIdx.x + 256u * k;
-            if (li < tcnt) {
-                const uint64_t key = packed_key(sym, li, bits, hc, width);
+        const uint32_t p0 = threadIdx.x * 16;
+        if (p0 < tcnt)
+            packed_keys16(sym, p0, bits, hc, width, [&](int i, uint64_t key) {
+                if (p0 + i < tcnt) {
 #pragma unroll
-                for (int p = 0; p < RC_MAXPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (8 * p)) & 0xffu], 1u);
-            }
-        }
+                    for (int p = 0; p < RC_MAXPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (8 * p)) & 0xffu], 1u);
+                }
+            });
     }
     __syncthreads();
     uint32_t *out = partial + ((uint64_t)b * ctas_per_block + blockIdx.x) * RC_MAXPASS * 256;
