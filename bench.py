@@ -34,6 +34,17 @@ BASE, MULT = 100000, 9
 SAMPLE_MB = 128  # bounded CPU sample (prefix of the same corpus)
 
 
+
+# stdout carries exactly ONE JSON line: everything else that a library may print there (e.g. NCCL's version banner) goes to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit_line(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -121,7 +132,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_desc},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def main():
@@ -327,7 +338,7 @@ def main():
                         "last_step": {k: round(float(e2e_stats[k]), 3) for k in ("ms_total", "ms_h2d", "ms_d2h")}},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "decompress": decompress, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
