@@ -237,6 +237,30 @@ def test_alternative_sort_paths_give_the_same_bits(monkeypatch):
                 monkeypatch.delenv(k)
 
 
+def test_alphabet_sizes_and_mixed_batches():
+    # round-0 keys are packed over each block's own alphabet: bits per symbol change at 2/3, 4/5, 8/9, 16/17, 32/33, 64/65, 128/129 used
+    # values, the number of symbols per key (16 .. 5) with them, and every block of a batch doubles from its own depth
+    rng = np.random.default_rng(20261018)
+    parts = []
+    for alpha in (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33, 64, 65, 128, 129, 200, 256):
+        vals = np.sort(rng.choice(256, size=alpha, replace=False)).astype(np.uint8)
+        body = vals[rng.integers(0, alpha, size=23_000)]
+        body[5000:5600] = body[4000:4600]                       # a repeat, so that some rotations stay tied for a few rounds
+        parts.append(body.tobytes())
+    d = b"".join(parts)
+    for mult, base, par in ((2, 10000, 64), (1, 100000, 3), (9, 100000, 8)):   # blocks of one alphabet each / of several / one block
+        out = comp(mult, base, par).compress(d)
+        assert out == oracle.compress(d, mult, base), (mult, base)
+        if base == 100000:
+            assert bz2.decompress(out) == d
+    c = comp(2, 10000, 64)                                       # per-block stages of a block with a 3-symbol and one with a 129-symbol alphabet
+    r = c.compress_blocks(d, True)
+    nb = len(r["crcs"])
+    for b in (nb - 1, nb - 2):
+        o = oracle.block_stages(d, b, 2, 10000)
+        assert (c.stage(b, api.STAGE_BWT) == o["L"]).all() and c.stage(b, api.STAGE_ORIGPTR)[0] == o["orig_ptr"]
+
+
 def test_lanes_never_change_the_stream(monkeypatch):
     # batches of a call run on 1..3 lanes (own stream + host thread each); the bit position passes from batch to batch in order,
     # so the stream, the per-block tables and the bytes drained so far are the same whatever the lane count or batch size

@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_v8_n2.json 2> gpurun_out/bench_v8_n2.err; echo n2_exit=$?; tail -3 gpurun_out/bench_v8_n2.err; cut -c1-700 gpurun_out/bench_v8_n2.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/bench_v8_n2_ref.json 2> gpurun_out/bench_v8_n2_ref.err; echo n2ref_exit=$?; cut -c1-300 gpurun_out/bench_v8_n2_ref.json
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+ncu --set full --clock-control none --import-source on -k regex:"k_bwt_local|k_mtf_ranks|k_bwt_gather_local|k_rle2_emit" -c 8 -f -o gpurun_out/prof_r01_v8_local_mtf python tools/ncu_probe.py 256 320 > gpurun_out/ncu_v8_full2.log 2>&1; echo ncu_full_exit=$?; tail -2 gpurun_out/ncu_v8_full2.log
