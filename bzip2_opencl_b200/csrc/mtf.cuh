@@ -112,6 +112,7 @@ struct MtfWarpSmem {
     uint8_t list[256];       // list[pos] = symbol
     uint8_t inv[256];        // inv[symbol] = pos
     uint8_t mark[256];       // symbol occurs in the current step
+    alignas(16) uint16_t tau16[32]; // the step's previous-occurrence times + 256, lane p at halfword (p < 16 ? 2 (15 - p) : 2 (31 - p) + 1)
 };
 
 __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, uint64_t stride,
@@ -169,11 +170,22 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__re
         const uint32_t v = S.inv[valid ? sym : 0u];
         const int tau = first ? -1 - (int)v : 31 - __clz((int)lower);
         const unsigned W = tau >= 0 ? (lt & ~((2u << tau) - 1u)) : lt;
+        // acc bit q = (tau_q < tau_j).  Every lane reads all 32 times with four broadcast loads; two 16-bit times per word are
+        // compared at once (x | 0x8000 - tau_j keeps bit 15 iff x >= tau_j, no borrow between the halves), and the halfword
+        // order in shared memory makes word k's two result bits land on bits 15 - k and 31 - k, i.e. on their lanes.
+        S.tau16[lane < 16 ? 2 * (15 - lane) : 2 * (31 - lane) + 1] = (uint16_t)(tau + 256);
+        __syncwarp();
         unsigned acc = 0;
+        {
+            const uint32_t tj2 = (uint32_t)(tau + 256) * 0x00010001u;
+            const uint4 *tp = reinterpret_cast<const uint4 *>(S.tau16);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const int tq = __shfl_sync(FULL, tau, q);
-            if (tq < tau) acc |= 1u << q;
+            for (int g = 0; g < 4; ++g) {
+                const uint4 t4 = tp[g];
+                const uint32_t ws[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc |= (~((ws[k] | 0x80008000u) - tj2) & 0x80008000u) >> (4 * g + k);
+            }
         }
         const uint32_t rank = __popc(acc & W) + (first ? v : 0u);
         if (valid) S.stage[c0 + lane] = (uint8_t)rank;
