@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(R2_THREADS) k_rle2_emit(const uint8_t *__restr
     __shared__ int s_i[34];
     __shared__ uint32_t s_u[34];
     __shared__ uint32_t s_hist[258];
+    __shared__ uint16_t s_out[R2_TILE + 64]; // the tile's symbols (a run of z zeros gives fewer than z digits; the carried-in run at most 20)
     const uint32_t b = blockIdx.y, tile = blockIdx.x;
     const uint32_t n = n_arr[b];
     const uint32_t base = tile * R2_TILE;
@@ -370,8 +371,9 @@ __global__ void __launch_bounds__(R2_THREADS) k_rle2_emit(const uint8_t *__restr
             p = (int)a;
         }
     }
-    uint32_t off = tile_obase[tidx] + block_excl_sum(emit, s_u, nullptr); // also orders the s_hist zeroing
-    uint16_t *out = mtf + (uint64_t)b * mtf_stride;
+    uint32_t total;
+    uint32_t off = block_excl_sum(emit, s_u, &total); // also orders the s_hist zeroing
+    uint16_t *out = s_out; // assembled in shared memory, stored to the block's symbol stream in one coalesced sweep
     uint32_t na = 0, nbn = 0;
     p = prev;
 #pragma unroll
@@ -390,6 +392,10 @@ __global__ void __launch_bounds__(R2_THREADS) k_rle2_emit(const uint8_t *__restr
     nbn = __reduce_add_sync(FULL, nbn);
     if (lane_id() == 0) { if (na) atomicAdd(&s_hist[0], na); if (nbn) atomicAdd(&s_hist[1], nbn); }
     __syncthreads();
+    {
+        uint16_t *dst = mtf + (uint64_t)b * mtf_stride + tile_obase[tidx];
+        for (uint32_t i = threadIdx.x; i < total; i += R2_THREADS) dst[i] = s_out[i];
+    }
     for (int i = threadIdx.x; i < 258; i += R2_THREADS) {
         uint32_t c = s_hist[i];
         if (c) atomicAdd(&freq[b * 258 + i], c);
