@@ -1471,7 +1471,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             KL(KID_k_dec_double, k_dec_double<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kB), ptr<uint64_t>(h->kA), d_counts, h->S, 2));
             KL(KID_k_dec_double, k_dec_double8<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->kA), ptr<uint64_t>(h->loc), ptr<uint32_t>(h->rank), d_counts, h->S));
             KL(KID_k_dec_double, k_dec_double16<<<gd, 256, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint32_t>(h->rank), ptr<uint64_t>(h->kB), ptr<uint32_t>(h->kA), d_counts, h->S));
-            KL(KID_k_dec_chase, k_dec_chase<<<(nb + 31) / 32, 32, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint64_t>(h->kB), ptr<uint32_t>(h->kA), h->S, ptr<DecInfo>(h->dec_info), nb,
+            KL(KID_k_dec_chase, k_dec_chase<<<(nb + 3) / 4, 128, 0, st>>>(ptr<uint64_t>(h->loc), ptr<uint64_t>(h->kB), ptr<uint32_t>(h->kA), h->S, ptr<DecInfo>(h->dec_info), nb,
                                                                       ptr<uint8_t>(h->rle), ptr<uint64_t>(h->dec_len)));
             h->stats.kernel_launches += 6;
         } else {

@@ -10,7 +10,7 @@
 //                     reference's bwtMergedPointers, BlockDecompressor.hpp:244-263)
 //   k_dec_double / k_dec_double8 / k_dec_double16   four rounds of pointer doubling: every merged pointer carries sixteen bytes
 //                     and the pointer sixteen steps on
-//   k_dec_chase       one thread per block follows them from origPtr (:265-282): the RLE1-coded block, 16 bytes per dependent load,
+//   k_dec_chase       one lane per block (a warp of its own) follows them from origPtr (:265-282): the RLE1-coded block, 16 bytes per dependent load,
 //                     and the RLE1 decoded length on the way
 //   k_dec_expand      RLE1 decode (:56-84) at the final offset: literal stretches copied by whole warps, only the four-equal
 //                     triggers parsed in order
@@ -497,14 +497,16 @@ __global__ void __launch_bounds__(256) k_dec_double16(const uint64_t *__restrict
     ptr16[o + j] = ptr8[o + q];
 }
 
-// one thread per block follows the sixteen-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
+// one lane per block follows the sixteen-byte elements from origPtr and writes the RLE1-coded block; the RLE1 state machine
 // (BlockDecompressor::read, :56-84) runs along to give the decoded length (its cost hides behind the dependent loads)
-__global__ void __launch_bounds__(32) k_dec_chase(const uint64_t *__restrict__ lo8, const uint64_t *__restrict__ hi8, const uint32_t *__restrict__ ptr16,
+__global__ void __launch_bounds__(128) k_dec_chase(const uint64_t *__restrict__ lo8, const uint64_t *__restrict__ hi8, const uint32_t *__restrict__ ptr16,
                                                    uint64_t stride, const DecInfo *__restrict__ info, uint32_t nb, uint8_t *__restrict__ rle,
                                                    uint64_t *__restrict__ out_len)
 {
-    const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bl >= nb) return;
+    // one block per WARP, lane 0 walks: threads of one warp move in lockstep, so 32 chains in a warp would each pay the slowest of
+    // 32 DRAM round trips at every step
+    const uint32_t bl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bl >= nb || (threadIdx.x & 31u) != 0u) return;
     const uint32_t n = info[bl].n;
     if (n == 0) { out_len[bl] = 0; return; }
     const uint64_t base = (uint64_t)bl * stride;
