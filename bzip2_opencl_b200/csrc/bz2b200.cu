@@ -69,6 +69,7 @@ struct bz2b200 {
     std::vector<bz2b200 *> lanes;   // parent: its lanes (empty: batches run on the handle itself)
     std::vector<std::thread> lane_thr;
     std::vector<char> lane_busy;
+    std::vector<uint32_t> lane_nb;  // blocks of the batch a busy lane is working on
     LaneCtl *ctl = nullptr;
     int n_lanes = 2, last_lane = 0;
     bool batch_ready = false;       // per-batch buffers allocated (a parent with lanes needs them for the decompress side only)
@@ -418,6 +419,7 @@ static int create_lanes(bz2b200 *h)
     }
     h->lane_thr.resize(nl);
     h->lane_busy.assign(nl, 0);
+    h->lane_nb.assign(nl, 0);
     return BZ2B200_OK;
 }
 
@@ -1121,6 +1123,7 @@ static int lane_dispatch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t 
             if (!h->lane_busy[k]) { idx = (int)k; break; }
         }
         h->lane_busy[idx] = 1;
+        h->lane_nb[idx] = nb;
     }
     if (h->lane_thr[idx].joinable()) h->lane_thr[idx].join();
     bz2b200 *l = h->lanes[idx];
@@ -1246,14 +1249,15 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
             bool go = b0 < h->w_found;
             if (go && laned) {
                 // A batch costs about the same wall time whatever its size (its one-warp-per-block kernels), so a lane is not spent
-                // on a few blocks while the other one is busy: wait until half a batch is known -- unless nothing more will come.
+                // on a few blocks while the others have real work: wait until half a batch is known -- unless nothing more will
+                // come, or what is in flight is small itself (the first blocks of a host buffer: the GPU is mostly idle then).
                 const uint64_t undis = h->w_found - b0;
                 const bool nothing_more = !pending && h->w_finished && !walk_more_input(h);
                 if (undis < (Gb + 1) / 2 && !nothing_more) {
                     std::lock_guard<std::mutex> lk(h->ctl->mu);
-                    bool busy = false;
-                    for (char c : h->lane_busy) busy |= c != 0;
-                    go = !busy;
+                    uint64_t inflight = 0;
+                    for (size_t i = 0; i < h->lane_busy.size(); ++i) inflight += h->lane_busy[i] ? h->lane_nb[i] : 0u;
+                    go = inflight < (Gb + 3) / 4;
                 }
             }
             if (go) {
