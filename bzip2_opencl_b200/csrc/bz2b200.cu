@@ -514,7 +514,8 @@ static int radix_sort(bz2b200 *h, uint64_t *k0, uint64_t *k1, const uint32_t *co
         KBYTES(KID_k_radix_count, total_elems * 8);
         int cur = 0;
         for (int p = 0; p < npass; ++p) {
-            cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, h->stream);
+            // status words of the tiles in use only (the bags of the later rounds fill a few tiles per block)
+            cudaMemset2DAsync(h->hist.p, (size_t)h->tilesR * 1024, 0, (size_t)tiles * 1024, nb, h->stream);
             cudaMemsetAsync(ticket, 0, 4, h->stream);
             KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), h->stream>>>(
                                          cur ? k1 : k0, cur ? k0 : k1, counts, h->S, VAL_BITS + 8 * p, ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256,
