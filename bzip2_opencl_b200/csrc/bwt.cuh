@@ -14,6 +14,7 @@
 // multi-split, shared-memory staged so that the global writes of one digit are contiguous).
 #pragma once
 #include "util.cuh"
+#include "packed_math.h"
 
 namespace bz {
 
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(256) k_bwt_bytehist(const uint8_t *__restrict_
 
 // Packed round-0 keys (see k_bwt_count_packed): thread v < 256 fills map[v] = rank of byte value v among the block's used values;
 // bits per symbol, symbols per key and their total width come back in every thread.
-__device__ __forceinline__ void packed_setup(const uint32_t *__restrict__ present, uint32_t b, uint8_t *map, int &bits, int &hc, int &width)
+__device__ __forceinline__ PackedShape packed_setup(const uint32_t *__restrict__ present, uint32_t b, uint8_t *map)
 {
     const uint32_t v = threadIdx.x;
     uint32_t alpha = 0, below = 0;
@@ -325,9 +326,7 @@ __device__ __forceinline__ void packed_setup(const uint32_t *__restrict__ presen
         else if ((uint32_t)w == (v >> 5)) below += __popc(m & ((1u << (v & 31u)) - 1u));
     }
     if (v < 256) map[v] = (uint8_t)below;
-    bits = alpha <= 2u ? 1 : 32 - __clz((int)alpha - 1);
-    hc = min(16, (40 + bits - 1) / bits);
-    width = hc * bits;
+    return packed_shape(alpha);
 }
 // Mapped symbols of positions [base, base + need) of the block (wrapping) into sym[], 16 per thread, all threads of the CTA.
 // Layout: symbol p lives at byte p + 4 * (p >> 4) (one pad word after every 16 symbols), so that threads walking 16 consecutive
@@ -352,17 +351,15 @@ __device__ __forceinline__ void packed_stage(const uint8_t *__restrict__ T, uint
 }
 // the packed keys of the 16 consecutive rotations starting at tile position p0 (a multiple of 16): a sliding window of hc symbols
 template <typename F>
-__device__ __forceinline__ void packed_keys16(const uint8_t *sym, uint32_t p0, int bits, int hc, int width, F &&emit)
+__device__ __forceinline__ void packed_keys16(const uint8_t *sym, uint32_t p0, const PackedShape &ps, F &&emit)
 {
     uint64_t c = 0;
-    for (int j = 0; j + 1 < hc; ++j) c = (c << bits) | sym[pk_addr(p0 + (uint32_t)j)];
-    const uint64_t m = (1ull << width) - 1ull; // width <= 47
-    const int down = width >= 40 ? width - 40 : 0, up = width >= 40 ? 0 : 40 - width;
-    const uint32_t tail = p0 + (uint32_t)hc - 1u;
+    for (int j = 0; j + 1 < ps.hc; ++j) c = (c << ps.bits) | sym[pk_addr(p0 + (uint32_t)j)];
+    const uint32_t tail = p0 + (uint32_t)ps.hc - 1u;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        c = ((c << bits) | sym[pk_addr(tail + (uint32_t)i)]) & m;
-        emit(i, (c >> down) << up);
+        c = packed_push(c, sym[pk_addr(tail + (uint32_t)i)], ps);
+        emit(i, packed_key_of(c, ps));
     }
 }
 
@@ -395,15 +392,14 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
     if (FROM_TEXT && text_bytes == 0) {
-        int bits, hc, width;
-        packed_setup(present, b, s_map, bits, hc, width);
+        const PackedShape ps = packed_setup(present, b, s_map);
         __syncthreads();
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
-        packed_stage(text + (uint64_t)b * stride, cnt, base, tcnt + (uint32_t)hc - 1u, s_map, tb);
+        packed_stage(text + (uint64_t)b * stride, cnt, base, tcnt + (uint32_t)ps.hc - 1u, s_map, tb);
         __syncthreads();
         // (this sweep ranks with atomics, so which thread holds which element does not matter: 16 consecutive rotations per thread)
         const uint32_t p0 = threadIdx.x * RS_ITEMS;
-        packed_keys16(tb, p0, bits, hc, width, [&](int i, uint64_t k) { key[i] = p0 + i < tcnt ? ((k << VAL_BITS) | (base + p0 + i)) : 0ull; });
+        packed_keys16(tb, p0, ps, [&](int i, uint64_t k) { key[i] = p0 + i < tcnt ? ((k << VAL_BITS) | (base + p0 + i)) : 0ull; });
     } else if (FROM_TEXT) {
         // stage the tile's bytes (+ text_bytes - 1 for the last key, wrapping around the block) in the output staging area
         uint8_t *tb = reinterpret_cast<uint8_t *>(sm.keys);
@@ -543,9 +539,8 @@ __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restr
     __shared__ uint32_t h[RC_MAXPASS][256];
     const uint32_t b = blockIdx.y, n = n_arr[b];
     const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
-    int bits, hc, width;
-    packed_setup(present, b, map, bits, hc, width);
-    if (blockIdx.x == 0 && threadIdx.x == 0) h0_out[b] = (uint32_t)min(16, 40 / bits);
+    const PackedShape ps = packed_setup(present, b, map);
+    if (blockIdx.x == 0 && threadIdx.x == 0) h0_out[b] = (uint32_t)ps.h0;
     if (base0 >= n) return;
     for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += 256) (&h[0][0])[i] = 0;
     const uint8_t *T = rle + (uint64_t)b * stride;
@@ -553,11 +548,11 @@ __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restr
     for (uint32_t base = base0; base < end; base += KP_TILE) {
         const uint32_t tcnt = min((uint32_t)KP_TILE, end - base);
         __syncthreads();
-        packed_stage(T, n, base, tcnt + (uint32_t)hc - 1u, map, sym);
+        packed_stage(T, n, base, tcnt + (uint32_t)ps.hc - 1u, map, sym);
         __syncthreads();
         const uint32_t p0 = threadIdx.x * 16;
         if (p0 < tcnt)
-            packed_keys16(sym, p0, bits, hc, width, [&](int i, uint64_t key) {
+            packed_keys16(sym, p0, ps, [&](int i, uint64_t key) {
                 if (p0 + i < tcnt) {
 #pragma unroll
                     for (int p = 0; p < RC_MAXPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (8 * p)) & 0xffu], 1u);

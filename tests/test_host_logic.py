@@ -34,6 +34,13 @@ def test_crc_combine_math(tmp_path):
     assert subprocess.check_output([exe]).decode().strip() == "OK"
 
 
+def test_packed_round0_key_math(tmp_path):
+    # csrc/packed_math.h: keys over the block's alphabet order the rotations by their first h0 bytes and never contradict the full order
+    exe = str(tmp_path / "packed_keys")
+    _compile("test_packed_keys.cpp", exe)
+    assert subprocess.check_output([exe]).decode().strip() == "OK"
+
+
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "bz2b200.h")).read()
     declared = set(re.findall(r"\b(bz2b200_[a-z_0-9]+)\s*\(", hdr))

@@ -1,2 +1,2 @@
-python bench.py > gpurun_out/bench_v11.json 2> gpurun_out/bench_v11.err; echo bench_exit=$?; tail -2 gpurun_out/bench_v11.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_v11.json')); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline']['traffic'], d['cpu_baseline']['value'], d['decompress']['value'], d['config']['parity_check'])"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
