@@ -72,6 +72,7 @@ struct bz2b200 {
     std::vector<uint32_t> lane_nb;  // blocks of the batch a busy lane is working on
     LaneCtl *ctl = nullptr;
     int n_lanes = 2, last_lane = 0;
+    uint64_t call_batches = 0;      // batches handed to lanes by the current call
     bool batch_ready = false;       // per-batch buffers allocated (a parent with lanes needs them for the decompress side only)
     uint64_t call_id = 0, lane_call = 0; // lane_call != parent's call_id: first batch of this call on the lane
     int device = 0;
@@ -1130,7 +1131,12 @@ static int lane_dispatch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t 
     bz2b200 *l = h->lanes[idx];
     l->profiling = h->profiling;
     h->last_lane = idx;
-    h->lane_thr[idx] = std::thread(lane_main, l, idx, d_in, b0, nb, d_out_words, seq);
+    ++h->call_batches;
+    try {
+        h->lane_thr[idx] = std::thread(lane_main, l, idx, d_in, b0, nb, d_out_words, seq);
+    } catch (...) { // no thread to be had: the batch runs here (its predecessors are on their way, so the ordered hand-overs still work)
+        lane_main(l, idx, d_in, b0, nb, d_out_words, seq);
+    }
     return BZ2B200_OK;
 }
 
@@ -1154,9 +1160,11 @@ static int lanes_finish(bz2b200 *h)
             l->k_ms[i] = 0; l->k_launches[i] = 0; l->k_bytes[i] = 0;
         }
     }
-    bz2b200 *last = h->lanes[h->last_lane];
-    h->last_b0 = last->last_b0;
-    h->last_nb = last->last_nb;
+    if (h->call_batches) { // the batch that stays resident for bz2b200_stage_dump
+        bz2b200 *last = h->lanes[h->last_lane];
+        h->last_b0 = last->last_b0;
+        h->last_nb = last->last_nb;
+    }
     if (h->ctl->rc) { h->err = h->ctl->err; return h->ctl->rc; }
     return BZ2B200_OK;
 }
@@ -1193,6 +1201,7 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->err.clear();
     h->stats = bz2b200_stats_t{};
     h->last_nb = 0;
+    h->call_batches = 0;
     h->t_call = now_ms();
     *out_nbits = 0; *consumed = 0; *n_blocks = 0;
     cudaStream_t st = h->stream;
