@@ -31,6 +31,7 @@ private:
     std::vector<uint8_t> data; // decoded bytes
     size_t position = 0;
     int parallelBlockCnt;
+    bool allStreams; // decode every concatenated stream (bzip2 -d behaviour) instead of the reference's first stream only
 
     void decodeAll()
     {
@@ -38,14 +39,15 @@ private:
         std::vector<uint8_t> in((std::istreambuf_iterator<char>(inputStream)), std::istreambuf_iterator<char>());
         if (in.size() < 4 || in[0] != 'B' || in[1] != 'Z' || in[2] != 'h' || in[3] < '1' || in[3] > '9')
             throw std::runtime_error("Invalid BZip2 header"); // InputStream.hpp:118-123
-        int rc = bz2b200_create(&handle, 0, BLOCKSIZE_DEFAULT, in[3] - '0', parallelBlockCnt);
+        int rc = bz2b200_create(&handle, 0, BLOCKSIZE_DEFAULT, allStreams ? 9 : in[3] - '0', parallelBlockCnt); // later streams may use larger blocks
         if (rc != BZ2B200_OK)
             throw std::runtime_error(std::string(bz2b200_strerror(rc)) + " (no CUDA device? there is no CPU path)");
         size_t cap = in.size() * 6 + (1u << 16), n = 0;
         for (;;)
         {
             data.resize(cap);
-            rc = bz2b200_decompress_stream(handle, in.data(), in.size(), data.data(), cap, &n);
+            rc = allStreams ? bz2b200_decompress_concat(handle, in.data(), in.size(), data.data(), cap, &n, nullptr)
+                            : bz2b200_decompress_stream(handle, in.data(), in.size(), data.data(), cap, &n);
             if (rc != BZ2B200_E_OUTPUT)
                 break;
             cap = (n > cap ? n : cap) * 2; // n = what the stream needed so far
@@ -58,8 +60,10 @@ private:
     }
 
 public:
-    // parallelBlockCnt: blocks decoded per device batch (not in the reference's signature; defaulted)
-    explicit InputStream(std::istream &in, int parallelBlockCnt = 256) : inputStream(in), parallelBlockCnt(parallelBlockCnt) {}
+    // parallelBlockCnt: blocks decoded per device batch; allStreams: go on behind the first stream while another "BZh" header follows
+    // (SURVEY 8f N4).  Neither is in the reference's signature; both are defaulted to its behaviour.
+    explicit InputStream(std::istream &in, int parallelBlockCnt = 256, bool allStreams = false)
+        : inputStream(in), parallelBlockCnt(parallelBlockCnt), allStreams(allStreams) {}
     InputStream(const InputStream &) = delete;
     InputStream &operator=(const InputStream &) = delete;
     ~InputStream()

@@ -1,8 +1,9 @@
 // Drives the reference-named InputStream facade the way app.cpp's decompress branch does (app.cpp:126-160).
-// usage: facade_decompress <input.bz2> <output> [bulk]      exit 0 = ok, 4 = std::runtime_error (text on stderr)
+// usage: facade_decompress <input.bz2> <output> [bulk|byte] [multi]     exit 0 = ok, 4 = std::runtime_error (text on stderr)
 #include <fstream>
 #include <iostream>
 #include <vector>
+#include <cstring>
 #include "InputStream.hpp"
 
 int main(int argc, char **argv)
@@ -12,8 +13,8 @@ int main(int argc, char **argv)
     std::ofstream out(argv[2], std::ios::binary);
     try
     {
-        InputStream bz2in(in);
-        if (argc > 3)
+        InputStream bz2in(in, 256, argc > 4 && !std::strcmp(argv[4], "multi"));
+        if (argc > 3 && !std::strcmp(argv[3], "bulk"))
         {
             std::vector<uint8_t> buffer(131072);
             int n;

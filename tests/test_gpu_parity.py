@@ -439,6 +439,12 @@ def test_cpp_input_stream_facade(tmp_path):
         dst = tmp_path / f"out_{bulk}"
         subprocess.check_call([exe, str(src), str(dst)] + (["bulk"] if bulk else []), env=env)
         assert dst.read_bytes() == d
+    cat = tmp_path / "cat.bz2"                                 # two streams: the reference's behaviour (first only) and the opt-in for all
+    cat.write_bytes(bz2.compress(d[:500_000], 1) + bz2.compress(d[500_000:], 9))
+    subprocess.check_call([exe, str(cat), str(tmp_path / "first"), "bulk"], env=env)
+    assert (tmp_path / "first").read_bytes() == d[:500_000]
+    subprocess.check_call([exe, str(cat), str(tmp_path / "all"), "bulk", "multi"], env=env)
+    assert (tmp_path / "all").read_bytes() == d
     bad = tmp_path / "bad.bz2"
     b = bytearray(src.read_bytes()); b[-2] ^= 1
     bad.write_bytes(b)
