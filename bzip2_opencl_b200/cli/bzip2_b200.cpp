@@ -21,14 +21,14 @@
 
 int main(int argc, char *argv[])
 {
-    const char *flags = "\n\n  [--help|-h]              print help\n  [--dec|-d]               decompress file\n  [--keep|-k]              keep original (de)compressed file\n  [--check|-c]             check compressed file integrity\n  [--size|-s <1-9>]        set block size (x BLOCKSIZE_DEFAULT)\n  [--parallel|-p <1+>]     blocks per device batch\n";
+    const char *flags = "\n\n  [--help|-h]              print help\n  [--dec|-d]               decompress file\n  [--keep|-k]              keep original (de)compressed file\n  [--check|-c]             check compressed file integrity\n  [--size|-s <1-9>]        set block size (x BLOCKSIZE_DEFAULT)\n  [--parallel|-p <1+>]     blocks per device batch\n  [--all-streams|-a]       with -d / -c: decode every concatenated stream (not in the reference)\n";
     if (argc < 2)
     {
         std::cerr << "\n  Usage: bzip2_b200 [file_path] [flags]" << flags << std::endl;
         return 1;
     }
     std::string filename;
-    bool decompress = false, keepFile = false, checkCRC = false;
+    bool decompress = false, keepFile = false, checkCRC = false, allStreams = false;
     int blockSize = 9;     // app.cpp:46
     int parallelCnt = 10;  // app.cpp:47
     for (int i = 1; i < argc; ++i)
@@ -39,6 +39,7 @@ int main(int argc, char *argv[])
         else if ((!std::strcmp(a, "--size") || !std::strcmp(a, "-s")) && i + 1 < argc) blockSize = std::atoi(argv[++i]);
         else if ((!std::strcmp(a, "--parallel") || !std::strcmp(a, "-p")) && i + 1 < argc) parallelCnt = std::atoi(argv[++i]);
         else if (!std::strcmp(a, "--check") || !std::strcmp(a, "-c")) checkCRC = true;
+        else if (!std::strcmp(a, "--all-streams") || !std::strcmp(a, "-a")) allStreams = true;
         else if (!std::strcmp(a, "--help") || !std::strcmp(a, "-h"))
         {
             std::cout << "\n  Usage: bzip2_b200 [file_path] [flags]" << flags << std::endl;
@@ -98,7 +99,7 @@ int main(int argc, char *argv[])
                 std::cerr << "Failed to open output file." << std::endl;
                 return 1;
             }
-            InputStream bz2in(inputFile, parallelCnt < 64 ? 64 : parallelCnt);
+            InputStream bz2in(inputFile, parallelCnt < 64 ? 64 : parallelCnt, allStreams);
             std::vector<uint8_t> buffer(1 << 20);
             int n;
             while ((n = bz2in.read(buffer, 0, (int)buffer.size())) != -1) outputFile.write((const char *)buffer.data(), n);
@@ -107,7 +108,7 @@ int main(int argc, char *argv[])
         }
         else
         {
-            InputStream bz2in(inputFile, parallelCnt < 64 ? 64 : parallelCnt);
+            InputStream bz2in(inputFile, parallelCnt < 64 ? 64 : parallelCnt, allStreams);
             std::vector<uint8_t> buffer(1 << 20);
             while (bz2in.read(buffer, 0, (int)buffer.size()) != -1)
                 ;

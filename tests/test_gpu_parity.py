@@ -475,6 +475,15 @@ def test_cli_front_end_round_trip(tmp_path):
     assert f.read_bytes() == d and not z.exists()
     subprocess.check_call([exe, str(f)], env=env)                                     # default -9, input removed
     assert not f.exists() and bz2.decompress(z.read_bytes()) == d
+    two = tmp_path / "two.bin.bz2"                                                   # concatenated streams: first one only, or all with -a
+    two.write_bytes(z.read_bytes() + bz2.compress(b"tail" * 1000, 1))
+    subprocess.check_call([exe, str(two), "-d", "-k"], env=env)
+    assert (tmp_path / "two.bin").read_bytes() == d
+    (tmp_path / "two.bin").unlink()
+    subprocess.check_call([exe, str(two), "-d", "-k", "-a"], env=env)
+    assert (tmp_path / "two.bin").read_bytes() == d + b"tail" * 1000
+    r = subprocess.run([exe, str(two), "-c", "--all-streams"], env=env, capture_output=True)
+    assert r.returncode == 0 and b"Integrity check passed!" in r.stdout
     b = bytearray(z.read_bytes()); b[len(b) // 2] ^= 1
     z.write_bytes(b)
     r = subprocess.run([exe, str(z), "-c"], env=env, capture_output=True)

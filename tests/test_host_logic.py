@@ -186,7 +186,7 @@ def test_cli_front_end_argument_handling(tmp_path):
     r = subprocess.run([exe], env=env, capture_output=True)
     assert r.returncode == 1 and b"Usage" in r.stderr
     r = subprocess.run([exe, "-h"], env=env, capture_output=True)
-    assert r.returncode == 0 and b"--parallel" in r.stdout
+    assert r.returncode == 0 and b"--parallel" in r.stdout and b"--all-streams" in r.stdout
     r = subprocess.run([exe, "file", "--bogus"], env=env, capture_output=True)
     assert r.returncode == 1 and b"Unknown flag!" in r.stderr
     r = subprocess.run([exe, str(tmp_path / "missing")], env=env, capture_output=True)
