@@ -108,6 +108,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def single_thread_reference(sample: bytes) -> dict:
+    """The same reference code on ONE host thread (north_star: single-thread next to all-cores), on the first 16 MiB of the sample."""
+    from oracle import refimpl
+    part = sample[:16 << 20]
+    t = time.perf_counter()
+    refimpl.compress(part, MULT, BASE, threads=1)
+    dt = time.perf_counter() - t
+    return {"value": round(len(part) / 1e6 / dt, 3), "unit": UNIT, "cores": 1, "sample": f"first {len(part) >> 20} MiB, {dt:.1f} s"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle/_ref), all host threads, bounded sample."""
     if rank != 0:
@@ -129,7 +139,8 @@ def run_reference(args, rank):
             "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args.gpus, args.size_mb), "sample": sample_desc},
-            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_desc},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_desc,
+                             "single_thread": single_thread_reference(sample)},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_line(line)
@@ -296,7 +307,8 @@ def main():
         ref_out = refimpl.compress(sample, MULT, BASE, threads=threads)
         dt = time.perf_counter() - t
         cpu_baseline = {"value": round(len(sample) / 1e6 / dt, 3), "unit": UNIT, "cores": threads, "kind": "reference",
-                        "sample": f"first {len(sample) >> 20} MiB of the workload, oracle/_ref (reference source built for the CPU), {dt:.1f} s"}
+                        "sample": f"first {len(sample) >> 20} MiB of the workload, oracle/_ref (reference source built for the CPU), {dt:.1f} s",
+                        "single_thread": single_thread_reference(sample)}
         ours = comp.compress(sample)
         parity = "bit-identical to oracle/_ref on the sample" if ours == ref_out else "MISMATCH vs oracle/_ref on the sample"
 
