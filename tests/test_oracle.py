@@ -80,6 +80,32 @@ def test_oracle_equals_real_reference_on_seeded_inputs(idx):
         assert (s1 == s2).all() and (l1 == l2).all() and (c1 == c2).all()
 
 
+def alphabet_sweep_input() -> bytes:
+    # the input of tests/test_gpu_parity.py::test_alphabet_sizes_and_mixed_batches (stretches over 1 .. 256 used byte values)
+    rng = np.random.default_rng(20261018)
+    parts = []
+    for alpha in (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33, 64, 65, 128, 129, 200, 256):
+        vals = np.sort(rng.choice(256, size=alpha, replace=False)).astype(np.uint8)
+        body = vals[rng.integers(0, alpha, size=23_000)]
+        body[5000:5600] = body[4000:4600]
+        parts.append(body.tobytes())
+    return b"".join(parts)
+
+
+@pytest.mark.skipif(not have_ref(100000) or not have_ref(10000), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_real_reference_on_the_alphabet_sweep():
+    # what the GPU path is compared with on that input is the oracle: pin the oracle to the reference's own code there as well
+    d = alphabet_sweep_input()
+    for mult, base in ((2, 10000), (1, 100000), (9, 100000)):
+        out, offs, nonprim = oracle.compress_ex(d, mult, base)
+        ref = refimpl.compress(d, mult, base, threads=2)
+        assert oracle.mask_origptr(out, offs, nonprim) == oracle.mask_origptr(ref, offs, nonprim)
+        if not nonprim.any():
+            assert out == ref
+        if base == 100000:
+            assert bz2.decompress(out) == d
+
+
 @pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
 def test_oracle_stage_dumps_equal_reference():
     d = corpus.word_text(250000, 77) + bytes(5000) + corpus.rand_bytes(40000, 3)
