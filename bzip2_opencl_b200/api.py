@@ -19,7 +19,9 @@ STAGE_RLE1, STAGE_PRESENT, STAGE_BWT, STAGE_ORIGPTR, STAGE_MTF, STAGE_FREQ, STAG
 
 EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200_max_output_bytes", "bz2b200_scan_blocks",
            "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_decompress_stream", "bz2b200_decompress_concat", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
-           "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times"]
+           "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times", "bz2b200_create_multi", "bz2b200_device_count_of",
+           "bz2b200_recommended_blocks", "bz2b200_host_alloc", "bz2b200_host_free", "bz2b200_scan_prepare", "bz2b200_scan_blocks_ex",
+           "bz2b200_compress_scanned", "bz2b200_shift_bits"]
 
 
 class Stats(C.Structure):
@@ -74,6 +76,24 @@ def load_library() -> C.CDLL:
     L.bz2b200_set_profiling.argtypes = [vp, C.c_int]
     L.bz2b200_kernel_times.restype = C.c_int
     L.bz2b200_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, u64p]
+    L.bz2b200_create_multi.restype = C.c_int
+    L.bz2b200_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.bz2b200_device_count_of.restype = C.c_int
+    L.bz2b200_device_count_of.argtypes = [vp]
+    L.bz2b200_recommended_blocks.restype = C.c_int
+    L.bz2b200_recommended_blocks.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.bz2b200_host_alloc.restype = vp
+    L.bz2b200_host_alloc.argtypes = [sz]
+    L.bz2b200_host_free.restype = None
+    L.bz2b200_host_free.argtypes = [vp]
+    L.bz2b200_scan_prepare.restype = C.c_int
+    L.bz2b200_scan_prepare.argtypes = [vp, vp, sz]
+    L.bz2b200_scan_blocks_ex.restype = C.c_int
+    L.bz2b200_scan_blocks_ex.argtypes = [vp, vp, sz, C.c_int, C.c_uint64, vp, sz, u64p, C.POINTER(sz)]
+    L.bz2b200_compress_scanned.restype = C.c_int
+    L.bz2b200_compress_scanned.argtypes = [vp, C.c_uint, vp, sz, u64p, vp, vp, sz, u64p]
+    L.bz2b200_shift_bits.restype = C.c_int
+    L.bz2b200_shift_bits.argtypes = [vp, vp, C.c_uint64, C.c_uint, C.c_uint, vp, sz]
     _lib = L
     return L
 
@@ -91,11 +111,19 @@ def _np_ptr(a: np.ndarray):
 class Compressor:
     """One handle = one GPU.  block size = base * multiplier; `parallel` = blocks per device batch (the reference's -p)."""
 
-    def __init__(self, multiplier: int = 9, parallel: int = 64, base: int = 100000, device: int = 0):
+    def __init__(self, multiplier: int = 9, parallel: int = 64, base: int = 100000, device: int = 0, devices=None):
+        """devices: a list of CUDA device ids -> one multi-device handle (bz2b200_create_multi); otherwise one handle on `device`."""
         self.lib = load_library()
         self.h = C.c_void_p()
         self.base, self.multiplier, self.parallel, self.device = base, multiplier, parallel, device
-        rc = self.lib.bz2b200_create(C.byref(self.h), device, base, multiplier, parallel)
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            ids = (C.c_int * len(self.devices))(*self.devices)
+            rc = self.lib.bz2b200_create_multi(C.byref(self.h), ids, len(self.devices), base, multiplier, parallel)
+            if rc == E_ARG:
+                raise ValueError("Invalid device list")
+        else:
+            rc = self.lib.bz2b200_create(C.byref(self.h), device, base, multiplier, parallel)
         if rc == E_BLOCKSIZE:
             raise ValueError("Invalid block size")  # std::invalid_argument, OutputStream.hpp:73-76
         if rc == E_PARALLEL:
@@ -175,6 +203,33 @@ class Compressor:
         nb = C.c_uint64(0)
         self._check(self.lib.bz2b200_scan_blocks(self.h, C.c_void_p(ptr), nbytes, _np_ptr(starts), cap, C.byref(nb)))
         return starts[:nb.value].copy()
+
+    # ---- slice primitives (one stream over several handles) ---------------------------------------------
+    def scan_prepare(self, ptr: int, nbytes: int):
+        self._check(self.lib.bz2b200_scan_prepare(self.h, C.c_void_p(ptr), nbytes))
+
+    def scan_blocks_ex(self, ptr: int, nbytes: int, is_final: bool, first_start: int = 0, want_starts: bool = True):
+        """Returns (block starts relative to ptr, consumed): consumed = where the first unfinished block starts (the next slice's first_start)."""
+        cap = self.max_blocks(nbytes) if want_starts else 0
+        starts = np.zeros(max(cap, 1), dtype=np.uint64)
+        nb = C.c_uint64(0)
+        used = C.c_size_t(0)
+        self._check(self.lib.bz2b200_scan_blocks_ex(self.h, C.c_void_p(ptr), nbytes, int(is_final), first_start, _np_ptr(starts) if want_starts else None, cap,
+                                                    C.byref(nb), C.byref(used)))
+        return starts[:nb.value].copy() if want_starts else int(nb.value), int(used.value)
+
+    def compress_scanned_ptr(self, out_ptr: int, out_cap: int, n_blocks: int, start_bit: int = 0):
+        cap = max(1, n_blocks)
+        crcs = np.zeros(cap, dtype=np.uint32)
+        nbits_b = np.zeros(cap, dtype=np.uint64)
+        nbits = C.c_uint64(0)
+        nb = C.c_uint64(0)
+        self._check(self.lib.bz2b200_compress_scanned(self.h, start_bit, C.c_void_p(out_ptr), out_cap, C.byref(nbits), _np_ptr(crcs), _np_ptr(nbits_b), cap,
+                                                      C.byref(nb)))
+        return dict(nbits=nbits.value, crcs=crcs[:nb.value].copy(), block_nbits=nbits_b[:nb.value].copy())
+
+    def shift_bits_ptr(self, src_ptr: int, nbits: int, shift: int, carry: int, dst_ptr: int, dst_cap: int):
+        self._check(self.lib.bz2b200_shift_bits(self.h, C.c_void_p(src_ptr), nbits, shift, carry, C.c_void_p(dst_ptr), dst_cap))
 
     # ---- raw-pointer API (host or device pointers) -----------------------------------------------------------
     def compress_blocks_ptr(self, in_ptr: int, nbytes: int, out_ptr: int, out_cap: int, is_final: bool = True, start_bit: int = 0):

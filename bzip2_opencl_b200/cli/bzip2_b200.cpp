@@ -11,6 +11,8 @@
 // (de)compression reports the exception text and keeps the input.
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -70,13 +72,15 @@ int main(int argc, char *argv[])
                 return 1;
             }
             OutputStream bz2out(outputFile, blockSize, parallelCnt);
-            std::vector<char> buffer(1 << 20);
-            while (inputFile)
+            // the file goes straight into the facade's pinned staging buffers (no per-byte write(int) as in app.cpp:112-115)
+            const int fd = ::open(filename.c_str(), O_RDONLY);
+            if (fd < 0)
             {
-                inputFile.read(buffer.data(), (std::streamsize)buffer.size());
-                const std::streamsize n = inputFile.gcount();
-                if (n > 0) bz2out.write(buffer, 0, (int)n);
+                std::cerr << "Failed to open input file." << std::endl;
+                return 1;
             }
+            bz2out.readFrom(fd);
+            ::close(fd);
             bz2out.close();
             outputFile.close();
         }

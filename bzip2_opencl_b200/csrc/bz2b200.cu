@@ -66,7 +66,10 @@ struct bz2b200 {
     int trace = 0;        // BZ2B200_TRACE=1: host-clock timeline of walk chunks and batches on stderr (development aid)
     double t_call = 0;
     bz2b200 *parent = nullptr;      // lane: the handle it works for
+    std::vector<bz2b200 *> children; // multi-device handle (bz2b200_create_multi): one single-device handle per entry; the parent owns no device state
+    int usable_children = 0;        // BZ2B200_MULTI_MAX: upper bound for the children a call may use (0 = all)
     std::vector<bz2b200 *> lanes;   // parent: its lanes (empty: batches run on the handle itself)
+    bool lanes_wanted = false;      // lanes are created at the first compress call (a handle used for decompression only never needs them)
     std::vector<std::thread> lane_thr;
     std::vector<char> lane_busy;
     std::vector<uint32_t> lane_nb;  // blocks of the batch a busy lane is working on
@@ -107,6 +110,7 @@ struct bz2b200 {
 
     // boundary walk, pipelined one batch ahead on a side stream
     cudaStream_t side = nullptr, copy = nullptr; // walk stream; output-drain stream (finished batches leave while the next one computes)
+    uint64_t out_cap_bits = 0;      // bits the call's device output buffer holds (k_bit_offsets never places a block behind it)
     uint8_t *drain_dst = nullptr;   // caller's output buffer (nullptr: no overlapped drain)
     size_t drain_cap = 0, drained = 0;
     bool drain_dev = false;
@@ -131,6 +135,13 @@ struct bz2b200 {
     uint64_t w_n = 0, w_cap = 0, w_req = 0, w_found = 0;
     int w_final = 0;
     bool w_finished = true;
+
+    // bz2b200_scan_prepare / bz2b200_scan_blocks_ex: the staged input, its summary tree and the block table stay valid for bz2b200_compress_scanned
+    bool prepared = false, scan_valid = false;
+    const uint8_t *prep_input = nullptr;
+    size_t prep_n = 0;
+    uint64_t scan_first = 0;
+    DevBuf shifted; // multi-device streams: this device's part moved to its bit offset in the stream (k_shift_bits)
 
     // last call
     bz2b200_stats_t stats{};
@@ -284,6 +295,11 @@ extern "C" const char *bz2b200_last_error(const bz2b200_t *h) { return h ? h->er
 extern "C" void bz2b200_destroy(bz2b200_t *h)
 {
     if (!h) return;
+    if (!h->children.empty()) {
+        for (bz2b200 *c : h->children) bz2b200_destroy(c);
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
     for (std::thread &t : h->lane_thr)
         if (t.joinable()) t.join();
@@ -457,9 +473,8 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (!h->prefix_walk) h->walk_growth = std::min(h->walk_growth, 4);
     if (const char *e = getenv("BZ2B200_TRACE")) h->trace = atoi(e);
     if (const char *e = getenv("BZ2B200_LANES")) h->n_lanes = std::max(1, std::min(4, atoi(e)));
-    const bool laned = h->n_lanes > 1 && h->G > 1;
-    int rc = create_impl(h, !laned);
-    if (rc == BZ2B200_OK && laned) rc = create_lanes(h);
+    h->lanes_wanted = h->n_lanes > 1 && h->G > 1;
+    int rc = create_impl(h, false); // per-batch buffers come with the first call that needs them: the lanes' at the first compress, the handle's own at the first decompress
     if (rc != BZ2B200_OK) {
         // keep the message reachable through a static for the failing create
         static thread_local std::string last;
@@ -585,6 +600,8 @@ static int is_device_ptr(const void *p)
 // walk_collect), ahead of the compression kernels on the main stream.
 static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
 {
+    h->scan_valid = false;
+    h->scan_first = 0;
     h->h_starts.assign(1, 0);
     h->h_rle_len.clear();
     h->w_in = d_in;
@@ -627,7 +644,7 @@ static int walk_extend(bz2b200 *h)
         for (; h->seg_copied < upto; ++h->seg_copied) {
             const uint64_t lo = h->seg_copied ? h->seg_end[h->seg_copied - 1] : 0, hi = h->seg_end[h->seg_copied];
             if (h->seg_copied == 0) CK(cudaEventRecord(h->ev[0], h->h2d));
-            CK(cudaMemcpyAsync(ptr<uint8_t>(h->in) + lo, h->host_src + lo, hi - lo, cudaMemcpyHostToDevice, h->h2d));
+            CK(cudaMemcpyAsync(ptr<uint8_t>(h->in) + lo, h->host_src + lo, hi - lo, cudaMemcpyDefault, h->h2d));
             CK(cudaEventRecord(h->ev_seg[h->seg_copied], h->h2d));
             if (h->seg_copied + 1 == h->seg_end.size()) CK(cudaEventRecord(h->ev[1], h->h2d));
         }
@@ -732,7 +749,8 @@ static int stage_input(bz2b200 *h, const uint8_t *input, size_t n, const uint8_t
     cudaError_t e = cudaPointerGetAttributes(&at, input);
     if (e != cudaSuccess) { (void)cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
     const bool dev = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-    if (dev) {
+    const bool remote = at.type == cudaMemoryTypeDevice && at.device != h->device; // another GPU's memory: copied like host input, over NVLink
+    if (dev && !remote) {
         h->seg_end.push_back(n);
         if ((reinterpret_cast<uintptr_t>(input) & 15u) == 0) { *d_in = input; return BZ2B200_OK; }
         ENSURE(h->in, n + 64);
@@ -754,37 +772,106 @@ static int stage_input(bz2b200 *h, const uint8_t *input, size_t n, const uint8_t
         h->ev_seg.push_back(ev);
     }
     h->host_src = input;
-    h->host_pinned = at.type == cudaMemoryTypeHost;
+    h->host_pinned = at.type == cudaMemoryTypeHost || remote;
     *d_in = ptr<uint8_t>(h->in);
     return BZ2B200_OK;
 }
 
-extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint64_t *block_starts, size_t capacity, uint64_t *n_blocks)
+// Stages `input` and builds the summary tree over all of it (asynchronously: copies and kernels are only queued).
+static int scan_prepare_impl(bz2b200 *h, const uint8_t *input, size_t n_bytes)
 {
-    if (!h || (!input && n_bytes) || !n_blocks) return BZ2B200_E_ARG;
-    CK(cudaSetDevice(h->device));
+    h->prepared = false;
     h->stats = bz2b200_stats_t{};
     const uint8_t *d_in = nullptr;
     int rc = stage_input(h, input, n_bytes, &d_in);
     if (rc) return rc;
-    rc = walk_setup(h, d_in, n_bytes, 1);
+    rc = walk_setup(h, d_in, n_bytes, 0);
     if (rc) return rc;
-    while (!h->w_finished || walk_more_input(h)) {
-        if (h->w_finished) {
-            rc = walk_extend(h);
+    while (walk_more_input(h)) {
+        rc = walk_extend(h);
+        if (rc) return rc;
+    }
+    h->prepared = true;
+    h->prep_input = input;
+    h->prep_n = n_bytes;
+    return BZ2B200_OK;
+}
+
+static int multi_scan_blocks(bz2b200 *P, const uint8_t *input, size_t n_bytes, int is_final, uint64_t *block_starts, size_t capacity, uint64_t *n_blocks,
+                             size_t *consumed);
+
+// The walk over a prepared input from `first_start` on; the block table stays in the handle for bz2b200_compress_scanned.
+static int scan_ex_impl(bz2b200 *h, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, uint64_t *block_starts, size_t capacity,
+                        uint64_t *n_blocks, size_t *consumed)
+{
+    if (first_start > n_bytes) { h->err = "first_start behind the input"; return BZ2B200_E_ARG; }
+    int rc;
+    if (!(h->prepared && h->prep_input == input && h->prep_n == n_bytes)) {
+        rc = scan_prepare_impl(h, input, n_bytes);
+        if (rc) return rc;
+    }
+    h->prepared = false; // one scan per preparation: the walk's device state is consumed
+    h->caller_final = is_final;
+    h->w_final = is_final ? 1 : 0; // every segment has been queued, so the walk sees the whole input
+    h->h_starts.assign(1, first_start);
+    h->h_rle_len.clear();
+    h->w_found = 0;
+    h->scan_first = first_start;
+    if (n_bytes) {
+        uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
+        h->h_pinned[40] = 0; h->h_pinned[41] = first_start; h->h_pinned[42] = 0; h->h_pinned[43] = first_start ? 1 : 0;
+        CK(cudaMemcpyAsync(d_info, h->h_pinned + 40, 32, cudaMemcpyHostToDevice, h->side));
+        h->w_finished = false;
+        while (!h->w_finished) {
+            rc = walk_launch(h, h->G);
+            if (rc) return rc;
+            rc = walk_collect(h);
             if (rc) return rc;
         }
-        rc = walk_launch(h, h->G);
-        if (rc) return rc;
-        rc = walk_collect(h);
-        if (rc) return rc;
     }
     CK(cudaStreamSynchronize(h->h2d));
     if (h->profiling) { CK(cudaStreamSynchronize(h->stream)); prof_collect(h); }
     const uint64_t nb = h->w_found;
+    h->scan_valid = true;
     *n_blocks = nb;
-    for (uint64_t i = 0; i < nb && i < capacity; ++i) block_starts[i] = h->h_starts[i];
-    return nb > capacity ? BZ2B200_E_OUTPUT : BZ2B200_OK;
+    if (consumed) *consumed = (size_t)h->h_starts[nb];
+    for (uint64_t i = 0; i < nb && i < capacity && block_starts; ++i) block_starts[i] = h->h_starts[i];
+    return (block_starts && nb > capacity) ? BZ2B200_E_OUTPUT : BZ2B200_OK;
+}
+
+extern "C" int bz2b200_scan_prepare(bz2b200_t *h, const uint8_t *input, size_t n_bytes)
+{
+    if (!h || (!input && n_bytes)) return BZ2B200_E_ARG;
+    if (!h->children.empty()) return BZ2B200_OK; // a multi-device handle prepares its slices inside the scan
+    CK(cudaSetDevice(h->device));
+    h->err.clear();
+    return scan_prepare_impl(h, input, n_bytes);
+}
+
+extern "C" int bz2b200_scan_blocks_ex(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, uint64_t *block_starts,
+                                      size_t capacity, uint64_t *n_blocks, size_t *consumed)
+{
+    if (!h || (!input && n_bytes) || !n_blocks) return BZ2B200_E_ARG;
+    if (!h->children.empty()) {
+        if (first_start) { h->err = "first_start is not supported on a multi-device handle"; return BZ2B200_E_ARG; }
+        return multi_scan_blocks(h, input, n_bytes, is_final, block_starts, capacity, n_blocks, consumed);
+    }
+    CK(cudaSetDevice(h->device));
+    h->err.clear();
+    int rc = scan_ex_impl(h, input, n_bytes, is_final, first_start, block_starts, capacity, n_blocks, consumed);
+    if (rc != BZ2B200_OK && rc != BZ2B200_E_OUTPUT) {
+        cudaStreamSynchronize(h->side);
+        cudaStreamSynchronize(h->h2d);
+        (void)cudaGetLastError();
+        h->scan_valid = false;
+    }
+    return rc;
+}
+
+extern "C" int bz2b200_scan_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint64_t *block_starts, size_t capacity, uint64_t *n_blocks)
+{
+    if (!block_starts && capacity) return BZ2B200_E_ARG;
+    return bz2b200_scan_blocks_ex(h, input, n_bytes, 1, 0, block_starts, capacity, n_blocks, nullptr);
 }
 
 // One batch: blocks [b0, b0 + nb) of the call, `seq` = number of the batch inside the call.  h is the handle itself or one of its
@@ -1032,7 +1119,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
             if (seq) CK(cudaStreamWaitEvent(st, ctl->ev_bits[(seq - 1) & 3], 0));
         }
         KL(KID_k_bit_offsets, k_bit_offsets<<<1, 1024, 0, st>>>(ptr<uint64_t>(h->nbits_b), nb, ptr<uint64_t>(P->scalars) + Scalars::BITPOS, ptr<uint64_t>(h->bitoff),
-                                                                d_scal + Scalars::BATCH_BITS));
+                                                                d_scal + Scalars::BATCH_BITS, P->out_cap_bits));
         if (ctl) {
             CK(cudaEventRecord(ctl->ev_bits[seq & 3], st));
             std::lock_guard<std::mutex> lk(ctl->mu);
@@ -1090,9 +1177,13 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     return BZ2B200_OK;
 }
 
+// scanned: compress the blocks found by the last bz2b200_scan_blocks_ex (input staged, block table in the handle) instead of staging and
+// walking `input`; keep_dev: leave the packed bits in the handle's own device buffer (h->out) -- multi-device streams move them from there
 static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                 size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                size_t block_capacity, uint64_t *n_blocks);
+                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev);
+static int multi_compress_blocks(bz2b200 *P, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out, size_t out_capacity,
+                                 uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks);
 
 // ---- lanes: one host thread per batch in flight
 static void lane_main(bz2b200 *l, int idx, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq)
@@ -1169,12 +1260,12 @@ static int lanes_finish(bz2b200 *h)
     return BZ2B200_OK;
 }
 
-extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
-                                       size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                       size_t block_capacity, uint64_t *n_blocks)
+static int compress_blocks_guarded(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
+                                   size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                   size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev)
 {
     int rc = compress_blocks_impl(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits,
-                                  block_capacity, n_blocks);
+                                  block_capacity, n_blocks, scanned, keep_dev);
     if (h) {
         // never leave batches, copies into the caller's buffer or a walk in flight, whatever the outcome
         (void)lanes_finish(h);
@@ -1183,14 +1274,36 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
         cudaStreamSynchronize(h->h2d);
         h->drain_dst = nullptr;
         h->host_src = nullptr;
+        h->scan_valid = false; // a block table is good for one compress call
         if (rc != BZ2B200_OK) (void)cudaGetLastError();
     }
     return rc;
 }
 
+extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
+                                       size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                       size_t block_capacity, uint64_t *n_blocks)
+{
+    if (h && !h->children.empty())
+        return multi_compress_blocks(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits, block_capacity,
+                                     n_blocks);
+    return compress_blocks_guarded(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits, block_capacity,
+                                   n_blocks, false, false);
+}
+
+extern "C" int bz2b200_compress_scanned(bz2b200_t *h, unsigned start_bit, uint8_t *out, size_t out_capacity, uint64_t *out_nbits, uint32_t *block_crcs,
+                                        uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks)
+{
+    if (!h) return BZ2B200_E_ARG;
+    if (!h->children.empty()) { h->err = "compress_scanned works on a single-device handle"; return BZ2B200_E_ARG; }
+    size_t consumed = 0;
+    return compress_blocks_guarded(h, nullptr, 0, 0, start_bit, out, out_capacity, out_nbits, &consumed, block_crcs, block_nbits, block_capacity, n_blocks,
+                                   true, false);
+}
+
 static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                 size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                size_t block_capacity, uint64_t *n_blocks)
+                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev)
 {
     if (!h) return BZ2B200_E_ARG;
     if ((!input && n_bytes) || !out_nbits || !consumed || !n_blocks || start_bit > 7 || (!out && out_capacity)) {
@@ -1199,6 +1312,16 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     }
     CK(cudaSetDevice(h->device));
     h->err.clear();
+    if (scanned && !h->scan_valid) { h->err = "no block table: call bz2b200_scan_blocks_ex first"; return BZ2B200_E_STATE; }
+    int rc;
+    if (h->lanes_wanted && h->lanes.empty()) {
+        rc = create_lanes(h);
+        if (rc) return rc;
+    }
+    if (h->lanes.empty() && !h->batch_ready) {
+        rc = alloc_batch(h);
+        if (rc) return rc;
+    }
     h->stats = bz2b200_stats_t{};
     h->last_nb = 0;
     h->call_batches = 0;
@@ -1206,11 +1329,17 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     *out_nbits = 0; *consumed = 0; *n_blocks = 0;
     cudaStream_t st = h->stream;
     const uint8_t *d_in = nullptr;
-    int rc = stage_input(h, input, n_bytes, &d_in);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev[10], st));
-    rc = walk_setup(h, d_in, n_bytes, is_final);
-    if (rc) return rc;
+    if (scanned) {
+        d_in = h->w_in;
+        n_bytes = (size_t)(h->h_starts[h->w_found] - h->scan_first); // the bytes the scanned blocks cover
+        CK(cudaEventRecord(h->ev[10], st));
+    } else {
+        rc = stage_input(h, input, n_bytes, &d_in);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[10], st));
+        rc = walk_setup(h, d_in, n_bytes, is_final);
+        if (rc) return rc;
+    }
     const uint64_t cap_blocks = n_bytes / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
     const size_t need = bz2b200_max_output_bytes(h, n_bytes) + 8;
     const size_t dcap = (need + 3) / 4 * 4;
@@ -1221,7 +1350,8 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->h_pinned[32] = start_bit;
     CK(cudaMemcpyAsync(d_scal + Scalars::BITPOS, h->h_pinned + 32, 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(h->out.p, 0, dcap, st));
-    h->drain_dst = out;
+    h->out_cap_bits = (uint64_t)dcap * 8;
+    h->drain_dst = keep_dev ? nullptr : out;
     h->drain_cap = out_capacity;
     h->drained = 0;
     h->drain_dev = out ? is_device_ptr(out) != 0 : false;
@@ -1285,7 +1415,7 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     h->last_total_blocks = nb;
     *n_blocks = nb;
     *consumed = (size_t)used;
-    h->stats.n_input = used;
+    h->stats.n_input = used - h->scan_first;
     h->stats.n_blocks = nb;
     if ((block_crcs || block_nbits) && nb > block_capacity) { h->err = "block_capacity too small"; return BZ2B200_E_OUTPUT; }
     CK(cudaEventRecord(h->ev[11], st));
@@ -1296,10 +1426,10 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
     const size_t out_bytes = (size_t)((endbit + 7) / 8);
     h->stats.ms_total = ev_ms(h->ev[10], h->ev[11]);
     h->stats.n_out_bits = bits;
-    if (out_bytes > dcap) { h->err = "internal: output bound exceeded"; return BZ2B200_E_CUDA; }
-    if (out_bytes > out_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    if (out_bytes > dcap) { h->err = "internal: output bound exceeded"; return BZ2B200_E_CUDA; } // (nothing was written past the buffer: k_bit_offsets)
+    if (!keep_dev && out_bytes > out_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
     *out_nbits = bits;
-    if (out_bytes) {
+    if (out_bytes && !keep_dev) {
         // the tail that was not drained while the batches ran (at least the last partial byte)
         CK(cudaStreamSynchronize(h->copy));
         CK(cudaEventRecord(h->ev[12], st));
@@ -1323,6 +1453,368 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         h->stats.n_rle = sum;
     }
     return BZ2B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- several GPUs, one stream
+// blocks share no state, so a stream is cut into contiguous byte slices, one per device, and every device compresses
+// the blocks that START in its slice.  What is sequential is only the question where those blocks start: the machine of
+// BlockCompressor::write (BlockCompressor.hpp:69-96) runs through the whole stream.  Every device therefore stages its slice plus the
+// HEAD bytes in front of it (no unfinished block is longer than HEAD raw bytes) and summarises them at once, all devices in parallel;
+// the walks then run as a chain: device d starts at the position where device d-1's last complete block ended, finds its blocks and
+// hands the start of its unfinished last block on to device d+1 (a number), and compresses while the chain moves on.  Slices shrink
+// geometrically so that devices further down the chain, which start later, finish together with the first ones.  Every device packs
+// its blocks from bit 0 of its own buffer; when the bit lengths are known each part is moved to its bit offset on its own device
+// (k_shift_bits) and copied to its place in the caller's buffer.  The reference does all of this on one device picked in
+// OutputStream.hpp:61 and batches in :190-240.
+struct MultiChain {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t> start;  // absolute stream offset where device d's first block starts
+    std::vector<char> known;
+    int rc = 0;
+    std::string err;
+};
+
+struct MultiPart {
+    uint64_t base = 0, lo = 0, hi = 0; // staged bytes [base, hi), blocks starting in [.., hi) are this device's
+    uint64_t nbits = 0, nblocks = 0, first = 0;
+    std::vector<uint32_t> crcs;
+    std::vector<uint64_t> nbits_b;
+    std::vector<uint64_t> starts; // multi_scan_blocks only
+    uint8_t tail[2] = {0, 0};
+    bz2b200_stats_t stats{};
+};
+
+static uint64_t multi_head_bytes(const bz2b200 *c)
+{
+    // an unfinished block holds at most (limit/5 + 1) full 255-byte chunks of a run plus what short runs add
+    const uint64_t limit = (uint64_t)c->bs - 6;
+    return ((limit / 5 + 2) * 255 + 2 * (uint64_t)c->bs + 4095) / 4096 * 4096;
+}
+
+static int multi_plan(bz2b200 *P, size_t n_bytes, std::vector<MultiPart> &parts)
+{
+    const bz2b200 *c0 = P->children[0];
+    size_t k = P->children.size();
+    if (P->usable_children > 0) k = std::min<size_t>(k, (size_t)P->usable_children);
+    const uint64_t min_slice = 16ull * (uint64_t)c0->bs; // a device is not woken for less
+    k = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(k, n_bytes / std::max<uint64_t>(1, min_slice)));
+    // device d starts about d walks later than device 0: sizes fall by the ratio walk time / compress time per byte
+    double r = 0.96;
+    if (const char *e = getenv("BZ2B200_MULTI_RATIO")) { const double v = atof(e); if (v > 0.1 && v <= 1.0) r = v; }
+    std::vector<double> w(k);
+    double tot = 0;
+    for (size_t d = 0; d < k; ++d) { w[d] = d ? w[d - 1] * r : 1.0; tot += w[d]; }
+    parts.assign(k, MultiPart());
+    const uint64_t head = multi_head_bytes(c0);
+    double acc = 0;
+    uint64_t lo = 0;
+    for (size_t d = 0; d < k; ++d) {
+        acc += w[d];
+        uint64_t hi = d + 1 == k ? (uint64_t)n_bytes : std::min<uint64_t>(n_bytes, (uint64_t)((double)n_bytes * (acc / tot)) / 4096 * 4096);
+        if (hi < lo) hi = lo;
+        parts[d].lo = lo;
+        parts[d].hi = hi;
+        parts[d].base = lo > head ? (lo - head) / 4096 * 4096 : 0;
+        lo = hi;
+    }
+    return BZ2B200_OK;
+}
+
+// runs fn(d) on one host thread per part (the calling thread takes part 0)
+template <typename F>
+static void multi_threads(size_t k, F fn)
+{
+    std::vector<std::thread> thr;
+    for (size_t d = 1; d < k; ++d) thr.emplace_back([&fn, d] { fn(d); });
+    fn(0);
+    for (std::thread &t : thr) t.join();
+}
+
+static void chain_publish(MultiChain &ch, size_t d, uint64_t start, int rc, const std::string &err)
+{
+    std::lock_guard<std::mutex> lk(ch.mu);
+    if (rc && !ch.rc) { ch.rc = rc; ch.err = err; }
+    if (d < ch.start.size()) { ch.start[d] = start; ch.known[d] = 1; }
+    ch.cv.notify_all();
+}
+
+// stage + summarise the part's bytes, wait for the chain, walk; returns the child's rc (chain already informed)
+static int multi_scan_part(bz2b200 *P, size_t d, const uint8_t *input, size_t n_bytes, int is_final, std::vector<MultiPart> &parts, MultiChain &ch)
+{
+    bz2b200 *c = P->children[d];
+    MultiPart &pt = parts[d];
+    const bool last = d + 1 == parts.size();
+    int rc = cudaSetDevice(c->device) == cudaSuccess ? BZ2B200_OK : BZ2B200_E_CUDA;
+    c->err.clear();
+    c->profiling = P->profiling;
+    if (rc == BZ2B200_OK && pt.hi > pt.base) rc = scan_prepare_impl(c, input + pt.base, (size_t)(pt.hi - pt.base));
+    uint64_t s = 0;
+    {
+        std::unique_lock<std::mutex> lk(ch.mu);
+        ch.cv.wait(lk, [&] { return ch.known[d] || ch.rc; });
+        if (ch.rc && !rc) rc = ch.rc;
+        s = ch.start[d];
+    }
+    uint64_t next = s;
+    if (rc == BZ2B200_OK && s < pt.hi) {
+        if (s < pt.base) { c->err = "internal: an unfinished block is longer than the staged head"; rc = BZ2B200_E_STATE; }
+        uint64_t nb = 0;
+        size_t used = 0;
+        if (rc == BZ2B200_OK)
+            rc = scan_ex_impl(c, input + pt.base, (size_t)(pt.hi - pt.base), (last && is_final) ? 1 : 0, s - pt.base, nullptr, 0, &nb, &used);
+        if (rc == BZ2B200_OK) {
+            pt.nblocks = nb;
+            pt.first = s;
+            next = pt.base + used;
+        }
+    }
+    chain_publish(ch, d + 1, next, rc, c->err);
+    (void)n_bytes;
+    return rc;
+}
+
+static int multi_scan_blocks(bz2b200 *P, const uint8_t *input, size_t n_bytes, int is_final, uint64_t *block_starts, size_t capacity, uint64_t *n_blocks,
+                             size_t *consumed)
+{
+    P->err.clear();
+    std::vector<MultiPart> parts;
+    multi_plan(P, n_bytes, parts);
+    MultiChain ch;
+    ch.start.assign(parts.size() + 1, 0);
+    ch.known.assign(parts.size() + 1, 0);
+    ch.known[0] = 1;
+    multi_threads(parts.size(), [&](size_t d) {
+        int rc = multi_scan_part(P, d, input, n_bytes, is_final, parts, ch);
+        if (rc == BZ2B200_OK && parts[d].nblocks) {
+            bz2b200 *c = P->children[d];
+            parts[d].starts.assign(c->h_starts.begin(), c->h_starts.begin() + (ptrdiff_t)parts[d].nblocks);
+            for (uint64_t &v : parts[d].starts) v += parts[d].base;
+        }
+        cudaStreamSynchronize(P->children[d]->side);
+        cudaStreamSynchronize(P->children[d]->h2d);
+        P->children[d]->scan_valid = false;
+    });
+    if (ch.rc) { P->err = ch.err; return ch.rc; }
+    uint64_t nb = 0;
+    for (const MultiPart &pt : parts)
+        for (uint64_t v : pt.starts) {
+            if (block_starts && nb < capacity) block_starts[nb] = v;
+            ++nb;
+        }
+    *n_blocks = nb;
+    if (consumed) *consumed = (size_t)ch.start[parts.size()];
+    return (block_starts && nb > capacity) ? BZ2B200_E_OUTPUT : BZ2B200_OK;
+}
+
+static int multi_compress_blocks(bz2b200 *P, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out, size_t out_capacity,
+                                 uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks)
+{
+    if ((!input && n_bytes) || !out_nbits || !consumed || !n_blocks || start_bit > 7 || (!out && out_capacity)) {
+        P->err = "bad argument";
+        return BZ2B200_E_ARG;
+    }
+    P->err.clear();
+    P->stats = bz2b200_stats_t{};
+    *out_nbits = 0; *consumed = 0; *n_blocks = 0;
+    const double t0 = now_ms();
+    std::vector<MultiPart> parts;
+    multi_plan(P, n_bytes, parts);
+    const size_t k = parts.size();
+    if (k == 1) { // too little for a second device: the first one takes the call as it is (walk, copies and kernels overlapped)
+        bz2b200 *c = P->children[0];
+        c->profiling = P->profiling;
+        int rc = compress_blocks_guarded(c, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits, block_capacity,
+                                         n_blocks, false, false);
+        P->stats = c->stats;
+        if (rc) P->err = c->err;
+        return rc;
+    }
+    MultiChain ch;
+    ch.start.assign(k + 1, 0);
+    ch.known.assign(k + 1, 0);
+    ch.known[0] = 1;
+    // ---- per device: stage + summarise, walk when the chain arrives, compress into the device's own buffer
+    multi_threads(k, [&](size_t d) {
+        bz2b200 *c = P->children[d];
+        MultiPart &pt = parts[d];
+        int rc = multi_scan_part(P, d, input, n_bytes, is_final, parts, ch);
+        if (rc == BZ2B200_OK && pt.nblocks) {
+            pt.crcs.resize(pt.nblocks);
+            pt.nbits_b.resize(pt.nblocks);
+            size_t used = 0;
+            uint64_t nb = 0;
+            rc = compress_blocks_guarded(c, nullptr, 0, 0, 0, nullptr, 0, &pt.nbits, &used, pt.crcs.data(), pt.nbits_b.data(), pt.nblocks, &nb, true, true);
+            if (rc == BZ2B200_OK && pt.nbits) { // the part's last two bytes: the bits the next part's first byte starts with
+                const uint64_t e = (pt.nbits - 1) >> 3;
+                if (cudaMemcpy(pt.tail, ptr<uint8_t>(c->out) + (e ? e - 1 : 0), e ? 2 : 1, cudaMemcpyDeviceToHost) != cudaSuccess) { c->err = "tail read failed"; rc = BZ2B200_E_CUDA; }
+                if (!e) { pt.tail[1] = pt.tail[0]; pt.tail[0] = 0; }
+            }
+            pt.stats = c->stats;
+        } else {
+            cudaStreamSynchronize(c->side);
+            cudaStreamSynchronize(c->h2d);
+            c->scan_valid = false;
+        }
+        if (rc) chain_publish(ch, k + 1, 0, rc, c->err);
+    });
+    if (ch.rc) { P->err = ch.err; return ch.rc; }
+    // ---- the stream: bit offsets, per-block tables
+    uint64_t total_blocks = 0, bitpos = start_bit;
+    for (const MultiPart &pt : parts) total_blocks += pt.nblocks;
+    *n_blocks = total_blocks;
+    *consumed = (size_t)ch.start[k];
+    if ((block_crcs || block_nbits) && total_blocks > block_capacity) { P->err = "block_capacity too small"; return BZ2B200_E_OUTPUT; }
+    {
+        uint64_t b = 0;
+        for (const MultiPart &pt : parts) {
+            for (uint64_t i = 0; i < pt.nblocks; ++i, ++b) {
+                if (block_crcs) block_crcs[b] = pt.crcs[i];
+                if (block_nbits) block_nbits[b] = pt.nbits_b[i];
+            }
+        }
+    }
+    std::vector<uint64_t> off(k, 0);
+    for (size_t d = 0; d < k; ++d) { off[d] = bitpos; bitpos += parts[d].nbits; }
+    const uint64_t bits = bitpos - start_bit;
+    const size_t out_bytes = (size_t)((bitpos + 7) / 8);
+    if (bits && out_bytes > out_capacity) { P->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    // ---- every part to its place: shifted on its own device, copied by its own device
+    int last_part = -1;
+    for (size_t d = 0; d < k; ++d)
+        if (parts[d].nbits) last_part = (int)d;
+    int rc_all = BZ2B200_OK;
+    std::mutex emu;
+    const bool out_dev = out && is_device_ptr(out);
+    multi_threads(k, [&](size_t d) {
+        bz2b200 *c = P->children[d];
+        const MultiPart &pt = parts[d];
+        if (!pt.nbits) return;
+        auto fail = [&](const char *what) {
+            std::lock_guard<std::mutex> lk(emu);
+            if (!rc_all) { rc_all = BZ2B200_E_CUDA; P->err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()); }
+        };
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail("cudaSetDevice");
+        const uint32_t shift = (uint32_t)(off[d] & 7);
+        uint32_t carry = 0;
+        if (shift) { // the last `shift` bits of the part in front (every non-empty part holds at least a block header)
+            int p = (int)d - 1;
+            while (p >= 0 && !parts[p].nbits) --p;
+            if (p >= 0) {
+                const MultiPart &q = parts[p];
+                const uint64_t e = (q.nbits - 1) >> 3;
+                const uint32_t v16 = ((uint32_t)q.tail[0] << 8) | q.tail[1];
+                const uint32_t have = (uint32_t)(q.nbits - 8 * (e ? e - 1 : 0)) + (e ? 0u : 8u); // bits of v16 (from its top) that belong to the part
+                carry = ((v16 >> (16 - have)) & ((1u << shift) - 1u)) << (8 - shift);
+            }
+        }
+        const uint64_t n_src = (pt.nbits + 7) / 8, n_dst = (shift + pt.nbits + 7) / 8;
+        const uint8_t *src = ptr<uint8_t>(c->out);
+        const uint8_t *from = src;
+        cudaStream_t st = c->stream;
+        if (shift) {
+            if (ensure(c, c->shifted, n_dst + 16) != BZ2B200_OK) return fail("cudaMalloc");
+            k_shift_bits<<<(unsigned)((n_dst + 16 * 256 - 1) / (16 * 256)), 256, 0, st>>>(src, n_src, ptr<uint8_t>(c->shifted), n_dst, shift, carry);
+            from = ptr<uint8_t>(c->shifted);
+        }
+        // the byte a later part starts in belongs to that part (it carries these bits in)
+        const bool shares_last = (int)d != last_part && ((off[d] + pt.nbits) & 7) != 0;
+        const uint64_t n_copy = n_dst - (shares_last ? 1 : 0);
+        if (n_copy && cudaMemcpyAsync(out + (off[d] >> 3), from, n_copy, out_dev ? cudaMemcpyDefault : cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("cudaMemcpyAsync");
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail("cudaStreamSynchronize");
+    });
+    if (rc_all) return rc_all;
+    *out_nbits = bits;
+    // ---- counters of the call
+    auto &s = P->stats;
+    for (const MultiPart &pt : parts) {
+        const auto &q = pt.stats;
+        s.ms_rle += q.ms_rle; s.ms_bwt_sort0 += q.ms_bwt_sort0; s.ms_bwt_rounds += q.ms_bwt_rounds; s.ms_bwt_finish += q.ms_bwt_finish;
+        s.ms_mtf += q.ms_mtf; s.ms_huffman += q.ms_huffman; s.ms_emit += q.ms_emit; s.ms_walk += q.ms_walk;
+        s.ms_h2d = std::max(s.ms_h2d, q.ms_h2d);
+        s.n_rle += q.n_rle;
+        s.bwt_rounds = std::max(s.bwt_rounds, q.bwt_rounds);
+        s.bwt_active_volume += q.bwt_active_volume;
+        s.kernel_launches += q.kernel_launches + (pt.nbits ? 1 : 0);
+    }
+    s.ms_total = (float)(now_ms() - t0); // host clock: the devices have no common event timeline
+    s.n_input = ch.start[k];
+    s.n_blocks = total_blocks;
+    s.n_out_bits = bits;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_create_multi(bz2b200_t **out, const int *device_ids, int n_devices, int base_block_size, int multiplier, int max_blocks_in_flight)
+{
+    if (!out) return BZ2B200_E_ARG;
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 64) return BZ2B200_E_ARG;
+    bz2b200 *P = new bz2b200();
+    P->device = device_ids[0];
+    P->base = base_block_size; P->mult = multiplier; P->bs = base_block_size * multiplier; P->G = (uint32_t)std::max(1, max_blocks_in_flight);
+    for (int i = 0; i < n_devices; ++i) {
+        bz2b200 *c = nullptr;
+        int rc = bz2b200_create(&c, device_ids[i], base_block_size, multiplier, max_blocks_in_flight);
+        if (rc != BZ2B200_OK) { bz2b200_destroy(P); return rc; }
+        P->children.push_back(c);
+    }
+    // parts leave over NVLink when the caller's buffers live on one of the devices
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < n_devices; ++j)
+            if (device_ids[i] != device_ids[j]) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[j]) == cudaSuccess && can) {
+                    cudaSetDevice(device_ids[i]);
+                    if (cudaDeviceEnablePeerAccess(device_ids[j], 0) != cudaSuccess) (void)cudaGetLastError();
+                }
+            }
+    (void)cudaGetLastError();
+    if (const char *e = getenv("BZ2B200_MULTI_MAX")) P->usable_children = std::max(0, atoi(e));
+    *out = P;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_device_count_of(const bz2b200_t *h) { return !h ? 0 : h->children.empty() ? 1 : (int)h->children.size(); }
+
+// One part of a multi-device / multi-process stream to its bit offset: dst = src shifted right by `shift` bits, `carry`
+// (already positioned in the top `shift` bits) in front.  src and dst are device pointers on the handle's device.
+extern "C" int bz2b200_shift_bits(bz2b200_t *h, const uint8_t *src, uint64_t nbits, unsigned shift, unsigned carry, uint8_t *dst, size_t dst_capacity)
+{
+    if (!h || shift > 7 || (nbits && (!src || !dst))) return BZ2B200_E_ARG;
+    if (!h->children.empty()) h = h->children[0];
+    CK(cudaSetDevice(h->device));
+    const uint64_t n_src = (nbits + 7) / 8, n_dst = (shift + nbits + 7) / 8;
+    if (n_dst > dst_capacity) { h->err = "output buffer too small"; return BZ2B200_E_OUTPUT; }
+    if (!n_dst) return BZ2B200_OK;
+    k_shift_bits<<<(unsigned)((n_dst + 16 * 256 - 1) / (16 * 256)), 256, 0, h->stream>>>(src, n_src, dst, n_dst, shift, carry & 0xffu);
+    CK(cudaStreamSynchronize(h->stream));
+    return BZ2B200_OK;
+}
+
+// pinned host memory for the caller's staging buffers (asynchronous copies need it; OutputStream double-buffers with it)
+extern "C" void *bz2b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void bz2b200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// blocks per device batch that keep the device busy without asking for more than a third of its free memory
+extern "C" int bz2b200_recommended_blocks(int device_id, int base_block_size, int multiplier)
+{
+    if (multiplier < 1 || multiplier > 9 || base_block_size < 1000 || base_block_size > 100000) return 0;
+    int ndev = bz2b200_device_count();
+    if (device_id < 0 || device_id >= ndev) return 0;
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    const uint64_t per_block = 50ull * ((uint64_t)base_block_size * multiplier + 64); // ~47 B per block byte (data layout)
+    const uint64_t fit = (uint64_t)(fr / 3) / per_block;
+    const uint64_t want = std::max<uint64_t>(64, 600ull * 900000 / ((uint64_t)base_block_size * multiplier)); // ~540 MB of input per batch pair
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(fit, want), 4096));
 }
 
 extern "C" int bz2b200_compress_stream(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes)
@@ -1451,7 +1943,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
         CK(cudaMemsetAsync(h->ranks.p, 0, (size_t)nb * h->S, st)); // rank 0 everywhere: runs are not stored
         KL(KID_k_dec_block, k_dec_block<<<(nb + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, DB_WARPS * sizeof(DecTables), st>>>(
                                 d_in, n_bits, ptr<uint64_t>(h->dec_cand), (uint32_t)c0, nb, stream_bs, ptr<uint8_t>(h->ranks), h->S, ptr<uint8_t>(h->sel), h->sel_stride,
-                                max_selectors, ptr<uint64_t>(h->dec_list0), ptr<DecInfo>(h->dec_info)));
+                                max_selectors, (uint32_t)std::min<uint64_t>(h->sel_stride, 0xffffffffull), ptr<uint64_t>(h->dec_list0), ptr<DecInfo>(h->dec_info)));
         uint32_t *d_counts = ptr<uint32_t>(h->cnts);
         KL(KID_k_dec_bases, k_dec_counts<<<(nb + 255) / 256, 256, 0, st>>>(ptr<DecInfo>(h->dec_info), nb, d_counts));
         CK(cudaMemcpyAsync(info.data(), h->dec_info.p, (size_t)nb * sizeof(DecInfo), cudaMemcpyDeviceToHost, st));
@@ -1586,6 +2078,11 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
 extern "C" int bz2b200_decompress_stream(bz2b200_t *h, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes)
 {
     if (!h) return BZ2B200_E_ARG;
+    if (!h->children.empty()) { // the decompress side runs on the first device
+        int rc = bz2b200_decompress_stream(h->children[0], input, n_bytes, out, out_capacity, out_bytes);
+        h->stats = h->children[0]->stats; h->err = h->children[0]->err;
+        return rc;
+    }
     if ((!input && n_bytes) || !out_bytes || (!out && out_capacity)) { h->err = "bad argument"; return BZ2B200_E_ARG; }
     CK(cudaSetDevice(h->device));
     h->err.clear();
@@ -1599,6 +2096,11 @@ extern "C" int bz2b200_decompress_concat(bz2b200_t *h, const uint8_t *input, siz
                                          uint64_t *n_streams)
 {
     if (!h) return BZ2B200_E_ARG;
+    if (!h->children.empty()) {
+        int rc = bz2b200_decompress_concat(h->children[0], input, n_bytes, out, out_capacity, out_bytes, n_streams);
+        h->stats = h->children[0]->stats; h->err = h->children[0]->err;
+        return rc;
+    }
     if ((!input && n_bytes) || !out_bytes || (!out && out_capacity)) { h->err = "bad argument"; return BZ2B200_E_ARG; }
     CK(cudaSetDevice(h->device));
     h->err.clear();
@@ -1611,6 +2113,7 @@ extern "C" int bz2b200_decompress_concat(bz2b200_t *h, const uint8_t *input, siz
 extern "C" int bz2b200_stage_dump(bz2b200_t *h, uint64_t block_index, int stage, void *dst, size_t cap, size_t *len_bytes)
 {
     if (!h || !dst || !len_bytes) return BZ2B200_E_ARG;
+    if (!h->children.empty()) return BZ2B200_E_STATE; // per-device batches: dump through a single-device handle
     if (block_index < h->last_b0 || block_index >= h->last_b0 + h->last_nb) return BZ2B200_E_STATE;
     CK(cudaSetDevice(h->device));
     const uint64_t bl = block_index - h->last_b0, S = h->S;
@@ -1660,6 +2163,7 @@ extern "C" int bz2b200_set_profiling(bz2b200_t *h, int on)
     if (!h) return BZ2B200_E_ARG;
     h->profiling = on != 0;
     for (int i = 0; i < KID_COUNT; ++i) { h->k_ms[i] = 0; h->k_launches[i] = 0; h->k_bytes[i] = 0; }
+    for (bz2b200 *c : h->children) bz2b200_set_profiling(c, on);
     return BZ2B200_OK;
 }
 
@@ -1671,6 +2175,7 @@ extern "C" int bz2b200_kernel_times(const bz2b200_t *h, int index, const char **
     *ms = h->k_ms[index];
     *launches = h->k_launches[index];
     *bytes = h->k_bytes[index];
+    for (const bz2b200 *c : h->children) { *ms += c->k_ms[index]; *launches += c->k_launches[index]; *bytes += c->k_bytes[index]; }
     return BZ2B200_OK;
 }
 

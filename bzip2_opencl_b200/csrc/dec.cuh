@@ -122,6 +122,7 @@ struct DecTables {
     uint16_t lut[6][1 << DEC_LUT_BITS]; // next DEC_LUT_BITS bits -> (symbol << 5) | code length, 0 = code longer than the window
     uint8_t len[258];
     uint8_t minlen[6];
+    uint8_t lutmin[6]; // first code length the limit search tries when the lookup window has no entry
 };
 
 constexpr int DB_WARPS = 4; // blocks per CTA of k_dec_block
@@ -132,7 +133,7 @@ constexpr int DB_WARPS = 4; // blocks per CTA of k_dec_block
 // afterwards (k_imtf_*).
 __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__restrict__ in, uint64_t n_bits, const uint64_t *__restrict__ cand, uint32_t c0,
                                                               uint32_t nb, uint32_t block_size, uint8_t *__restrict__ ranks, uint64_t stride,
-                                                              uint8_t *__restrict__ sel_scratch, uint64_t sel_stride, uint32_t max_selectors,
+                                                              uint8_t *__restrict__ sel_scratch, uint64_t sel_stride, uint32_t max_selectors, uint32_t sel_cap,
                                                               uint64_t *__restrict__ list0, DecInfo *__restrict__ info)
 {
     extern __shared__ __align__(16) unsigned char dec_smem[];
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
         }
     list0[(uint64_t)bl * 32 + lane] = list;
     const int eob = nsym + 1, alpha = nsym + 2;
-    const uint32_t ntab = br.bits(3), nsel = br.bits(15);
+    const uint32_t ntab = br.bits(3);
+    uint32_t nsel = br.bits(15);
     if (br.overrun) I.err = DEC_E_DATA;
     else if (ntab < 2 || ntab > 6 || nsel < 1 || nsel > max_selectors) I.err = DEC_E_TABLES;
     else if (randomised) I.err = DEC_E_RANDOMISED;
@@ -177,10 +179,14 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
             while (br.bit()) { if (++u > 5 || br.overrun) break; }
             if (u > 5) { I.err = DEC_E_TABLES; break; } // (the reference indexes past its table list here; a 2..6-table stream never does)
             const uint32_t v = (tmtf >> (4 * u)) & 15u;
+            if (v >= ntab) { I.err = DEC_E_TABLES; break; } // a table that the block does not define (the reference would index past its list)
             const uint32_t lowmask = (1u << (4 * u)) - 1u;
             tmtf = (tmtf & ~((lowmask << 4) | 15u)) | ((tmtf & lowmask) << 4) | v;
-            if (lane == 0) sel[i] = (uint8_t)v;
+            // A block of the handle's size never needs more than sel_cap groups; selectors beyond that are read and dropped (the slot
+            // holds sel_cap bytes -- a declared count above it must not reach the neighbouring blocks' slots).
+            if (lane == 0 && i < sel_cap) sel[i] = (uint8_t)v;
         }
+        nsel = min(nsel, sel_cap);
     }
     if (I.err == DEC_OK) {
         for (uint32_t t = 0; t < ntab && I.err == DEC_OK; ++t) { // delta-coded lengths (:169-183), then createHuffmanDecodingTables
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
             }
             if (I.err != DEC_OK) break;
             __syncwarp();
+            int oversub = 0; // Kraft sum above 1: canonical codes of some length do not fit that length
             if (lane == 0) {
                 int32_t *bases = T.base[t], *limits = T.limit[t];
                 for (int i = 0; i < DEC_MAXLEN + 2; ++i) { bases[i] = 0; limits[i] = -1; }
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
                 for (int i = mn; i <= mx; ++i) {
                     const int b0 = code;
                     code += bases[i + 1] - bases[i];
+                    if (code > (1 << i)) oversub = 1;
                     bases[i] = b0 - bases[i];
                     limits[i] = code - 1;
                     code <<= 1;
@@ -212,12 +220,16 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
                     for (int s = 0; s < alpha; ++s)
                         if (T.len[s] == bits) T.perm[t][ci++] = (uint16_t)s;
                 T.minlen[t] = (uint8_t)mn;
+                T.lutmin[t] = (uint8_t)(oversub ? mn : max(mn, DEC_LUT_BITS + 1));
             }
+            oversub = __shfl_sync(FULL, oversub, 0);
             __syncwarp();
-            // lookup window: every symbol with a code of at most DEC_LUT_BITS bits fills its 2^(window - length) slots
+            // lookup window: every symbol with a code of at most DEC_LUT_BITS bits fills its 2^(window - length) slots.  An
+            // over-subscribed length set (which the reference's limit search still decodes, HuffmanStageDecoder.hpp:62-74) gets no
+            // window at all: its codes would run past the table, and every symbol then goes through the same limit search.
             for (int k = lane; k < (1 << DEC_LUT_BITS); k += 32) T.lut[t][k] = 0;
             __syncwarp();
-            for (int ci = lane; ci < alpha; ci += 32) { // canonical order: ci-th code
+            for (int ci = lane; ci < alpha && !oversub; ci += 32) { // canonical order: ci-th code
                 const int sym = T.perm[t][ci];
                 const int l = T.len[sym];
                 if (l <= DEC_LUT_BITS) {
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_dec_block(const uint8_t *__re
             const uint32_t e = lutp[v >> (32 - DEC_LUT_BITS)];
             if (e) { sym = (int)(e >> 5); len = e & 31u; }
             else { // longer than the lookup window: the reference's limit search (HuffmanStageDecoder.hpp:62-74)
-                for (int clen = max((int)T.minlen[tbl], DEC_LUT_BITS + 1); clen <= DEC_MAXLEN; ++clen) {
+                for (int clen = (int)T.lutmin[tbl]; clen <= DEC_MAXLEN; ++clen) {
                     const int32_t code = (int32_t)(v >> (32 - clen));
                     if (code <= T.limit[tbl][clen]) {
                         const int32_t idx = code - T.base[tbl][clen];

@@ -65,8 +65,11 @@ __global__ void __launch_bounds__(128) k_block_bits(const HuffBlock *__restrict_
 }
 
 // single CTA: bitoff[b] = *bitpos + exclusive sum; *bitpos advances by the batch total (so batches chain without a host sync)
+// A block whose bits would end behind cap_bits (the output buffer) gets the offset BIT_NOWHERE and is not written at all: the
+// position still advances, so the host sees the overrun in the final bit count before anything was stored out of bounds.
+constexpr uint64_t BIT_NOWHERE = ~0ull;
 __global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict__ nbits, uint32_t n_blocks, uint64_t *__restrict__ bitpos,
-                                                       uint64_t *__restrict__ bitoff, uint64_t *__restrict__ batch_end)
+                                                       uint64_t *__restrict__ bitoff, uint64_t *__restrict__ batch_end, uint64_t cap_bits)
 {
     __shared__ uint64_t s_w[33];
     __shared__ uint64_t s_carry;
@@ -85,7 +88,10 @@ __global__ void __launch_bounds__(1024) k_bit_offsets(const uint64_t *__restrict
             if (lane_id() == 31) s_w[32] = xi;
         }
         __syncthreads();
-        if (b < n_blocks) bitoff[b] = s_carry + s_w[warp_id()] + inc - v;
+        if (b < n_blocks) {
+            const uint64_t at = s_carry + s_w[warp_id()] + inc - v;
+            bitoff[b] = at + v <= cap_bits ? at : BIT_NOWHERE;
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += s_w[32];
         __syncthreads();
@@ -121,6 +127,10 @@ __global__ void __launch_bounds__(256) k_emit_header(const HuffBlock *__restrict
     const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (b >= n_blocks) return;
     const int lane = lane_id();
+    if (bitoff[b] == BIT_NOWHERE) { // does not fit the output buffer (k_bit_offsets)
+        if (lane == 0) data_start[b] = BIT_NOWHERE;
+        return;
+    }
     const HuffBlock h = hb[b];
     uint32_t ranges = 0;
     for (int w = 0; w < 8; ++w) {
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(HP_THREADS) k_emit_data(const uint16_t *__rest
     const uint32_t b = blockIdx.y;
     const HuffBlock h = hb[b];
     const uint32_t sym0 = blockIdx.x * HP_SYMS;
-    if (sym0 >= h.m) return;
+    if (sym0 >= h.m || data_start[b] == BIT_NOWHERE) return;
     const uint32_t nsym = min((uint32_t)HP_SYMS, h.m - sym0);
     const uint32_t *C = codes + (uint64_t)b * HUFF_MAXTABLES * HUFF_MAXALPHA;
     for (uint32_t i = threadIdx.x; i < h.ntab * HUFF_MAXALPHA; i += HP_THREADS) (&s_code[0][0])[i] = C[i];
@@ -291,6 +301,47 @@ __global__ void __launch_bounds__(HP_THREADS) k_emit_data(const uint16_t *__rest
         uint32_t v = s_stage[i];
         if (i == 0 || i == nwords - 1) { if (v) atomicOr(dst + i, bswap32(v)); }
         else dst[i] = bswap32(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- bit shift
+// Multi-GPU streams: every device packs the blocks of its slice from bit 0 of its own buffer; once the bit lengths of the
+// slices in front are known, the part moves to its place in the stream -- `shift` (0..7) bits to the right, the top `shift` bits of
+// its first byte taken from `carry` (the trailing bits of the part in front).  This is the device-side form of the reference's
+// leftBuffer hand-over between blocks (BitOutputStream.hpp:30-45, OutputStream.hpp:225-239).  src has `n_src` bytes (zero bits behind
+// the part's last bit); dst gets n_dst = ceil((shift + nbits) / 8) bytes.  16 output bytes per thread.
+__global__ void __launch_bounds__(256) k_shift_bits(const uint8_t *__restrict__ src, uint64_t n_src, uint8_t *__restrict__ dst, uint64_t n_dst, uint32_t shift,
+                                                     uint32_t carry)
+{
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n_dst) return;
+    // dst byte i = (src[i-1] << (8 - shift) | src[i] >> shift) & 0xff, src[-1] = carry bits
+    uint8_t in[17];
+    in[0] = i0 == 0 ? (uint8_t)0 : src[i0 - 1];
+    if (i0 + 16 <= n_src && ((reinterpret_cast<uintptr_t>(src) + i0) & 15u) == 0) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(src + i0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) in[1 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) in[1 + k] = i0 + k < n_src ? src[i0 + k] : (uint8_t)0;
+    }
+    uint8_t o[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = (uint8_t)((((uint32_t)in[k] << 8) | in[k + 1]) >> shift);
+    if (i0 == 0) o[0] = (uint8_t)((o[0] & (0xffu >> shift)) | carry);
+    if (i0 + 16 <= n_dst && ((reinterpret_cast<uintptr_t>(dst) + i0) & 15u) == 0) {
+        uint4 q;
+        q.x = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+        q.y = o[4] | (o[5] << 8) | (o[6] << 16) | ((uint32_t)o[7] << 24);
+        q.z = o[8] | (o[9] << 8) | (o[10] << 16) | ((uint32_t)o[11] << 24);
+        q.w = o[12] | (o[13] << 8) | (o[14] << 16) | ((uint32_t)o[15] << 24);
+        *reinterpret_cast<uint4 *>(dst + i0) = q;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (i0 + k < n_dst) dst[i0 + k] = o[k];
     }
 }
 

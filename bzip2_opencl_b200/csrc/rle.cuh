@@ -397,6 +397,15 @@ __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restric
     uint64_t nb = info[0], s = info[1];
     RleState g;
     g.bl = info[12]; g.cur = (uint32_t)(info[13] >> 32); g.run = (uint32_t)info[13];
+    // info[3] != 0: the walk starts inside the buffer (a slice of a longer stream, see bz2b200_scan_blocks_ex): the global machine's
+    // state at s is the prefix state of its tile pushed through the tile's bytes in front of s
+    uint64_t seek = info[3];
+    if (seek && s < n_bytes) {
+        const uint64_t t0 = s / RLE_TILE;
+        g = ps(t0);
+        if (s % RLE_TILE) g = scan(t0 * RLE_TILE, s, g, ~0ull).st;
+        seek = 0;
+    }
     const uint64_t target = nb + max_new;
     uint64_t finished = 0;
     __syncwarp();
@@ -421,6 +430,7 @@ __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restric
         info[0] = nb;
         info[1] = s;
         info[2] = finished;
+        info[3] = seek;
         info[12] = g.bl;
         info[13] = ((uint64_t)g.cur << 32) | g.run;
     }

@@ -1,23 +1,38 @@
 // OutputStream.hpp -- facade of the reference's OutputStream (/root/reference/include/OutputStream.hpp:35-241) on top
 // of the C ABI in include/bz2b200.h.  Same constructor, write(int), write(vector,off,len), close(); same exceptions
 // (std::invalid_argument "Invalid block size" / "Invalid parallel block count", :73-81; std::runtime_error
-// "Write beyond end of stream", :133-136).  An unmodified app.cpp compress branch (app.cpp:93-125) compiles against it.
+// "Write beyond end of stream", :133-136).  The unmodified app.cpp compiles against it (tests/test_host_logic.py).
 //
-// What changed underneath: the reference pushes every byte through a host BlockCompressor and ships 16 bool-bytes per
-// input byte to and from the device each batch (:131-142,190-240).  Here write() only appends to a host staging buffer;
-// when `parallelBlockCnt` blocks' worth of input has accumulated (and at close()) the raw bytes go to
-// bz2b200_compress_blocks, which finds the block boundaries, does RLE1/CRC/BWT/MTF/Huffman on the GPU and returns the
-// packed bit stream of all complete blocks plus how many input bytes they consumed.  The carry of < 8 bits between calls
-// is the reference's leftBuffer (:225-239); header, end marker, folded stream CRC and padding stay here (:126-128,169-172,202).
+// What changed underneath: the reference pushes every byte through a host BlockCompressor, and once parallelBlockCnt
+// blocks are full it ships 16 bool-bytes per input byte to and from ONE device and waits (:131-142,190-240, device picked
+// in :61).  Here:
+//   * write() only appends to one of TWO pinned staging buffers (bz2b200_host_alloc).  When a buffer holds a batch, a worker
+//     thread hands it to bz2b200_compress_blocks -- which finds the block boundaries and does RLE1/CRC/BWT/MTF/Huffman on
+//     the GPUs, copying the input in segments while earlier blocks are already being compressed -- and writes the packed
+//     bits to the ostream, while the caller keeps filling the other buffer (file reading and compression overlap);
+//   * every visible GPU is used: one multi-device handle (bz2b200_create_multi) instead of the reference's single Device;
+//   * parallelBlockCnt is a MINIMUM: batches are as large as the devices can hold (bz2b200_recommended_blocks), because a
+//     five-block device batch -- the reference CLI's default -p 10 at two lanes -- leaves a B200 idle.  The output never depends on it.
+// The bytes of the last, unfinished block of a batch are carried into the next batch (each buffer keeps `head` bytes of room
+// in front: no unfinished block is longer than that).  The < 8 bits between calls are the reference's leftBuffer (:225-239);
+// header, end marker, folded stream CRC and padding stay here (:126-128,169-172,202).
+// Extensions (not in the reference): write(const void*, size_t) and readFrom(fd) fill the staging buffers without the
+// per-byte call of app.cpp:112-115; BZ2B200_DEVICES=0,1,.. / BZ2B200_FACADE_BLOCKS=n override device list and batch size.
 #ifndef OUTPUT_STREAM_HPP
 #define OUTPUT_STREAM_HPP
 
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <mutex>
 #include <ostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
-#include <cstdint>
-#include <cstring>
+#include <unistd.h>
 
 #include "Config.hpp"
 #include "BitOutputStream.hpp"
@@ -33,36 +48,64 @@ private:
     int parallelBlockCnt;
     int streamCRC = 0;
     bz2b200_t *handle = nullptr;
-    std::vector<uint8_t> staging;   // raw input not yet handed to the device
-    size_t flushThreshold;
-    std::vector<uint8_t> outBits;
+    int deviceCount = 1;
+
+    // two pinned staging buffers: [head room for the carried-over bytes | new input]
+    uint8_t *stage[2] = {nullptr, nullptr};
+    size_t head = 0, cap = 0; // new input goes to [head, cap)
+    int cur = 0;              // buffer being filled
+    size_t fill = 0;          // next free byte in stage[cur]
+    uint8_t *outBits = nullptr; // pinned: packed bits of one batch
+    size_t outCap = 0;
     std::vector<uint32_t> blockCRCs;
-    bool carryBits[8];              // < 8 bits waiting for the next byte (the reference's leftBuffer)
+    bool carryBits[8]; // < 8 bits waiting for the next byte (the reference's leftBuffer)
     size_t carryCount = 0;
 
-    [[noreturn]] void fail(int rc)
+    // the batch in flight
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool jobPosted = false, jobDone = true, quit = false;
+    int jobBuf = 0;
+    size_t jobBegin = 0, jobEnd = 0;
+    bool jobFinal = false;
+    size_t leftBegin = 0, leftEnd = 0; // bytes of the finished job that belong to the next batch
+    int leftBuf = 0;
+    std::exception_ptr failure;
+
+    static std::vector<int> deviceList()
     {
-        std::string msg = std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle);
-        throw std::runtime_error(msg);
+        std::vector<int> ids;
+        if (const char *e = std::getenv("BZ2B200_DEVICES"))
+        {
+            for (const char *p = e; *p;)
+            {
+                char *q = nullptr;
+                long v = std::strtol(p, &q, 10);
+                if (q == p)
+                    break;
+                ids.push_back(static_cast<int>(v));
+                p = (*q == ',') ? q + 1 : q;
+            }
+        }
+        if (ids.empty())
+        {
+            const int n = bz2b200_device_count();
+            for (int i = 0; i < n; ++i)
+                ids.push_back(i);
+        }
+        return ids;
     }
 
-    // closeBlocks(), reference :190-240: every complete block of the staged input -> bits -> outputStream
-    void closeBlocks(bool final)
+    // closeBlocks(), reference :190-240: every complete block of the batch -> bits -> outputStream.  Worker thread.
+    void closeBlocks(uint8_t *buf, size_t begin, size_t end, bool final)
     {
-        if (staging.empty() && !final)
-            return;
-        const size_t cap = bz2b200_max_output_bytes(handle, staging.size()) + 16;
-        if (outBits.size() < cap)
-            outBits.resize(cap);
-        const size_t maxBlocks = staging.size() / static_cast<size_t>((streamBlockSize - 5) * 4 / 5 > 0 ? (streamBlockSize - 5) * 4 / 5 : 1) + 4;
-        if (blockCRCs.size() < maxBlocks)
-            blockCRCs.resize(maxBlocks);
         uint64_t nbits = 0, nblocks = 0;
         size_t consumed = 0;
-        int rc = bz2b200_compress_blocks(handle, staging.data(), staging.size(), final ? 1 : 0, static_cast<unsigned>(carryCount), outBits.data(),
-                                         outBits.size(), &nbits, &consumed, blockCRCs.data(), nullptr, blockCRCs.size(), &nblocks);
+        int rc = bz2b200_compress_blocks(handle, buf + begin, end - begin, final ? 1 : 0, static_cast<unsigned>(carryCount), outBits, outCap, &nbits,
+                                         &consumed, blockCRCs.data(), nullptr, blockCRCs.size(), &nblocks);
         if (rc != BZ2B200_OK)
-            fail(rc);
+            throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
         for (uint64_t i = 0; i < nblocks; ++i) // reference :201-202
             streamCRC = ((streamCRC << 1) | (static_cast<unsigned int>(streamCRC) >> 31)) ^ static_cast<int>(blockCRCs[i]);
         if (nbits)
@@ -74,12 +117,85 @@ private:
             outBits[0] = static_cast<uint8_t>(outBits[0] | first);
             const uint64_t total = carryCount + nbits;
             const size_t whole = static_cast<size_t>(total / 8);
-            outputStream.write(reinterpret_cast<const char *>(outBits.data()), static_cast<std::streamsize>(whole));
+            outputStream.write(reinterpret_cast<const char *>(outBits), static_cast<std::streamsize>(whole));
             carryCount = static_cast<size_t>(total % 8);
             for (size_t i = 0; i < carryCount; ++i)
                 carryBits[i] = (outBits[whole] >> (7 - i)) & 1;
         }
-        staging.erase(staging.begin(), staging.begin() + static_cast<std::ptrdiff_t>(consumed));
+        leftBegin = begin + consumed;
+        leftEnd = end;
+    }
+
+    void workerMain()
+    {
+        for (;;)
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return jobPosted || quit; });
+            if (!jobPosted)
+                return;
+            jobPosted = false;
+            const int b = jobBuf;
+            const size_t jb = jobBegin, je = jobEnd;
+            const bool fin = jobFinal;
+            lk.unlock();
+            try
+            {
+                closeBlocks(stage[b], jb, je, fin);
+                leftBuf = b;
+            }
+            catch (...)
+            {
+                failure = std::current_exception();
+                leftBegin = leftEnd = 0;
+            }
+            lk.lock();
+            jobDone = true;
+            cv.notify_all();
+        }
+    }
+
+    void waitIdle()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return jobDone; });
+        if (failure)
+        {
+            std::exception_ptr f = failure;
+            failure = nullptr;
+            std::rethrow_exception(f);
+        }
+    }
+
+    // hands the filled buffer to the worker (after the previous batch has finished: its unfinished tail goes in front) and
+    // goes on with the other buffer
+    void submit(bool final)
+    {
+        waitIdle();
+        size_t begin = head;
+        const size_t left = leftEnd - leftBegin;
+        if (left)
+        {
+            if (left > head)
+                throw std::runtime_error("internal: an unfinished block is longer than the staging head"); // cannot happen: bz2b200.h, slice primitives
+            begin = head - left;
+            std::memcpy(stage[cur] + begin, stage[leftBuf] + leftBegin, left);
+            leftBegin = leftEnd = 0;
+        }
+        if (begin == fill && !final)
+            return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobBuf = cur;
+            jobBegin = begin;
+            jobEnd = fill;
+            jobFinal = final;
+            jobPosted = true;
+            jobDone = false;
+        }
+        cv.notify_all();
+        cur ^= 1;
+        fill = head;
     }
 
 public:
@@ -90,14 +206,48 @@ public:
             throw std::invalid_argument("Invalid block size");
         if (parallelBlockCnt < 1)
             throw std::invalid_argument("Invalid parallel block count");
-        int rc = bz2b200_create(&handle, 0, BLOCKSIZE_DEFAULT, blockSizeMultiplier, parallelBlockCnt);
+        const std::vector<int> ids = deviceList();
+        if (ids.empty())
+            throw std::runtime_error("bz2b200_create: no CUDA device (a CUDA device is required; there is no CPU fallback)");
+        // -p is a minimum: the device batch is what the devices can hold
+        int blocks = parallelBlockCnt;
+        if (const char *e = std::getenv("BZ2B200_FACADE_BLOCKS"))
+            blocks = std::atoi(e) > 0 ? std::atoi(e) : blocks;
+        else
+        {
+            int rec = bz2b200_recommended_blocks(ids[0], BLOCKSIZE_DEFAULT, blockSizeMultiplier);
+            if (rec > blocks)
+                blocks = rec;
+        }
+        int rc = ids.size() > 1 ? bz2b200_create_multi(&handle, ids.data(), static_cast<int>(ids.size()), BLOCKSIZE_DEFAULT, blockSizeMultiplier, blocks)
+                                : bz2b200_create(&handle, ids[0], BLOCKSIZE_DEFAULT, blockSizeMultiplier, blocks);
         if (rc == BZ2B200_E_BLOCKSIZE)
             throw std::invalid_argument("Invalid block size");
         if (rc == BZ2B200_E_PARALLEL)
             throw std::invalid_argument("Invalid parallel block count");
         if (rc != BZ2B200_OK)
             throw std::runtime_error(std::string("bz2b200_create: ") + bz2b200_strerror(rc) + " (a CUDA device is required; there is no CPU fallback)");
-        flushThreshold = static_cast<size_t>(streamBlockSize) * static_cast<size_t>(parallelBlockCnt) + static_cast<size_t>(streamBlockSize);
+        deviceCount = static_cast<int>(ids.size());
+        // staging: no unfinished block is longer than `head` raw bytes (255-byte run chunks of 5 encoded bytes each)
+        head = ((static_cast<size_t>(streamBlockSize) / 5 + 2) * 255 + 2 * static_cast<size_t>(streamBlockSize) + 4095) / 4096 * 4096;
+        size_t batch = static_cast<size_t>(streamBlockSize) * static_cast<size_t>(blocks) * static_cast<size_t>(deviceCount);
+        const size_t maxBatch = static_cast<size_t>(2) << 30;
+        if (batch > maxBatch)
+            batch = maxBatch;
+        cap = head + batch;
+        for (int i = 0; i < 2; ++i)
+        {
+            stage[i] = static_cast<uint8_t *>(bz2b200_host_alloc(cap));
+            if (!stage[i])
+                throw std::runtime_error("bz2b200_host_alloc failed");
+        }
+        outCap = bz2b200_max_output_bytes(handle, cap) + 16;
+        outBits = static_cast<uint8_t *>(bz2b200_host_alloc(outCap));
+        if (!outBits)
+            throw std::runtime_error("bz2b200_host_alloc failed");
+        blockCRCs.resize(cap / static_cast<size_t>((streamBlockSize - 5) * 4 / 5 > 0 ? (streamBlockSize - 5) * 4 / 5 : 1) + 4);
+        fill = head;
+        worker = std::thread([this] { workerMain(); });
         // stream header, reference :126-128
         const char hdr[4] = {'B', 'Z', 'h', static_cast<char>('0' + blockSizeMultiplier)};
         outputStream.write(hdr, 4);
@@ -106,33 +256,84 @@ public:
     OutputStream(const OutputStream &) = delete;
     OutputStream &operator=(const OutputStream &) = delete;
 
-    ~OutputStream() { bz2b200_destroy(handle); }
+    ~OutputStream()
+    {
+        if (worker.joinable())
+        {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return jobDone; });
+                quit = true;
+            }
+            cv.notify_all();
+            worker.join();
+        }
+        bz2b200_host_free(stage[0]);
+        bz2b200_host_free(stage[1]);
+        bz2b200_host_free(outBits);
+        bz2b200_destroy(handle);
+    }
 
     void write(int value) // reference :131-142
     {
         if (streamFinished)
             throw std::runtime_error("Write beyond end of stream");
-        staging.push_back(static_cast<uint8_t>(value & 0xff));
-        if (staging.size() >= flushThreshold)
-            closeBlocks(false);
+        stage[cur][fill++] = static_cast<uint8_t>(value & 0xff);
+        if (fill == cap)
+            submit(false);
+    }
+
+    void write(const void *data, size_t length) // extension: any number of bytes at once
+    {
+        if (streamFinished)
+            throw std::runtime_error("Write beyond end of stream");
+        const uint8_t *p = static_cast<const uint8_t *>(data);
+        while (length)
+        {
+            const size_t n = length < cap - fill ? length : cap - fill;
+            std::memcpy(stage[cur] + fill, p, n);
+            fill += n;
+            p += n;
+            length -= n;
+            if (fill == cap)
+                submit(false);
+        }
     }
 
     void write(const std::vector<char> &data, int offset, int length) // reference :144-161
     {
+        write(data.data() + offset, static_cast<size_t>(length));
+    }
+
+    // extension: everything the file descriptor still holds, read straight into the staging buffers (no intermediate copy)
+    size_t readFrom(int fd)
+    {
         if (streamFinished)
             throw std::runtime_error("Write beyond end of stream");
-        const uint8_t *p = reinterpret_cast<const uint8_t *>(data.data()) + offset;
-        staging.insert(staging.end(), p, p + length);
-        if (staging.size() >= flushThreshold)
-            closeBlocks(false);
+        size_t total = 0;
+        for (;;)
+        {
+            const ssize_t n = ::read(fd, stage[cur] + fill, cap - fill);
+            if (n < 0)
+                throw std::runtime_error("read failed");
+            if (n == 0)
+                return total;
+            fill += static_cast<size_t>(n);
+            total += static_cast<size_t>(n);
+            if (fill == cap)
+                submit(false);
+        }
     }
+
+    int devices() const { return deviceCount; } // extension
 
     void close() // reference :163-176
     {
         if (streamFinished)
             return;
         streamFinished = true;
-        closeBlocks(true);
+        submit(true);
+        waitIdle();
         bool bits[8 + 48 + 32 + 8];
         size_t cnt = 0;
         for (size_t i = 0; i < carryCount; ++i)

@@ -1,12 +1,161 @@
-"""Multi-GPU host logic: blocks share no state (Thesis p.30), so a stream is sharded by CONTIGUOUS BLOCK RANGES,
-one process per GPU, with no data-path collective.  The only exchange is metadata: the block start offsets (found by one
-boundary scan, bz2b200_scan_blocks) going out, and each rank's packed bit stream + block CRCs coming back to rank 0, which
-concatenates them at bit granularity and folds the stream CRC (OutputStream.hpp:202,225-239)."""
+"""Multi-GPU host logic, one PROCESS per GPU: blocks share no state (Thesis p.30), so one stream is cut into
+contiguous byte slices, one per rank, and every rank compresses the blocks that START in its slice.  There is no data-path
+collective; what moves between ranks is
+
+  * a halo: the `head_bytes` bytes in front of a slice (context for a block that began in the previous slice), once, up front;
+  * one number along a chain: the stream offset where the previous rank's last complete block ended (the sequential machine of
+    BlockCompressor::write, BlockCompressor.hpp:69-96, restarts there);
+  * metadata for the assembly: every rank's bit count, its trailing bits and its block CRCs;
+  * each rank's packed bits, shifted on its own GPU to their bit offset, to wherever the stream is assembled.
+
+The same scheme runs inside one process behind bz2b200_create_multi (csrc/bz2b200.cu, multi_compress_blocks); this module is the
+process-per-GPU form on top of the slice primitives of the C ABI (bz2b200_scan_prepare / bz2b200_scan_blocks_ex /
+bz2b200_compress_scanned / bz2b200_shift_bits).  The older block-range helpers (one rank scans, everyone compresses a block range,
+rank 0 concatenates on the host) are kept below: tests use them to cross-check the two assemblies.
+"""
 from __future__ import annotations
 
 import numpy as np
 
 
+# ---------------------------------------------------------------------------------------------------------------- slices
+def head_bytes(block_size: int) -> int:
+    """Raw bytes an unfinished block can hold at the very most: limit/5 + 1 full 255-byte run chunks, plus slack (same rule as
+    multi_head_bytes in csrc/bz2b200.cu)."""
+    limit = block_size - 6
+    return ((limit // 5 + 2) * 255 + 2 * block_size + 4095) // 4096 * 4096
+
+
+def plan_slices(total: int, world: int, block_size: int, ratio: float = 0.96, min_slice: int | None = None):
+    """[(base, lo, hi)] per rank: rank r owns the blocks that start in [lo, hi) and stages bytes [base, hi) (base = lo - head).
+    Slices shrink by `ratio` along the chain (rank r starts about r walks later than rank 0); ranks that would get less than
+    `min_slice` bytes get nothing (lo == hi == total)."""
+    if min_slice is None:
+        min_slice = 16 * block_size
+    k = max(1, min(world, total // max(1, min_slice)))
+    w = [ratio ** d for d in range(k)]
+    tot = sum(w)
+    head = head_bytes(block_size)
+    out, lo, acc = [], 0, 0.0
+    for d in range(world):
+        if d < k:
+            acc += w[d]
+            hi = total if d + 1 == k else min(total, int(total * (acc / tot)) // 4096 * 4096)
+            hi = max(hi, lo)
+        else:
+            hi = total
+        base = (lo - head) // 4096 * 4096 if lo > head else 0
+        out.append((base, lo, hi))
+        lo = hi
+    return out
+
+
+def chain_walk(scan, entry, rank: int, world: int, is_final: bool, recv_start, send_start):
+    """The walk of one rank.  scan(first_start_rel, final) -> (n_blocks, consumed_rel) runs bz2b200_scan_blocks_ex on the staged
+    bytes [base, hi); recv_start() -> absolute offset where this rank's first block starts (rank 0: 0); send_start(v) hands the
+    next rank its start.  Returns (first, n_blocks, next)."""
+    base, lo, hi = entry
+    s = 0 if rank == 0 else recv_start()
+    n_blocks, nxt = 0, s
+    if s < hi:
+        if s < base:
+            raise RuntimeError("an unfinished block is longer than the staged head")
+        n_blocks, used = scan(s - base, bool(is_final and rank == world - 1))
+        nxt = base + used
+    if rank + 1 < world:
+        send_start(nxt)
+    return s, n_blocks, nxt
+
+
+def tail_of(last_two: bytes, nbits: int) -> int:
+    """16-bit window over the part's last two bytes (bytes e-1, e with e = (nbits-1)//8; one byte if the part has only one)."""
+    if nbits == 0:
+        return 0
+    if len(last_two) == 1:
+        return last_two[0]
+    return (last_two[0] << 8) | last_two[1]
+
+
+def place_parts(nbits_all, tails_all, start_bit: int = 0):
+    """Where every rank's bits go.  Returns [(bit offset, shift, carry byte, first stream byte, bytes to copy)] per rank:
+    the part is shifted right by `shift` bits with `carry` (the trailing bits of the part in front) in the top of its first byte,
+    and copies `n_copy` bytes to stream byte `byte0`; the byte a later part starts in belongs to that later part."""
+    k = len(nbits_all)
+    off, pos = [], start_bit
+    for nb in nbits_all:
+        off.append(pos)
+        pos += int(nb)
+    last = max([d for d in range(k) if nbits_all[d]], default=-1)
+    out = []
+    for d in range(k):
+        nb = int(nbits_all[d])
+        if nb == 0:
+            out.append((off[d], 0, 0, off[d] >> 3, 0))
+            continue
+        shift = off[d] & 7
+        carry = 0
+        if shift:
+            p = d - 1
+            while p >= 0 and not nbits_all[p]:
+                p -= 1
+            if p >= 0:
+                q = int(nbits_all[p])
+                e = (q - 1) >> 3
+                have = q - 8 * (e - 1) if e else q + 8
+                carry = ((int(tails_all[p]) >> (16 - have)) & ((1 << shift) - 1)) << (8 - shift)
+        n_dst = (shift + nb + 7) // 8
+        shares_last = d != last and ((off[d] + nb) & 7) != 0
+        out.append((off[d], shift, carry, off[d] >> 3, n_dst - (1 if shares_last else 0)))
+    return out
+
+
+def fold_crcs(crc_lists) -> int:
+    """crc = rotl(crc, 1) ^ blockCRC over all blocks in stream order (OutputStream.hpp:202)."""
+    crc = 0
+    for crcs in crc_lists:
+        for c in crcs:
+            crc = (((crc << 1) | (crc >> 31)) ^ int(c)) & 0xffffffff
+    return crc
+
+
+def trailer_bytes(end_bit: int, last_byte: int, crc: int) -> bytes:
+    """End-of-stream magic, combined CRC and padding (OutputStream.hpp:169-172) from bit `end_bit` on; `last_byte` is the stream
+    byte that bit lies in (its low bits zero).  Returns the bytes from stream byte end_bit // 8 on."""
+    used = end_bit & 7
+    v = ((last_byte >> (8 - used)) << 80 if used else 0) | (0x177245 << 56) | (0x385090 << 32) | (crc & 0xffffffff)
+    total = used + 80
+    pad = (-total) % 8
+    return int(v << pad).to_bytes((total + pad) // 8, "big")
+
+
+def shift_bits_host(bits: bytes, nbits: int, shift: int, carry: int) -> bytes:
+    """Host restatement of k_shift_bits (tests / CPU stand-ins)."""
+    n_dst = (shift + nbits + 7) // 8
+    if n_dst == 0:
+        return b""
+    a = np.frombuffer(bits, dtype=np.uint8)[:(nbits + 7) // 8]
+    wide = np.zeros(n_dst + 1, dtype=np.uint16)
+    wide[1:1 + len(a)] = a
+    out = ((((wide[:-1].astype(np.uint32) << 8) | wide[1:]) >> shift) & 0xff).astype(np.uint8)
+    out[0] = (out[0] & (0xff >> shift)) | carry
+    return out.tobytes()
+
+
+def assemble_stream(multiplier: int, shifted_parts, placement, nbits_all, crc: int) -> bytes:
+    """The whole .bz2 stream on the host from the ranks' shifted parts (rank order; placement = place_parts(nbits_all, tails, 32):
+    the body starts behind the 4-byte header).  Every stream byte comes from exactly one part; the trailer goes behind the last bit."""
+    body = bytearray(b"BZh" + bytes([ord("0") + multiplier]))
+    for (off, shift, carry, byte0, n_copy), p in zip(placement, shifted_parts):
+        if n_copy:
+            assert byte0 == len(body), "parts are not contiguous"
+            body += bytes(p[:n_copy])
+    end_bit = 32 + sum(int(x) for x in nbits_all)
+    last = body.pop() if end_bit & 7 else 0
+    assert len(body) == end_bit >> 3
+    return bytes(body) + trailer_bytes(end_bit, last, crc)
+
+
+# ---------------------------------------------------------------------------------------------------------------- block ranges (round 1)
 def shard_block_ranges(n_blocks: int, world: int):
     """[(b_lo, b_hi)] per rank: contiguous ranges of ceil(B / world) blocks (keeps each GPU's input slice contiguous)."""
     per = -(-n_blocks // world) if n_blocks else 0

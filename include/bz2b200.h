@@ -14,8 +14,10 @@
  * or a device pointer on the handle's device; the library detects which.  All work is CUDA (sm_100a); there
  * is no CPU fallback: without a usable device bz2b200_create fails with BZ2B200_E_CUDA.
  *
- * Threading: one handle = one host thread at a time.  One handle drives one GPU; multi-GPU jobs use one
- * handle (one process) per GPU over disjoint block ranges (blocks share no state -- SURVEY 8(e)).
+ * Threading: one handle = one host thread at a time.  bz2b200_create makes a handle for one GPU; bz2b200_create_multi makes one
+ * handle that fans a stream out over several GPUs of the box inside the call (blocks share no state -- SURVEY 8(e)) and is
+ * accepted by every function below.  Jobs with one PROCESS per GPU build the same stream from the slice primitives
+ * (bz2b200_scan_prepare / bz2b200_scan_blocks_ex / bz2b200_compress_scanned / bz2b200_shift_bits).
  */
 #ifndef BZ2B200_H
 #define BZ2B200_H
@@ -55,6 +57,29 @@ int bz2b200_device_count(void);
  */
 int bz2b200_create(bz2b200_t **handle, int device_id, int base_block_size, int multiplier, int max_blocks_in_flight);
 
+/*
+ * One handle over several GPUs: device_ids[0..n_devices) (a device may be named more than once), max_blocks_in_flight per device.
+ * Replaces the reference's single `Device device{select_device_with_most_flops()}` (OutputStream.hpp:61): where the reference
+ * batches parallelBlockCnt blocks on one device (OutputStream.hpp:190-240), a multi handle cuts the input of a call into one
+ * contiguous byte slice per device, finds the block boundaries with a chain of walks (device d starts where device d-1's last
+ * complete block ended), compresses every slice on its own device and places each device's bits at their bit offset in the
+ * caller's buffer.  The bytes produced are identical to those of a one-GPU handle.  Inputs of less than 16 blocks per extra
+ * device use fewer devices.  BZ2B200_E_ARG for a bad list; otherwise as bz2b200_create.
+ */
+int bz2b200_create_multi(bz2b200_t **handle, const int *device_ids, int n_devices, int base_block_size, int multiplier, int max_blocks_in_flight);
+
+/* Devices behind a handle (1 for bz2b200_create). */
+int bz2b200_device_count_of(const bz2b200_t *handle);
+
+/* Blocks per device batch that keep `device_id` busy without taking more than a third of its free memory (0: no such device).
+ * The facade uses it so that the reference's small default of -p (app.cpp:41) does not turn into five-block device batches. */
+int bz2b200_recommended_blocks(int device_id, int base_block_size, int multiplier);
+
+/* Pinned (page-locked, portable) host memory for staging buffers handed to the calls below: copies from and to it are
+ * asynchronous and overlap with the kernels.  Replaces the host arrays of Memory<T> (opencl.hpp:250-262). NULL on failure. */
+void *bz2b200_host_alloc(size_t bytes);
+void bz2b200_host_free(void *p);
+
 /* Releases every device and pinned buffer (Memory<T>::~Memory, opencl.hpp:276-278). NULL is allowed. */
 void bz2b200_destroy(bz2b200_t *handle);
 
@@ -71,6 +96,32 @@ size_t bz2b200_max_output_bytes(const bz2b200_t *handle, size_t n_bytes);
  */
 int bz2b200_scan_blocks(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint64_t *block_starts, size_t capacity,
                         uint64_t *n_blocks);
+
+/*
+ * The slice primitives: one stream over several handles (one per GPU, in one or in several processes).
+ *
+ * bz2b200_scan_prepare     queue the staging of input[0..n_bytes) (host input: segmented copies) and the summary tree over it;
+ *                          returns without waiting, so every device of a job prepares its slice at the same time.
+ * bz2b200_scan_blocks_ex   the walk of bz2b200_scan_blocks over a slice: starts with a fresh machine at input[first_start]
+ *                          (the position where the previous slice's last complete block ended; the bytes in front of it are only
+ *                          context) and, with is_final == 0, stops in front of the first block whose refusing byte is not in the
+ *                          slice; *consumed = offset of that block's first byte = the next slice's first_start, relative to
+ *                          `input`.  Uses the preparation of the same (input, n_bytes) if there is one.  block_starts may be NULL.
+ *                          A slice must begin at most one unfinished block (255 * (block size / 5 + 2) raw bytes at the very most)
+ *                          in front of first_start, but may begin anywhere before that.
+ * bz2b200_compress_scanned compress exactly the blocks the last bz2b200_scan_blocks_ex on this handle found (the input stays
+ *                          staged from the scan); arguments as for bz2b200_compress_blocks.
+ * bz2b200_shift_bits       move a part to its bit offset in the stream: dst = src (nbits bits, device memory) shifted right by
+ *                          shift = 0..7 bits, the top `shift` bits of dst[0] taken from `carry` (the part in front's trailing
+ *                          bits, already in the top bits of the byte).  This is the reference's leftBuffer hand-over
+ *                          (BitOutputStream.hpp:30-45, OutputStream.hpp:225-239) between devices.
+ */
+int bz2b200_scan_prepare(bz2b200_t *handle, const uint8_t *input, size_t n_bytes);
+int bz2b200_scan_blocks_ex(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, uint64_t *block_starts,
+                           size_t capacity, uint64_t *n_blocks, size_t *consumed);
+int bz2b200_compress_scanned(bz2b200_t *handle, unsigned start_bit, uint8_t *out, size_t out_capacity, uint64_t *out_nbits, uint32_t *block_crcs,
+                             uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks);
+int bz2b200_shift_bits(bz2b200_t *handle, const uint8_t *src, uint64_t nbits, unsigned shift, unsigned carry, uint8_t *dst, size_t dst_capacity);
 
 /*
  * The hot path.  Compress input[0..n_bytes) into bzip2 blocks: RLE1 + CRC32 + symbol map, BWT, MTF/RLE2,

@@ -43,6 +43,7 @@ def build(force=False):
     shim = os.path.join(HERE, "ref_shim.cpp")
     if not force and all(os.path.exists(l) and os.path.getmtime(l) > os.path.getmtime(shim) and
                          os.path.getmtime(l) > os.path.getmtime(__file__) for l in libs):
+        build_app()
         return True
     gen_cpp = os.path.join(OUT, "gen.cpp")
     with open(gen_cpp, "w") as f:
@@ -71,6 +72,38 @@ def build(force=False):
         open(os.path.join(d, "Config.hpp"), "w").write(c)
         run(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-pthread",
              f"-I{d}", f"-I{REF}/include", shim, "-o", os.path.join(OUT, f"libref_{base}.so")])
+    build_app()
+    return True
+
+
+def build_app():
+    """The reference's UNMODIFIED app.cpp compiled against the product's facade headers (bzip2_opencl_b200/include) and linked with
+    libbz2b200.so: the drop-in claim, as a binary (oracle/_ref/app_b200_<base>) that the GPU tests run.  app.cpp includes
+    "include/OutputStream.hpp" relative to its own directory, so it is fed to the compiler on stdin from a directory whose
+    include/ is the facade; nothing of the reference is copied."""
+    root = os.path.dirname(HERE)
+    prod = os.path.join(root, "bzip2_opencl_b200")
+    lib = os.path.join(prod, "libbz2b200.so")
+    app = os.path.join(REF, "app.cpp")
+    if not os.path.exists(lib) or not os.path.exists(app):
+        return False
+    shim = os.path.join(OUT, "facade_shim")
+    os.makedirs(shim, exist_ok=True)
+    link = os.path.join(shim, "include")
+    if not os.path.islink(link):
+        os.symlink(os.path.join(prod, "include"), link)
+    inc = os.path.join(prod, "include")
+    newest = max([os.path.getmtime(app), os.path.getmtime(os.path.join(root, "include", "bz2b200.h")), os.path.getmtime(__file__)] +
+                 [os.path.getmtime(os.path.join(inc, f)) for f in os.listdir(inc)])
+    for base in (10000, 100000):
+        exe = os.path.join(OUT, f"app_b200_{base}")
+        if os.path.exists(exe) and os.path.getmtime(exe) > newest:
+            continue
+        cmd = ["g++", "-std=c++17", "-O2", "-w", "-x", "c++", "-", "-o", exe, f"-DBZ2B200_BLOCKSIZE_DEFAULT={base}",
+               "-I" + os.path.join(root, "include"), "-L" + prod, "-lbz2b200", "-Wl,-rpath," + prod, "-pthread"]
+        print("+ (cd", shim, "&&", " ".join(cmd), "<", app + ")", flush=True)
+        with open(app, "rb") as f:
+            subprocess.check_call(cmd, stdin=f, cwd=shim)
     return True
 
 

@@ -1,3 +1,5 @@
 # scratch command file for `gpurun -- 'bash tools/_run.sh'` (development aid): the round's usual check
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -8
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -15
+timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo bench_exit=$?; tail -2 gpurun_out/bench.err
