@@ -32,7 +32,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
         print("+", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    build_tools(force)
     return LIB
+
+
+def build_tools(force: bool = False) -> None:
+    """Host programs on top of the facade headers (g++): facade_bench (bench.py's e2e_facade leg)."""
+    src = os.path.join(HERE, "tools_src", "facade_bench.cpp")
+    exe = os.path.join(HERE, "facade_bench")
+    deps = [src, LIB] + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(d) <= os.path.getmtime(exe) for d in deps):
+        return
+    cmd = ["g++", "-std=c++17", "-O2", src, "-o", exe, "-DBZ2B200_BLOCKSIZE_DEFAULT=100000", "-I" + os.path.join(HERE, "include"),
+           "-I" + os.path.join(HERE, "..", "include"), "-L" + HERE, "-lbz2b200", "-Wl,-rpath," + HERE, "-pthread"]
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
 
 
 if __name__ == "__main__":

@@ -1176,12 +1176,87 @@ __global__ void __launch_bounds__(256) k_bwt_gather(uint64_t *__restrict__ keys,
     keys[o + a] = e | ((uint64_t)rank[o + p] << VAL_BITS);
 }
 
-// origPtr = rank[0] = first position of rotation 0's tie group (kernel.cpp:3114-3116)
-__global__ void __launch_bounds__(128) k_bwt_finish(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ n_arr, uint64_t stride, uint32_t n_blocks,
-                                                     uint32_t *__restrict__ orig)
+// origPtr = rank[0] = first position of rotation 0's tie group (kernel.cpp:3114-3116).  A block that was sorted through its root
+// (k_bwt_period: n = m * p) has m equal rotations in every group: its groups start m times further on.
+__global__ void __launch_bounds__(128) k_bwt_finish(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ n_arr, const uint32_t *__restrict__ root_arr,
+                                                     uint64_t stride, uint32_t n_blocks, uint32_t *__restrict__ orig)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_blocks) orig[b] = n_arr[b] ? rank[(uint64_t)b * stride] : 0u;
+    if (b >= n_blocks) return;
+    const uint32_t n = n_arr[b], p = root_arr[b];
+    orig[b] = n ? rank[(uint64_t)b * stride] * (n / p) : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------ non-primitive blocks
+// A block that is a power of a shorter word, T = w^m (all zeros after RLE1: (0,0,0,0,251)^m; short-period patterns), never resolves
+// under prefix doubling: every rotation has m - 1 equal twins, so all ceil(log2 n) rounds run over the whole block (SURVEY 8d:
+// rho = 19 for zeros).  Its BWT follows from the root's: the sorted rotations of T are the sorted rotations of w, each m times, so
+// L_T[k * m + j] = L_w[k] and the first position of rotation 0's group is m times its position among w's rotations -- the origPtr
+// convention of the oracle for such blocks.  k_bwt_period finds the smallest p | n, p <= BP_MAX, with T[i] = T[i + p] for
+// all i (root_len[b] = p, else n); the sort then runs on the first p bytes only and k_bwt_expand writes the block's last column.
+constexpr uint32_t BP_MAX = 4096; // longest root looked for (longer exact periods are not worth a search: such blocks sort normally)
+constexpr int BP_THREADS = 256;
+
+__global__ void __launch_bounds__(BP_THREADS) k_bwt_period(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride,
+                                                            uint32_t *__restrict__ root_len)
+{
+    __shared__ uint32_t s_cand[128];
+    __shared__ uint32_t s_ncand, s_best, s_fail;
+    const uint32_t b = blockIdx.x, n = n_arr[b];
+    const uint8_t *T = rle + (uint64_t)b * stride;
+    if (threadIdx.x == 0) { s_ncand = 0; s_best = n; }
+    __syncthreads();
+    // candidates: divisors of n whose first 32 positions repeat
+    for (uint32_t p = threadIdx.x + 1; p <= BP_MAX && 2 * p <= n; p += BP_THREADS) {
+        if (n % p) continue;
+        bool ok = true;
+        for (uint32_t j = 0; j < 32 && p + j < n && ok; ++j) ok = T[j] == T[p + j];
+        if (ok) {
+            const uint32_t k = atomicAdd(&s_ncand, 1u);
+            if (k < 128) s_cand[k] = p;
+        }
+    }
+    __syncthreads();
+    uint32_t nc = min(s_ncand, 128u);
+    // smallest candidate first; the first one that holds for the whole block is the root
+    while (nc) {
+        uint32_t mn = 0xffffffffu, at = 0;
+        for (uint32_t k = 0; k < nc; ++k)
+            if (s_cand[k] < mn) { mn = s_cand[k]; at = k; }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_cand[at] = s_cand[nc - 1]; s_fail = 0; }
+        __syncthreads();
+        bool bad = false;
+        for (uint32_t i = threadIdx.x; i + mn < n && !bad; i += BP_THREADS) bad = T[i] != T[i + mn];
+        if (bad) s_fail = 1;
+        __syncthreads();
+        if (!s_fail) {
+            if (threadIdx.x == 0) s_best = mn;
+            break;
+        }
+        --nc;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) root_len[b] = s_best;
+}
+
+// the root's last column (first p bytes of L) aside, then every byte of it m = n / p times
+__global__ void __launch_bounds__(256) k_bwt_expand_copy(const uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, const uint32_t *__restrict__ root_arr,
+                                                          uint64_t stride, uint8_t *__restrict__ scratch)
+{
+    const uint32_t b = blockIdx.y, p = root_arr[b];
+    if (p == n_arr[b]) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p) scratch[(uint64_t)b * stride + i] = L[(uint64_t)b * stride + i];
+}
+__global__ void __launch_bounds__(256) k_bwt_expand(uint8_t *__restrict__ L, const uint32_t *__restrict__ n_arr, const uint32_t *__restrict__ root_arr, uint64_t stride,
+                                                     const uint8_t *__restrict__ scratch)
+{
+    const uint32_t b = blockIdx.y, n = n_arr[b], p = root_arr[b];
+    if (p == n) return;
+    const uint32_t m = n / p;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) L[(uint64_t)b * stride + q] = scratch[(uint64_t)b * stride + q / m];
 }
 
 } // namespace bz

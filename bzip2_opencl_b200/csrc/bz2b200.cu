@@ -24,8 +24,8 @@
 
 using namespace bz;
 
-enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_dec_scan, KID_k_dec_block, KID_k_imtf_tiles, KID_k_imtf_compose, KID_k_dec_bases, KID_k_dec_double, KID_k_dec_chase, KID_k_dec_expand, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
-static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_dec_scan", "k_dec_block", "k_imtf_tiles", "k_imtf_compose", "k_dec_counts", "k_dec_double", "k_dec_chase", "k_dec_expand", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
+enum KernelId { KID_k_radix_hist, KID_k_radix_scatter, KID_k_radix_scan, KID_k_radix_count, KID_k_radix_bases, KID_k_radix_onesweep, KID_k_bwt_bytehist, KID_k_dec_scan, KID_k_dec_block, KID_k_imtf_tiles, KID_k_imtf_compose, KID_k_dec_bases, KID_k_dec_double, KID_k_dec_chase, KID_k_dec_expand, KID_k_rle_tile_seg, KID_k_rle_reduce, KID_k_rle_walk, KID_k_rle_btile_seg, KID_k_rle_btile_scan, KID_k_rle_emit, KID_k_crc_chunks, KID_k_crc_finish, KID_k_bwt_keys0, KID_k_bwt_regroup, KID_k_bwt_roundstats, KID_k_bwt_gather, KID_k_bwt_gather_local, KID_k_bwt_local, KID_k_bwt_finish, KID_k_bwt_period, KID_k_bwt_expand, KID_k_mtf_recency, KID_k_mtf_ranks, KID_k_mtf_compose, KID_k_rle2_scan, KID_k_rle2_emit, KID_k_huff_seeds, KID_k_huff_pass, KID_k_huff_lengths, KID_k_huff_codes, KID_k_huff_selmtf, KID_k_block_bits, KID_k_bit_offsets, KID_k_emit_header, KID_k_data_tilebits, KID_k_data_scan, KID_k_emit_data, KID_COUNT };
+static const char *const kKernelNames[KID_COUNT] = { "k_radix_hist", "k_radix_scatter", "k_radix_scan", "k_radix_count", "k_radix_bases", "k_radix_onesweep", "k_bwt_bytehist", "k_dec_scan", "k_dec_block", "k_imtf_tiles", "k_imtf_compose", "k_dec_counts", "k_dec_double", "k_dec_chase", "k_dec_expand", "k_rle_tile_seg", "k_rle_reduce", "k_rle_walk", "k_rle_btile_seg", "k_rle_btile_scan", "k_rle_emit", "k_crc_chunks", "k_crc_finish", "k_bwt_keys0", "k_bwt_regroup", "k_bwt_roundstats", "k_bwt_gather", "k_bwt_gather_local", "k_bwt_local", "k_bwt_finish", "k_bwt_period", "k_bwt_expand", "k_mtf_recency", "k_mtf_ranks", "k_mtf_compose", "k_rle2_scan", "k_rle2_emit", "k_huff_seeds", "k_huff_pass", "k_huff_lengths", "k_huff_codes", "k_huff_selmtf", "k_block_bits", "k_bit_offsets", "k_emit_header", "k_data_tilebits", "k_data_scan", "k_emit_data" };
 
 namespace {
 
@@ -91,6 +91,7 @@ struct bz2b200 {
     uint64_t seg_first = 16ull << 20, seg_rest = 64ull << 20; // host input: bytes per H2D segment (BZ2B200_SEG_MB=first,rest)
     int pack_keys = 1;    // round-0 keys over the block's own alphabet (k_bwt_keys_packed); BZ2B200_PACK=0: the first key0_bytes bytes
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
+    int root_sort = 1;    // BZ2B200_ROOT=0: non-primitive blocks go through the full prefix doubling instead of their root (k_bwt_period)
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
     cudaStream_t stream = 0;
     std::string err;
@@ -101,7 +102,7 @@ struct bz2b200 {
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
-        h0, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
+        h0, root, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int ctasC = 0;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
@@ -385,6 +386,7 @@ static int alloc_batch(bz2b200 *h)
     ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
     ENSURE(h->h0, G * 4);
+    ENSURE(h->root, G * 4);
     ENSURE(h->lists, G * h->tilesM * 256);
     ENSURE(h->dcount, G * h->tilesM * 4);
     ENSURE(h->r2tiles, G * h->tilesR2 * sizeof(R2Tile));
@@ -428,7 +430,7 @@ static int create_lanes(bz2b200 *h)
         h->lanes.push_back(l);
         l->parent = h;
         l->device = h->device; l->base = h->base; l->mult = h->mult; l->bs = h->bs; l->S = h->S; l->nbits = h->nbits;
-        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->n_lanes = 1;
+        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->root_sort = h->root_sort; l->n_lanes = 1;
         l->G = (h->G + nl - 1) / nl;
         int rc = create_impl(l, true);
         if (rc == BZ2B200_OK && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) rc = BZ2B200_E_CUDA;
@@ -466,6 +468,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     }
     if (const char *e = getenv("BZ2B200_PACK")) h->pack_keys = atoi(e);
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
+    if (const char *e = getenv("BZ2B200_ROOT")) h->root_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK_GROWTH")) h->walk_growth = std::max(1, atoi(e));
@@ -928,6 +931,13 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     uint32_t *bag_cnt[2] = {ptr<uint32_t>(h->cnts), ptr<uint32_t>(h->cnts) + (size_t)h->G};
     int res = 0;
     uint32_t *d_h0 = ptr<uint32_t>(h->h0);
+    // non-primitive blocks (T = w^m) are sorted through their root w: d_n is the length the SORT works on, d_nfull the block's
+    const uint32_t *d_nfull = d_n;
+    if (h->root_sort) {
+        KL(KID_k_bwt_period, k_bwt_period<<<nb, BP_THREADS, 0, st>>>(ptr<uint8_t>(h->rle), d_nfull, S, ptr<uint32_t>(h->root)));
+        stt.kernel_launches += 1;
+        d_n = ptr<uint32_t>(h->root);
+    }
     if (h->onesweep && h->pack_keys) {
         // keys over each block's own alphabet: byte histogram -> presence bitmap -> packed keys (+ the depth h0 they order by)
         const uint32_t nc = (max_n + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
@@ -1062,8 +1072,14 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     stt.bwt_rounds = std::max<uint64_t>(stt.bwt_rounds, rounds);
     CK(cudaEventRecord(h->ev[5], st));
     {
-        KL(KID_k_bwt_finish, k_bwt_finish<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->rank), d_n, S, nb, ptr<uint32_t>(h->orig)));
+        KL(KID_k_bwt_finish, k_bwt_finish<<<(nb + 127) / 128, 128, 0, st>>>(ptr<uint32_t>(h->rank), d_nfull, d_n, S, nb, ptr<uint32_t>(h->orig)));
         stt.kernel_launches += 1;
+        if (h->root_sort) {
+            KL(KID_k_bwt_expand, k_bwt_expand_copy<<<dim3((BP_MAX + 255) / 256, nb), 256, 0, st>>>(ptr<uint8_t>(h->L), d_nfull, d_n, S, ptr<uint8_t>(h->ranks)));
+            KL(KID_k_bwt_expand, k_bwt_expand<<<dim3(64, nb), 256, 0, st>>>(ptr<uint8_t>(h->L), d_nfull, d_n, S, ptr<uint8_t>(h->ranks)));
+            stt.kernel_launches += 2;
+        }
+        d_n = d_nfull;
     }
     CK(cudaEventRecord(h->ev[6], st));
 

@@ -112,21 +112,7 @@ __device__ __forceinline__ bool lane_short_runs(uint64_t eq) { return (eq & (eq 
 __device__ __forceinline__ Seg lane_seg(const uint8_t *sm, uint32_t cnt)
 {
     const uint8_t *p = sm + lane_id() * RLE_SM_STRIDE;
-    if (cnt == RLE_LANE_BYTES) {
-        const uint64_t eq = lane_eq_mask(p);
-        if (lane_short_runs(eq)) { // every run is shorter than 4: it is encoded as itself (BlockCompressor.hpp:134-154)
-            Seg s;
-            s.pad = 0;
-            s.len = RLE_LANE_BYTES;
-            s.lead = (uint64_t)__ffsll((long long)~(eq >> 1));
-            s.trail = 1ull + (uint64_t)__clzll((long long)~eq);
-            s.mid = RLE_LANE_BYTES - s.lead - s.trail;
-            s.first = p[0];
-            s.last = p[RLE_LANE_BYTES - 1];
-            s.uniform = 0;
-            return s;
-        }
-    }
+    if (cnt == RLE_LANE_BYTES) return seg_from_eq_mask(p[0], p[RLE_LANE_BYTES - 1], lane_eq_mask(p)); // (rle_seg.h)
     return seg_from_bytes([p](uint32_t i) { return (uint32_t)p[i]; }, cnt);
 }
 
@@ -164,33 +150,132 @@ struct WalkLevels {
     int n_levels;
 };
 
+// inclusive warp scan of 32-bit summaries: two shuffles per field pair instead of one per 64-bit half
+__device__ __forceinline__ TSeg shfl_up_tseg(const TSeg &s, int d)
+{
+    // len/lead/trail/mid fit 13 bits, first/last 8: three words
+    const uint32_t a = s.len | (s.lead << 13) | ((s.first & 0x3fu) << 26), b = s.trail | (s.mid << 13) | ((s.last & 0x3fu) << 26),
+                   c = (s.first >> 6) | ((s.last >> 6) << 2);
+    const uint32_t a2 = __shfl_up_sync(FULL, a, d), b2 = __shfl_up_sync(FULL, b, d), c2 = __shfl_up_sync(FULL, c, d);
+    TSeg r;
+    r.len = a2 & 0x1fffu; r.lead = (a2 >> 13) & 0x1fffu; r.first = (a2 >> 26) | ((c2 & 3u) << 6);
+    r.trail = b2 & 0x1fffu; r.mid = (b2 >> 13) & 0x1fffu; r.last = (b2 >> 26) | (((c2 >> 2) & 3u) << 6);
+    return r;
+}
+__device__ __forceinline__ TSeg warp_tseg_incl_scan(TSeg s)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const TSeg o = shfl_up_tseg(s, d);
+        if (lane_id() >= d) s = tseg_combine(o, s);
+    }
+    return s;
+}
+
+// The walk's tile simulation: bytes [lo, hi) of one tile with the machine in state `st` at lo -> first refused byte (st.bl > limit
+// in front of it) and the state there, or hi and the state behind the last byte.  One warp.
+//   * a full tile in which no run of four or more equal bytes forms (text): the state in front of every byte is closed form
+//     (short_run_search, rle_seg.h), nothing is scanned;
+//   * otherwise the lanes' 64-byte summaries are scanned (32-bit fields) and the ONE lane that can hold the refusal is scanned again
+//     with two bytes per lane.
 struct DevTileScan {
     const uint8_t *in;
     uint8_t *sm;
     __device__ TileScanResult operator()(uint64_t lo, uint64_t hi, RleState st, uint64_t limit) const
     {
         const int lane = lane_id();
-        uint32_t n = (uint32_t)(hi - lo);
+        const uint32_t n = (uint32_t)(hi - lo);
         __syncwarp();
         warp_load_tile(in, lo, n, sm);
-        uint32_t cnt = lane_count(n);
-        Seg incl = warp_seg_incl_scan(lane_seg(sm, cnt));
-        Seg excl = shfl_up_seg(incl, 1);
-        if (lane == 0) excl = seg_empty();
-        RleState s = state_apply(excl, st);
-        bool found = false;
-        uint64_t fpos = hi;
+        const uint32_t cnt = lane_count(n);
         const uint8_t *p = sm + lane * RLE_SM_STRIDE;
-        for (uint32_t i = 0; i < cnt; ++i) {
-            if (s.bl > limit) { found = true; fpos = lo + (uint64_t)lane * RLE_LANE_BYTES + i; break; }
-            state_step(s, p[i]);
-        }
-        unsigned ballot = __ballot_sync(FULL, found);
-        int src = ballot ? (__ffs(ballot) - 1) : (int)((n - 1) / RLE_LANE_BYTES);
+        const uint8_t *tile = sm;
+        auto get = [tile](uint32_t j) { return (uint32_t)tile[(j >> 6) * RLE_SM_STRIDE + (j & 63u)]; };
         TileScanResult r;
-        r.pos = shfl_u64(fpos, src);
-        r.st = shfl_state(s, src);
-        if (!ballot) r.pos = hi;
+        uint64_t eq = 0;
+        bool lane_short = false; // a full lane without a run of four (the carried run not considered)
+        if (cnt == RLE_LANE_BYTES) {
+            eq = lane_eq_mask(p);
+            lane_short = lane_short_runs(eq);
+        }
+        if (n == RLE_TILE) {
+            // no run of four anywhere, joins across lanes and with the carried run included?
+            const uint32_t my_last = p[RLE_LANE_BYTES - 1];
+            uint32_t prev_last = __shfl_up_sync(FULL, my_last, 1);
+            uint32_t prev_top = __shfl_up_sync(FULL, (uint32_t)(eq >> 62), 1); // bit 1: bytes 63,62 equal; bit 0: bytes 62,61 equal
+            bool prev_any = true;
+            if (lane == 0) {
+                prev_any = st.run > 0;
+                prev_last = st.cur;
+                prev_top = (st.run >= 2 ? 2u : 0u) | (st.run >= 3 ? 1u : 0u);
+            }
+            const bool b0 = prev_any && prev_last == (uint32_t)p[0];
+            // (lane > 0: the previous lane's bit 0 is not in prev_top, but a run through a whole lane is not short anyway)
+            bool bad = !lane_short || (lane == 0 && st.run >= 4);
+            bad |= b0 && (prev_top == 3u);                                  // x x x | x
+            bad |= b0 && (prev_top & 2u) && (eq & 2ull);                    // x x | x x
+            bad |= b0 && ((eq & 6ull) == 6ull);                             // x | x x x
+            if (!__any_sync(FULL, bad)) {
+                uint32_t pos;
+                r.st = short_run_search(get, n, st, limit, 0u, pos);
+                r.pos = lo + pos;
+                __syncwarp();
+                return r;
+            }
+        }
+        const TSeg mine = tseg_of(lane_seg(sm, cnt));
+        const TSeg incl = warp_tseg_incl_scan(mine);
+        TSeg excl = shfl_up_tseg(incl, 1);
+        if (lane == 0) excl = tseg_of(seg_empty());
+        const RleState s0 = tstate_apply(excl, st); // in front of the lane's first byte
+        const unsigned have = __ballot_sync(FULL, cnt > 0);
+        const int z = 31 - __clz((int)have);       // last lane with bytes
+        const unsigned over = __ballot_sync(FULL, cnt > 0 && s0.bl > limit);
+        // the refusal is at the first byte of the first lane that starts over the limit, or inside the lane in front of it; with no
+        // such lane, inside the last lane or nowhere
+        const int f = over ? __ffs((int)over) - 1 : z + 1;
+        const int c = f - 1; // the one lane whose interior (bytes 1 .. cnt-1) can hold the refusal
+        bool found = false;
+        uint32_t fi = 0;
+        RleState fs = s0;
+        const uint32_t cnt_c = c >= 0 ? __shfl_sync(FULL, cnt, c) : 0u;
+        if (cnt_c > 1) { // (warp-uniform) lane c's bytes two per lane: the same scan one level down gives the state in front of each of them
+            const RleState sc = shfl_state(s0, c);
+            const uint8_t *q = sm + c * RLE_SM_STRIDE;
+            const uint32_t i0 = 2u * (uint32_t)lane;
+            const uint32_t v0 = i0 < cnt_c ? q[i0] : 0u, v1 = i0 + 1 < cnt_c ? q[i0 + 1] : 0u;
+            TSeg piece;
+            piece.len = i0 + 1 < cnt_c ? 2u : (i0 < cnt_c ? 1u : 0u);
+            piece.first = v0;
+            piece.last = piece.len == 2u ? v1 : v0;
+            piece.lead = piece.trail = (piece.len == 2u && v0 != v1) ? 1u : piece.len;
+            piece.mid = 0;
+            const TSeg pin = warp_tseg_incl_scan(piece);
+            TSeg pex = shfl_up_tseg(pin, 1);
+            if (lane == 0) pex = tseg_of(seg_empty());
+            const RleState e0 = tstate_apply(pex, sc); // in front of byte i0
+            RleState e1 = e0;                          // in front of byte i0 + 1
+            if (i0 < cnt_c) state_step(e1, v0);
+            const bool h0 = i0 >= 1 && i0 < cnt_c && e0.bl > limit, h1 = i0 + 1 < cnt_c && e1.bl > limit;
+            const unsigned hb = __ballot_sync(FULL, h0 || h1);
+            if (hb) {
+                const int w = __ffs((int)hb) - 1;
+                found = true; // (uniform)
+                const uint32_t my_i = h0 ? i0 : i0 + 1;
+                fi = __shfl_sync(FULL, my_i, w);
+                fs = shfl_state(h0 ? e0 : e1, w);
+            }
+        }
+        if (found) { // inside lane c
+            r.pos = lo + (uint64_t)c * RLE_LANE_BYTES + fi;
+            r.st = fs;
+        } else if (over) { // at the first byte of lane f
+            r.pos = lo + (uint64_t)f * RLE_LANE_BYTES;
+            r.st = shfl_state(s0, f);
+        } else { // nowhere: the state behind the last byte
+            r.pos = hi;
+            r.st = shfl_state(tstate_apply(mine, s0), z);
+        }
         __syncwarp();
         return r;
     }
@@ -344,9 +429,29 @@ struct DevRunEnd {
     }
 };
 
-struct DevByte {
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// v = in[s], r = end of the run of v that starts at s, vr = in[r]: one 32-byte look behind s settles nearly every block start
+struct DevHead {
     const uint8_t *in;
-    __device__ uint32_t operator()(uint64_t q) const { return __ldg(in + q); }
+    uint64_t n;
+    DevRunEnd run_end;
+    __device__ void operator()(uint64_t s, uint32_t &v, uint64_t &r, uint32_t &vr) const
+    {
+        const int lane = lane_id();
+        const uint64_t q = s + (uint64_t)lane;
+        const uint32_t mine = q < n ? (uint32_t)__ldg(in + q) : 0x100u; // (past the end: differs from every byte)
+        v = __shfl_sync(FULL, mine, 0);
+        const unsigned diff = __ballot_sync(FULL, mine != v);
+        if (diff) {
+            const int f = __ffs((int)diff) - 1;
+            r = min(n, s + (uint64_t)f);
+            vr = __shfl_sync(FULL, mine, f) & 0xffu;
+            return;
+        }
+        r = run_end(s); // a run of 32 or more: tile by tile, then whole uniform nodes of the tree
+        vr = r < n ? (uint32_t)__ldg(in + r) : 0u;
+    }
 };
 
 struct DevPState {
@@ -360,23 +465,58 @@ struct DevPState {
     }
 };
 
+// smallest t > t_lo with ps[t].bl > lim (ps[].bl is non-decreasing), n_tiles + 1 if none; before = ps[t - 1].
+// Blocks of one input are about equally long, so the answer is looked for first in a window of 32 prefix states around
+// "as many tiles further on as the last block took"; the window is loaded (preload) before the bytes at the block start are
+// looked at, so that the two round trips overlap.  A miss falls back to 32 probes 16 tiles apart, then 16 in a row.
 struct DevFirstOver {
     const PState *ps;
     uint64_t n_tiles;
-    // smallest t > t_lo with ps[t].bl > lim (ps[].bl is non-decreasing), n_tiles + 1 if none: 32 probes 16 tiles apart, then 16 in a row
-    __device__ uint64_t operator()(uint64_t t_lo, uint64_t lim) const
+    uint64_t w0;   // the preloaded window holds ps[w0 + lane]
+    PState mine;
+    bool have;
+    __device__ void preload(uint64_t first)
+    {
+        w0 = first;
+        have = true;
+        const uint64_t t = min(n_tiles, first + (uint64_t)lane_id());
+        const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(ps + t));
+        mine.bl = q.x; mine.cur = (uint32_t)q.y; mine.run = (uint32_t)(q.y >> 32);
+    }
+    __device__ static RleState as_state(const PState &p) { RleState r; r.bl = p.bl; r.cur = p.cur; r.run = p.run; return r; }
+    __device__ uint64_t operator()(uint64_t t_lo, uint64_t lim, RleState &before)
     {
         const int lane = lane_id();
+        if (have && w0 + 31 <= n_tiles) {
+            // lane f = first tile of the window that lies behind t_lo and is over the limit.  If f >= 1, the tile in front of it is
+            // either t_lo itself or a tile behind t_lo that is not over the limit (and then, bl being monotone, no earlier one is):
+            // the answer, with its predecessor's state in lane f - 1.  f == 0 says nothing about the tiles in front of the window.
+            const bool over = (w0 + (uint64_t)lane > t_lo) && mine.bl > lim;
+            const unsigned m = __ballot_sync(FULL, over);
+            if (m) {
+                const int f = __ffs((int)m) - 1;
+                if (f >= 1) {
+                    before.bl = shfl_u64(mine.bl, f - 1);
+                    before.cur = __shfl_sync(FULL, mine.cur, f - 1);
+                    before.run = __shfl_sync(FULL, mine.run, f - 1);
+                    return w0 + (uint64_t)f;
+                }
+            } else if (w0 + 31 > t_lo) {
+                t_lo = w0 + 31; // nothing up to the window's last tile is over the limit
+            }
+        }
         for (;;) {
             if (t_lo >= n_tiles) return n_tiles + 1;
             const uint64_t t = min(n_tiles, (uint64_t)(t_lo + 16u * (uint64_t)(lane + 1)));
             const unsigned m = __ballot_sync(FULL, ps[t].bl > lim);
             if (m) {
                 const int f = __ffs((int)m) - 1;
-                const uint64_t base = t_lo + 16ull * (uint64_t)f; // ps[base].bl <= lim
+                const uint64_t base = t_lo + 16ull * (uint64_t)f; // ps[base].bl <= lim (or base == t_lo)
                 const uint64_t t2 = min(n_tiles, (uint64_t)(base + 1 + (uint64_t)(lane & 15)));
                 const unsigned m2 = __ballot_sync(FULL, ps[t2].bl > lim) & 0xffffu;
-                return base + 1 + (uint64_t)(__ffs((int)m2) - 1); // m2 != 0: the probe 16 further on was over the limit
+                const uint64_t ans = base + 1 + (uint64_t)(__ffs((int)m2) - 1); // m2 != 0: the probe 16 further on was over the limit
+                before = as_state(ps[ans - 1]);
+                return ans;
             }
             t_lo = min(n_tiles, (uint64_t)(t_lo + 512ull));
         }
@@ -391,9 +531,11 @@ __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restric
     __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
     DevTileScan scan{in, sm};
     DevRunEnd run_end{in, n_bytes, lv};
-    DevByte byte{in};
+    DevHead head{in, n_bytes, run_end};
     DevPState ps{pstate};
-    DevFirstOver first_over{pstate, (n_bytes + RLE_TILE - 1) / RLE_TILE};
+    const uint64_t n_tiles = (n_bytes + RLE_TILE - 1) / RLE_TILE;
+    DevFirstOver first_over{pstate, n_tiles, 0, PState{0, 0, 0}, false};
+    const int lane = lane_id();
     uint64_t nb = info[0], s = info[1];
     RleState g;
     g.bl = info[12]; g.cur = (uint32_t)(info[13] >> 32); g.run = (uint32_t)info[13];
@@ -408,24 +550,48 @@ __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restric
     }
     const uint64_t target = nb + max_new;
     uint64_t finished = 0;
+    uint64_t dt = (limit + RLE_TILE) / RLE_TILE; // tiles the last block took (start: a block without runs)
     __syncwarp();
     while (nb < target) {
         if (s >= n_bytes) { finished = 1; break; }
+        const uint64_t ts0 = s / RLE_TILE;
+        // the window of prefix states where this block should end, and -- into L2 only -- the tiles around that place and around
+        // the place where the NEXT block should end together with its window: every later round trip of the chain stops at L2
+        {
+            const uint64_t guess = ts0 + dt;
+            first_over.preload(guess > 14 ? guess - 14 : 0);
+            const uint64_t ta = guess > 1 ? guess - 1 : 0;                       // tiles ta .. ta+2: 48 lines of 128 B
+            for (uint32_t l = lane; l < 48; l += 32) {
+                const uint64_t off = ta * RLE_TILE + (uint64_t)l * 128;
+                if (off < n_bytes) prefetch_l2(in + off);
+            }
+            const uint64_t g2 = guess + dt;
+            const uint64_t tb = g2 > 2 ? g2 - 2 : 0;                             // next block: tiles tb .. tb+4, states tb-30 .. tb+34
+            for (uint32_t l = lane; l < 80; l += 32) {
+                const uint64_t off = tb * RLE_TILE + (uint64_t)l * 128;
+                if (off < n_bytes) prefetch_l2(in + off);
+            }
+            if (lane < 8) {
+                const uint64_t t8 = (tb > 30 ? tb - 30 : 0) + 8ull * (uint64_t)lane;
+                if (t8 <= n_tiles) prefetch_l2(pstate + t8);
+            }
+        }
         RleState st, g2 = g;
-        const uint64_t e = walk_block_prefix(s, n_bytes, limit, g2, run_end, byte, ps, first_over, scan, st);
+        const uint64_t e = walk_block_prefix(s, n_bytes, limit, g2, head, ps, first_over, scan, st);
         const bool complete = (e < n_bytes) || is_final; // e == n_bytes without a refusal: flushed only when the stream ends
         if (!complete) { finished = 1; break; }
-        if (lane_id() == 0 && nb < cap) {
+        if (lane == 0 && nb < cap) {
             starts[nb] = s;
             rle_len[nb] = (uint32_t)state_final_length(st);
         }
         ++nb;
+        dt = max((uint64_t)1, e / RLE_TILE - ts0);
         s = e;
         g = g2;
     }
     if (s >= n_bytes) finished = 1;
     __syncwarp();
-    if (lane_id() == 0) {
+    if (lane == 0) {
         if (nb <= cap) starts[nb] = s;
         info[0] = nb;
         info[1] = s;

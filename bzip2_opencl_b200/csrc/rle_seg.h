@@ -324,6 +324,134 @@ BZ_HD uint64_t walk_block_wide(uint64_t start, uint64_t n_bytes, uint64_t limit,
     return r.pos;
 }
 
+// ---- a full lane (64 bytes) from its equality mask ----
+#if defined(__CUDA_ARCH__)
+BZ_HD uint32_t bz_ffs64(uint64_t x) { return (uint32_t)__ffsll((long long)x); }
+BZ_HD uint32_t bz_clz64(uint64_t x) { return (uint32_t)__clzll((long long)x); }
+BZ_HD uint32_t bz_popc64(uint64_t x) { return (uint32_t)__popcll(x); }
+#else
+BZ_HD uint32_t bz_ffs64(uint64_t x) { return (uint32_t)__builtin_ffsll((long long)x); }
+BZ_HD uint32_t bz_clz64(uint64_t x) { return x ? (uint32_t)__builtin_clzll(x) : 64u; }
+BZ_HD uint32_t bz_popc64(uint64_t x) { return (uint32_t)__builtin_popcountll(x); }
+#endif
+// eq: bit j (1..63) set when byte j equals byte j-1, bit 0 clear.  Inside 64 bytes a run of L equal bytes is encoded as L bytes
+// (L < 4) or as 5 (4 <= L <= 64), so the encoded length of all runs is 64 - sum over long runs of (L - 5); a long run shows as L - 3
+// consecutive bits of eq & eq>>1 & eq>>2, hence sum (L - 3) = popcount of that mask and the number of long runs = its rising edges.
+BZ_HD Seg seg_from_eq_mask(uint32_t first, uint32_t last, uint64_t eq)
+{
+    Seg s;
+    s.pad = 0;
+    s.len = RLE_LANE_BYTES;
+    s.first = first;
+    s.last = last;
+    const uint32_t lead = bz_ffs64(~(eq >> 1)); // 64 when all bytes are equal (eq >> 1 has 63 ones, bit 63 is clear)
+    if (lead == RLE_LANE_BYTES) {
+        s.uniform = 1;
+        s.lead = s.trail = RLE_LANE_BYTES;
+        s.mid = 0;
+        return s;
+    }
+    const uint32_t trail = 1u + bz_clz64(~eq);
+    const uint64_t m3 = eq & (eq >> 1) & (eq >> 2);
+    const uint32_t all = RLE_LANE_BYTES - bz_popc64(m3) + 2u * bz_popc64(m3 & ~(m3 << 1));
+    s.uniform = 0;
+    s.lead = lead;
+    s.trail = trail;
+    s.mid = all - (lead < 4u ? lead : 5u) - (trail < 4u ? trail : 5u);
+    return s;
+}
+
+// ---- summaries of at most 4096 bytes in 32-bit fields (the walk's tile simulation scans 32 of them per block: two shuffles per step
+// instead of eleven) ----
+struct TSeg {
+    uint32_t len, lead, trail, mid, first, last; // as in Seg; uniform <=> lead == len
+};
+BZ_HD TSeg tseg_of(const Seg &s)
+{
+    TSeg t;
+    t.len = (uint32_t)s.len; t.lead = (uint32_t)s.lead; t.trail = (uint32_t)s.trail; t.mid = (uint32_t)s.mid; t.first = s.first; t.last = s.last;
+    return t;
+}
+BZ_HD uint32_t rle_enc_run32(uint32_t len) { return 5u * (len / 255u) + rle_enc_small(len % 255u); }
+BZ_HD TSeg tseg_combine(const TSeg &A, const TSeg &B)
+{
+    if (A.len == 0) return B;
+    if (B.len == 0) return A;
+    TSeg R;
+    R.len = A.len + B.len;
+    R.first = A.first;
+    R.last = B.last;
+    const bool au = A.lead == A.len, bu = B.lead == B.len, join = A.last == B.first;
+    if (au && bu && join) { R.lead = R.trail = R.len; R.mid = 0; return R; }
+    R.mid = A.mid + B.mid;
+    if (join) {
+        R.lead = au ? A.len + B.lead : A.lead;
+        R.trail = bu ? A.trail + B.len : B.trail;
+        if (!au && !bu) R.mid += rle_enc_run32(A.trail + B.lead);
+    } else {
+        R.lead = A.lead;
+        R.trail = B.trail;
+        if (!au) R.mid += rle_enc_run32(A.trail);
+        if (!bu) R.mid += rle_enc_run32(B.lead);
+    }
+    return R;
+}
+// state_apply for a TSeg (the carried run is at most 254 long, the segment at most 4096)
+BZ_HD RleState tstate_apply(const TSeg &S, RleState s)
+{
+    if (S.len == 0) return s;
+    const bool uni = S.lead == S.len;
+    uint32_t add = 0, tot;
+    if (s.run > 0 && s.cur == S.first) tot = s.run + S.lead;
+    else { add = rle_enc_small(s.run); tot = S.lead; }
+    if (uni) {
+        add += 5u * (tot / 255u);
+        s.run = tot % 255u;
+        s.cur = S.first;
+    } else {
+        add += rle_enc_run32(tot) + S.mid + 5u * (S.trail / 255u);
+        s.run = S.trail % 255u;
+        s.cur = S.last;
+    }
+    s.bl += add;
+    return s;
+}
+
+// First refused byte of a segment in which NO run of four or more equal bytes forms, the run carried in by `in` included
+// (promise of the caller): every flushed run then counts as its own length, so the machine's state in front of byte i is
+// closed form -- bl = in.bl + in.run + i - (pending run), pending run = the 1..3 equal bytes ending at i-1 (+ in.run when they reach
+// the segment's start and continue the carried run) -- and the first i with bl > limit is one of three neighbours.
+//   get(j) = byte j of the segment (0 <= j < n); looks at positions i_min <= i < n; pos = n if no byte is refused.
+// Returns the state in front of byte pos (pos == n: behind the segment).
+template <typename Get>
+BZ_HD RleState short_run_search(Get get, uint32_t n, const RleState &in, uint64_t limit, uint32_t i_min, uint32_t &pos)
+{
+    auto state_at = [&](uint32_t i) {
+        if (i == 0) return in;
+        const uint32_t v = get(i - 1);
+        uint32_t r = 1;
+        while (r < 3 && r < i && get(i - 1 - r) == v) ++r;
+        if (r == i && in.run > 0 && in.cur == v) r += in.run;
+        RleState st;
+        st.bl = in.bl + in.run + i - r;
+        st.cur = v;
+        st.run = r;
+        return st;
+    };
+    if (i_min == 0 && in.bl > limit) { pos = 0; return in; }
+    // i - pending > K with pending in 1..3: the first such i is K+2, K+3 or K+4
+    const int64_t K = (int64_t)limit - (int64_t)(in.bl + in.run);
+    int64_t start = K + 2;
+    if (start < 1) start = 1;
+    if (start < (int64_t)i_min) start = (int64_t)i_min;
+    for (int64_t i = start; i < start + 3 && i < (int64_t)n; ++i) {
+        const RleState st = state_at((uint32_t)i);
+        if (st.bl > limit) { pos = (uint32_t)i; return st; }
+    }
+    pos = n;
+    return state_at(n);
+}
+
 // ---- the same walk on PREFIX states: one tile simulation per block instead of a tree descent ----
 // Let the GLOBAL machine be the one that never starts a new block (it runs from byte 0), and pstate(t) its state at the first
 // byte of tile t (a parallel scan of the tile summaries).  A block's fresh machine, started at s, and the global machine agree
@@ -331,19 +459,21 @@ BZ_HD uint64_t walk_block_wide(uint64_t start, uint64_t n_bytes, uint64_t limit,
 // then on their blockLengths differ by a constant D.  So "first byte refused by the fresh machine" = "first byte where the
 // global blockLength exceeds limit + D": a search in the monotone pstate[].bl plus one exact tile simulation.
 //   gstate       in: global state at s; out: global state at the returned position
-//   run_end(s)   first q > s with in[q] != in[s], or n_bytes
-//   byte(q)      in[q]
+//   head(s, v, r, vr)   v = in[s]; r = first q > s with in[q] != in[s], or n_bytes; vr = in[r] when r < n_bytes (one look at the
+//                bytes behind s answers all three)
 //   pstate(t)    global state at byte t * RLE_TILE for t <= n_tiles (pstate(n_tiles) = state at n_bytes)
-//   first_over(t_lo, lim)  smallest t > t_lo with pstate(t).bl > lim, or n_tiles + 1 if none
+//   first_over(t_lo, lim, before)  smallest t > t_lo with pstate(t).bl > lim, or n_tiles + 1 if none; when it is <= n_tiles,
+//                before = pstate(t - 1) (the search has usually just read it)
 //   scan(lo, hi, state, lim) as above (any state / limit)
 // Returns the end position; st_end = FRESH machine state there (for the block's RLE1 length).
-template <typename RunEnd, typename Byte, typename PState, typename FirstOver, typename Scan>
-BZ_HD uint64_t walk_block_prefix(uint64_t s, uint64_t n_bytes, uint64_t limit, RleState &gstate, RunEnd run_end, Byte byte, PState pstate,
-                                 FirstOver first_over, Scan scan, RleState &st_end)
+template <typename Head, typename PState, typename FirstOver, typename Scan>
+BZ_HD uint64_t walk_block_prefix(uint64_t s, uint64_t n_bytes, uint64_t limit, RleState &gstate, Head head, PState pstate, FirstOver first_over, Scan scan,
+                                 RleState &st_end)
 {
     const uint64_t n_tiles = (n_bytes + RLE_TILE - 1) / RLE_TILE;
-    const uint32_t v = byte(s);
-    const uint64_t r = run_end(s);
+    uint32_t v, vr;
+    uint64_t r;
+    head(s, v, r, vr);
     const uint64_t L1 = r - s;
     // the block ends inside its first run: 255-byte chunks of 5 encoded bytes each
     const uint64_t k = limit / 5 + 1;
@@ -358,39 +488,35 @@ BZ_HD uint64_t walk_block_prefix(uint64_t s, uint64_t n_bytes, uint64_t limit, R
     RleState g = state_apply(first_run, gstate);
     if (r >= n_bytes) { st_end = f; gstate = g; return n_bytes; }
     // both machines take byte r: the first run is flushed in both, (cur, run) agree from here on
-    state_step(f, byte(r));
-    state_step(g, byte(r));
+    state_step(f, vr);
+    state_step(g, vr);
     const uint64_t D = g.bl - f.bl;
     const uint64_t limD = limit + D;
-    uint64_t pos = r + 1; // next byte to enter, global state g
+    const uint64_t pos = r + 1; // next byte to enter, global state g
     if (g.bl > limD) { st_end = f; gstate = g; return pos; }
     if (pos >= n_bytes) { st_end = f; gstate = g; return n_bytes; }
-    uint64_t t = pos / RLE_TILE; // tile of pos
-    // rest of the current tile, only if the refusal can be inside it
-    {
-        const uint64_t t_next = t + 1;
-        const RleState pn = pstate(t_next <= n_tiles ? t_next : n_tiles);
-        const uint64_t hi = t_next * RLE_TILE < n_bytes ? t_next * RLE_TILE : n_bytes;
-        if (pn.bl > limD) {
-            if (pos < hi) {
-                TileScanResult res = scan(pos, hi, g, limD);
-                gstate = res.st;
-                st_end = res.st; st_end.bl -= D;
-                return res.pos; // refusal inside [pos, hi) or exactly at hi (then res.st.bl > limD)
-            }
-            gstate = pn; st_end = pn; st_end.bl -= D;
-            return hi;
-        }
-    }
-    // whole tiles: first tile boundary whose global blockLength is over the limit
-    const uint64_t ts = first_over(t + 1, limD); // > t + 1 by the test above
+    const uint64_t t = pos / RLE_TILE; // tile of pos
+    // first tile boundary behind pos whose global blockLength is over the limit: the refusal is in the tile in front of it
+    RleState before;
+    const uint64_t ts = first_over(t, limD, before);
     if (ts > n_tiles) { // never: the block runs to the end of the input
         const RleState pe = pstate(n_tiles);
         gstate = pe; st_end = pe; st_end.bl -= D;
         return n_bytes;
     }
-    const uint64_t lo = (ts - 1) * RLE_TILE, hi = ts * RLE_TILE < n_bytes ? ts * RLE_TILE : n_bytes;
-    TileScanResult res = scan(lo, hi, pstate(ts - 1), limD);
+    const uint64_t hi = ts * RLE_TILE < n_bytes ? ts * RLE_TILE : n_bytes;
+    if (ts == t + 1) { // the rest of the tile pos lies in
+        if (pos < hi) {
+            TileScanResult res = scan(pos, hi, g, limD);
+            gstate = res.st;
+            st_end = res.st; st_end.bl -= D;
+            return res.pos; // refusal inside [pos, hi) or exactly at hi (then res.st.bl > limD)
+        }
+        const RleState pn = pstate(ts);
+        gstate = pn; st_end = pn; st_end.bl -= D;
+        return hi;
+    }
+    TileScanResult res = scan((ts - 1) * RLE_TILE, hi, before, limD);
     gstate = res.st;
     st_end = res.st; st_end.bl -= D;
     return res.pos;

@@ -247,6 +247,14 @@ public:
             throw std::runtime_error("bz2b200_host_alloc failed");
         blockCRCs.resize(cap / static_cast<size_t>((streamBlockSize - 5) * 4 / 5 > 0 ? (streamBlockSize - 5) * 4 / 5 : 1) + 4);
         fill = head;
+        {
+            // an empty call makes the handle allocate its per-batch device buffers now instead of inside the first batch
+            uint64_t nbits = 0, nblocks = 0;
+            size_t consumed = 0;
+            rc = bz2b200_compress_blocks(handle, nullptr, 0, 0, 0, outBits, outCap, &nbits, &consumed, nullptr, nullptr, 0, &nblocks);
+            if (rc != BZ2B200_OK)
+                throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
+        }
         worker = std::thread([this] { workerMain(); });
         // stream header, reference :126-128
         const char hdr[4] = {'B', 'Z', 'h', static_cast<char>('0' + blockSizeMultiplier)};

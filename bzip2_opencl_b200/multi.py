@@ -194,3 +194,114 @@ def gather_stream(multiplier: int, part, rank: int, world: int, group=None):
     if rank != 0:
         return None
     return stream_from_blocks(multiplier, parts)
+
+
+# ---------------------------------------------------------------------------------------------------------------- one rank of a stream
+class StreamRank:
+    """One process (= one GPU) of `world` compressing ONE stream of `total` bytes by byte slices.  torch.distributed must be
+    initialised; `meta_group` is a gloo group for the few numbers that travel between ranks (the chain of block starts, bit
+    counts, CRCs), the packed bits travel over the default (NCCL) group.  Used by bench.py --gpus N and the tests."""
+
+    def __init__(self, comp, total: int, rank: int, world: int, meta_group=None, ratio: float = 0.96, is_final: bool = True):
+        import torch
+        self.torch = torch
+        self.comp, self.total, self.rank, self.world, self.meta, self.is_final = comp, total, rank, world, meta_group, is_final
+        self.plan = plan_slices(total, world, comp.block_size, ratio)
+        self.base, self.lo, self.hi = self.plan[rank]
+        self.halo = self.lo - self.base
+        self.cap = comp.max_output_bytes(self.hi - self.base) + 64
+        self.out = torch.zeros(self.cap, dtype=torch.uint8, device="cuda")
+        self.shifted = torch.zeros(self.cap + 16, dtype=torch.uint8, device="cuda")
+        self.max_blocks = comp.max_blocks(total)
+
+    # -- device-resident input: `buf` holds [base, hi) with the slice itself in buf[halo:]; the halo comes from the rank(s) in front
+    def exchange_halo(self, buf):
+        import torch.distributed as dist
+        ops = []
+        if self.rank + 1 < self.world:
+            nb, nlo, nhi = self.plan[self.rank + 1]
+            need = nlo - nb
+            if need:
+                assert need <= self.hi - self.base, "halo longer than the slice in front"
+                ops.append(dist.P2POp(dist.isend, buf[buf.numel() - need:], self.rank + 1))
+        if self.rank > 0 and self.halo:
+            ops.append(dist.P2POp(dist.irecv, buf[:self.halo], self.rank - 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _recv_start(self):
+        import torch.distributed as dist
+        t = self.torch.zeros(1, dtype=self.torch.int64)
+        dist.recv(t, src=self.rank - 1, group=self.meta)
+        return int(t[0])
+
+    def _send_start(self, v):
+        import torch.distributed as dist
+        dist.send(self.torch.tensor([v], dtype=self.torch.int64), dst=self.rank + 1, group=self.meta)
+
+    def compress(self, ptr: int):
+        """ptr -> bytes [base, hi) of the stream (host or device memory).  Leaves this rank's bits, shifted to their bit offset in
+        the stream (32 header bits in front), in self.shifted; returns dict(placement of every rank, nbits of every rank, crc,
+        n_copy, byte0, end_bit)."""
+        import torch.distributed as dist
+        torch = self.torch
+        c = self.comp
+        n = self.hi - self.base
+        if n:
+            c.scan_prepare(ptr, n)
+        box = {}
+
+        def scan(first_rel, final):
+            nb, used = c.scan_blocks_ex(ptr, n, final, first_rel, want_starts=False)
+            return nb, used
+        s, nb, nxt = chain_walk(scan, self.plan[self.rank], self.rank, self.world, self.is_final, self._recv_start, self._send_start)
+        nbits, crcs, tail = 0, np.zeros(0, dtype=np.uint32), 0
+        if nb:
+            q = c.compress_scanned_ptr(self.out.data_ptr(), self.cap, nb)
+            nbits, crcs = int(q["nbits"]), q["crcs"]
+            e = (nbits - 1) >> 3
+            tail = tail_of(bytes(self.out[max(0, e - 1):e + 1].cpu().numpy()), nbits)
+        # metadata: bit count, trailing bits, block CRCs of every rank
+        mine = torch.zeros(3 + self.max_blocks, dtype=torch.int64)
+        mine[0], mine[1], mine[2] = nbits, tail, len(crcs)
+        if len(crcs):
+            mine[3:3 + len(crcs)] = torch.from_numpy(crcs.astype(np.int64))
+        allm = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allm, mine, group=self.meta)
+        nbits_all = [int(m[0]) for m in allm]
+        placement = place_parts(nbits_all, [int(m[1]) for m in allm], 32)
+        off, shift, carry, byte0, n_copy = placement[self.rank]
+        if nbits:
+            c.shift_bits_ptr(self.out.data_ptr(), nbits, shift, carry, self.shifted.data_ptr(), self.cap + 16)
+        crc = fold_crcs([m[3:3 + int(m[2])].tolist() for m in allm])
+        return dict(placement=placement, nbits_all=nbits_all, crc=crc, n_copy=n_copy, byte0=byte0, end_bit=32 + sum(nbits_all), n_blocks=nb,
+                    blocks_all=[int(m[2]) for m in allm])
+
+    def gather_device(self, res, dst):
+        """Every rank's shifted bytes to rank 0's device buffer `dst` (the whole stream: header, parts, trailer).  Returns the
+        stream length in bytes on rank 0."""
+        import torch.distributed as dist
+        torch = self.torch
+        ops = []
+        if self.rank == 0:
+            if res["n_copy"]:
+                dst[res["byte0"]:res["byte0"] + res["n_copy"]].copy_(self.shifted[:res["n_copy"]])
+            for r in range(1, self.world):
+                off, shift, carry, byte0, n_copy = res["placement"][r]
+                if n_copy:
+                    ops.append(dist.P2POp(dist.irecv, dst[byte0:byte0 + n_copy], r))
+        elif res["n_copy"]:
+            ops.append(dist.P2POp(dist.isend, self.shifted[:res["n_copy"]], 0))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.rank != 0:
+            return 0
+        end_bit = res["end_bit"]
+        last = int(dst[end_bit >> 3]) if end_bit & 7 else 0
+        tr = trailer_bytes(end_bit, last, res["crc"])
+        head = torch.tensor(list(b"BZh" + bytes([ord("0") + self.comp.multiplier])), dtype=torch.uint8)
+        dst[:4].copy_(head)
+        dst[end_bit >> 3:(end_bit >> 3) + len(tr)].copy_(torch.tensor(list(tr), dtype=torch.uint8))
+        return (end_bit >> 3) + len(tr)

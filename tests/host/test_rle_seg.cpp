@@ -124,10 +124,20 @@ static Blocks prefix_walk(const std::vector<uint8_t> &in, uint64_t limit)
             if (t < nt) acc = seg_combine(acc, l0[t]);
         }
     }
-    auto run_end = [&](uint64_t s) { uint64_t q = s + 1; while (q < n && in[q] == in[s]) ++q; return q; };
-    auto byte = [&](uint64_t q) { return (uint32_t)in[q]; };
+    auto head = [&](uint64_t s, uint32_t &v, uint64_t &r, uint32_t &vr) {
+        v = in[s];
+        uint64_t q = s + 1;
+        while (q < n && in[q] == in[s]) ++q;
+        r = q;
+        vr = q < n ? in[q] : 0u;
+    };
     auto pstate = [&](uint64_t t) { return ps[t]; };
-    auto first_over = [&](uint64_t t_lo, uint64_t lim) { uint64_t t = t_lo + 1; while (t <= nt && ps[t].bl <= lim) ++t; return t; };
+    auto first_over = [&](uint64_t t_lo, uint64_t lim, RleState &before) {
+        uint64_t t = t_lo + 1;
+        while (t <= nt && ps[t].bl <= lim) ++t;
+        if (t <= nt) before = ps[t - 1];
+        return t;
+    };
     auto scan = [&](uint64_t lo, uint64_t hi, RleState st, uint64_t lim) {
         TileScanResult res; res.pos = hi;
         RleState s = st;
@@ -143,7 +153,7 @@ static Blocks prefix_walk(const std::vector<uint8_t> &in, uint64_t limit)
     RleState g = state_fresh();
     while (s < n) {
         RleState st;
-        uint64_t e = walk_block_prefix(s, n, limit, g, run_end, byte, pstate, first_over, scan, st);
+        uint64_t e = walk_block_prefix(s, n, limit, g, head, pstate, first_over, scan, st);
         b.starts.push_back(s); b.lens.push_back(state_final_length(st));
         if (e <= s) { printf("prefix walk made no progress at %llu\n", (unsigned long long)s); exit(4); }
         s = e;
@@ -152,10 +162,95 @@ static Blocks prefix_walk(const std::vector<uint8_t> &in, uint64_t limit)
 }
 
 static uint64_t rng = 88172645463325252ull;
+static uint32_t rnd();
+
+// TSeg (32-bit summaries) against Seg, and the closed-form search against the literal machine
+static void check_tseg_and_short_runs()
+{
+    for (int iter = 0; iter < 20000; ++iter) {
+        const uint32_t n = rnd() % 300 + 1;
+        std::vector<uint8_t> b(n);
+        const int mode = iter % 4;
+        for (uint32_t i = 0; i < n;) {
+            uint32_t v = rnd() & (mode == 0 ? 1 : 0xff), run = mode == 3 ? rnd() % 3 + 1 : (mode == 2 ? rnd() % 600 + 1 : rnd() % 5 + 1);
+            for (uint32_t k = 0; k < run && i < n; ++k) b[i++] = (uint8_t)v;
+        }
+        // split in up to 5 pieces, combine as Seg and as TSeg
+        Seg acc = seg_empty();
+        TSeg tacc = tseg_of(seg_empty());
+        uint32_t a = 0;
+        while (a < n) {
+            uint32_t e = a + rnd() % (n - a) + 1;
+            const uint8_t *p = b.data() + a;
+            Seg sg = seg_from_bytes([&](uint32_t i) { return (uint32_t)p[i]; }, e - a);
+            acc = seg_combine(acc, sg);
+            tacc = tseg_combine(tacc, tseg_of(sg));
+            a = e;
+        }
+        RleState in = state_fresh();
+        in.bl = rnd() % 100000;
+        if (rnd() % 2) { in.run = rnd() % 254 + 1; in.cur = (rnd() % 2) ? b[0] : (rnd() & 0xff); }
+        RleState x = state_apply(acc, in), y = tstate_apply(tacc, in);
+        if (x.bl != y.bl || x.run != y.run || (x.run && x.cur != y.cur) || tacc.len != acc.len || tacc.mid != acc.mid) { printf("TSeg mismatch iter %d\n", iter); exit(5); }
+        // closed-form search where the promise holds
+        RleState in2 = in;
+        if (in2.run > 3) in2.run = rnd() % 4;
+        bool longrun = false;
+        {
+            uint32_t r = (in2.run > 0 && in2.cur == b[0]) ? in2.run + 1 : 1;
+            if (r >= 4) longrun = true;
+            for (uint32_t i = 1; i < n; ++i) { r = b[i] == b[i - 1] ? r + 1 : 1; if (r >= 4) longrun = true; }
+        }
+        if (!longrun) {
+            for (int rep = 0; rep < 3; ++rep) {
+                const uint64_t limit = in2.bl + (rep == 0 ? 0 : rnd() % (n + 8)) - (rep == 2 && in2.bl > 3 ? rnd() % 3 : 0);
+                const uint32_t i_min = rnd() % 3 == 0 ? 1 : 0;
+                // literal
+                RleState st = in2;
+                uint32_t lit = n;
+                RleState lit_st;
+                bool found = false;
+                for (uint32_t i = 0; i < n; ++i) {
+                    if (i >= i_min && st.bl > limit) { lit = i; lit_st = st; found = true; break; }
+                    state_step(st, b[i]);
+                }
+                if (!found) lit_st = st;
+                uint32_t pos;
+                RleState got = short_run_search([&](uint32_t j) { return (uint32_t)b[j]; }, n, in2, limit, i_min, pos);
+                if (pos != lit || got.bl != lit_st.bl || got.run != lit_st.run || (got.run && got.cur != lit_st.cur)) {
+                    printf("short_run_search mismatch iter %d rep %d: pos %u vs %u, bl %llu vs %llu, run %u vs %u\n", iter, rep, pos, lit, (unsigned long long)got.bl,
+                           (unsigned long long)lit_st.bl, got.run, lit_st.run);
+                    exit(6);
+                }
+            }
+        }
+    }
+}
+
 static uint32_t rnd() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 11); }
+
+// a full lane's summary from its equality mask (seg_from_eq_mask) against the byte-by-byte summary
+static void check_eq_mask_summary()
+{
+    for (int it = 0; it < 300000; ++it) {
+        uint8_t p[64];
+        const int mode = it % 4;
+        for (int i = 0; i < 64;) {
+            const uint32_t v = rnd() & (mode == 0 ? 1 : 255), run = mode == 1 ? rnd() % 3 + 1 : (mode == 2 ? rnd() % 70 + 1 : rnd() % 7 + 1);
+            for (uint32_t k = 0; k < run && i < 64; ++k) p[i++] = (uint8_t)v;
+        }
+        uint64_t eq = 0;
+        for (int j = 1; j < 64; ++j)
+            if (p[j] == p[j - 1]) eq |= 1ull << j;
+        const Seg ref = seg_from_bytes([&](uint32_t i) { return (uint32_t)p[i]; }, 64), s = seg_from_eq_mask(p[0], p[63], eq);
+        if (s.uniform != ref.uniform || s.lead != ref.lead || s.trail != ref.trail || s.mid != ref.mid || s.first != ref.first || s.last != ref.last) { printf("eq-mask summary mismatch %d\n", it); exit(7); }
+    }
+}
 
 int main()
 {
+    check_eq_mask_summary();
+    check_tseg_and_short_runs();
     int cases = 0;
     for (int iter = 0; iter < 400; ++iter) {
         size_t n = rnd() % 300000 + 1;
