@@ -91,6 +91,9 @@ struct bz2b200 {
     uint64_t seg_first = 16ull << 20, seg_rest = 64ull << 20; // host input: bytes per H2D segment (BZ2B200_SEG_MB=first,rest)
     int pack_keys = 1;    // round-0 keys over the block's own alphabet (k_bwt_keys_packed); BZ2B200_PACK=0: the first key0_bytes bytes
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
+    int r0_group = 0;     // BZ2B200_R0_GROUP=g: the five round-0 sweeps run group by group of g blocks so that a group's elements stay in L2 (measured: the
+                          // small launches cost more than the HBM traffic they save, profiles/r02_*); 0 = every sweep over the whole batch
+    int bulk_copy = 1;    // BZ2B200_BULK=0: block-relative tiles are staged with byte loads instead of the TMA bulk copy (cp.async.bulk + mbarrier)
     int root_sort = 1;    // BZ2B200_ROOT=0: non-primitive blocks go through the full prefix doubling instead of their root (k_bwt_period)
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
     cudaStream_t stream = 0;
@@ -101,7 +104,7 @@ struct bz2b200 {
     DevBuf in, seg[RLE_MAX_LEVELS], segP[RLE_MAX_LEVELS], pstate, starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
-    DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, digit_base, rc_partial, cnts, scalars,
+    DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, tickets, digit_base, rc_partial, cnts, scalars,
         h0, root, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int ctasC = 0;
@@ -381,7 +384,8 @@ static int alloc_batch(bz2b200 *h)
     ENSURE(h->loc_cnt, G * h->tilesG * 4);
     ENSURE(h->rank, G * S * 4);
     ENSURE(h->mtf, G * S * 2);
-    ENSURE(h->hist, G * h->tilesR * 256 * 4);
+    ENSURE(h->hist, (size_t)RC_MAXPASS * G * h->tilesR * 256 * 4); // status words: one region per sweep of round 0
+    ENSURE(h->tickets, (size_t)RC_MAXPASS * G * 4);
     ENSURE(h->digit_base, G * 256 * 4 * RC_MAXPASS);
     ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
@@ -430,7 +434,7 @@ static int create_lanes(bz2b200 *h)
         h->lanes.push_back(l);
         l->parent = h;
         l->device = h->device; l->base = h->base; l->mult = h->mult; l->bs = h->bs; l->S = h->S; l->nbits = h->nbits;
-        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->root_sort = h->root_sort; l->n_lanes = 1;
+        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->root_sort = h->root_sort; l->r0_group = h->r0_group; l->bulk_copy = h->bulk_copy; l->n_lanes = 1;
         l->G = (h->G + nl - 1) / nl;
         int rc = create_impl(l, true);
         if (rc == BZ2B200_OK && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) rc = BZ2B200_E_CUDA;
@@ -469,6 +473,8 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (const char *e = getenv("BZ2B200_PACK")) h->pack_keys = atoi(e);
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ROOT")) h->root_sort = atoi(e);
+    if (const char *e = getenv("BZ2B200_BULK")) h->bulk_copy = atoi(e);
+    if (const char *e = getenv("BZ2B200_R0_GROUP")) h->r0_group = std::max(0, atoi(e));
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK_GROWTH")) h->walk_growth = std::max(1, atoi(e));
@@ -910,10 +916,10 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     CK(cudaEventRecord(h->ev[2], st));
     {
         dim3 grid((unsigned)((max_tiles + RLE_WARPS - 1) / RLE_WARPS), nb);
-        KL(KID_k_rle_btile_seg, k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles));
+        KL(KID_k_rle_btile_seg, k_rle_btile_seg<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<Seg>(h->segB), max_tiles, h->bulk_copy));
         KL(KID_k_rle_btile_scan, k_rle_btile_scan<<<(nb + RLE_WARPS - 1) / RLE_WARPS, RLE_WARPS * 32, 0, st>>>(ptr<Seg>(h->segB), d_starts, (uint32_t)b0, nb, ptr<uint64_t>(h->tstate),
                                                                                        max_tiles));
-        KL(KID_k_rle_emit, k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S));
+        KL(KID_k_rle_emit, k_rle_emit<<<grid, RLE_WARPS * 32, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint64_t>(h->tstate), max_tiles, ptr<uint8_t>(h->rle), S, h->bulk_copy));
         dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), nb);
         KL(KID_k_crc_chunks, k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_in, d_starts, (uint32_t)b0, ptr<uint32_t>(h->crc)));
         KL(KID_k_crc_finish, k_crc_finish<<<(nb + 127) / 128, 128, 0, st>>>(d_starts, (uint32_t)b0, nb, ptr<uint32_t>(h->crc)));
@@ -950,21 +956,41 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         stt.kernel_launches += 4;
         KBYTES(KID_k_bwt_bytehist, sum_n);
         KBYTES(KID_k_bwt_keys0, sum_n);
-        uint32_t *ticket = reinterpret_cast<uint32_t *>(ptr<uint64_t>(h->scalars) + Scalars::TICKET);
         uint64_t *kA = ptr<uint64_t>(h->kA), *kB = ptr<uint64_t>(h->kB);
-        for (int p = 0; p < RC_MAXPASS && tiles; ++p) { // five sweeps; the first builds its elements from the text
-            CK(cudaMemsetAsync(h->hist.p, 0, (size_t)nb * h->tilesR * 256 * 4, st));
-            CK(cudaMemsetAsync(ticket, 0, 4, st));
-            uint32_t *db = ptr<uint32_t>(h->digit_base) + (size_t)p * nb * 256;
-            if (p == 0)
-                KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
-                                             nullptr, kB, d_n, S, VAL_BITS, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, ptr<uint8_t>(h->rle), 0, ptr<uint32_t>(h->present)));
-            else
-                KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(tiles, nb), RS_THREADS, sizeof(ScatterSmem), st>>>(
-                                             (p & 1) ? kB : kA, (p & 1) ? kA : kB, d_n, S, VAL_BITS + 8 * p, db, ptr<uint32_t>(h->hist), h->tilesR, ticket, nullptr, 0, nullptr));
-            stt.kernel_launches += 1;
-            KBYTES(KID_k_radix_onesweep, sum_n * (p == 0 ? 9 : 16));
+        // Five sweeps; the first builds its elements from the text.  They run GROUP by group of a few blocks, all five sweeps of a
+        // group back to back: a block's elements (2 x 7.2 MB at 900k) then stay in the 126 MB L2 from sweep to sweep, and only the
+        // text read of the first and the element write of the last sweep go to HBM.  Every (sweep, group) has its own ticket and every
+        // sweep its own region of status words, zeroed once per batch.
+        const uint32_t gsz = h->r0_group ? (uint32_t)h->r0_group : nb;
+        const size_t pass_words = (size_t)h->G * h->tilesR * 256;
+        if (tiles) {
+            for (int p = 0; p < RC_MAXPASS; ++p) CK(cudaMemsetAsync(ptr<uint32_t>(h->hist) + (size_t)p * pass_words, 0, (size_t)nb * h->tilesR * 256 * 4, st));
+            CK(cudaMemsetAsync(h->tickets.p, 0, (size_t)RC_MAXPASS * h->G * 4, st));
         }
+        uint32_t launch_no = 0;
+        for (uint32_t g0 = 0; g0 < nb && tiles; g0 += gsz) {
+            const uint32_t gc = std::min(gsz, nb - g0);
+            uint32_t gmax = 0;
+            for (uint32_t i = 0; i < gc; ++i) gmax = std::max(gmax, P->h_rle_len[b0 + g0 + i]);
+            const uint32_t gt = (gmax + RS_TILE - 1) / RS_TILE;
+            if (!gt) continue;
+            const uint64_t go = (uint64_t)g0 * S;
+            for (int p = 0; p < RC_MAXPASS; ++p) {
+                uint32_t *db = ptr<uint32_t>(h->digit_base) + ((size_t)p * nb + g0) * 256;
+                uint32_t *status = ptr<uint32_t>(h->hist) + (size_t)p * pass_words + (size_t)g0 * h->tilesR * 256;
+                uint32_t *ticket = ptr<uint32_t>(h->tickets) + launch_no++;
+                if (p == 0)
+                    KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                                 nullptr, kB + go, d_n + g0, S, VAL_BITS, db, status, h->tilesR, ticket, ptr<uint8_t>(h->rle) + go, 0,
+                                                 ptr<uint32_t>(h->present) + (size_t)g0 * 8));
+                else
+                    KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                                 ((p & 1) ? kB : kA) + go, ((p & 1) ? kA : kB) + go, d_n + g0, S, VAL_BITS + 8 * p, db, status, h->tilesR, ticket, nullptr, 0,
+                                                 nullptr));
+                stt.kernel_launches += 1;
+            }
+        }
+        KBYTES(KID_k_radix_onesweep, sum_n * (9 + 4 * 16));
         res = 1; // five sweeps end in kB
     } else if (h->onesweep && h->key0_bytes >= 4) {
         k_fill_u32<<<(nb + 255) / 256, 256, 0, st>>>(d_h0, nb, (uint32_t)h->key0_bytes);

@@ -84,6 +84,56 @@ __device__ __forceinline__ void warp_load_tile(const uint8_t *__restrict__ in, u
     __syncwarp();
 }
 
+// ---- the same staging through the TMA engine (Blackwell / Hopper bulk copy) --------------------------------------------------
+// Block-relative tiles start at arbitrary bytes of the input, so the generic path above falls back to byte loads (64 LDG.U8 + 64
+// STS.U8 per lane).  Instead ONE lane asks the copy engine for the 16-byte aligned span that covers the tile
+// (cp.async.bulk.shared::cluster.global, completion on an mbarrier: SASS UBLKCP + SYNCS), and the warp then moves the bytes from that
+// linear landing buffer into the padded tile, 32 consecutive words per step, shifted by the tile's offset inside its first word.
+//   lin   16-byte aligned landing buffer of RLE_BULK_BYTES bytes (per warp);  bar  the warp's mbarrier (8 bytes, initialised by
+//   bulk_init); phase  parity of this use (0 for the first copy through the barrier, then alternating)
+constexpr uint32_t RLE_BULK_BYTES = RLE_TILE + 32;
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_init(uint64_t *bar)
+{
+    if (lane_id() == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_load_tile_bulk(const uint8_t *__restrict__ in, uint64_t lo, uint32_t n, uint8_t *sm, uint8_t *lin, uint64_t *bar, uint32_t phase)
+{
+    const int lane = lane_id();
+    const uint64_t a0 = lo & ~15ull;
+    const uint32_t skew = (uint32_t)(lo - a0);
+    const uint32_t bytes = (skew + n + 15u) & ~15u;
+    if (lane == 0) {
+        const uint32_t b = smem_addr(bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(lin)), "l"(in + a0), "r"(bytes), "r"(b)
+                     : "memory");
+    }
+    {
+        const uint32_t b = smem_addr(bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b), "r"(phase) : "memory");
+        }
+    }
+    // linear -> padded (RLE_SM_STRIDE bytes per 64): word k of the tile = bytes skew + 4k .. of the landing buffer
+    const uint32_t *lw = reinterpret_cast<const uint32_t *>(lin);
+    const uint32_t w0 = skew >> 2, sh = 8u * (skew & 3u);
+    const uint32_t nw = (n + 3u) >> 2;
+    for (uint32_t k0 = 0; k0 < nw; k0 += 32) {
+        const uint32_t k = k0 + (uint32_t)lane;
+        const uint32_t x = lw[w0 + min(k, nw)]; // (word nw is the last one the copy can have touched: skew + n <= 4 (w0 + nw) + 3)
+        uint32_t y = __shfl_down_sync(FULL, x, 1);
+        if (lane == 31) y = lw[w0 + min(k + 1, nw)];
+        if (k < nw) *reinterpret_cast<uint32_t *>(sm + (k >> 4) * RLE_SM_STRIDE + ((k & 15u) << 2)) = __funnelshift_r(x, y, sh);
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ uint32_t lane_count(uint32_t n)
 {
     int c = (int)n - lane_id() * (int)RLE_LANE_BYTES;
@@ -614,15 +664,21 @@ __device__ __forceinline__ bool btile_range(const uint64_t *starts, uint32_t b, 
 }
 
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_btile_seg(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
-                                                                    Seg *__restrict__ segB, uint64_t max_tiles)
+                                                                    Seg *__restrict__ segB, uint64_t max_tiles, int bulk)
 {
     __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
+    __shared__ __align__(16) uint8_t lin_all[RLE_WARPS][RLE_BULK_BYTES];
+    __shared__ __align__(8) uint64_t bar_all[RLE_WARPS];
     uint64_t k = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
     uint32_t bl = blockIdx.y;
     uint64_t lo; uint32_t n;
     if (k >= max_tiles || !btile_range(starts, b0 + bl, k, lo, n)) return;
     uint8_t *sm = sm_all[warp_id()];
-    warp_load_tile(in, lo, n, sm);
+    if (bulk) {
+        bulk_init(&bar_all[warp_id()]);
+        warp_load_tile_bulk(in, lo, n, sm, lin_all[warp_id()], &bar_all[warp_id()], 0u);
+    } else
+        warp_load_tile(in, lo, n, sm);
     Seg s = warp_seg_incl_scan(lane_seg(sm, lane_count(n)));
     if (lane_id() == 31) segB[(uint64_t)bl * max_tiles + k] = s;
 }
@@ -681,17 +737,23 @@ constexpr int RLE_OUT_STAGE = 2640; // bytes a tile can emit (2048 * 5/4 + carri
 
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ starts, uint32_t b0,
                                                                const uint64_t *__restrict__ tstate, uint64_t max_tiles, uint8_t *__restrict__ rle,
-                                                               uint64_t stride)
+                                                               uint64_t stride, int bulk)
 {
     __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
     __shared__ __align__(16) uint8_t so_all[RLE_WARPS][RLE_OUT_STAGE];
+    __shared__ __align__(8) uint64_t bar_all[RLE_WARPS];
+    static_assert(RLE_OUT_STAGE >= RLE_BULK_BYTES, "the output staging area doubles as the bulk copy's landing buffer");
     uint64_t k = (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
     uint32_t bl = blockIdx.y;
     uint64_t lo; uint32_t n;
     if (k >= max_tiles || !btile_range(starts, b0 + bl, k, lo, n)) return;
     const int lane = lane_id();
     uint8_t *sm = sm_all[warp_id()];
-    warp_load_tile(in, lo, n, sm);
+    if (bulk) { // the landing buffer is the output staging area: it is not written before the tile has been moved out of it
+        bulk_init(&bar_all[warp_id()]);
+        warp_load_tile_bulk(in, lo, n, sm, so_all[warp_id()], &bar_all[warp_id()], 0u);
+    } else
+        warp_load_tile(in, lo, n, sm);
     uint32_t cnt = lane_count(n);
     Seg incl = warp_seg_incl_scan(lane_seg(sm, cnt));
     Seg excl = shfl_up_seg(incl, 1);

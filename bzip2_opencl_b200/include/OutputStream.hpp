@@ -32,6 +32,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "Config.hpp"
@@ -53,6 +54,8 @@ private:
     // two pinned staging buffers: [head room for the carried-over bytes | new input]
     uint8_t *stage[2] = {nullptr, nullptr};
     size_t head = 0, cap = 0; // new input goes to [head, cap)
+    size_t target = 0;        // bytes of new input that make a batch: small at first (the GPUs start early), then doubling up to cap - head
+    size_t limit() const { return head + target; }
     int cur = 0;              // buffer being filled
     size_t fill = 0;          // next free byte in stage[cur]
     uint8_t *outBits = nullptr; // pinned: packed bits of one batch
@@ -196,6 +199,7 @@ private:
         cv.notify_all();
         cur ^= 1;
         fill = head;
+        target = target * 2 < cap - head ? target * 2 : cap - head;
     }
 
 public:
@@ -230,11 +234,14 @@ public:
         deviceCount = static_cast<int>(ids.size());
         // staging: no unfinished block is longer than `head` raw bytes (255-byte run chunks of 5 encoded bytes each)
         head = ((static_cast<size_t>(streamBlockSize) / 5 + 2) * 255 + 2 * static_cast<size_t>(streamBlockSize) + 4095) / 4096 * 4096;
-        size_t batch = static_cast<size_t>(streamBlockSize) * static_cast<size_t>(blocks) * static_cast<size_t>(deviceCount);
-        const size_t maxBatch = static_cast<size_t>(2) << 30;
-        if (batch > maxBatch)
-            batch = maxBatch;
+        // a batch: what the devices hold in flight, but not more than 384 MiB per device -- beyond that a longer batch gains little, while
+        // the pinned buffers cost set-up time and the first batch waits for its bytes to be read
+        size_t batch = static_cast<size_t>(streamBlockSize) * static_cast<size_t>(blocks);
+        if (batch > (static_cast<size_t>(384) << 20))
+            batch = static_cast<size_t>(384) << 20;
+        batch *= static_cast<size_t>(deviceCount);
         cap = head + batch;
+        target = batch < (static_cast<size_t>(128) << 20) * static_cast<size_t>(deviceCount) ? batch : (static_cast<size_t>(128) << 20) * static_cast<size_t>(deviceCount);
         for (int i = 0; i < 2; ++i)
         {
             stage[i] = static_cast<uint8_t *>(bz2b200_host_alloc(cap));
@@ -287,7 +294,7 @@ public:
         if (streamFinished)
             throw std::runtime_error("Write beyond end of stream");
         stage[cur][fill++] = static_cast<uint8_t>(value & 0xff);
-        if (fill == cap)
+        if (fill == limit())
             submit(false);
     }
 
@@ -298,12 +305,12 @@ public:
         const uint8_t *p = static_cast<const uint8_t *>(data);
         while (length)
         {
-            const size_t n = length < cap - fill ? length : cap - fill;
+            const size_t n = length < limit() - fill ? length : limit() - fill;
             std::memcpy(stage[cur] + fill, p, n);
             fill += n;
             p += n;
             length -= n;
-            if (fill == cap)
+            if (fill == limit())
                 submit(false);
         }
     }
@@ -313,22 +320,61 @@ public:
         write(data.data() + offset, static_cast<size_t>(length));
     }
 
-    // extension: everything the file descriptor still holds, read straight into the staging buffers (no intermediate copy)
+    // extension: everything the file descriptor still holds, read straight into the staging buffers (no intermediate copy).
+    // A regular file is read by four threads at once (pread on disjoint ranges: one thread copies out of the page cache at a
+    // few GB/s, less than a GPU compresses).
     size_t readFrom(int fd)
     {
         if (streamFinished)
             throw std::runtime_error("Write beyond end of stream");
         size_t total = 0;
+        struct stat sb;
+        const off_t at = ::lseek(fd, 0, SEEK_CUR);
+        if (::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && at >= 0)
+        {
+            size_t pos = static_cast<size_t>(at);
+            const size_t end = static_cast<size_t>(sb.st_size);
+            while (pos < end)
+            {
+                const size_t n = end - pos < limit() - fill ? end - pos : limit() - fill;
+                const int T = n >= (size_t(8) << 20) ? 4 : 1;
+                std::vector<std::thread> th;
+                bool ok = true;
+                uint8_t *dst = stage[cur] + fill;
+                for (int t = 0; t < T; ++t)
+                    th.emplace_back([=, &ok] {
+                        size_t a = n * static_cast<size_t>(t) / T;
+                        const size_t e = n * static_cast<size_t>(t + 1) / T;
+                        while (a < e)
+                        {
+                            const ssize_t r = ::pread(fd, dst + a, e - a, static_cast<off_t>(pos + a));
+                            if (r <= 0) { ok = false; return; }
+                            a += static_cast<size_t>(r);
+                        }
+                    });
+                for (std::thread &x : th)
+                    x.join();
+                if (!ok)
+                    throw std::runtime_error("read failed");
+                fill += n;
+                pos += n;
+                total += n;
+                if (fill == limit())
+                    submit(false);
+            }
+            ::lseek(fd, static_cast<off_t>(end), SEEK_SET);
+            return total;
+        }
         for (;;)
         {
-            const ssize_t n = ::read(fd, stage[cur] + fill, cap - fill);
+            const ssize_t n = ::read(fd, stage[cur] + fill, limit() - fill);
             if (n < 0)
                 throw std::runtime_error("read failed");
             if (n == 0)
                 return total;
             fill += static_cast<size_t>(n);
             total += static_cast<size_t>(n);
-            if (fill == cap)
+            if (fill == limit())
                 submit(false);
         }
     }
