@@ -593,6 +593,13 @@ struct RoundArgs {
     const uint32_t *h0;         // [G] bytes the round-0 key of each block orders its rotations by (differs per block with packed keys)
     uint32_t round;             // rotations of block b are now ordered by their first h0[b] << round bytes
     int split;                  // 0: keep every group in the bag (debug)
+    // Local regions that hold elements, as a list of region ids (block * tiles_per_block + tile): the kernels of a round are launched
+    // over the list instead of over every (tile, block) pair -- after the first rounds most regions are empty, and an empty CTA still
+    // costs its launch.  work_in: the regions of this round; work_out / work_out_cnt: whoever makes a region non-empty for the next
+    // round (its own local sort keeping elements, or the first regroup CTA that appends to an empty one) adds it.
+    const uint32_t *work_in;
+    uint32_t *work_out;
+    uint32_t *work_out_cnt;
 };
 __device__ __forceinline__ uint32_t sorted_len_of(const RoundArgs &A, uint32_t b) { return A.h0[b] << A.round; } // h0 <= 16, round <= 20
 
@@ -803,6 +810,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
     if (threadIdx.x == 0) {
         s_base = total_g ? atomicAdd(&bag_cnt[b], total_g) : 0u;
         s_lbase = total_m ? atomicAdd(&lc[tmain], total_m) : 0u;
+        if (total_m && s_lbase == 0) A.work_out[atomicAdd(A.work_out_cnt, 1u)] = b * (uint32_t)A.tiles_per_block + tmain;
     }
     const unsigned omask = lmask & ~mmask;
     if (omask) {
@@ -816,7 +824,11 @@ __global__ void __launch_bounds__(RG_THREADS) k_bwt_regroup(const uint64_t *__re
 #pragma unroll
         for (int i = 0; i < RG_ITEMS; ++i) {
             if (tl[i] != 0xffffffffu) {
-                if (i == 0 || tl[(i + RG_ITEMS - 1) % RG_ITEMS] != tl[i]) reg = A.loc + o + (uint64_t)tl[i] * RG_TILE + atomicAdd(&lc[tl[i]], len[i]);
+                if (i == 0 || tl[(i + RG_ITEMS - 1) % RG_ITEMS] != tl[i]) {
+                    const uint32_t at = atomicAdd(&lc[tl[i]], len[i]);
+                    if (at == 0) A.work_out[atomicAdd(A.work_out_cnt, 1u)] = b * (uint32_t)A.tiles_per_block + tl[i];
+                    reg = A.loc + o + (uint64_t)tl[i] * RG_TILE + at;
+                }
                 *reg++ = ((uint64_t)(v.P[i] & (RG_TILE - 1)) << GPOS_SHIFT) | (e[i] & VAL_MASK);
             }
         }
@@ -889,7 +901,8 @@ struct LocalSmem {
 __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs A)
 {
     __shared__ __align__(16) LocalSmem sm;
-    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t rid = A.work_in[blockIdx.x];
+    const uint32_t b = rid / (uint32_t)A.tiles_per_block, t = rid % (uint32_t)A.tiles_per_block;
     uint32_t *cnt_p = A.loc_cnt + (uint64_t)b * A.tiles_per_block + t;
     const uint32_t c = *cnt_p;
     if (c == 0) return;
@@ -1138,14 +1151,18 @@ __global__ void __launch_bounds__(LS_THREADS, BZ_LS_MINB) k_bwt_local(RoundArgs 
         if (kmask & (1u << i)) reg[off++] = ((uint64_t)v.P[i] << GPOS_SHIFT) | (e[i] & VAL_MASK);
     if (threadIdx.x == 0) {
         *cnt_p = total;
-        if (total) atomicAdd(A.totals, (unsigned long long)total);
+        if (total) {
+            atomicAdd(A.totals, (unsigned long long)total);
+            A.work_out[atomicAdd(A.work_out_cnt, 1u)] = rid;
+        }
     }
 }
 
 // local regions: element |= rank[(i + h) mod n] << 20
 __global__ void __launch_bounds__(256) k_bwt_gather_local(RoundArgs A)
 {
-    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t rid = A.work_in[blockIdx.x];
+    const uint32_t b = rid / (uint32_t)A.tiles_per_block, t = rid % (uint32_t)A.tiles_per_block;
     const uint32_t c = A.loc_cnt[(uint64_t)b * A.tiles_per_block + t];
     if (c == 0) return;
     const uint32_t n = A.n_arr[b], h = sorted_len_of(A, b);

@@ -105,7 +105,7 @@ struct bz2b200 {
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, tickets, digit_base, rc_partial, cnts, scalars,
-        h0, root, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
+        h0, root, work, lists, dcount, r2tiles, zin, obase, present, crc, orig, freq, m_arr, alpha_arr, hb, lens, tf, codes, sel, selpos, selbits, tabbits,
         databits, nbits_b, bitoff, datastart, tilebits, selbitoff, pertab;
     int ctasC = 0;
     int tilesR = 0, tilesG = 0, tilesM = 0, tilesR2 = 0, tilesD = 0;
@@ -391,6 +391,7 @@ static int alloc_batch(bz2b200 *h)
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
     ENSURE(h->h0, G * 4);
     ENSURE(h->root, G * 4);
+    ENSURE(h->work, 2 * G * (size_t)h->tilesG * 4); // two lists of region ids (this round's, the next round's)
     ENSURE(h->lists, G * h->tilesM * 256);
     ENSURE(h->dcount, G * h->tilesM * 4);
     ENSURE(h->r2tiles, G * h->tilesR2 * sizeof(R2Tile));
@@ -506,7 +507,7 @@ extern "C" size_t bz2b200_max_output_bytes(const bz2b200_t *h, size_t n)
 }
 
 struct Scalars { // layout of h->scalars (u64 each)
-    enum { BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 4 entries */, ROUND = 8 /* kept rotations, max bag, sum of bags */, TICKET = 12 };
+    enum { BITPOS = 1, BATCH_BITS = 2, WALK_INFO = 4 /* 4 entries */, ROUND = 8 /* kept rotations, max bag, sum of bags, regions with elements */, TICKET = 12 };
 };
 
 static void radix_pass(bz2b200 *h, const uint64_t *kin, uint64_t *kout, const uint32_t *counts, int shift, int bits, uint32_t nb, uint32_t max_count,
@@ -1020,6 +1021,9 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     A.tiles_per_block = h->tilesG;
     A.totals = reinterpret_cast<unsigned long long *>(d_scal + Scalars::ROUND);
     A.split = h->local_sort != 0;
+    uint32_t *work_list[2] = {ptr<uint32_t>(h->work), ptr<uint32_t>(h->work) + (size_t)h->G * h->tilesG};
+    A.work_out_cnt = reinterpret_cast<uint32_t *>(d_scal + Scalars::ROUND + 3);
+    int wcur = 0; // work_list[wcur]: the regions that hold elements for the coming round
 
     const int round_bits = 2 * VAL_BITS;
     const dim3 gtiles((max_n + RG_TILE - 1) / RG_TILE, nb);
@@ -1032,7 +1036,9 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         uint64_t *sorted = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
         uint64_t *bag = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
         A.round = round_no;
-        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
+        A.work_in = work_list[0];
+        A.work_out = work_list[0];
+        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 32, st));
         CK(cudaMemsetAsync(bag_cnt[0], 0, (size_t)nb * 4, st));
         KL(KID_k_bwt_regroup, k_bwt_regroup<true><<<gtiles, RG_THREADS, 0, st>>>(sorted, d_n, A, bag, bag_cnt[0]));
         KL(KID_k_bwt_roundstats, k_bwt_roundstats<<<(nb + 255) / 256, 256, 0, st>>>(bag_cnt[0], nb, A.totals));
@@ -1044,11 +1050,11 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
     // kept element out (8); known once the next round's counts are back
     uint64_t prev_regroup_in = sum_n, prev_local_in = 0, prev_active = sum_n;
     for (;;) {
-        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::ROUND, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_pinned, d_scal + Scalars::ROUND, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h->profiling) prof_collect(h);
         const uint64_t active = h->h_pinned[0], total_b = h->h_pinned[2];
-        const uint32_t max_b = (uint32_t)h->h_pinned[1];
+        const uint32_t max_b = (uint32_t)h->h_pinned[1], n_regions = (uint32_t)(h->h_pinned[3] & 0xffffffffull);
         if (h->profiling) {
             const uint64_t in = prev_regroup_in + prev_local_in, fin = prev_active > active ? prev_active - active : 0; // final this round
             const uint64_t kept_r = in ? (uint64_t)((double)active * prev_regroup_in / in) : 0;
@@ -1064,10 +1070,13 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         // next round: key = (group position, rank of the rotation sorted_len further on)
         uint64_t *bag = res ? ptr<uint64_t>(h->kB) : ptr<uint64_t>(h->kA);
         uint64_t *other = res ? ptr<uint64_t>(h->kA) : ptr<uint64_t>(h->kB);
-        const bool have_local = active > total_b;
-        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 24, st));
+        const bool have_local = n_regions > 0;
+        CK(cudaMemsetAsync(d_scal + Scalars::ROUND, 0, 32, st));
+        A.work_in = work_list[wcur];
+        A.work_out = work_list[wcur ^ 1];
+        wcur ^= 1;
         if (have_local) {
-            KL(KID_k_bwt_gather_local, k_bwt_gather_local<<<gtiles, 256, 0, st>>>(A));
+            KL(KID_k_bwt_gather_local, k_bwt_gather_local<<<n_regions, 256, 0, st>>>(A));
             stt.kernel_launches += 1;
             KBYTES(KID_k_bwt_gather_local, (active - total_b) * 20);
         }
@@ -1078,7 +1087,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         }
         A.round = round_no + 1;
         if (have_local) {
-            KL(KID_k_bwt_local, k_bwt_local<<<gtiles, LS_THREADS, 0, st>>>(A));
+            KL(KID_k_bwt_local, k_bwt_local<<<n_regions, LS_THREADS, 0, st>>>(A));
             stt.kernel_launches += 1;
         }
         CK(cudaMemsetAsync(bag_cnt[cs ^ 1], 0, (size_t)nb * 4, st));
@@ -1115,7 +1124,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         dim3 gq((max_n + MR_WARPS * MTF_TILE - 1) / (MR_WARPS * MTF_TILE), nb);
         KL(KID_k_mtf_recency, k_mtf_recency<<<gq, MR_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists),
                                                                           ptr<uint32_t>(h->dcount), h->tilesM));
-        KL(KID_k_mtf_compose, k_mtf_compose<<<(nb + MTF_WARPS - 1) / MTF_WARPS, MTF_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
+        KL(KID_k_mtf_compose, k_mtf_compose<<<nb, MC_WARPS * 32, 0, st>>>(d_n, ptr<uint64_t>(h->lists), ptr<uint32_t>(h->dcount), h->tilesM, nb));
         KL(KID_k_mtf_ranks, k_mtf_ranks<<<gm, MW_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->L), d_n, S, ptr<uint32_t>(h->present), ptr<uint64_t>(h->lists), h->tilesM,
                                                                    ptr<uint8_t>(h->ranks), ptr<R2Tile>(h->r2tiles)));
         dim3 gr((max_n + R2_TILE - 1) / R2_TILE, nb);
@@ -1139,12 +1148,12 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         for (int it = 0; it < 4; ++it) {
             KL(KID_k_huff_pass, k_huff_pass<<<gh, HP_THREADS, 0, st>>>(ptr<uint16_t>(h->mtf), S, ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->sel),
                                                     h->sel_stride));
-            KL(KID_k_huff_lengths, k_huff_lengths<<<dim3(HUFF_MAXTABLES, nb), 32, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->databits),
+            KL(KID_k_huff_lengths, k_huff_lengths<<<dim3(HUFF_MAXTABLES, nb), HL_THREADS, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->tf), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->databits),
                                                                      it == 3));
         }
         KL(KID_k_huff_codes, k_huff_codes<<<(nb * HUFF_MAXTABLES + 63) / 64, 64, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->lens), ptr<uint32_t>(h->codes), ptr<uint32_t>(h->tabbits),
                                                                       ptr<uint32_t>(h->pertab), nb));
-        KL(KID_k_huff_selmtf, k_huff_selmtf<<<(nb + 7) / 8, 256, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos),
+        KL(KID_k_huff_selmtf, k_huff_selmtf<<<nb, SM_THREADS, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint8_t>(h->sel), h->sel_stride, ptr<uint8_t>(h->selpos),
                                                                        ptr<uint32_t>(h->selbitoff), ptr<uint32_t>(h->selbits), nb));
         stt.kernel_launches += 11;
     }
@@ -1168,7 +1177,7 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
             ctl->bits_issued = seq + 1;
             ctl->cv.notify_all();
         }
-        KL(KID_k_emit_header, k_emit_header<<<(nb + 7) / 8, 256, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
+        KL(KID_k_emit_header, k_emit_header<<<nb, EH_THREADS, 0, st>>>(ptr<HuffBlock>(h->hb), ptr<uint32_t>(h->present), ptr<uint32_t>(h->crc), ptr<uint32_t>(h->orig),
                                                                        ptr<uint8_t>(h->selpos), ptr<uint32_t>(h->selbitoff), h->sel_stride, ptr<uint32_t>(h->selbits),
                                                                        ptr<uint32_t>(h->pertab), ptr<uint8_t>(h->lens), ptr<uint64_t>(h->bitoff), nb, d_out_words,
                                                                        ptr<uint64_t>(h->datastart)));

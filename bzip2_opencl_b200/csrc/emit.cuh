@@ -115,78 +115,99 @@ __device__ __forceinline__ void or_bits(uint32_t *out, uint64_t pos, uint32_t le
     }
 }
 
-// One warp per block: everything in front of the coded symbols.  Lane 0 writes the fixed fields, all lanes write the selector
-// unary codes at their precomputed offsets, lanes 0..T-1 write one delta-coded table each.
-__global__ void __launch_bounds__(256) k_emit_header(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ crc,
-                                                      const uint32_t *__restrict__ orig, const uint8_t *__restrict__ selpos,
-                                                      const uint32_t *__restrict__ selbitoff, uint64_t sel_stride, const uint32_t *__restrict__ sel_bits,
-                                                      const uint32_t *__restrict__ per_table_bits, const uint8_t *__restrict__ lens,
-                                                      const uint64_t *__restrict__ bitoff, uint32_t n_blocks, uint32_t *__restrict__ out,
-                                                      uint64_t *__restrict__ data_start)
+// One CTA per block: everything in front of the coded symbols.  Thread 0 writes the fixed fields, all threads write the selector
+// unary codes at their precomputed offsets, warp t writes table t: the bit offset of every symbol's delta code (1 + 2 |difference to
+// the previous length| bits, kernel.cpp:3015-3040) is a prefix sum, so the 258 symbols of a table are written in parallel.
+constexpr int EH_THREADS = 256;
+__global__ void __launch_bounds__(EH_THREADS) k_emit_header(const HuffBlock *__restrict__ hb, const uint32_t *__restrict__ present, const uint32_t *__restrict__ crc,
+                                                             const uint32_t *__restrict__ orig, const uint8_t *__restrict__ selpos,
+                                                             const uint32_t *__restrict__ selbitoff, uint64_t sel_stride, const uint32_t *__restrict__ sel_bits,
+                                                             const uint32_t *__restrict__ per_table_bits, const uint8_t *__restrict__ lens,
+                                                             const uint64_t *__restrict__ bitoff, uint32_t n_blocks, uint32_t *__restrict__ out,
+                                                             uint64_t *__restrict__ data_start)
 {
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const uint32_t b = blockIdx.x;
     if (b >= n_blocks) return;
-    const int lane = lane_id();
+    const int lane = lane_id(), w = warp_id();
     if (bitoff[b] == BIT_NOWHERE) { // does not fit the output buffer (k_bit_offsets)
-        if (lane == 0) data_start[b] = BIT_NOWHERE;
+        if (threadIdx.x == 0) data_start[b] = BIT_NOWHERE;
         return;
     }
     const HuffBlock h = hb[b];
     uint32_t ranges = 0;
-    for (int w = 0; w < 8; ++w) {
-        uint32_t p = present[b * 8 + w];
+    for (int k = 0; k < 8; ++k) {
+        uint32_t p = present[b * 8 + k];
         ranges += (p & 0xffffu) ? 1u : 0u;
         ranges += (p >> 16) ? 1u : 0u;
     }
     const uint64_t sel_start = bitoff[b] + 48 + 32 + 1 + 24 + 16 + 16ull * ranges + 3 + 15;
-    if (lane == 0) {
-        BitWriter w;
-        w.init(out, bitoff[b]);
-        w.put(24, 0x314159u); w.put(24, 0x265359u);       // OutputStream.hpp:208-209
-        w.put(32, crc[b]);                                  // :210 writeInteger
-        w.put(1, 0);                                        // :211 randomised = 0
-        w.put(24, orig[b]);                                 // kernel.cpp:3116
+    if (threadIdx.x == 0) {
+        BitWriter bw;
+        bw.init(out, bitoff[b]);
+        bw.put(24, 0x314159u); bw.put(24, 0x265359u);       // OutputStream.hpp:208-209
+        bw.put(32, crc[b]);                                   // :210 writeInteger
+        bw.put(1, 0);                                         // :211 randomised = 0
+        bw.put(24, orig[b]);                                  // kernel.cpp:3116
         // writeSymbolMap, kernel.cpp:2483-2511: value v is bit (v & 31) of present[v >> 5]
         uint32_t used16 = 0;
         for (int r = 0; r < 16; ++r) {
             uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
             if (bits16) used16 |= 1u << (15 - r);
         }
-        w.put(16, used16);
+        bw.put(16, used16);
         for (int r = 0; r < 16; ++r) {
             uint32_t bits16 = (present[b * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
-            if (bits16) w.put(16, __brev(bits16) >> 16); // value k of the range goes out k-th: MSB first
+            if (bits16) bw.put(16, __brev(bits16) >> 16); // value k of the range goes out k-th: MSB first
         }
-        w.put(3, h.ntab);                                   // kernel.cpp:3001
-        w.put(15, h.nsel);                                  // :3002
-        w.finish();
+        bw.put(3, h.ntab);                                    // kernel.cpp:3001
+        bw.put(15, h.nsel);                                   // :3002
+        bw.finish();
     }
     const uint8_t *sp = selpos + (uint64_t)b * sel_stride;
     const uint32_t *so = selbitoff + (uint64_t)b * sel_stride;
-    for (uint32_t g = lane; g < h.nsel; g += 32) {          // writeUnary, :3010: p ones then a zero
+    for (uint32_t g = threadIdx.x; g < h.nsel; g += EH_THREADS) { // writeUnary, :3010: p ones then a zero
         const uint32_t p = sp[g];
         or_bits(out, sel_start + so[g], p + 1, ((1u << p) - 1u) << 1);
     }
     uint64_t tstart = sel_start + sel_bits[b];
-    for (uint32_t t = 0; t < h.ntab; ++t) {                 // :3015-3040
-        const uint32_t tb = per_table_bits[b * HUFF_MAXTABLES + t];
-        if ((uint32_t)lane == t) {
+    for (uint32_t t = 0; t < h.ntab; ++t) {                   // :3015-3040
+        if ((uint32_t)w == t) {
             const uint8_t *L = lens + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_LEN_STRIDE;
-            BitWriter w;
-            w.init(out, tstart);
-            int cur = L[0];
-            w.put(5, (uint32_t)cur);
-            for (uint32_t j = 0; j < h.alpha; ++j) {
-                int l = L[j];
-                while (cur < l) { w.put(2, 2); ++cur; }
-                while (cur > l) { w.put(2, 3); --cur; }
-                w.put(1, 0);
+            if (lane == 0) or_bits(out, tstart, 5, (uint32_t)L[0]);
+            // lane l owns symbols 9 l .. 9 l + 8 (258 <= 32 * 9)
+            const uint32_t j0 = 9u * (uint32_t)lane;
+            int prev = j0 == 0 ? (int)L[0] : (j0 - 1 < h.alpha ? (int)L[j0 - 1] : 0);
+            int len9[9];
+            uint32_t mybits = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const uint32_t j = j0 + (uint32_t)k;
+                len9[k] = j < h.alpha ? (int)L[j] : -1;
+                if (len9[k] >= 0) { const int d = len9[k] - prev; mybits += 2u * (uint32_t)(d < 0 ? -d : d) + 1u; prev = len9[k]; }
             }
-            w.finish();
+            uint64_t pos = tstart + 5 + warp_incl_sum(mybits) - mybits;
+            prev = j0 == 0 ? (int)L[0] : (j0 - 1 < h.alpha ? (int)L[j0 - 1] : 0);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (len9[k] < 0) continue;
+                const int d = len9[k] - prev;
+                int steps = d < 0 ? -d : d;              // `steps` two-bit codes (10 = up, 11 = down), then a zero
+                const uint32_t two = d < 0 ? 3u : 2u;
+                while (steps > 0) {
+                    const int take = steps < 15 ? steps : 15;
+                    uint32_t v = 0;
+                    for (int q = 0; q < take; ++q) v = (v << 2) | two;
+                    or_bits(out, pos, 2u * (uint32_t)take, v);
+                    pos += 2u * (uint32_t)take;
+                    steps -= take;
+                }
+                pos += 1; // the terminating zero bit (the buffer is zero-initialised)
+                prev = len9[k];
+            }
         }
-        tstart += tb;
+        tstart += per_table_bits[b * HUFF_MAXTABLES + t];
     }
-    if (lane == 0) data_start[b] = tstart;
+    if (threadIdx.x == 0) data_start[b] = tstart;
 }
 
 // bits of the coded symbols per tile of HP_SYMS symbols

@@ -167,24 +167,28 @@ __device__ __forceinline__ void mk_allocate(int *a, int len, int maxLen)
     }
 }
 
-// one warp per (block, table)
-__global__ void __launch_bounds__(32) k_huff_lengths(const HuffBlock *__restrict__ hb, uint32_t *__restrict__ tf, uint8_t *__restrict__ lens,
-                                                      uint32_t *__restrict__ data_bits, int last_pass)
+// one CTA of four warps per (block, table): the sort is shared by 128 threads, the allocator itself is serial (thread 0)
+constexpr int HL_THREADS = 128;
+__global__ void __launch_bounds__(HL_THREADS) k_huff_lengths(const HuffBlock *__restrict__ hb, uint32_t *__restrict__ tf, uint8_t *__restrict__ lens,
+                                                              uint32_t *__restrict__ data_bits, int last_pass)
 {
     __shared__ uint32_t key[512];
     __shared__ int arr[HUFF_MAXALPHA + 2];
     const uint32_t b = blockIdx.y, t = blockIdx.x;
     const HuffBlock h = hb[b];
     if (t >= h.ntab) return;
-    const int lane = lane_id();
+    const int tid = threadIdx.x;
     const int alpha = (int)h.alpha;
+    // (sorting the next power of two >= alpha keys is enough: the padding keys are larger than every real one)
+    int npad = 2;
+    while (npad < alpha) npad <<= 1;
     uint32_t *f = tf + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_MAXALPHA;
-    for (int i = lane; i < 512; i += 32) key[i] = i < alpha ? ((f[i] << 9) | (uint32_t)i) : 0xffffffffu;
-    __syncwarp();
-    // bitonic sort of 512 keys, ascending (keys are distinct: same order as sortArr, kernel.cpp:2820-2833)
-    for (int k = 2; k <= 512; k <<= 1) {
+    for (int i = tid; i < npad; i += HL_THREADS) key[i] = i < alpha ? ((f[i] << 9) | (uint32_t)i) : 0xffffffffu;
+    __syncthreads();
+    // bitonic sort, ascending (keys are distinct: same order as sortArr, kernel.cpp:2820-2833)
+    for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < 512; i += 32) {
+            for (int i = tid; i < npad; i += HL_THREADS) {
                 int p = i ^ j;
                 if (p > i) {
                     uint32_t x = key[i], y = key[p];
@@ -192,25 +196,25 @@ __global__ void __launch_bounds__(32) k_huff_lengths(const HuffBlock *__restrict
                     if ((x > y) == up) { key[i] = y; key[p] = x; }
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }
     }
-    for (int i = lane; i < alpha; i += 32) arr[i] = (int)(key[i] >> 9);
-    __syncwarp();
-    if (lane == 0) mk_allocate(arr, alpha, HUFF_MAXLEN);
-    __syncwarp();
+    for (int i = tid; i < alpha; i += HL_THREADS) arr[i] = (int)(key[i] >> 9);
+    __syncthreads();
+    if (tid == 0) mk_allocate(arr, alpha, HUFF_MAXLEN);
+    __syncthreads();
     uint8_t *L = lens + ((uint64_t)b * HUFF_MAXTABLES + t) * HUFF_LEN_STRIDE;
     uint32_t bits = 0;
-    for (int i = lane; i < alpha; i += 32) {
+    for (int i = tid; i < alpha; i += HL_THREADS) {
         uint32_t s = key[i] & 0x1ffu;
         L[s] = (uint8_t)arr[i];
         bits += (key[i] >> 9) * (uint32_t)arr[i];
     }
     if (last_pass) {
         bits = __reduce_add_sync(FULL, bits);
-        if (lane == 0 && bits) atomicAdd(&data_bits[b], bits);
+        if (lane_id() == 0 && bits) atomicAdd(&data_bits[b], bits);
     } else {
-        for (int i = lane; i < HUFF_MAXALPHA; i += 32) f[i] = 0; // fresh frequencies for the next pass (patch P1)
+        for (int i = tid; i < HUFF_MAXALPHA; i += HL_THREADS) f[i] = 0; // fresh frequencies for the next pass (patch P1)
     }
 }
 
@@ -250,52 +254,82 @@ __global__ void __launch_bounds__(64) k_huff_codes(const HuffBlock *__restrict__
     per_table_bits[b * HUFF_MAXTABLES + t] = tb;
 }
 
-// One warp per block: MTF positions of the selectors (kernel.cpp:3004-3012), the bit offset of every selector's unary code and
-// their total length.  Position of selector g = number of OTHER tables used more recently than sel[g]; "last use" per table is
-// a prefix maximum, so 32 selectors are resolved per step with six warp max-scans instead of a serial 6-entry list.
-__global__ void __launch_bounds__(256) k_huff_selmtf(const HuffBlock *__restrict__ hb, const uint8_t *__restrict__ sel, uint64_t sel_stride,
-                                                      uint8_t *__restrict__ selpos, uint32_t *__restrict__ selbitoff, uint32_t *__restrict__ sel_bits,
-                                                      uint32_t n_blocks)
+// One CTA per block: MTF positions of the selectors (kernel.cpp:3004-3012), the bit offset of every selector's unary code and
+// their total length.  Position of selector g = number of OTHER tables used more recently than sel[g]; "last use of table t
+// before g" is a prefix maximum, so every thread takes a contiguous chunk of selectors: (1) last use of every table inside the
+// chunk, (2) exclusive prefix maximum over the chunks, (3) the chunk again with the true history -> positions and code lengths,
+// (4) exclusive sum of the chunks' bit totals -> offsets.  The serial chain is one chunk (<= 71 selectors), not the block.
+constexpr int SM_THREADS = 256;
+constexpr int SM_MAXSEL = 18048; // >= HUFFMAN_MAXIMUM_SELECTORS (Config.hpp:41), a multiple of 64
+__global__ void __launch_bounds__(SM_THREADS) k_huff_selmtf(const HuffBlock *__restrict__ hb, const uint8_t *__restrict__ sel, uint64_t sel_stride,
+                                                             uint8_t *__restrict__ selpos, uint32_t *__restrict__ selbitoff, uint32_t *__restrict__ sel_bits,
+                                                             uint32_t n_blocks)
 {
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    __shared__ uint8_t s_sel[SM_MAXSEL];
+    __shared__ int s_last[SM_THREADS / 32][HUFF_MAXTABLES];
+    __shared__ uint32_t s_u[34];
+    const uint32_t b = blockIdx.x;
     if (b >= n_blocks) return;
-    const int lane = lane_id();
-    const uint32_t ns = hb[b].nsel;
+    const uint32_t ns = min(hb[b].nsel, (uint32_t)SM_MAXSEL);
     const uint8_t *s = sel + (uint64_t)b * sel_stride;
     uint8_t *o = selpos + (uint64_t)b * sel_stride;
     uint32_t *bo = selbitoff + (uint64_t)b * sel_stride;
-    int last[HUFF_MAXTABLES]; // last use of table t before the current chunk; the initial list 0,1,..,5 == virtual uses at -1-t
+    for (uint32_t i = threadIdx.x * 16; i < ns; i += SM_THREADS * 16) // (slots are 64-byte multiples: whole 16-byte loads)
+        *reinterpret_cast<uint4 *>(s_sel + i) = __ldg(reinterpret_cast<const uint4 *>(s + i));
+    __syncthreads();
+    const uint32_t ch = (ns + SM_THREADS - 1) / SM_THREADS;
+    const uint32_t g0 = min(ns, threadIdx.x * ch), g1 = min(ns, g0 + ch);
+    // (1) last use inside the chunk
+    int last[HUFF_MAXTABLES];
 #pragma unroll
-    for (int t = 0; t < HUFF_MAXTABLES; ++t) last[t] = -1 - t;
-    uint32_t bits_before = 0;
-    for (uint32_t g0 = 0; g0 < ns; g0 += 32) {
-        const uint32_t g = g0 + lane;
-        const bool valid = g < ns;
-        const int v = valid ? (int)s[g] : -1;
-        int lt[HUFF_MAXTABLES]; // last use of table t strictly before g
+    for (int t = 0; t < HUFF_MAXTABLES; ++t) last[t] = -1000;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const int v = s_sel[g];
+#pragma unroll
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) last[t] = v == t ? (int)g : last[t];
+    }
+    // (2) exclusive prefix maximum over threads; the initial list 0,1,..,5 == virtual uses at -1-t
+    int before[HUFF_MAXTABLES];
+    const int lane = lane_id(), w = warp_id();
+#pragma unroll
+    for (int t = 0; t < HUFF_MAXTABLES; ++t) {
+        const int inc = warp_incl_max(last[t]);
+        int ex = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) ex = -1000;
+        before[t] = ex;
+        if (lane == 31) s_last[w][t] = inc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < HUFF_MAXTABLES; ++t) {
+        int carry = -1 - t;
+        for (int ww = 0; ww < w; ++ww) carry = max(carry, s_last[ww][t]);
+        before[t] = max(before[t], carry);
+    }
+    // (3) positions; the code of position p has p + 1 bits
+    uint32_t bits = 0;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const int v = s_sel[g];
         int mine = 0;
 #pragma unroll
-        for (int t = 0; t < HUFF_MAXTABLES; ++t) {
-            int x = (v == t) ? (int)g : -1000;
-            int inc = warp_incl_max(x);
-            int ex = __shfl_up_sync(FULL, inc, 1);
-            if (lane == 0) ex = -1000;
-            lt[t] = max(last[t], ex);
-            last[t] = max(last[t], __shfl_sync(FULL, inc, 31));
-            if (v == t) mine = lt[t];
-        }
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) mine = v == t ? before[t] : mine;
         uint32_t pos = 0;
 #pragma unroll
-        for (int t = 0; t < HUFF_MAXTABLES; ++t) pos += (t != v && lt[t] > mine) ? 1u : 0u;
-        const uint32_t nb_ = valid ? pos + 1 : 0u;
-        const uint32_t inc = warp_incl_sum(nb_);
-        if (valid) {
-            o[g] = (uint8_t)pos;
-            bo[g] = bits_before + inc - nb_;
-        }
-        bits_before += __shfl_sync(FULL, inc, 31);
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) pos += (t != v && before[t] > mine) ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < HUFF_MAXTABLES; ++t) before[t] = v == t ? (int)g : before[t];
+        o[g] = (uint8_t)pos;
+        s_sel[g] = (uint8_t)pos; // (only this thread reads its chunk)
+        bits += pos + 1;
     }
-    if (lane == 0) sel_bits[b] = bits_before;
+    // (4) offsets
+    uint32_t total;
+    uint32_t off = block_excl_sum(bits, s_u, &total);
+    for (uint32_t g = g0; g < g1; ++g) {
+        bo[g] = off;
+        off += (uint32_t)s_sel[g] + 1u;
+    }
+    if (threadIdx.x == 0) sel_bits[b] = total;
 }
 
 } // namespace bz

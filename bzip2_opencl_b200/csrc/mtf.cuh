@@ -244,42 +244,103 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_mtf_ranks(const uint8_t *__re
     }
 }
 
-// One warp per block: lists[t] (final list from identity, first dcount[t] entries = recency order) -> lists[t] = list at tile start.
-__global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_compose(const uint32_t *__restrict__ n_arr, uint64_t *__restrict__ lists,
-                                                                 const uint32_t *__restrict__ dcount, int tiles_per_block, uint32_t n_blocks)
+// One CTA per block: lists[t] (first dcount[t] entries = the tile's distinct symbols by recency) -> lists[t] = list at tile start.
+// "Move the tile's symbols to the front in recency order" composes associatively -- a range of tiles acts like one tile whose
+// recency order is its tiles' orders merged, newest first -- so the chain over the block's tiles is cut into MC_WARPS chunks:
+// every warp (1) merges its chunk's orders into one partial list, (2) warp 0 pushes the identity list through the chunk
+// summaries, (3) every warp walks its chunk again from its true start list and publishes the list in front of every tile.
+// The serial chain is 2 * tiles / MC_WARPS + MC_WARPS steps instead of `tiles`.
+constexpr int MC_WARPS = 8;
+
+// cur[0 .. len) <- F[0 .. d) followed by the entries of cur that are not in F, order kept; returns the new length.  One warp;
+// mark[] is all zero on entry and on exit.
+__device__ __forceinline__ uint32_t mtf_compose_step(uint8_t *&cur, uint8_t *&nw, uint8_t *mark, const uint8_t *F, uint32_t d, uint32_t len)
 {
-    __shared__ uint8_t s_cur[MTF_WARPS][256], s_new[MTF_WARPS][256], s_mark[MTF_WARPS][256], s_f[MTF_WARPS][256];
-    const uint32_t b = blockIdx.x * MTF_WARPS + warp_id();
+    const int lane = lane_id();
+    for (uint32_t i = lane; i < d; i += 32) { const uint8_t s = F[i]; mark[s] = 1; nw[i] = s; }
+    __syncwarp();
+    // survivors of the old list keep their order behind the d recent symbols
+    uint32_t keep = 0;
+    uint8_t mine[8];
+    const uint64_t c8 = *reinterpret_cast<const uint64_t *>(cur + lane * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mine[k] = (uint8_t)(c8 >> (8 * k)); keep += ((uint32_t)(lane * 8 + k) < len && !mark[mine[k]]) ? 1u : 0u; }
+    const uint32_t inc = warp_incl_sum(keep);
+    uint32_t off = d + inc - keep;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if ((uint32_t)(lane * 8 + k) < len && !mark[mine[k]]) nw[off++] = mine[k];
+    const uint32_t newlen = d + __shfl_sync(FULL, inc, 31);
+    __syncwarp();
+    for (uint32_t i = lane; i < d; i += 32) mark[F[i]] = 0;
+    uint8_t *tmp = cur; cur = nw; nw = tmp;
+    __syncwarp();
+    return newlen;
+}
+
+__global__ void __launch_bounds__(MC_WARPS * 32) k_mtf_compose(const uint32_t *__restrict__ n_arr, uint64_t *__restrict__ lists,
+                                                                const uint32_t *__restrict__ dcount, int tiles_per_block, uint32_t n_blocks)
+{
+    __shared__ __align__(8) uint8_t s_a[MC_WARPS][256], s_b[MC_WARPS][256], s_mark[MC_WARPS][256], s_f[MC_WARPS][256];
+    __shared__ __align__(8) uint8_t s_sum[MC_WARPS][256];  // chunk summaries, then the list in front of every chunk
+    __shared__ uint32_t s_len[MC_WARPS];
+    const uint32_t b = blockIdx.x;
     if (b >= n_blocks) return;
     const int lane = lane_id(), w = warp_id();
     const uint32_t n = n_arr[b];
     const uint32_t nt = (n + MTF_TILE - 1) / MTF_TILE;
-    uint8_t *cur = s_cur[w], *nw = s_new[w], *mark = s_mark[w], *F = s_f[w];
-    for (int i = lane; i < 256; i += 32) { cur[i] = (uint8_t)i; mark[i] = 0; }
+    const uint32_t per = (nt + MC_WARPS - 1) / MC_WARPS;
+    const uint32_t t0 = min(nt, (uint32_t)w * per), t1 = min(nt, t0 + per);
+    uint8_t *cur = s_a[w], *nw = s_b[w], *mark = s_mark[w], *F = s_f[w];
+    for (int i = lane; i < 256; i += 32) mark[i] = 0;
     __syncwarp();
-    for (uint32_t t = 0; t < nt; ++t) {
-        const uint64_t lidx = ((uint64_t)b * tiles_per_block + t) * 32 + lane;
-        uint64_t f = lists[lidx];
-        const uint32_t d = dcount[(uint64_t)b * tiles_per_block + t];
-        // publish the start list of tile t
-        uint64_t c8 = *reinterpret_cast<const uint64_t *>(cur + lane * 8);
-        lists[lidx] = c8;
-        *reinterpret_cast<uint64_t *>(F + lane * 8) = f;
+    const uint64_t base = (uint64_t)b * tiles_per_block;
+    // (1) the chunk's summary: its tiles' recency orders merged, starting from an empty list
+    {
+        uint32_t len = 0;
+        uint64_t f_next = t0 < t1 ? lists[(base + t0) * 32 + lane] : 0ull;
+        uint32_t d_next = t0 < t1 ? dcount[base + t0] : 0u;
+        for (uint32_t t = t0; t < t1; ++t) {
+            const uint64_t f = f_next;
+            const uint32_t d = d_next;
+            if (t + 1 < t1) { f_next = lists[(base + t + 1) * 32 + lane]; d_next = dcount[base + t + 1]; }
+            *reinterpret_cast<uint64_t *>(F + lane * 8) = f;
+            __syncwarp();
+            len = mtf_compose_step(cur, nw, mark, F, d, len);
+        }
+        *reinterpret_cast<uint64_t *>(s_sum[w] + lane * 8) = *reinterpret_cast<const uint64_t *>(cur + lane * 8);
+        if (lane == 0) s_len[w] = len;
+    }
+    __syncthreads();
+    // (2) warp 0: the identity list pushed through the chunk summaries; s_sum[c] becomes the list in front of chunk c
+    if (w == 0) {
+        for (int i = lane; i < 256; i += 32) cur[i] = (uint8_t)i;
         __syncwarp();
-        for (uint32_t i = lane; i < d; i += 32) { uint8_t s = F[i]; mark[s] = 1; nw[i] = s; }
+        for (int c = 0; c < MC_WARPS; ++c) {
+            const uint64_t sum8 = *reinterpret_cast<const uint64_t *>(s_sum[c] + lane * 8);
+            const uint32_t d = s_len[c];
+            *reinterpret_cast<uint64_t *>(s_sum[c] + lane * 8) = *reinterpret_cast<const uint64_t *>(cur + lane * 8);
+            *reinterpret_cast<uint64_t *>(F + lane * 8) = sum8;
+            __syncwarp();
+            (void)mtf_compose_step(cur, nw, mark, F, d, 256u);
+        }
+    }
+    __syncthreads();
+    // (3) the chunk again from its true start list: publish the list in front of every tile
+    {
+        *reinterpret_cast<uint64_t *>(cur + lane * 8) = *reinterpret_cast<const uint64_t *>(s_sum[w] + lane * 8);
         __syncwarp();
-        // survivors of the old list keep their order behind the d recent symbols
-        uint32_t keep = 0;
-        uint8_t mine[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { mine[k] = (uint8_t)(c8 >> (8 * k)); keep += mark[mine[k]] ? 0u : 1u; }
-        uint32_t off = d + warp_incl_sum(keep) - keep;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (!mark[mine[k]]) nw[off++] = mine[k];
-        __syncwarp();
-        for (uint32_t i = lane; i < d; i += 32) mark[F[i]] = 0;
-        uint8_t *tmp = cur; cur = nw; nw = tmp;
-        __syncwarp();
+        uint64_t f_next = t0 < t1 ? lists[(base + t0) * 32 + lane] : 0ull;
+        uint32_t d_next = t0 < t1 ? dcount[base + t0] : 0u;
+        for (uint32_t t = t0; t < t1; ++t) {
+            const uint64_t lidx = (base + t) * 32 + lane;
+            const uint64_t f = f_next;
+            const uint32_t d = d_next;
+            if (t + 1 < t1) { f_next = lists[lidx + 32]; d_next = dcount[base + t + 1]; }
+            lists[lidx] = *reinterpret_cast<const uint64_t *>(cur + lane * 8); // the start list of tile t
+            *reinterpret_cast<uint64_t *>(F + lane * 8) = f;
+            __syncwarp();
+            (void)mtf_compose_step(cur, nw, mark, F, d, 256u);
+        }
     }
 }
 

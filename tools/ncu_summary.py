@@ -3,7 +3,7 @@
 import csv, subprocess, sys, io
 
 COLS = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rdMB"), ("dram__bytes_write.sum", "wrMB"),
-        ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"), ("sm__inst_executed.avg.per_cycle_elapsed", "ipc"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("launch__registers_per_thread", "regs"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "bankconf"),
