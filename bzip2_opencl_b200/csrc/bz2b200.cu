@@ -101,7 +101,7 @@ struct bz2b200 {
     std::vector<DevBuf *> all;
 
     // per-call (grow only)
-    DevBuf in, seg[RLE_MAX_LEVELS], segP[RLE_MAX_LEVELS], pstate, starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
+    DevBuf in, seg[RLE_MAX_LEVELS], segP[RLE_MAX_LEVELS], pstate, ltab, starts, rle_len, info, out, all_crc, all_nbits, segB, tstate;
     DevBuf dec_cand, dec_info, dec_list0, dec_len, dec_off, dec_starts, dec_crc; // decompress side (dec.cuh), allocated on first use
     // per-batch, fixed size
     DevBuf rle, L, ranks, kA, kB, loc, loc_cnt, rank, mtf, hist, tickets, digit_base, rc_partial, cnts, scalars,
@@ -625,6 +625,7 @@ static int walk_setup(bz2b200 *h, const uint8_t *d_in, uint64_t n, int is_final)
     if (n == 0) { h->seg_end.clear(); return BZ2B200_OK; }
     uint64_t c = (n + RLE_TILE - 1) / RLE_TILE;
     ENSURE(h->pstate, (c + 1) * sizeof(PState));
+    if (h->prefix_walk) ENSURE(h->ltab, (c + 1) * 32 * 8); // lane prefix table: 256 B per 2 KiB tile
     for (int l = 0; l < RLE_MAX_LEVELS; ++l) {
         ENSURE(h->seg[l], c * sizeof(Seg));
         if (l > 0) ENSURE(h->segP[l], c * sizeof(Seg));
@@ -669,7 +670,7 @@ static int walk_extend(bz2b200 *h)
     while (cnt[nl - 1] > 1 && nl < RLE_MAX_LEVELS) { cnt[nl] = (cnt[nl - 1] + RLE_FANOUT - 1) / RLE_FANOUT; ++nl; }
     const uint64_t t0 = h->tiles_done, nt = cnt[0] - t0;
     CK(cudaEventRecord(h->ev_t0, h->side));
-    k_rle_tile_seg<<<(unsigned)((nt + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(h->w_in, n, ptr<Seg>(h->seg[0]), t0, cnt[0]);
+    k_rle_tile_seg<<<(unsigned)((nt + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(h->w_in, n, ptr<Seg>(h->seg[0]), t0, cnt[0], h->prefix_walk ? ptr<uint64_t>(h->ltab) : nullptr);
     for (int l = 1; l < nl; ++l)
         k_rle_reduce<<<(unsigned)((cnt[l] + RLE_WARPS - 1) / RLE_WARPS), RLE_WARPS * 32, 0, h->side>>>(ptr<Seg>(h->seg[l - 1]), cnt[l - 1], ptr<Seg>(h->seg[l]), cnt[l]);
     if (h->prefix_walk) {
@@ -704,7 +705,7 @@ static int walk_launch(bz2b200 *h, uint64_t max_new)
     CK(cudaEventRecord(h->ev_w0, h->side));
     if (h->prefix_walk)
         k_rle_walk_prefix<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<PState>(h->pstate), ptr<uint64_t>(h->starts),
-                                                  ptr<uint32_t>(h->rle_len), h->w_cap, d_info, max_new);
+                                                  ptr<uint32_t>(h->rle_len), h->w_cap, d_info, max_new, ptr<uint64_t>(h->ltab));
     else
         k_rle_walk<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), h->w_cap,
                                            d_info, max_new);
@@ -1551,7 +1552,7 @@ static int multi_plan(bz2b200 *P, size_t n_bytes, std::vector<MultiPart> &parts)
     const uint64_t min_slice = 16ull * (uint64_t)c0->bs; // a device is not woken for less
     k = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(k, n_bytes / std::max<uint64_t>(1, min_slice)));
     // device d starts about d walks later than device 0: sizes fall by the ratio walk time / compress time per byte
-    double r = 0.96;
+    double r = 0.975;
     if (const char *e = getenv("BZ2B200_MULTI_RATIO")) { const double v = atof(e); if (v > 0.1 && v <= 1.0) r = v; }
     std::vector<double> w(k);
     double tot = 0;

@@ -167,8 +167,22 @@ __device__ __forceinline__ Seg lane_seg(const uint8_t *sm, uint32_t cnt)
 }
 
 // ---------------------------------------------------------------- level 0 summaries of the raw input
+// ltab (may be null): the summary of the lanes IN FRONT of every lane of the tile, packed into 64 bits (pack_lane_prefix) -- the walk
+// reads the machine's state at any 64-byte boundary of a tile from it instead of staging and scanning the tile again.
+__device__ __forceinline__ uint64_t pack_lane_prefix(const Seg &s)
+{
+    return (uint64_t)s.lead | ((uint64_t)s.trail << 12) | ((uint64_t)s.mid << 24) | ((uint64_t)(s.first & 0xffu) << 36) | ((uint64_t)(s.last & 0xffu) << 44);
+}
+__device__ __forceinline__ TSeg unpack_lane_prefix(uint64_t v, uint32_t len)
+{
+    TSeg t;
+    t.len = len;
+    t.lead = (uint32_t)v & 0xfffu; t.trail = (uint32_t)(v >> 12) & 0xfffu; t.mid = (uint32_t)(v >> 24) & 0xfffu;
+    t.first = (uint32_t)(v >> 36) & 0xffu; t.last = (uint32_t)(v >> 44) & 0xffu;
+    return t;
+}
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_tile_seg(const uint8_t *__restrict__ in, uint64_t n_bytes, Seg *__restrict__ seg0, uint64_t tile0,
-                                                                   uint64_t n_tiles)
+                                                                   uint64_t n_tiles, uint64_t *__restrict__ ltab)
 {
     __shared__ __align__(16) uint8_t sm_all[RLE_WARPS][32 * RLE_SM_STRIDE];
     uint64_t tile = tile0 + (uint64_t)blockIdx.x * RLE_WARPS + warp_id();
@@ -179,6 +193,25 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_rle_tile_seg(const uint8_t *
     warp_load_tile(in, lo, n, sm);
     Seg s = warp_seg_incl_scan(lane_seg(sm, lane_count(n)));
     if (lane_id() == 31) seg0[tile] = s;
+    if (ltab) {
+        Seg ex = shfl_up_seg(s, 1);
+        if (lane_id() == 0) ex = seg_empty();
+        uint64_t v = pack_lane_prefix(ex); // (lanes behind a partial lane are empty and never looked at)
+        // bit 63 of lane 0's entry: a full tile in which no run of four or more equal bytes forms (runs across lanes included; the
+        // run carried in from the tile in front is the walk's to check) -- the walk then needs no scan at all (short_run_search)
+        bool bad = n != RLE_TILE;
+        if (!bad) {
+            const uint8_t *p = sm + lane_id() * RLE_SM_STRIDE;
+            const uint64_t eq = lane_eq_mask(p);
+            const uint32_t prev_last = __shfl_up_sync(FULL, (uint32_t)p[RLE_LANE_BYTES - 1], 1);
+            const uint32_t prev_top = __shfl_up_sync(FULL, (uint32_t)(eq >> 62), 1);
+            const bool b0 = lane_id() > 0 && prev_last == (uint32_t)p[0];
+            bad = !lane_short_runs(eq) || (b0 && prev_top == 3u) || (b0 && (prev_top & 2u) && (eq & 2ull)) || (b0 && (eq & 6ull) == 6ull);
+        }
+        const bool short_tile = !__any_sync(FULL, bad);
+        if (lane_id() == 0 && short_tile) v |= 1ull << 63;
+        ltab[tile * 32 + lane_id()] = v;
+    }
 }
 
 // ---------------------------------------------------------------- tree level k -> k+1
@@ -231,10 +264,79 @@ __device__ __forceinline__ TSeg warp_tseg_incl_scan(TSeg s)
 struct DevTileScan {
     const uint8_t *in;
     uint8_t *sm;
+    const uint64_t *ltab; // lane prefix table of k_rle_tile_seg (null: every tile is staged and scanned here)
+
+    // the 64 bytes (cnt_c of them valid) of one lane, two per thread: the refusal inside them, if any.  v0, v1 = bytes 2 lane, 2 lane + 1.
+    __device__ __forceinline__ bool inside_lane(uint32_t v0, uint32_t v1, uint32_t cnt_c, const RleState &sc, uint64_t limit, uint32_t &fi, RleState &fs,
+                                                RleState *behind) const
+    {
+        const int lane = lane_id();
+        const uint32_t i0 = 2u * (uint32_t)lane;
+        TSeg piece;
+        piece.len = i0 + 1 < cnt_c ? 2u : (i0 < cnt_c ? 1u : 0u);
+        piece.first = v0;
+        piece.last = piece.len == 2u ? v1 : v0;
+        piece.lead = piece.trail = (piece.len == 2u && v0 != v1) ? 1u : piece.len;
+        piece.mid = 0;
+        const TSeg pin = warp_tseg_incl_scan(piece);
+        TSeg pex = shfl_up_tseg(pin, 1);
+        if (lane == 0) pex = tseg_of(seg_empty());
+        const RleState e0 = tstate_apply(pex, sc); // in front of byte i0
+        RleState e1 = e0;                          // in front of byte i0 + 1
+        if (i0 < cnt_c) state_step(e1, v0);
+        if (behind) *behind = shfl_state(tstate_apply(pin, sc), 31); // behind the lane's last byte
+        const bool h0 = i0 >= 1 && i0 < cnt_c && e0.bl > limit, h1 = i0 + 1 < cnt_c && e1.bl > limit;
+        const unsigned hb = __ballot_sync(FULL, h0 || h1);
+        if (!hb) return false;
+        const int w = __ffs((int)hb) - 1;
+        const uint32_t my_i = h0 ? i0 : i0 + 1;
+        fi = __shfl_sync(FULL, my_i, w);
+        fs = shfl_state(h0 ? e0 : e1, w);
+        return true;
+    }
+
     __device__ TileScanResult operator()(uint64_t lo, uint64_t hi, RleState st, uint64_t limit) const
     {
         const int lane = lane_id();
         const uint32_t n = (uint32_t)(hi - lo);
+        if (ltab && n == RLE_TILE && (lo % RLE_TILE) == 0) {
+            // a whole tile: the state in front of every lane from the table, then the one lane that can hold the refusal, two bytes per thread
+            TileScanResult r;
+            const uint64_t raw = __ldg(ltab + (lo / RLE_TILE) * 32 + lane);
+            // (loaded next to the table: the 32 bytes around the place where a tile without long runs would refuse -- the state in front
+            // of byte i is then st.bl + st.run + i - pending run, short_run_search in rle_seg.h)
+            const int64_t K = (int64_t)limit - (int64_t)(st.bl + st.run);
+            const uint32_t wbase = K < 4 ? 0u : (K - 4 > (int64_t)(RLE_TILE - 32) ? RLE_TILE - 32 : (uint32_t)(K - 4));
+            const uint32_t wbyte = __ldg(in + lo + wbase + lane);
+            const TSeg excl = unpack_lane_prefix(raw, 64u * (uint32_t)lane);
+            if (__shfl_sync(FULL, (uint32_t)(raw >> 63), 0) && st.run < 4) {
+                const uint32_t first = __shfl_sync(FULL, excl.first, 1), lead0 = __shfl_sync(FULL, excl.lead, 1); // lane 1's prefix = lane 0's summary
+                if (!(st.run > 0 && st.cur == first) || st.run + lead0 < 4) {
+                    uint32_t pos;
+                    r.st = short_run_search([wbyte, wbase](uint32_t j) { return __shfl_sync(FULL, wbyte, (int)(j - wbase)); }, RLE_TILE, st, limit, 0u, pos);
+                    r.pos = lo + pos;
+                    return r;
+                }
+            }
+            const RleState s0 = tstate_apply(excl, st);
+            const unsigned over = __ballot_sync(FULL, s0.bl > limit);
+            const int f = over ? __ffs((int)over) - 1 : 32;
+            const int c = f - 1;
+            if (c >= 0) {
+                const uint16_t two = __ldg(reinterpret_cast<const uint16_t *>(in + lo + (uint64_t)c * RLE_LANE_BYTES) + lane); // (tiles are 16-byte aligned)
+                uint32_t fi;
+                RleState fs, behind;
+                if (inside_lane(two & 0xffu, two >> 8, RLE_LANE_BYTES, shfl_state(s0, c), limit, fi, fs, &behind)) {
+                    r.pos = lo + (uint64_t)c * RLE_LANE_BYTES + fi;
+                    r.st = fs;
+                    return r;
+                }
+                if (!over) { r.pos = hi; r.st = behind; return r; }
+            }
+            r.pos = lo + (uint64_t)f * RLE_LANE_BYTES; // at the first byte of lane f
+            r.st = shfl_state(s0, f);
+            return r;
+        }
         __syncwarp();
         warp_load_tile(in, lo, n, sm);
         const uint32_t cnt = lane_count(n);
@@ -273,7 +375,7 @@ struct DevTileScan {
                 return r;
             }
         }
-        const TSeg mine = tseg_of(lane_seg(sm, cnt));
+        const TSeg mine = tseg_of(cnt == RLE_LANE_BYTES ? seg_from_eq_mask(p[0], p[RLE_LANE_BYTES - 1], eq) : lane_seg(sm, cnt));
         const TSeg incl = warp_tseg_incl_scan(mine);
         TSeg excl = shfl_up_tseg(incl, 1);
         if (lane == 0) excl = tseg_of(seg_empty());
@@ -290,31 +392,9 @@ struct DevTileScan {
         RleState fs = s0;
         const uint32_t cnt_c = c >= 0 ? __shfl_sync(FULL, cnt, c) : 0u;
         if (cnt_c > 1) { // (warp-uniform) lane c's bytes two per lane: the same scan one level down gives the state in front of each of them
-            const RleState sc = shfl_state(s0, c);
             const uint8_t *q = sm + c * RLE_SM_STRIDE;
             const uint32_t i0 = 2u * (uint32_t)lane;
-            const uint32_t v0 = i0 < cnt_c ? q[i0] : 0u, v1 = i0 + 1 < cnt_c ? q[i0 + 1] : 0u;
-            TSeg piece;
-            piece.len = i0 + 1 < cnt_c ? 2u : (i0 < cnt_c ? 1u : 0u);
-            piece.first = v0;
-            piece.last = piece.len == 2u ? v1 : v0;
-            piece.lead = piece.trail = (piece.len == 2u && v0 != v1) ? 1u : piece.len;
-            piece.mid = 0;
-            const TSeg pin = warp_tseg_incl_scan(piece);
-            TSeg pex = shfl_up_tseg(pin, 1);
-            if (lane == 0) pex = tseg_of(seg_empty());
-            const RleState e0 = tstate_apply(pex, sc); // in front of byte i0
-            RleState e1 = e0;                          // in front of byte i0 + 1
-            if (i0 < cnt_c) state_step(e1, v0);
-            const bool h0 = i0 >= 1 && i0 < cnt_c && e0.bl > limit, h1 = i0 + 1 < cnt_c && e1.bl > limit;
-            const unsigned hb = __ballot_sync(FULL, h0 || h1);
-            if (hb) {
-                const int w = __ffs((int)hb) - 1;
-                found = true; // (uniform)
-                const uint32_t my_i = h0 ? i0 : i0 + 1;
-                fi = __shfl_sync(FULL, my_i, w);
-                fs = shfl_state(h0 ? e0 : e1, w);
-            }
+            found = inside_lane(i0 < cnt_c ? q[i0] : 0u, i0 + 1 < cnt_c ? q[i0 + 1] : 0u, cnt_c, shfl_state(s0, c), limit, fi, fs, nullptr);
         }
         if (found) { // inside lane c
             r.pos = lo + (uint64_t)c * RLE_LANE_BYTES + fi;
@@ -371,7 +451,7 @@ __global__ void __launch_bounds__(32) k_rle_walk(const uint8_t *__restrict__ in,
                                                   uint64_t max_new)
 {
     __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
-    DevTileScan scan{in, sm};
+    DevTileScan scan{in, sm, nullptr};
     DevSiblingStep step{lv};
     uint64_t nb = info[0], s = info[1];
     const uint64_t target = nb + max_new;
@@ -576,10 +656,10 @@ struct DevFirstOver {
 // Resumable like k_rle_walk (same info[] protocol); info[12], info[13] carry the global machine's state at info[1].
 __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t limit, int is_final, WalkLevels lv,
                                                          const PState *__restrict__ pstate, uint64_t *__restrict__ starts, uint32_t *__restrict__ rle_len,
-                                                         uint64_t cap, uint64_t *__restrict__ info, uint64_t max_new)
+                                                         uint64_t cap, uint64_t *__restrict__ info, uint64_t max_new, const uint64_t *__restrict__ ltab)
 {
     __shared__ __align__(16) uint8_t sm[32 * RLE_SM_STRIDE];
-    DevTileScan scan{in, sm};
+    DevTileScan scan{in, sm, ltab};
     DevRunEnd run_end{in, n_bytes, lv};
     DevHead head{in, n_bytes, run_end};
     DevPState ps{pstate};
@@ -624,6 +704,9 @@ __global__ void __launch_bounds__(32) k_rle_walk_prefix(const uint8_t *__restric
             if (lane < 8) {
                 const uint64_t t8 = (tb > 30 ? tb - 30 : 0) + 8ull * (uint64_t)lane;
                 if (t8 <= n_tiles) prefetch_l2(pstate + t8);
+            } else if (ltab && lane < 16) { // the lane prefix tables (256 B each) of the tiles where this block and the next should end
+                const uint64_t t2 = (lane < 12 ? ta : tb + 1) + (uint64_t)((lane - 8) & 3) / 2, half = (uint64_t)(lane & 1);
+                if (t2 < n_tiles) prefetch_l2(ltab + t2 * 32 + half * 16);
             }
         }
         RleState st, g2 = g;

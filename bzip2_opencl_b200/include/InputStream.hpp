@@ -39,7 +39,13 @@ private:
         std::vector<uint8_t> in((std::istreambuf_iterator<char>(inputStream)), std::istreambuf_iterator<char>());
         if (in.size() < 4 || in[0] != 'B' || in[1] != 'Z' || in[2] != 'h' || in[3] < '1' || in[3] > '9')
             throw std::runtime_error("Invalid BZip2 header"); // InputStream.hpp:118-123
-        int rc = bz2b200_create(&handle, 0, BLOCKSIZE_DEFAULT, allStreams ? 9 : in[3] - '0', parallelBlockCnt); // later streams may use larger blocks
+        // blocks decoded per device batch: the entropy decode is one warp per block, so throughput grows with the blocks in flight --
+        // parallelBlockCnt is a minimum, the device's memory the limit (half as many again as the compressor keeps in flight)
+        const int mult = allStreams ? 9 : in[3] - '0';
+        int blocks = bz2b200_recommended_blocks(0, BLOCKSIZE_DEFAULT, mult) * 3 / 2;
+        if (blocks < parallelBlockCnt)
+            blocks = parallelBlockCnt;
+        int rc = bz2b200_create(&handle, 0, BLOCKSIZE_DEFAULT, mult, blocks); // later streams may use larger blocks
         if (rc != BZ2B200_OK)
             throw std::runtime_error(std::string(bz2b200_strerror(rc)) + " (no CUDA device? there is no CPU path)");
         size_t cap = in.size() * 6 + (1u << 16), n = 0;

@@ -26,7 +26,7 @@ def head_bytes(block_size: int) -> int:
     return ((limit // 5 + 2) * 255 + 2 * block_size + 4095) // 4096 * 4096
 
 
-def plan_slices(total: int, world: int, block_size: int, ratio: float = 0.96, min_slice: int | None = None):
+def plan_slices(total: int, world: int, block_size: int, ratio: float = 0.975, min_slice: int | None = None):
     """[(base, lo, hi)] per rank: rank r owns the blocks that start in [lo, hi) and stages bytes [base, hi) (base = lo - head).
     Slices shrink by `ratio` along the chain (rank r starts about r walks later than rank 0); ranks that would get less than
     `min_slice` bytes get nothing (lo == hi == total)."""
@@ -202,7 +202,7 @@ class StreamRank:
     initialised; `meta_group` is a gloo group for the few numbers that travel between ranks (the chain of block starts, bit
     counts, CRCs), the packed bits travel over the default (NCCL) group.  Used by bench.py --gpus N and the tests."""
 
-    def __init__(self, comp, total: int, rank: int, world: int, meta_group=None, ratio: float = 0.96, is_final: bool = True):
+    def __init__(self, comp, total: int, rank: int, world: int, meta_group=None, ratio: float = 0.975, is_final: bool = True):
         import torch
         self.torch = torch
         self.comp, self.total, self.rank, self.world, self.meta, self.is_final = comp, total, rank, world, meta_group, is_final
@@ -244,24 +244,39 @@ class StreamRank:
         """ptr -> bytes [base, hi) of the stream (host or device memory).  Leaves this rank's bits, shifted to their bit offset in
         the stream (32 header bits in front), in self.shifted; returns dict(placement of every rank, nbits of every rank, crc,
         n_copy, byte0, end_bit)."""
+        import time
         import torch.distributed as dist
         torch = self.torch
         c = self.comp
         n = self.hi - self.base
+        ph = {}
+        t0 = time.perf_counter()
         if n:
             c.scan_prepare(ptr, n)
-        box = {}
+        ph["prepare_queue"] = time.perf_counter() - t0
+
+        def recv_start():
+            t = time.perf_counter()
+            v = self._recv_start()
+            ph["wait_for_start"] = time.perf_counter() - t
+            return v
 
         def scan(first_rel, final):
+            t = time.perf_counter()
             nb, used = c.scan_blocks_ex(ptr, n, final, first_rel, want_starts=False)
+            ph["walk"] = time.perf_counter() - t
             return nb, used
-        s, nb, nxt = chain_walk(scan, self.plan[self.rank], self.rank, self.world, self.is_final, self._recv_start, self._send_start)
+        s, nb, nxt = chain_walk(scan, self.plan[self.rank], self.rank, self.world, self.is_final, recv_start, self._send_start)
+        ph["start_known_at"] = time.perf_counter() - t0
         nbits, crcs, tail = 0, np.zeros(0, dtype=np.uint32), 0
+        t = time.perf_counter()
         if nb:
             q = c.compress_scanned_ptr(self.out.data_ptr(), self.cap, nb)
             nbits, crcs = int(q["nbits"]), q["crcs"]
             e = (nbits - 1) >> 3
             tail = tail_of(bytes(self.out[max(0, e - 1):e + 1].cpu().numpy()), nbits)
+        ph["compress"] = time.perf_counter() - t
+        t = time.perf_counter()
         # metadata: bit count, trailing bits, block CRCs of every rank
         mine = torch.zeros(3 + self.max_blocks, dtype=torch.int64)
         mine[0], mine[1], mine[2] = nbits, tail, len(crcs)
@@ -275,6 +290,9 @@ class StreamRank:
         if nbits:
             c.shift_bits_ptr(self.out.data_ptr(), nbits, shift, carry, self.shifted.data_ptr(), self.cap + 16)
         crc = fold_crcs([m[3:3 + int(m[2])].tolist() for m in allm])
+        ph["meta_and_shift"] = time.perf_counter() - t
+        ph["done_at"] = time.perf_counter() - t0
+        self.phases = {k: round(1e3 * v, 3) for k, v in ph.items()}  # host clock, ms, this rank
         return dict(placement=placement, nbits_all=nbits_all, crc=crc, n_copy=n_copy, byte0=byte0, end_bit=32 + sum(nbits_all), n_blocks=nb,
                     blocks_all=[int(m[2]) for m in allm])
 
