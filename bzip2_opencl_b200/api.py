@@ -21,7 +21,10 @@ EXPORTS = ["bz2b200_device_count", "bz2b200_create", "bz2b200_destroy", "bz2b200
            "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_decompress_stream", "bz2b200_decompress_concat", "bz2b200_get_stats", "bz2b200_stage_dump", "bz2b200_strerror",
            "bz2b200_last_error", "bz2b200_set_profiling", "bz2b200_kernel_times", "bz2b200_create_multi", "bz2b200_device_count_of",
            "bz2b200_recommended_blocks", "bz2b200_host_alloc", "bz2b200_host_free", "bz2b200_scan_prepare", "bz2b200_scan_blocks_ex",
-           "bz2b200_compress_scanned", "bz2b200_shift_bits"]
+           "bz2b200_compress_scanned", "bz2b200_shift_bits", "bz2b200_compress_blocks_from"]
+
+
+WALKED_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_void_p)  # bz2b200_walked_fn
 
 
 class Stats(C.Structure):
@@ -92,6 +95,8 @@ def load_library() -> C.CDLL:
     L.bz2b200_scan_blocks_ex.argtypes = [vp, vp, sz, C.c_int, C.c_uint64, vp, sz, u64p, C.POINTER(sz)]
     L.bz2b200_compress_scanned.restype = C.c_int
     L.bz2b200_compress_scanned.argtypes = [vp, C.c_uint, vp, sz, u64p, vp, vp, sz, u64p]
+    L.bz2b200_compress_blocks_from.restype = C.c_int
+    L.bz2b200_compress_blocks_from.argtypes = [vp, vp, sz, C.c_int, C.c_uint64, C.c_uint, vp, sz, u64p, C.POINTER(sz), vp, vp, sz, u64p, WALKED_FN, vp]
     L.bz2b200_shift_bits.restype = C.c_int
     L.bz2b200_shift_bits.argtypes = [vp, vp, C.c_uint64, C.c_uint, C.c_uint, vp, sz]
     _lib = L
@@ -227,6 +232,20 @@ class Compressor:
         self._check(self.lib.bz2b200_compress_scanned(self.h, start_bit, C.c_void_p(out_ptr), out_cap, C.byref(nbits), _np_ptr(crcs), _np_ptr(nbits_b), cap,
                                                       C.byref(nb)))
         return dict(nbits=nbits.value, crcs=crcs[:nb.value].copy(), block_nbits=nbits_b[:nb.value].copy())
+
+    def compress_blocks_from_ptr(self, in_ptr: int, nbytes: int, out_ptr: int, out_cap: int, is_final: bool, first_start: int, on_walked=None, start_bit: int = 0):
+        """Scan + compress of a slice (bz2b200_compress_blocks_from): on_walked(next_start) is called from inside the call as soon as the walk
+        has been through the slice.  Returns dict(nbits, consumed, crcs, block_nbits)."""
+        cap = self.max_blocks(nbytes)
+        crcs = np.zeros(cap, dtype=np.uint32)
+        nbits_b = np.zeros(cap, dtype=np.uint64)
+        nbits = C.c_uint64(0)
+        consumed = C.c_size_t(0)
+        nb = C.c_uint64(0)
+        cb = WALKED_FN(lambda nxt, _u: on_walked(int(nxt))) if on_walked is not None else WALKED_FN(0)
+        self._check(self.lib.bz2b200_compress_blocks_from(self.h, C.c_void_p(in_ptr), nbytes, int(is_final), first_start, start_bit, C.c_void_p(out_ptr), out_cap,
+                                                          C.byref(nbits), C.byref(consumed), _np_ptr(crcs), _np_ptr(nbits_b), cap, C.byref(nb), cb, None))
+        return dict(nbits=nbits.value, consumed=consumed.value, crcs=crcs[:nb.value].copy(), block_nbits=nbits_b[:nb.value].copy())
 
     def shift_bits_ptr(self, src_ptr: int, nbits: int, shift: int, carry: int, dst_ptr: int, dst_cap: int):
         self._check(self.lib.bz2b200_shift_bits(self.h, C.c_void_p(src_ptr), nbits, shift, carry, C.c_void_p(dst_ptr), dst_cap))

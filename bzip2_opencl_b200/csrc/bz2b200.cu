@@ -1231,9 +1231,16 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
 
 // scanned: compress the blocks found by the last bz2b200_scan_blocks_ex (input staged, block table in the handle) instead of staging and
 // walking `input`; keep_dev: leave the packed bits in the handle's own device buffer (h->out) -- multi-device streams move them from there
+// from: the first block starts at input[from->first_start] (a slice of a longer stream); from->on_walked is called with the offset of
+// the first unfinished block as soon as the walk has been through the slice -- long before the blocks are compressed
+struct FromArgs {
+    uint64_t first_start = 0;
+    void (*on_walked)(uint64_t next_start, void *user) = nullptr;
+    void *user = nullptr;
+};
 static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                 size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev);
+                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev, const FromArgs *from = nullptr);
 static int multi_compress_blocks(bz2b200 *P, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out, size_t out_capacity,
                                  uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks);
 
@@ -1250,18 +1257,22 @@ static void lane_main(bz2b200 *l, int idx, const uint8_t *d_in, uint64_t b0, uin
 }
 
 // hands the batch to a free lane (waits for one); with profiling on, batches run one at a time so that per-kernel times are clean
-static int lane_dispatch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq)
+// (wait == false: returns LANES_BUSY instead of waiting when no lane is free)
+enum { LANES_BUSY = 1 };
+static int lane_dispatch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, uint32_t *d_out_words, uint64_t seq, bool wait = true)
 {
     LaneCtl *ctl = h->ctl;
     int idx = -1;
     {
         std::unique_lock<std::mutex> lk(ctl->mu);
-        ctl->cv.wait(lk, [&] {
+        auto free_lane = [&] {
             if (ctl->rc) return true;
             size_t busy = 0;
             for (char b : h->lane_busy) busy += b ? 1 : 0;
             return h->profiling ? busy == 0 : busy < h->lane_busy.size();
-        });
+        };
+        if (!wait && !free_lane()) return LANES_BUSY;
+        ctl->cv.wait(lk, free_lane);
         if (ctl->rc) { h->err = ctl->err; return ctl->rc; }
         for (size_t i = 0; i < h->lane_busy.size(); ++i) {
             const size_t k = (seq + i) % h->lane_busy.size(); // alternate, so that a profiled pass uses every lane too
@@ -1314,10 +1325,10 @@ static int lanes_finish(bz2b200 *h)
 
 static int compress_blocks_guarded(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                    size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                   size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev)
+                                   size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev, const FromArgs *from = nullptr)
 {
     int rc = compress_blocks_impl(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits,
-                                  block_capacity, n_blocks, scanned, keep_dev);
+                                  block_capacity, n_blocks, scanned, keep_dev, from);
     if (h) {
         // never leave batches, copies into the caller's buffer or a walk in flight, whatever the outcome
         (void)lanes_finish(h);
@@ -1343,6 +1354,20 @@ extern "C" int bz2b200_compress_blocks(bz2b200_t *h, const uint8_t *input, size_
                                    n_blocks, false, false);
 }
 
+extern "C" int bz2b200_compress_blocks_from(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, unsigned start_bit,
+                                            uint8_t *out, size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs,
+                                            uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks, bz2b200_walked_fn on_walked, void *user)
+{
+    if (!h) return BZ2B200_E_ARG;
+    if (!h->children.empty()) { h->err = "compress_blocks_from works on a single-device handle"; return BZ2B200_E_ARG; }
+    FromArgs fa;
+    fa.first_start = first_start;
+    fa.on_walked = on_walked;
+    fa.user = user;
+    return compress_blocks_guarded(h, input, n_bytes, is_final, start_bit, out, out_capacity, out_nbits, consumed, block_crcs, block_nbits, block_capacity,
+                                   n_blocks, false, false, &fa);
+}
+
 extern "C" int bz2b200_compress_scanned(bz2b200_t *h, unsigned start_bit, uint8_t *out, size_t out_capacity, uint64_t *out_nbits, uint32_t *block_crcs,
                                         uint64_t *block_nbits, size_t block_capacity, uint64_t *n_blocks)
 {
@@ -1355,7 +1380,7 @@ extern "C" int bz2b200_compress_scanned(bz2b200_t *h, unsigned start_bit, uint8_
 
 static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_bytes, int is_final, unsigned start_bit, uint8_t *out,
                                 size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
-                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev)
+                                size_t block_capacity, uint64_t *n_blocks, bool scanned, bool keep_dev, const FromArgs *from)
 {
     if (!h) return BZ2B200_E_ARG;
     if ((!input && n_bytes) || !out_nbits || !consumed || !n_blocks || start_bit > 7 || (!out && out_capacity)) {
@@ -1385,12 +1410,29 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         d_in = h->w_in;
         n_bytes = (size_t)(h->h_starts[h->w_found] - h->scan_first); // the bytes the scanned blocks cover
         CK(cudaEventRecord(h->ev[10], st));
+    } else if (h->prepared && h->prep_input == input && h->prep_n == n_bytes) {
+        // bz2b200_scan_prepare has staged this input and queued its summary tree: only the walk is left
+        h->prepared = false;
+        d_in = h->w_in;
+        h->caller_final = is_final;
+        h->w_final = is_final ? 1 : 0;
+        h->w_finished = n_bytes == 0;
+        CK(cudaEventRecord(h->ev[10], st));
     } else {
+        h->prepared = false;
         rc = stage_input(h, input, n_bytes, &d_in);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[10], st));
         rc = walk_setup(h, d_in, n_bytes, is_final);
         if (rc) return rc;
+    }
+    if (from && from->first_start > n_bytes) { h->err = "first_start behind the input"; return BZ2B200_E_ARG; }
+    if (from && !scanned && n_bytes) { // the walk starts inside the buffer (k_rle_walk_prefix derives the machine's state there)
+        uint64_t *d_info = ptr<uint64_t>(h->scalars) + Scalars::WALK_INFO;
+        h->h_pinned[40] = 0; h->h_pinned[41] = from->first_start; h->h_pinned[42] = 0; h->h_pinned[43] = from->first_start ? 1 : 0;
+        CK(cudaMemcpyAsync(d_info, h->h_pinned + 40, 32, cudaMemcpyHostToDevice, h->side));
+        h->h_starts.assign(1, from->first_start);
+        h->scan_first = from->first_start;
     }
     const uint64_t cap_blocks = n_bytes / (uint64_t)std::max(1, (h->bs - 5) * 4 / 5) + 2;
     const size_t need = bz2b200_max_output_bytes(h, n_bytes) + 8;
@@ -1422,6 +1464,10 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         // the walk runs one chunk ahead on the side stream; a small first chunk keeps its exposed latency short
         bool pending = false;
         uint64_t b0 = 0, chunk = std::max<uint64_t>(1, std::min<uint64_t>(h->G, (uint64_t)h->walk_first) / (uint64_t)h->walk_growth);
+        // A slice of a longer stream (from->on_walked): the device behind this one waits for the walk's end, so the walk never waits
+        // for a lane -- batches are handed out only while a lane is free until the walk is through and its end has been passed on.
+        bool walk_first = from && from->on_walked && !scanned;
+        if (scanned && from && from->on_walked) from->on_walked(h->h_starts[h->w_found], from->user);
         while (pending || b0 < h->w_found || !h->w_finished || walk_more_input(h)) {
             if (pending) {
                 rc = walk_collect(h);
@@ -1438,7 +1484,12 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 if (rc) return rc;
                 pending = true;
             }
+            if (walk_first && !pending && h->w_finished && !walk_more_input(h)) { // the walk has seen the whole slice
+                walk_first = false;
+                from->on_walked(h->h_starts[h->w_found], from->user);
+            }
             bool go = b0 < h->w_found;
+            if (go && walk_first && !laned) go = false; // (batches on the calling thread would hold the walk up)
             if (go && laned) {
                 // A batch costs about the same wall time whatever its size (its one-warp-per-block kernels), so a lane is not spent
                 // on a few blocks while the others have real work: wait until half a batch is known -- unless nothing more will
@@ -1454,12 +1505,14 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
             }
             if (go) {
                 uint32_t cnt = (uint32_t)std::min<uint64_t>(Gb, h->w_found - b0);
-                rc = laned ? lane_dispatch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq) : run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq);
+                rc = laned ? lane_dispatch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq, !walk_first) : run_batch(h, d_in, b0, cnt, ptr<uint32_t>(h->out), seq);
+                if (rc == LANES_BUSY) continue; // (the walk goes on; the loop comes back when its next chunk has been collected)
                 if (rc) return rc;
                 b0 += cnt;
                 ++seq;
             }
         }
+        if (walk_first) from->on_walked(h->h_starts[h->w_found], from->user); // (nothing to walk)
     }
     rc = lanes_finish(h);
     if (rc) return rc;
@@ -1686,28 +1739,62 @@ static int multi_compress_blocks(bz2b200 *P, const uint8_t *input, size_t n_byte
     ch.start.assign(k + 1, 0);
     ch.known.assign(k + 1, 0);
     ch.known[0] = 1;
-    // ---- per device: stage + summarise, walk when the chain arrives, compress into the device's own buffer
+    // ---- per device: stage + summarise at once; when the chain arrives, walk (handing the chain on as soon as the walk is through) and
+    // compress into the device's own buffer
+    const uint64_t cap_blocks = n_bytes / (uint64_t)std::max(1, (P->bs - 5) * 4 / 5) + 4;
     multi_threads(k, [&](size_t d) {
         bz2b200 *c = P->children[d];
         MultiPart &pt = parts[d];
-        int rc = multi_scan_part(P, d, input, n_bytes, is_final, parts, ch);
-        if (rc == BZ2B200_OK && pt.nblocks) {
-            pt.crcs.resize(pt.nblocks);
-            pt.nbits_b.resize(pt.nblocks);
-            size_t used = 0;
-            uint64_t nb = 0;
-            rc = compress_blocks_guarded(c, nullptr, 0, 0, 0, nullptr, 0, &pt.nbits, &used, pt.crcs.data(), pt.nbits_b.data(), pt.nblocks, &nb, true, true);
-            if (rc == BZ2B200_OK && pt.nbits) { // the part's last two bytes: the bits the next part's first byte starts with
-                const uint64_t e = (pt.nbits - 1) >> 3;
-                if (cudaMemcpy(pt.tail, ptr<uint8_t>(c->out) + (e ? e - 1 : 0), e ? 2 : 1, cudaMemcpyDeviceToHost) != cudaSuccess) { c->err = "tail read failed"; rc = BZ2B200_E_CUDA; }
-                if (!e) { pt.tail[1] = pt.tail[0]; pt.tail[0] = 0; }
+        const bool last = d + 1 == k;
+        int rc = cudaSetDevice(c->device) == cudaSuccess ? BZ2B200_OK : BZ2B200_E_CUDA;
+        c->err.clear();
+        c->profiling = P->profiling;
+        const uint8_t *src = input + pt.base;
+        const size_t len = (size_t)(pt.hi - pt.base);
+        if (rc == BZ2B200_OK && len && d > 0) rc = scan_prepare_impl(c, src, len); // (device 0 starts at once: its copies run under its kernels)
+        uint64_t s = 0;
+        {
+            std::unique_lock<std::mutex> lk(ch.mu);
+            ch.cv.wait(lk, [&] { return ch.known[d] || ch.rc; });
+            if (ch.rc && !rc) rc = ch.rc;
+            s = ch.start[d];
+        }
+        bool published = false;
+        struct Hand { MultiChain *ch; size_t d; uint64_t base; bool *published; } hand{&ch, d + 1, pt.base, &published};
+        if (rc == BZ2B200_OK && s < pt.hi) {
+            if (s < pt.base) { c->err = "internal: an unfinished block is longer than the staged head"; rc = BZ2B200_E_STATE; }
+            if (rc == BZ2B200_OK) {
+                pt.crcs.resize(cap_blocks);
+                pt.nbits_b.resize(cap_blocks);
+                FromArgs fa;
+                fa.first_start = s - pt.base;
+                fa.user = &hand;
+                fa.on_walked = [](uint64_t next, void *u) {
+                    Hand *hd = static_cast<Hand *>(u);
+                    *hd->published = true;
+                    chain_publish(*hd->ch, hd->d, hd->base + next, BZ2B200_OK, std::string());
+                };
+                size_t used = 0;
+                uint64_t nb = 0;
+                rc = compress_blocks_guarded(c, src, len, (last && is_final) ? 1 : 0, 0, nullptr, 0, &pt.nbits, &used, pt.crcs.data(), pt.nbits_b.data(), cap_blocks, &nb,
+                                             false, true, &fa);
+                if (rc == BZ2B200_OK) {
+                    pt.nblocks = nb;
+                    pt.first = s;
+                    if (pt.nbits) { // the part's last two bytes: the bits the next part's first byte starts with
+                        const uint64_t e = (pt.nbits - 1) >> 3;
+                        if (cudaMemcpy(pt.tail, ptr<uint8_t>(c->out) + (e ? e - 1 : 0), e ? 2 : 1, cudaMemcpyDeviceToHost) != cudaSuccess) { c->err = "tail read failed"; rc = BZ2B200_E_CUDA; }
+                        if (!e) { pt.tail[1] = pt.tail[0]; pt.tail[0] = 0; }
+                    }
+                    pt.stats = c->stats;
+                }
             }
-            pt.stats = c->stats;
-        } else {
+        } else if (rc == BZ2B200_OK) {
             cudaStreamSynchronize(c->side);
             cudaStreamSynchronize(c->h2d);
-            c->scan_valid = false;
+            c->prepared = false;
         }
+        if (!published) chain_publish(ch, d + 1, s, rc, c->err); // nothing walked (or a failure): the chain passes through
         if (rc) chain_publish(ch, k + 1, 0, rc, c->err);
     });
     if (ch.rc) { P->err = ch.err; return ch.rc; }

@@ -251,30 +251,34 @@ class StreamRank:
         n = self.hi - self.base
         ph = {}
         t0 = time.perf_counter()
-        if n:
-            c.scan_prepare(ptr, n)
+        if n and self.rank > 0:
+            c.scan_prepare(ptr, n)   # (rank 0 starts at once: its copies run under its kernels)
         ph["prepare_queue"] = time.perf_counter() - t0
-
-        def recv_start():
+        s = 0
+        if self.rank > 0:
             t = time.perf_counter()
-            v = self._recv_start()
+            s = self._recv_start()
             ph["wait_for_start"] = time.perf_counter() - t
-            return v
-
-        def scan(first_rel, final):
-            t = time.perf_counter()
-            nb, used = c.scan_blocks_ex(ptr, n, final, first_rel, want_starts=False)
-            ph["walk"] = time.perf_counter() - t
-            return nb, used
-        s, nb, nxt = chain_walk(scan, self.plan[self.rank], self.rank, self.world, self.is_final, recv_start, self._send_start)
         ph["start_known_at"] = time.perf_counter() - t0
-        nbits, crcs, tail = 0, np.zeros(0, dtype=np.uint32), 0
+        nbits, crcs, tail, nb = 0, np.zeros(0, dtype=np.uint32), 0, 0
+        handed = [False]
+
+        def on_walked(nxt):   # called from inside the compress call as soon as the walk is through the slice
+            handed[0] = True
+            ph["walked_at"] = time.perf_counter() - t0
+            if self.rank + 1 < self.world:
+                self._send_start(self.base + nxt)
         t = time.perf_counter()
-        if nb:
-            q = c.compress_scanned_ptr(self.out.data_ptr(), self.cap, nb)
-            nbits, crcs = int(q["nbits"]), q["crcs"]
-            e = (nbits - 1) >> 3
-            tail = tail_of(bytes(self.out[max(0, e - 1):e + 1].cpu().numpy()), nbits)
+        if s < self.hi:
+            if s < self.base:
+                raise RuntimeError("an unfinished block is longer than the staged head")
+            q = c.compress_blocks_from_ptr(ptr, n, self.out.data_ptr(), self.cap, bool(self.is_final and self.rank == self.world - 1), s - self.base, on_walked)
+            nbits, crcs, nb = int(q["nbits"]), q["crcs"], len(q["crcs"])
+            if nbits:
+                e = (nbits - 1) >> 3
+                tail = tail_of(bytes(self.out[max(0, e - 1):e + 1].cpu().numpy()), nbits)
+        if not handed[0] and self.rank + 1 < self.world:
+            self._send_start(s)       # nothing of this slice starts a block: the chain passes through
         ph["compress"] = time.perf_counter() - t
         t = time.perf_counter()
         # metadata: bit count, trailing bits, block CRCs of every rank

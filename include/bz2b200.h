@@ -115,7 +115,18 @@ int bz2b200_scan_blocks(bz2b200_t *handle, const uint8_t *input, size_t n_bytes,
  *                          shift = 0..7 bits, the top `shift` bits of dst[0] taken from `carry` (the part in front's trailing
  *                          bits, already in the top bits of the byte).  This is the reference's leftBuffer hand-over
  *                          (BitOutputStream.hpp:30-45, OutputStream.hpp:225-239) between devices.
+ *
+ * bz2b200_compress_blocks_from   scan + compress of a slice in one call, the form the chain of a multi-GPU stream uses: the first block
+ *                          starts at input[first_start]; on_walked(next_start, user) (may be NULL) is called from inside the call as
+ *                          soon as the walk has been through the slice -- next_start is what bz2b200_scan_blocks_ex would return in
+ *                          *consumed -- so that the next device's walk starts while this one still compresses (the walk never waits
+ *                          for the kernels; batches start as soon as blocks are known).  Uses the preparation of the same
+ *                          (input, n_bytes) if there is one; otherwise host input is copied in segments under the kernels.
  */
+typedef void (*bz2b200_walked_fn)(uint64_t next_start, void *user);
+int bz2b200_compress_blocks_from(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, unsigned start_bit,
+                                 uint8_t *out, size_t out_capacity, uint64_t *out_nbits, size_t *consumed, uint32_t *block_crcs, uint64_t *block_nbits,
+                                 size_t block_capacity, uint64_t *n_blocks, bz2b200_walked_fn on_walked, void *user);
 int bz2b200_scan_prepare(bz2b200_t *handle, const uint8_t *input, size_t n_bytes);
 int bz2b200_scan_blocks_ex(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, int is_final, uint64_t first_start, uint64_t *block_starts,
                            size_t capacity, uint64_t *n_blocks, size_t *consumed);

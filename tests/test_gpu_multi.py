@@ -85,6 +85,51 @@ def test_slice_primitives_reproduce_the_stream():
                 c.close()
 
 
+def test_compress_blocks_from_hands_the_chain_on_early():
+    """bz2b200_compress_blocks_from: scan + compress of a slice in one call; the callback delivers the next slice's start from inside the
+    call (before the blocks are compressed); prepared and unprepared slices, host and device memory"""
+    import torch
+    for mult, base, n in ((2, 10000, 5_000_000), (9, 100000, 40_000_000)):
+        d = _runs_and_text(n, 31) if n < 10_000_000 else corpus.mixed_corpus(n, 1 << 22)
+        exp = refimpl.compress(d, mult, base, threads=os.cpu_count() or 8) if (n > 10_000_000 and have_ref(base)) else oracle.compress(d, mult, base)
+        bs = mult * base
+        src = np.frombuffer(d, dtype=np.uint8)
+        dev = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+        for world, on_device in ((3, False), (2, True)):
+            plan = multi.plan_slices(len(d), world, bs, ratio=0.85, min_slice=2 * bs)
+            handles = [api.Compressor(mult, 8, base) for _ in range(world)]
+            ptr0 = dev.data_ptr() if on_device else src.ctypes.data
+            for r, (b0, lo, hi) in enumerate(plan):
+                if r > 0 and r % 2 == 1:                       # some slices are prepared, some are not
+                    handles[r].scan_prepare(ptr0 + b0, hi - b0)
+            s, res = 0, []
+            for r, (b0, lo, hi) in enumerate(plan):
+                c = handles[r]
+                got = {}
+                cap = c.max_output_bytes(hi - b0) + 64
+                out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+                order = []
+
+                def cb(nxt, got=got, order=order):
+                    got["next"] = nxt
+                    order.append("walked")
+                assert b0 <= s < hi
+                q = c.compress_blocks_from_ptr(ptr0 + b0, hi - b0, out.data_ptr(), cap, r == world - 1, s - b0, cb)
+                order.append("returned")
+                assert order == ["walked", "returned"] and got["next"] == q["consumed"]
+                e = (q["nbits"] - 1) >> 3
+                res.append((q["nbits"], bytes(out[:(q["nbits"] + 7) // 8].cpu().numpy()), q["crcs"],
+                            multi.tail_of(bytes(out[max(0, e - 1):e + 1].cpu().numpy()), q["nbits"])))
+                s = b0 + got["next"]
+            assert s == len(d)
+            nbits_all = [x[0] for x in res]
+            placement = multi.place_parts(nbits_all, [x[3] for x in res], 32)
+            shifted = [multi.shift_bits_host(x[1], x[0], pl[1], pl[2]) for x, pl in zip(res, placement)]
+            assert multi.assemble_stream(mult, shifted, placement, nbits_all, multi.fold_crcs([x[2] for x in res])) == exp, (mult, base, world)
+            for c in handles:
+                c.close()
+
+
 def test_scan_blocks_ex_from_an_offset_and_not_final():
     d = _runs_and_text(2_500_000, 9)
     mult, base = 2, 10000

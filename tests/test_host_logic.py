@@ -66,6 +66,23 @@ def test_c_abi_argument_errors_without_gpu():
         assert lib.bz2b200_create(C.byref(h), 0, 100000, 9, 4) == api.E_CUDA
         with pytest.raises(api.Bz2Error):
             api.Compressor()
+    # the multi-device and slice entry points check their arguments before they touch a device
+    ids = (C.c_int * 2)(0, 0)
+    assert lib.bz2b200_create_multi(C.byref(h), None, 2, 100000, 9, 4) == api.E_ARG
+    assert lib.bz2b200_create_multi(C.byref(h), ids, 0, 100000, 9, 4) == api.E_ARG
+    assert lib.bz2b200_create_multi(C.byref(h), ids, 2, 100000, 0, 4) == api.E_BLOCKSIZE
+    assert lib.bz2b200_create_multi(C.byref(h), ids, 2, 100000, 9, 0) == api.E_PARALLEL
+    assert lib.bz2b200_device_count_of(None) == 0
+    assert lib.bz2b200_recommended_blocks(0, 100000, 0) == 0 and lib.bz2b200_recommended_blocks(-1, 100000, 9) == 0
+    n = C.c_uint64(0)
+    assert lib.bz2b200_scan_blocks_ex(None, None, 0, 1, 0, None, 0, C.byref(n), None) == api.E_ARG
+    assert lib.bz2b200_compress_scanned(None, 0, None, 0, None, None, None, 0, None) == api.E_ARG
+    assert lib.bz2b200_shift_bits(None, None, 0, 0, 0, None, 0) == api.E_ARG
+    lib.bz2b200_host_free(None)
+    if lib.bz2b200_device_count() == 0:
+        assert lib.bz2b200_create_multi(C.byref(h), ids, 2, 100000, 9, 4) == api.E_CUDA
+        assert lib.bz2b200_recommended_blocks(0, 100000, 9) == 0
+        assert not lib.bz2b200_host_alloc(4096)   # pinned memory needs the CUDA runtime: no silent malloc fallback
     with pytest.raises(ValueError, match="Invalid block size"):
         api.Compressor(multiplier=0)
     with pytest.raises(ValueError, match="Invalid parallel block count"):
