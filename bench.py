@@ -290,7 +290,7 @@ def run_multi(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ratio = float(os.environ.get("BZ2B200_MULTI_RATIO", "0.975"))
+    ratio = float(os.environ.get("BZ2B200_MULTI_RATIO", "0.95"))
     comp = api.Compressor(MULT, args.parallel, BASE, device=local_rank)
     data = make_corpus(args.size_mb)
     n1 = len(data)

@@ -93,6 +93,10 @@ struct bz2b200 {
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
     int r0_group = 0;     // BZ2B200_R0_GROUP=g: the five round-0 sweeps run group by group of g blocks so that a group's elements stay in L2 (measured: the
                           // small launches cost more than the HBM traffic they save, profiles/r02_*); 0 = every sweep over the whole batch
+    int chain_overlap = 1; // BZ2B200_CHAIN_OVERLAP=0: a slice's batches start only when its walk is through (the walk alone on the device is ~30 % faster,
+                           // but the slice's own compression then starts a walk later; measured equal at 8 GPUs, better overlapped at 2)
+    int walk_smem = 190;   // BZ2B200_WALK_SMEM=KiB: dynamic shared memory of a chain's walk kernel (large: its warp has an SM to itself; 6.2 -> 5.6 ms/GiB)
+    bool chain_walk = false; // the current call hands a chain on (bz2b200_compress_blocks_from with a callback)
     int bulk_copy = 1;    // BZ2B200_BULK=0: block-relative tiles are staged with byte loads instead of the TMA bulk copy (cp.async.bulk + mbarrier)
     int root_sort = 1;    // BZ2B200_ROOT=0: non-primitive blocks go through the full prefix doubling instead of their root (k_bwt_period)
     int local_sort = 1;   // sort tile-local groups in shared memory (BZ2B200_LOCALSORT=0 sends everything through the global radix sort)
@@ -261,6 +265,7 @@ static int upload_constants(bz2b200 *h)
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_rle_walk_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
     CK(cudaFuncSetAttribute(k_dec_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DB_WARPS * sizeof(DecTables))));
     // shared-memory heavy kernels: ask for the largest shared-memory carveout so several CTAs stay resident per SM
     CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -358,7 +363,11 @@ static int create_impl(bz2b200 *h, bool with_batch)
     CK(cudaMallocHost(&h->pin_starts, (G + 2) * sizeof(uint64_t)));
     CK(cudaMallocHost(&h->pin_len, (G + 2) * sizeof(uint32_t)));
     CK(cudaMallocHost(&h->pin_info, 4 * sizeof(uint64_t)));
-    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    {
+        int lo_p = 0, hi_p = 0; // the walk is one warp on the critical path of every call: its stream goes first
+        if (cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p) != cudaSuccess) { (void)cudaGetLastError(); hi_p = 0; }
+        CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_p));
+    }
     CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev_t0));
@@ -475,6 +484,8 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (const char *e = getenv("BZ2B200_LOCALSORT")) h->local_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_ROOT")) h->root_sort = atoi(e);
     if (const char *e = getenv("BZ2B200_BULK")) h->bulk_copy = atoi(e);
+    if (const char *e = getenv("BZ2B200_CHAIN_OVERLAP")) h->chain_overlap = atoi(e);
+    if (const char *e = getenv("BZ2B200_WALK_SMEM")) h->walk_smem = std::max(0, std::min(200, atoi(e)));
     if (const char *e = getenv("BZ2B200_R0_GROUP")) h->r0_group = std::max(0, atoi(e));
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
@@ -704,7 +715,7 @@ static int walk_launch(bz2b200 *h, uint64_t max_new)
     h->w_req = max_new;
     CK(cudaEventRecord(h->ev_w0, h->side));
     if (h->prefix_walk)
-        k_rle_walk_prefix<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<PState>(h->pstate), ptr<uint64_t>(h->starts),
+        k_rle_walk_prefix<<<1, 32, h->chain_walk ? (size_t)h->walk_smem << 10 : 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<PState>(h->pstate), ptr<uint64_t>(h->starts),
                                                   ptr<uint32_t>(h->rle_len), h->w_cap, d_info, max_new, ptr<uint64_t>(h->ltab));
     else
         k_rle_walk<<<1, 32, 0, h->side>>>(h->w_in, h->w_n, (uint64_t)h->bs - 6, h->w_final, h->wl, ptr<uint64_t>(h->starts), ptr<uint32_t>(h->rle_len), h->w_cap,
@@ -1338,6 +1349,7 @@ static int compress_blocks_guarded(bz2b200_t *h, const uint8_t *input, size_t n_
         h->drain_dst = nullptr;
         h->host_src = nullptr;
         h->scan_valid = false; // a block table is good for one compress call
+        h->chain_walk = false;
         if (rc != BZ2B200_OK) (void)cudaGetLastError();
     }
     return rc;
@@ -1467,6 +1479,8 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
         // A slice of a longer stream (from->on_walked): the device behind this one waits for the walk's end, so the walk never waits
         // for a lane -- batches are handed out only while a lane is free until the walk is through and its end has been passed on.
         bool walk_first = from && from->on_walked && !scanned;
+        h->chain_walk = walk_first;
+        if (walk_first && !h->host_src && !h->chain_overlap) chunk = h->G; // resident input: the walk goes through in as few launches as possible
         if (scanned && from && from->on_walked) from->on_walked(h->h_starts[h->w_found], from->user);
         while (pending || b0 < h->w_found || !h->w_finished || walk_more_input(h)) {
             if (pending) {
@@ -1489,7 +1503,10 @@ static int compress_blocks_impl(bz2b200_t *h, const uint8_t *input, size_t n_byt
                 from->on_walked(h->h_starts[h->w_found], from->user);
             }
             bool go = b0 < h->w_found;
-            if (go && walk_first && !laned) go = false; // (batches on the calling thread would hold the walk up)
+            // (until the chain has been handed on, batches start only while input is still on its way from the host -- the walk waits
+            // for those bytes anyway; with the whole slice resident the walk is a few milliseconds alone on the device, and several
+            // times that next to the compression kernels)
+            if (go && walk_first && (!laned || !(h->chain_overlap || (h->host_src && walk_more_input(h))))) go = false;
             if (go && laned) {
                 // A batch costs about the same wall time whatever its size (its one-warp-per-block kernels), so a lane is not spent
                 // on a few blocks while the others have real work: wait until half a batch is known -- unless nothing more will
@@ -1605,7 +1622,7 @@ static int multi_plan(bz2b200 *P, size_t n_bytes, std::vector<MultiPart> &parts)
     const uint64_t min_slice = 16ull * (uint64_t)c0->bs; // a device is not woken for less
     k = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(k, n_bytes / std::max<uint64_t>(1, min_slice)));
     // device d starts about d walks later than device 0: sizes fall by the ratio walk time / compress time per byte
-    double r = 0.975;
+    double r = 0.95;
     if (const char *e = getenv("BZ2B200_MULTI_RATIO")) { const double v = atof(e); if (v > 0.1 && v <= 1.0) r = v; }
     std::vector<double> w(k);
     double tot = 0;

@@ -26,7 +26,7 @@ def head_bytes(block_size: int) -> int:
     return ((limit // 5 + 2) * 255 + 2 * block_size + 4095) // 4096 * 4096
 
 
-def plan_slices(total: int, world: int, block_size: int, ratio: float = 0.975, min_slice: int | None = None):
+def plan_slices(total: int, world: int, block_size: int, ratio: float = 0.95, min_slice: int | None = None):
     """[(base, lo, hi)] per rank: rank r owns the blocks that start in [lo, hi) and stages bytes [base, hi) (base = lo - head).
     Slices shrink by `ratio` along the chain (rank r starts about r walks later than rank 0); ranks that would get less than
     `min_slice` bytes get nothing (lo == hi == total)."""
@@ -202,7 +202,7 @@ class StreamRank:
     initialised; `meta_group` is a gloo group for the few numbers that travel between ranks (the chain of block starts, bit
     counts, CRCs), the packed bits travel over the default (NCCL) group.  Used by bench.py --gpus N and the tests."""
 
-    def __init__(self, comp, total: int, rank: int, world: int, meta_group=None, ratio: float = 0.975, is_final: bool = True):
+    def __init__(self, comp, total: int, rank: int, world: int, meta_group=None, ratio: float = 0.95, is_final: bool = True):
         import torch
         self.torch = torch
         self.comp, self.total, self.rank, self.world, self.meta, self.is_final = comp, total, rank, world, meta_group, is_final
