@@ -672,21 +672,21 @@ def main():
             fac = {}
             import hashlib
             want = None
-            for mode, size in (("fd", n1), ("vec", n1), ("byte", min(n1, 256 << 20))):
+            for mode, size in (("fd", n1), ("fd_null", n1), ("vec", n1), ("byte", min(n1, 256 << 20))):
                 if size != n1:
                     with open(fin, "wb") as f:
                         f.write(data[:size])
                 best_f = None
                 for _ in range(2):
-                    r = subprocess.run([exe, fin, fout, str(MULT), "10", mode], capture_output=True, text=True, timeout=600,
-                                       env=dict(os.environ, BZ2B200_DEVICES=str(local_rank)))
+                    r = subprocess.run([exe, fin, "/dev/null" if mode == "fd_null" else fout, str(MULT), "10", mode.split("_")[0]], capture_output=True, text=True,
+                                       timeout=600, env=dict(os.environ, BZ2B200_DEVICES=str(local_rank)))
                     if r.returncode != 0:
                         raise RuntimeError(r.stderr[-200:])
                     j = json.loads(r.stdout.strip().splitlines()[-1])
                     if best_f is None or j["ms"] < best_f["ms"]:
                         best_f = j
                 fac[mode] = {"value": round(size / 1e6 / (best_f["ms"] / 1e3), 2), "ms": best_f["ms"], "setup_ms": best_f["setup_ms"], "bytes_in": size,
-                             "bytes_out": best_f["bytes_out"]}
+                             "bytes_out": best_f["bytes_out"] if mode != "fd_null" else None}
                 if mode == "fd":
                     got = hashlib.sha256(open(fout, "rb").read()).hexdigest()
                     want = hashlib.sha256(stream).hexdigest() if stream is not None else None
@@ -697,7 +697,9 @@ def main():
                                     "what": "file in /dev/shm -> OutputStream facade (readFrom(fd): pinned double-buffered staging, worker thread, -p 10 as a minimum) -> "
                                             ".bz2 file in /dev/shm; first write .. close(), constructor (setup_ms) apart; best of 2",
                                     "modes": fac,
-                                    "modes_note": "fd = readFrom(fd) (what the CLI uses); vec = write(vector,off,len) in 1 MiB pieces (reference API); "
+                                    "modes_note": "fd = readFrom(fd) (what the CLI uses), output file in /dev/shm; fd_null = the same with /dev/null as the output "
+                                                  "(a single thread writing fresh tmpfs pages is slower than the GPU compresses: the difference is the sink); "
+                                                  "vec = write(vector,off,len) in 1 MiB pieces (reference API); "
                                                   "byte = write(int) per byte, the loop of the reference's app.cpp:105-116 (host-bound)"}
         except Exception as e:
             extras["e2e_facade"] = {"error": str(e)[:300]}

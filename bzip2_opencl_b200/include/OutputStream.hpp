@@ -58,8 +58,18 @@ private:
     size_t limit() const { return head + target; }
     int cur = 0;              // buffer being filled
     size_t fill = 0;          // next free byte in stage[cur]
-    uint8_t *outBits = nullptr; // pinned: packed bits of one batch
+    uint8_t *outBuf[2] = {nullptr, nullptr}; // pinned: packed bits of a batch; one is written to the ostream while the next batch fills the other
+    uint8_t *outBits = nullptr;               // the one the running batch fills
+    int outCur = 0;
     size_t outCap = 0;
+    // the writer: the ostream takes the bits of batch k while batch k+1 is being compressed
+    std::thread writer;
+    std::mutex wmu;
+    std::condition_variable wcv;
+    bool wPosted = false, wDone = true, wQuit = false;
+    const uint8_t *wPtr = nullptr;
+    size_t wLen = 0;
+    std::exception_ptr wFailure;
     std::vector<uint32_t> blockCRCs;
     bool carryBits[8]; // < 8 bits waiting for the next byte (the reference's leftBuffer)
     size_t carryCount = 0;
@@ -120,13 +130,66 @@ private:
             outBits[0] = static_cast<uint8_t>(outBits[0] | first);
             const uint64_t total = carryCount + nbits;
             const size_t whole = static_cast<size_t>(total / 8);
-            outputStream.write(reinterpret_cast<const char *>(outBits), static_cast<std::streamsize>(whole));
             carryCount = static_cast<size_t>(total % 8);
             for (size_t i = 0; i < carryCount; ++i)
                 carryBits[i] = (outBits[whole] >> (7 - i)) & 1;
+            postWrite(outBits, whole); // (waits for the previous batch's bytes to be out, then returns: the other buffer is free)
+            outCur ^= 1;
+            outBits = outBuf[outCur];
         }
         leftBegin = begin + consumed;
         leftEnd = end;
+    }
+
+    void writerMain()
+    {
+        for (;;)
+        {
+            std::unique_lock<std::mutex> lk(wmu);
+            wcv.wait(lk, [&] { return wPosted || wQuit; });
+            if (!wPosted)
+                return;
+            wPosted = false;
+            const uint8_t *p = wPtr;
+            const size_t n = wLen;
+            lk.unlock();
+            try
+            {
+                outputStream.write(reinterpret_cast<const char *>(p), static_cast<std::streamsize>(n));
+            }
+            catch (...)
+            {
+                wFailure = std::current_exception();
+            }
+            lk.lock();
+            wDone = true;
+            wcv.notify_all();
+        }
+    }
+
+    void waitWritten()
+    {
+        std::unique_lock<std::mutex> lk(wmu);
+        wcv.wait(lk, [&] { return wDone; });
+        if (wFailure)
+        {
+            std::exception_ptr f = wFailure;
+            wFailure = nullptr;
+            std::rethrow_exception(f);
+        }
+    }
+
+    void postWrite(const uint8_t *p, size_t n)
+    {
+        waitWritten();
+        {
+            std::lock_guard<std::mutex> lk(wmu);
+            wPtr = p;
+            wLen = n;
+            wPosted = true;
+            wDone = false;
+        }
+        wcv.notify_all();
     }
 
     void workerMain()
@@ -249,9 +312,13 @@ public:
                 throw std::runtime_error("bz2b200_host_alloc failed");
         }
         outCap = bz2b200_max_output_bytes(handle, cap) + 16;
-        outBits = static_cast<uint8_t *>(bz2b200_host_alloc(outCap));
-        if (!outBits)
-            throw std::runtime_error("bz2b200_host_alloc failed");
+        for (int i = 0; i < 2; ++i)
+        {
+            outBuf[i] = static_cast<uint8_t *>(bz2b200_host_alloc(outCap));
+            if (!outBuf[i])
+                throw std::runtime_error("bz2b200_host_alloc failed");
+        }
+        outBits = outBuf[0];
         blockCRCs.resize(cap / static_cast<size_t>((streamBlockSize - 5) * 4 / 5 > 0 ? (streamBlockSize - 5) * 4 / 5 : 1) + 4);
         fill = head;
         {
@@ -263,6 +330,7 @@ public:
                 throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
         }
         worker = std::thread([this] { workerMain(); });
+        writer = std::thread([this] { writerMain(); });
         // stream header, reference :126-128
         const char hdr[4] = {'B', 'Z', 'h', static_cast<char>('0' + blockSizeMultiplier)};
         outputStream.write(hdr, 4);
@@ -283,9 +351,20 @@ public:
             cv.notify_all();
             worker.join();
         }
+        if (writer.joinable())
+        {
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return wDone; });
+                wQuit = true;
+            }
+            wcv.notify_all();
+            writer.join();
+        }
         bz2b200_host_free(stage[0]);
         bz2b200_host_free(stage[1]);
-        bz2b200_host_free(outBits);
+        bz2b200_host_free(outBuf[0]);
+        bz2b200_host_free(outBuf[1]);
         bz2b200_destroy(handle);
     }
 
@@ -321,7 +400,7 @@ public:
     }
 
     // extension: everything the file descriptor still holds, read straight into the staging buffers (no intermediate copy).
-    // A regular file is read by four threads at once (pread on disjoint ranges: one thread copies out of the page cache at a
+    // A regular file is read by eight threads at once (pread on disjoint ranges: one thread copies out of the page cache at a
     // few GB/s, less than a GPU compresses).
     size_t readFrom(int fd)
     {
@@ -337,7 +416,7 @@ public:
             while (pos < end)
             {
                 const size_t n = end - pos < limit() - fill ? end - pos : limit() - fill;
-                const int T = n >= (size_t(8) << 20) ? 4 : 1;
+                const int T = n >= (size_t(8) << 20) ? 8 : 1;
                 std::vector<std::thread> th;
                 bool ok = true;
                 uint8_t *dst = stage[cur] + fill;
@@ -388,6 +467,7 @@ public:
         streamFinished = true;
         submit(true);
         waitIdle();
+        waitWritten();
         bool bits[8 + 48 + 32 + 8];
         size_t cnt = 0;
         for (size_t i = 0; i < carryCount; ++i)

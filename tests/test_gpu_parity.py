@@ -348,6 +348,42 @@ def test_config4_random_bytes_full_blocks_properties():
     assert 1.0 < len(full) / len(d) < 1.01
 
 
+@pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
+def test_config4_random_bytes_vs_real_reference_and_sharded_over_devices():
+    # random data at 900k against the reference itself on more than two blocks -- 24 MiB of the C4 generator through one
+    # device and through a multi-device handle (on a one-GPU box the same device several times), and the first 96 MiB of BASELINE
+    # configs[3] compared between the two paths bit for bit
+    d = corpus.rand_bytes(24 << 20, 4)
+    ref = refimpl.compress(d, 9, 100000, threads=os.cpu_count() or 8)
+    one = api.Compressor(9, 32, 100000)
+    assert one.compress(d) == ref
+    ndev = api.load_library().bz2b200_device_count()
+    many = api.Compressor(9, 16, 100000, devices=[i % ndev for i in range(4)])
+    big = corpus.rand_bytes(96 << 20, 4)
+    a, b = one.compress(big), many.compress(big)
+    assert a == b
+    assert bz2.decompress(b) == big
+    one.close()
+    many.close()
+
+
+@pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
+def test_config2_mixed_corpus_prefix_and_config5_block_sizes_vs_real_reference():
+    # bounded forms of BASELINE configs[1] and [4] inside the driver-visible suite (tools/run_configs.py runs them at full size):
+    # the first 96 MiB of the mixed corpus at -9, and every block size -1..-9 on 24 MiB of the C5 text, against the reference itself
+    threads = os.cpu_count() or 8
+    d = corpus.mixed_corpus(96 << 20, workers=min(16, threads))
+    c = api.Compressor(9, 64, 100000)
+    assert c.compress(d) == refimpl.compress(d, 9, 100000, threads=threads)
+    c.close()
+    t = corpus.word_text(24 << 20, 5, markov=True)
+    for mult in range(1, 10):
+        out = comp(mult, 100000, 64).compress(t)
+        assert out == refimpl.compress(t, mult, 100000, threads=threads), f"-{mult}"
+        if mult in (1, 9):
+            assert bz2.decompress(out) == t
+
+
 def test_cpp_facade_end_to_end(tmp_path):
     # the reference-named C++ surface (OutputStream.hpp ...) driven exactly like app.cpp:103-117, both write() overloads
     exe = str(tmp_path / "facade")
