@@ -111,13 +111,15 @@ __global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist,
 }
 
 // ------------------------------------------------------------------------------------------------ radix: stable scatter
-struct ScatterSmem {
-    uint32_t warp_hist[RS_WARPS][256];
-    uint32_t tile_base[256];
-    uint32_t gofs[256];
+template <int DB>
+struct ScatterSmemT {
+    uint32_t warp_hist[RS_WARPS][1 << DB];
+    uint32_t tile_base[1 << DB];
+    uint32_t gofs[1 << DB];
     uint32_t scratch[34];
     alignas(16) uint64_t keys[RS_TILE];
 };
+using ScatterSmem = ScatterSmemT<8>;
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs, uint64_t stride,
@@ -207,6 +209,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t *__
 #ifndef BZ_OS_MINB
 #define BZ_OS_MINB 3
 #endif
+#ifndef BZ_OS_MBATCH
+#define BZ_OS_MBATCH 1 // keys whose MATCH.ANY are issued back to back in a sweep before their counters are updated; 1, 4, 8, 16 measured equal (30.4 / 30.0 / 31.1 / 29.9 ms per GiB): the ADU pipe is throughput-bound, not latency-bound
+#endif
 constexpr int RC_TILES = 16;                 // radix tiles per counting CTA
 constexpr int RC_MAXPASS = 5;
 constexpr uint32_t LB_AGG = 1u << 30, LB_PREFIX = 2u << 30, LB_VALUE = (1u << 30) - 1u;
@@ -281,6 +286,34 @@ __global__ void __launch_bounds__(256) k_radix_bases(const uint32_t *__restrict_
         }
         const uint32_t ex = block_excl_sum(tot, scratch, nullptr);
         for (int r = 0; r < (npass == 1 ? nrep : 1); ++r) digit_base[((uint64_t)(p + r) * n_blocks + b) * 256 + d] = ex;
+    }
+}
+// the same for digits of DB bits (1 << DB bins per pass, (1 << DB) / 256 consecutive bins per thread)
+template <int DB>
+__global__ void __launch_bounds__(256) k_radix_bases_wide(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ counts, int npass, int ctas_per_block,
+                                                           uint32_t n_blocks, uint32_t *__restrict__ digit_base)
+{
+    constexpr int NB = 1 << DB, DPT = NB / 256;
+    __shared__ uint32_t scratch[33];
+    const uint32_t b = blockIdx.x;
+    const uint32_t cnt = counts[b];
+    const uint32_t nc = (cnt + RC_TILES * RS_TILE - 1) / (RC_TILES * RS_TILE);
+    for (int p = 0; p < npass; ++p) {
+        uint32_t tot[DPT], mine = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            const uint32_t d = threadIdx.x * DPT + q;
+            uint32_t t = 0;
+            for (uint32_t c = 0; c < nc; ++c) t += partial[(((uint64_t)b * ctas_per_block + c) * npass + p) * NB + d];
+            tot[q] = t;
+            mine += t;
+        }
+        uint32_t ex = block_excl_sum(mine, scratch, nullptr);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            digit_base[((uint64_t)p * n_blocks + b) * NB + threadIdx.x * DPT + q] = ex;
+            ex += tot[q];
+        }
     }
 }
 
@@ -365,15 +398,17 @@ __device__ __forceinline__ void packed_keys16(const uint8_t *sym, uint32_t p0, c
 
 // FROM_TEXT: the first pass of round 0 builds its elements on the fly, (first text_bytes bytes of rotation i, big-endian) << 20 | i,
 // from the block `text` instead of reading them from keys_in.
-template <bool FROM_TEXT>
+template <bool FROM_TEXT, int DB = 8>
 __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                 const uint32_t *__restrict__ counts, uint64_t stride, int shift,
                                                                 const uint32_t *__restrict__ digit_base, uint32_t *__restrict__ tile_state,
                                                                 int tiles_per_block, uint32_t *__restrict__ ticket, const uint8_t *__restrict__ text,
                                                                 int text_bytes, const uint32_t *__restrict__ present)
 {
+    constexpr uint32_t NB = 1u << DB, DMASK = NB - 1u; // bins of one pass
+    constexpr int DPT = (int)NB / RS_THREADS;          // consecutive bins per thread in the scan
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    ScatterSmemT<DB> &sm = *reinterpret_cast<ScatterSmemT<DB> *>(smem_raw);
     __shared__ uint8_t s_map[256]; // text_bytes == 0: keys over the block's own alphabet
     // tiles are taken in ticket order, so the tiles a CTA looks back at are always held by CTAs that are already running
     if (threadIdx.x == 0) sm.scratch[33] = atomicAdd(ticket, 1u);
@@ -388,7 +423,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     const uint32_t tcnt = min((uint32_t)RS_TILE, cnt - base);
     const int lane = lane_id(), w = warp_id();
     const unsigned lt = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * (int)NB; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
     uint64_t key[RS_ITEMS];
     uint16_t rnk[RS_ITEMS];
     if (FROM_TEXT && text_bytes == 0) {
@@ -438,59 +473,81 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t li = contig ? threadIdx.x * RS_ITEMS + i : w * RS_WARP_ELEMS + i * 32 + lane;
-            if (li < tcnt) rnk[i] = (uint16_t)atomicAdd(&sm.warp_hist[0][(uint32_t)(key[i] >> shift) & 0xffu], 1u);
+            if (li < tcnt) rnk[i] = (uint16_t)atomicAdd(&sm.warp_hist[0][(uint32_t)(key[i] >> shift) & DMASK], 1u);
         }
     } else {
+        // the matches of BZ_OS_MBATCH keys are issued back to back (their latency overlaps), then the counters are updated in key order
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const uint32_t li = w * RS_WARP_ELEMS + i * 32 + lane;
-            const bool valid = li < tcnt;
-            const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 0xffu) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(FULL, d);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (valid && lane == leader) {
-                old = sm.warp_hist[w][d];
-                sm.warp_hist[w][d] = old + __popc(peers);
+        for (int h = 0; h < RS_ITEMS; h += BZ_OS_MBATCH) {
+            unsigned peers[BZ_OS_MBATCH];
+#pragma unroll
+            for (int j = 0; j < BZ_OS_MBATCH; ++j) {
+                const uint32_t li = w * RS_WARP_ELEMS + (h + j) * 32 + lane;
+                const uint32_t d = li < tcnt ? ((uint32_t)(key[h + j] >> shift) & DMASK) : 0xffffffffu;
+                peers[j] = __match_any_sync(FULL, d);
             }
-            old = __shfl_sync(FULL, old, leader);
-            rnk[i] = (uint16_t)(old + __popc(peers & lt));
-            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < BZ_OS_MBATCH; ++j) {
+                const uint32_t li = w * RS_WARP_ELEMS + (h + j) * 32 + lane;
+                const bool valid = li < tcnt;
+                const uint32_t d = (uint32_t)(key[h + j] >> shift) & DMASK;
+                const int leader = __ffs(peers[j]) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader) {
+                    old = sm.warp_hist[w][d];
+                    sm.warp_hist[w][d] = old + __popc(peers[j]);
+                }
+                old = __shfl_sync(FULL, old, leader);
+                rnk[h + j] = (uint16_t)(old + __popc(peers[j] & lt));
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
     {
-        const uint32_t d = threadIdx.x; // RS_THREADS == 256: one digit per thread
-        uint32_t sum = 0;
+        // every thread owns DPT consecutive digits (RS_THREADS == 256; DPT = 1 for 8-bit digits)
+        uint32_t sums[DPT], mine = 0;
+        volatile uint32_t *st = tile_state + ((uint64_t)b * tiles_per_block) * NB;
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ++ww) {
-            const uint32_t t = sm.warp_hist[ww][d];
-            sm.warp_hist[ww][d] = sum;
-            sum += t;
-        }
-        volatile uint32_t *st = tile_state + ((uint64_t)b * tiles_per_block) * 256 + d;
-        // publish this tile's count, then add up the tiles in front of it
-        st[(uint64_t)tile * 256] = (tile == 0 ? LB_PREFIX : LB_AGG) | sum;
-        const uint32_t tb = block_excl_sum(sum, sm.scratch, nullptr);
-        uint32_t before = 0;
-        if (tile > 0) {
-            for (int t = (int)tile - 1;; --t) {
-                uint32_t v;
-                do { v = st[(uint64_t)t * 256]; } while ((v & ~LB_VALUE) == 0);
-                before += v & LB_VALUE;
-                if (v & LB_PREFIX) break;
+        for (int q = 0; q < DPT; ++q) {
+            const uint32_t d = threadIdx.x * DPT + q;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) {
+                const uint32_t t = sm.warp_hist[ww][d];
+                sm.warp_hist[ww][d] = sum;
+                sum += t;
             }
-            st[(uint64_t)tile * 256] = LB_PREFIX | (before + sum);
+            sums[q] = sum;
+            mine += sum;
+            // publish this tile's count, then add up the tiles in front of it
+            st[(uint64_t)tile * NB + d] = (tile == 0 ? LB_PREFIX : LB_AGG) | sum;
         }
-        sm.tile_base[d] = tb;
-        sm.gofs[d] = digit_base[b * 256 + d] + before - tb;
+        uint32_t tb = block_excl_sum(mine, sm.scratch, nullptr);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            const uint32_t d = threadIdx.x * DPT + q;
+            uint32_t before = 0;
+            if (tile > 0) {
+                for (int t = (int)tile - 1;; --t) {
+                    uint32_t v;
+                    do { v = st[(uint64_t)t * NB + d]; } while ((v & ~LB_VALUE) == 0);
+                    before += v & LB_VALUE;
+                    if (v & LB_PREFIX) break;
+                }
+                st[(uint64_t)tile * NB + d] = LB_PREFIX | (before + sums[q]);
+            }
+            sm.tile_base[d] = tb;
+            sm.gofs[d] = digit_base[b * NB + d] + before - tb;
+            tb += sums[q];
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const uint32_t li = contig ? threadIdx.x * RS_ITEMS + i : w * RS_WARP_ELEMS + i * 32 + lane;
         if (li < tcnt) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+            const uint32_t d = (uint32_t)(key[i] >> shift) & DMASK;
             sm.keys[sm.tile_base[d] + (unstable ? 0u : sm.warp_hist[w][d]) + rnk[i]] = key[i];
         }
     }
@@ -498,7 +555,7 @@ __global__ void __launch_bounds__(RS_THREADS, BZ_OS_MINB) k_radix_onesweep(const
     uint64_t *ko = keys_out + (uint64_t)b * stride;
     for (uint32_t p = threadIdx.x; p < tcnt; p += RS_THREADS) {
         const uint64_t k = sm.keys[p];
-        ko[sm.gofs[(uint32_t)(k >> shift) & 0xffu] + p] = k;
+        ko[sm.gofs[(uint32_t)(k >> shift) & DMASK] + p] = k;
     }
 }
 
@@ -530,19 +587,21 @@ __global__ void __launch_bounds__(256) k_bwt_keys0(const uint8_t *__restrict__ r
 constexpr int KP_TILE = 4096;
 // digit histograms of the packed keys for all five passes, straight from the text (the keys themselves are built again by the first
 // sweep): partial[] in k_radix_count's layout, one CTA per RC_TILES radix tiles
+template <int DB, int NPASS>
 __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restrict__ rle, const uint32_t *__restrict__ n_arr, uint64_t stride,
                                                            const uint32_t *__restrict__ present, uint32_t *__restrict__ partial, int ctas_per_block,
                                                            uint32_t *__restrict__ h0_out)
 {
+    constexpr int NB = 1 << DB;
     __shared__ uint8_t map[256];
     __shared__ __align__(16) uint8_t sym[PK_STAGE_BYTES];
-    __shared__ uint32_t h[RC_MAXPASS][256];
+    __shared__ uint32_t h[NPASS][NB];
     const uint32_t b = blockIdx.y, n = n_arr[b];
     const uint32_t base0 = blockIdx.x * (RC_TILES * RS_TILE);
     const PackedShape ps = packed_setup(present, b, map);
     if (blockIdx.x == 0 && threadIdx.x == 0) h0_out[b] = (uint32_t)ps.h0;
     if (base0 >= n) return;
-    for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += 256) (&h[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < NPASS * NB; i += 256) (&h[0][0])[i] = 0;
     const uint8_t *T = rle + (uint64_t)b * stride;
     const uint32_t end = min(n, base0 + RC_TILES * RS_TILE);
     for (uint32_t base = base0; base < end; base += KP_TILE) {
@@ -555,13 +614,13 @@ __global__ void __launch_bounds__(256) k_bwt_count_packed(const uint8_t *__restr
             packed_keys16(sym, p0, ps, [&](int i, uint64_t key) {
                 if (p0 + i < tcnt) {
 #pragma unroll
-                    for (int p = 0; p < RC_MAXPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (8 * p)) & 0xffu], 1u);
+                    for (int p = 0; p < NPASS; ++p) atomicAdd(&h[p][(uint32_t)(key >> (DB * p)) & (uint32_t)(NB - 1)], 1u);
                 }
             });
     }
     __syncthreads();
-    uint32_t *out = partial + ((uint64_t)b * ctas_per_block + blockIdx.x) * RC_MAXPASS * 256;
-    for (int i = threadIdx.x; i < RC_MAXPASS * 256; i += 256) out[i] = (&h[0][0])[i];
+    uint32_t *out = partial + ((uint64_t)b * ctas_per_block + blockIdx.x) * NPASS * NB;
+    for (int i = threadIdx.x; i < NPASS * NB; i += 256) out[i] = (&h[0][0])[i];
 }
 
 __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ p, uint32_t n, uint32_t v)

@@ -91,6 +91,8 @@ struct bz2b200 {
     uint64_t seg_first = 16ull << 20, seg_rest = 64ull << 20; // host input: bytes per H2D segment (BZ2B200_SEG_MB=first,rest)
     int pack_keys = 1;    // round-0 keys over the block's own alphabet (k_bwt_keys_packed); BZ2B200_PACK=0: the first key0_bytes bytes
     int onesweep = 1;     // BZ2B200_ONESWEEP=0: histogram + scan + scatter kernels per radix pass instead of the single-sweep pass
+    int r0_bits = 8;      // BZ2B200_R0_BITS=10: four round-0 sweeps over 10-bit digits instead of five over 8-bit ones (measured SLOWER: 33.6 vs 30.6 ms of
+                          // sweeps per GiB -- 1024 bins cost shared memory, a four times longer scan and look-back, and more distinct digits per MATCH)
     int r0_group = 0;     // BZ2B200_R0_GROUP=g: the five round-0 sweeps run group by group of g blocks so that a group's elements stay in L2 (measured: the
                           // small launches cost more than the HBM traffic they save, profiles/r02_*); 0 = every sweep over the whole batch
     int chain_overlap = 1; // BZ2B200_CHAIN_OVERLAP=0: a slice's batches start only when its walk is through (the walk alone on the device is ~30 % faster,
@@ -264,6 +266,10 @@ static int upload_constants(bz2b200 *h)
     CK(cudaFuncSetAttribute(k_radix_onesweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
     CK(cudaFuncSetAttribute(k_radix_onesweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmemT<10>)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<false, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmemT<10>)));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<true, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bwt_local, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_rle_walk_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
     CK(cudaFuncSetAttribute(k_dec_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DB_WARPS * sizeof(DecTables))));
@@ -340,6 +346,7 @@ extern "C" void bz2b200_destroy(bz2b200_t *h)
 }
 
 static int alloc_batch(bz2b200 *h);
+constexpr size_t R0_WORDS = 4 * 1024; // >= RC_MAXPASS * 256: digit counters of all round-0 sweeps of one block (tile)
 
 static int create_impl(bz2b200 *h, bool with_batch)
 {
@@ -393,10 +400,10 @@ static int alloc_batch(bz2b200 *h)
     ENSURE(h->loc_cnt, G * h->tilesG * 4);
     ENSURE(h->rank, G * S * 4);
     ENSURE(h->mtf, G * S * 2);
-    ENSURE(h->hist, (size_t)RC_MAXPASS * G * h->tilesR * 256 * 4); // status words: one region per sweep of round 0
+    ENSURE(h->hist, (size_t)R0_WORDS * G * h->tilesR * 4); // status words: one region per sweep of round 0 (5 x 256 or 4 x 1024 bins)
     ENSURE(h->tickets, (size_t)RC_MAXPASS * G * 4);
-    ENSURE(h->digit_base, G * 256 * 4 * RC_MAXPASS);
-    ENSURE(h->rc_partial, G * h->ctasC * RC_MAXPASS * 256 * 4);
+    ENSURE(h->digit_base, G * (size_t)R0_WORDS * 4);
+    ENSURE(h->rc_partial, G * h->ctasC * (size_t)R0_WORDS * 4);
     ENSURE(h->cnts, 2 * G * 4); // bag sizes, double buffered
     ENSURE(h->h0, G * 4);
     ENSURE(h->root, G * 4);
@@ -444,7 +451,7 @@ static int create_lanes(bz2b200 *h)
         h->lanes.push_back(l);
         l->parent = h;
         l->device = h->device; l->base = h->base; l->mult = h->mult; l->bs = h->bs; l->S = h->S; l->nbits = h->nbits;
-        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->root_sort = h->root_sort; l->r0_group = h->r0_group; l->bulk_copy = h->bulk_copy; l->n_lanes = 1;
+        l->key0_bytes = h->key0_bytes; l->pack_keys = h->pack_keys; l->onesweep = h->onesweep; l->local_sort = h->local_sort; l->root_sort = h->root_sort; l->r0_group = h->r0_group; l->r0_bits = h->r0_bits; l->bulk_copy = h->bulk_copy; l->n_lanes = 1;
         l->G = (h->G + nl - 1) / nl;
         int rc = create_impl(l, true);
         if (rc == BZ2B200_OK && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) rc = BZ2B200_E_CUDA;
@@ -487,6 +494,7 @@ extern "C" int bz2b200_create(bz2b200_t **out, int device_id, int base_block_siz
     if (const char *e = getenv("BZ2B200_CHAIN_OVERLAP")) h->chain_overlap = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK_SMEM")) h->walk_smem = std::max(0, std::min(200, atoi(e)));
     if (const char *e = getenv("BZ2B200_R0_GROUP")) h->r0_group = std::max(0, atoi(e));
+    if (const char *e = getenv("BZ2B200_R0_BITS")) h->r0_bits = atoi(e) == 10 ? 10 : 8;
     if (const char *e = getenv("BZ2B200_ONESWEEP")) h->onesweep = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK")) h->prefix_walk = atoi(e);
     if (const char *e = getenv("BZ2B200_WALK_GROWTH")) h->walk_growth = std::max(1, atoi(e));
@@ -963,9 +971,17 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         KL(KID_k_bwt_bytehist, k_bwt_bytehist<<<dim3(nc, nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->rc_partial), h->ctasC));
         KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, 1, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, ptr<uint32_t>(h->present)));
         const uint32_t tiles = (max_n + RS_TILE - 1) / RS_TILE;
-        KL(KID_k_bwt_keys0, k_bwt_count_packed<<<dim3(std::max(nc, 1u), nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->present), ptr<uint32_t>(h->rc_partial),
-                                                                                          h->ctasC, d_h0)); // (h0 is written by the first CTA of every block, empty or not)
-        KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, RC_MAXPASS, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, nullptr));
+        const bool wide = h->r0_bits == 10;         // 4 sweeps over 10-bit digits instead of 5 over 8-bit ones
+        const int r0_pass = wide ? 4 : RC_MAXPASS, r0_bins = wide ? 1024 : 256;
+        if (wide) {
+            KL(KID_k_bwt_keys0, k_bwt_count_packed<10, 4><<<dim3(std::max(nc, 1u), nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->present),
+                                                                                                     ptr<uint32_t>(h->rc_partial), h->ctasC, d_h0));
+            KL(KID_k_radix_bases, k_radix_bases_wide<10><<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, 4, h->ctasC, nb, ptr<uint32_t>(h->digit_base)));
+        } else {
+            KL(KID_k_bwt_keys0, k_bwt_count_packed<8, RC_MAXPASS><<<dim3(std::max(nc, 1u), nb), 256, 0, st>>>(ptr<uint8_t>(h->rle), d_n, S, ptr<uint32_t>(h->present),
+                                                                                                               ptr<uint32_t>(h->rc_partial), h->ctasC, d_h0)); // (h0 is written by the first CTA of every block, empty or not)
+            KL(KID_k_radix_bases, k_radix_bases<<<nb, 256, 0, st>>>(ptr<uint32_t>(h->rc_partial), d_n, RC_MAXPASS, h->ctasC, nb, ptr<uint32_t>(h->digit_base), 1, nullptr));
+        }
         stt.kernel_launches += 4;
         KBYTES(KID_k_bwt_bytehist, sum_n);
         KBYTES(KID_k_bwt_keys0, sum_n);
@@ -975,9 +991,9 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
         // text read of the first and the element write of the last sweep go to HBM.  Every (sweep, group) has its own ticket and every
         // sweep its own region of status words, zeroed once per batch.
         const uint32_t gsz = h->r0_group ? (uint32_t)h->r0_group : nb;
-        const size_t pass_words = (size_t)h->G * h->tilesR * 256;
+        const size_t pass_words = (size_t)h->G * h->tilesR * r0_bins;
         if (tiles) {
-            for (int p = 0; p < RC_MAXPASS; ++p) CK(cudaMemsetAsync(ptr<uint32_t>(h->hist) + (size_t)p * pass_words, 0, (size_t)nb * h->tilesR * 256 * 4, st));
+            for (int p = 0; p < r0_pass; ++p) CK(cudaMemsetAsync(ptr<uint32_t>(h->hist) + (size_t)p * pass_words, 0, (size_t)nb * h->tilesR * r0_bins * 4, st));
             CK(cudaMemsetAsync(h->tickets.p, 0, (size_t)RC_MAXPASS * h->G * 4, st));
         }
         uint32_t launch_no = 0;
@@ -988,23 +1004,35 @@ static int run_batch(bz2b200 *h, const uint8_t *d_in, uint64_t b0, uint32_t nb, 
             const uint32_t gt = (gmax + RS_TILE - 1) / RS_TILE;
             if (!gt) continue;
             const uint64_t go = (uint64_t)g0 * S;
-            for (int p = 0; p < RC_MAXPASS; ++p) {
-                uint32_t *db = ptr<uint32_t>(h->digit_base) + ((size_t)p * nb + g0) * 256;
-                uint32_t *status = ptr<uint32_t>(h->hist) + (size_t)p * pass_words + (size_t)g0 * h->tilesR * 256;
+            for (int p = 0; p < r0_pass; ++p) {
+                uint32_t *db = ptr<uint32_t>(h->digit_base) + ((size_t)p * nb + g0) * r0_bins;
+                uint32_t *status = ptr<uint32_t>(h->hist) + (size_t)p * pass_words + (size_t)g0 * h->tilesR * r0_bins;
                 uint32_t *ticket = ptr<uint32_t>(h->tickets) + launch_no++;
-                if (p == 0)
-                    KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
-                                                 nullptr, kB + go, d_n + g0, S, VAL_BITS, db, status, h->tilesR, ticket, ptr<uint8_t>(h->rle) + go, 0,
-                                                 ptr<uint32_t>(h->present) + (size_t)g0 * 8));
-                else
-                    KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
-                                                 ((p & 1) ? kB : kA) + go, ((p & 1) ? kA : kB) + go, d_n + g0, S, VAL_BITS + 8 * p, db, status, h->tilesR, ticket, nullptr, 0,
-                                                 nullptr));
+                // sweep p reads the buffer sweep p-1 wrote; the LAST sweep must end in kB (the regroup reads it there)
+                const bool to_b = ((r0_pass - 1 - p) & 1) == 0;
+                uint64_t *src = (to_b ? kA : kB) + go, *dst = (to_b ? kB : kA) + go;
+                if (wide) {
+                    if (p == 0)
+                        KL(KID_k_radix_onesweep, k_radix_onesweep<true, 10><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmemT<10>), st>>>(
+                                                     nullptr, dst, d_n + g0, S, VAL_BITS, db, status, h->tilesR, ticket, ptr<uint8_t>(h->rle) + go, 0,
+                                                     ptr<uint32_t>(h->present) + (size_t)g0 * 8));
+                    else
+                        KL(KID_k_radix_onesweep, k_radix_onesweep<false, 10><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmemT<10>), st>>>(
+                                                     src, dst, d_n + g0, S, VAL_BITS + 10 * p, db, status, h->tilesR, ticket, nullptr, 0, nullptr));
+                } else {
+                    if (p == 0)
+                        KL(KID_k_radix_onesweep, k_radix_onesweep<true><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                                     nullptr, dst, d_n + g0, S, VAL_BITS, db, status, h->tilesR, ticket, ptr<uint8_t>(h->rle) + go, 0,
+                                                     ptr<uint32_t>(h->present) + (size_t)g0 * 8));
+                    else
+                        KL(KID_k_radix_onesweep, k_radix_onesweep<false><<<dim3(gt, gc), RS_THREADS, sizeof(ScatterSmem), st>>>(
+                                                     src, dst, d_n + g0, S, VAL_BITS + 8 * p, db, status, h->tilesR, ticket, nullptr, 0, nullptr));
+                }
                 stt.kernel_launches += 1;
             }
         }
-        KBYTES(KID_k_radix_onesweep, sum_n * (9 + 4 * 16));
-        res = 1; // five sweeps end in kB
+        KBYTES(KID_k_radix_onesweep, sum_n * (9 + (uint64_t)(r0_pass - 1) * 16));
+        res = 1; // the last sweep ends in kB
     } else if (h->onesweep && h->key0_bytes >= 4) {
         k_fill_u32<<<(nb + 255) / 256, 256, 0, st>>>(d_h0, nb, (uint32_t)h->key0_bytes);
         radix_sort_round0(h, d_n, nb, max_n, sum_n);
