@@ -225,7 +225,11 @@ def test_alternative_sort_paths_give_the_same_bits(monkeypatch):
     exp = oracle.compress(d, 9, 100000)
     # byte keys instead of keys over the block's alphabet (5 and 4 bytes)
     for env in ({"BZ2B200_ONESWEEP": "0"}, {"BZ2B200_LOCALSORT": "0"}, {"BZ2B200_ONESWEEP": "0", "BZ2B200_LOCALSORT": "0"},
-                {"BZ2B200_PACK": "0"}, {"BZ2B200_PACK": "0", "BZ2B200_KEY0_BYTES": "4"}):
+                {"BZ2B200_PACK": "0"}, {"BZ2B200_PACK": "0", "BZ2B200_KEY0_BYTES": "4"},
+                # round-2 switches: 10-bit digits / grouped sweeps in round 0, blocks never sorted through their root, byte loads
+                # instead of the TMA bulk copy, the tree-descent walk
+                {"BZ2B200_R0_BITS": "10"}, {"BZ2B200_R0_GROUP": "2"}, {"BZ2B200_R0_BITS": "10", "BZ2B200_R0_GROUP": "3"}, {"BZ2B200_ROOT": "0"},
+                {"BZ2B200_BULK": "0"}, {"BZ2B200_WALK": "0"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         c = api.Compressor(9, 8, 100000)
