@@ -6,14 +6,19 @@
 
 Metric (BASELINE.json): input MB/s (10^6 bytes of uncompressed input) compressed into a bit-exact .bz2, 900k blocks.
 Workload at N=1 = BASELINE configs[1]: 1 GiB mixed synthetic corpus (text + source-code-like + binary), -9, on one B200.
-N > 1 is weak scaling: the stream is N GiB (the 1 GiB corpus repeated N times), its block boundaries are found by one
-boundary scan, and every rank compresses a contiguous range of ceil(B/N) blocks -- no data-path collective.
-A step = one pass of the whole hot path (boundary scan, RLE1+CRC, BWT, MTF/RLE2, Huffman, bit packing) over the rank's shard.
+A step = one pass of the whole hot path (boundary walk, RLE1+CRC, BWT, MTF/RLE2, Huffman, bit packing).
+N > 1 (torchrun, one rank per GPU) compresses ONE stream: N GiB (the corpus repeated N times; weak scaling) cut into contiguous byte
+slices; inside the timed region: halo exchange, summary trees, the CHAINED boundary walk over the whole stream, every rank's
+compression, the bit shift of every part on its own GPU and the gather of all parts into rank 0's HBM (multi.StreamRank; no
+data-path collective).  The line also carries `strong` = BASELINE config 4 (8 GiB of LCG bytes, fixed total size) and
+`parity_check`: sha256 of the N-GPU stream against the stream one GPU produces for the same bytes.
 
   value     device-resident: input already in HBM, packed bits left in HBM; CUDA events on the launching stream, max over ranks
   e2e       same work through the C ABI with HOST buffers: pinned host input -> H2D -> kernels -> D2H of the bit stream
   roofline  dominant kernel (by summed CUDA-event time over the timed steps) against the measured HBM copy bandwidth
   cpu_baseline  the reference's own code built for the CPU (oracle/_ref), all host threads, on a bounded sample
+  (N = 1 only) strong / config3_repetitive / e2e_facade / decompress: BASELINE configs 4 and 3 on this GPU, the drop-in path file ->
+  OutputStream facade -> file, the decompress side with the reference decoder's host time next to it
 """
 from __future__ import annotations
 
@@ -57,7 +62,7 @@ def load_peaks():
 
 def workload_name(n_gpus, size_mb):
     return (f"{size_mb} MiB mixed synthetic corpus (text/code/binary segments of 16 MiB, corpus.mixed_corpus), -9 = 900k blocks, base 100000"
-            + (f", repeated x{n_gpus} and sharded by contiguous block ranges over {n_gpus} GPUs" if n_gpus > 1 else ", 1 B200"))
+            + (f", repeated x{n_gpus}: ONE stream over {n_gpus} GPUs by contiguous byte slices (chained boundary walk)" if n_gpus > 1 else ", 1 B200"))
 
 
 def make_corpus(size_mb):

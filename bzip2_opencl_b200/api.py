@@ -188,7 +188,7 @@ class Compressor:
             else:
                 rc = self.lib.bz2b200_decompress_stream(self.h, _np_ptr(src), len(stream), _np_ptr(out), cap, C.byref(n))
             if rc == E_OUTPUT and out_capacity is None:
-                cap = max(2 * cap, int(n.value) * 2)
+                cap = int(n.value) if int(n.value) > cap else 2 * cap   # n = what the stream decodes to: one retry
                 continue
             self._check(rc)
             return out[:n.value].tobytes()

@@ -2108,7 +2108,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     std::vector<uint32_t> crc(G);
     uint64_t expected = 32, total_out = 0;
     uint32_t stream_crc = 0;
-    bool ended = false;
+    bool ended = false, sizing = false;
     size_t ci = 0;
     uint64_t nblocks = 0, nstreams = 0;
     for (;;) { // one iteration per stream
@@ -2173,6 +2173,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
         if (h->profiling) prof_collect(h);
         // chain walk over the batch
         uint32_t n_acc = 0;
+        uint64_t written_end = total_out;
         const uint64_t batch_out0 = total_out;
         bool stop_batch = false;
         for (uint32_t i = 0; i < nb; ++i) {
@@ -2182,36 +2183,37 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
             if (pos < expected) continue;                 // a magic inside the previous block's bits
             if (pos > expected) { stop_batch = true; continue; } // resolved by the outer loop (end marker or format error)
             if (info[i].err != DEC_OK) return fail(dec_err_text(info[i].err));
-            if (total_out + len[i] > out_capacity) {
-                *out_bytes = (size_t)(total_out + len[i]);
-                h->err = "output buffer too small";
-                return BZ2B200_E_OUTPUT;
+            // the output does not fit: go on WITHOUT writing (lengths only), so that the caller learns the size the stream needs and
+            // retries once instead of doubling its buffer and decoding again and again
+            if (total_out + len[i] > out_capacity) sizing = true;
+            if (!sizing) {
+                off[i] = total_out;
+                starts[n_acc] = total_out;
+                crc[n_acc] = info[i].crc;
+                ++n_acc;
+                written_end = total_out + len[i];
             }
-            off[i] = total_out;
-            starts[n_acc] = total_out;
-            crc[n_acc] = info[i].crc;
-            ++n_acc;
             total_out += len[i];
             expected = info[i].end_bit;
             ++nblocks;
         }
-        if (n_acc == 0) return fail("BZip2 stream format error");
-        starts[n_acc] = total_out;
+        if (n_acc == 0 && !sizing) return fail("BZip2 stream format error");
+        starts[n_acc] = written_end;
         CK(cudaMemcpyAsync(h->dec_off.p, off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->dec_starts.p, starts.data(), (size_t)(n_acc + 1) * 8, cudaMemcpyHostToDevice, st));
         KL(KID_k_dec_expand, k_dec_expand<<<(nb + DX_WARPS - 1) / DX_WARPS, DX_WARPS * 32, 0, st>>>(ptr<uint8_t>(h->rle), h->S, ptr<DecInfo>(h->dec_info), nb, ptr<uint64_t>(h->dec_off), d_out));
         // block CRCs over the decoded bytes (BlockDecompressor::checkCRC, :99-106)
         uint64_t max_len = 0;
         for (uint32_t i = 0; i < n_acc; ++i) max_len = std::max(max_len, starts[i + 1] - starts[i]);
-        CK(cudaMemsetAsync(h->dec_crc.p, 0, (size_t)n_acc * 4, st));
+        if (n_acc) CK(cudaMemsetAsync(h->dec_crc.p, 0, (size_t)n_acc * 4, st));
         if (max_len) {
             dim3 cgrid((unsigned)((max_len + CRC_CHUNK - 1) / CRC_CHUNK), n_acc);
             KL(KID_k_crc_chunks, k_crc_chunks<<<cgrid, CRC_THREADS, 0, st>>>(d_out, ptr<uint64_t>(h->dec_starts), 0u, ptr<uint32_t>(h->dec_crc)));
         }
-        KL(KID_k_crc_finish, k_crc_finish<<<(n_acc + 127) / 128, 128, 0, st>>>(ptr<uint64_t>(h->dec_starts), 0u, n_acc, ptr<uint32_t>(h->dec_crc)));
+        if (n_acc) KL(KID_k_crc_finish, k_crc_finish<<<(n_acc + 127) / 128, 128, 0, st>>>(ptr<uint64_t>(h->dec_starts), 0u, n_acc, ptr<uint32_t>(h->dec_crc)));
         h->stats.kernel_launches += 3;
         std::vector<uint32_t> got(n_acc);
-        CK(cudaMemcpyAsync(got.data(), h->dec_crc.p, (size_t)n_acc * 4, cudaMemcpyDeviceToHost, st));
+        if (n_acc) CK(cudaMemcpyAsync(got.data(), h->dec_crc.p, (size_t)n_acc * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h->profiling) prof_collect(h);
         for (uint32_t i = 0; i < n_acc; ++i) {
@@ -2232,7 +2234,7 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     uint64_t w = 0;
     for (int k = 0; k < 8; ++k) w = (w << 8) | tail[k];
     const uint32_t stored = (uint32_t)((w << ((expected + 48) & 7)) >> 32);
-    if (stored != stream_crc) return fail("BZip2 stream CRC error");
+    if (stored != stream_crc && !sizing) return fail("BZip2 stream CRC error");
     ++nstreams;
     if (!multi) break;
     const uint64_t nxt = (expected + 48 + 32 + 7) >> 3; // the padding ends the stream on a byte boundary (OutputStream.hpp:172)
@@ -2244,6 +2246,12 @@ static int decompress_impl(bz2b200_t *h, const uint8_t *input, size_t n_in, uint
     expected = nxt * 8 + 32;
     } // streams
     if (n_streams) *n_streams = nstreams;
+    if (sizing) { // every block has been decoded far enough to know its length: this is what the caller's buffer must hold
+        CK(cudaStreamSynchronize(st));
+        *out_bytes = (size_t)total_out;
+        h->err = "output buffer too small";
+        return BZ2B200_E_OUTPUT;
+    }
     CK(cudaEventRecord(h->ev[11], st));
     if (!out_dev && total_out) {
         CK(cudaEventRecord(h->ev[12], st));

@@ -56,7 +56,7 @@ private:
                             : bz2b200_decompress_stream(handle, in.data(), in.size(), data.data(), cap, &n);
             if (rc != BZ2B200_E_OUTPUT)
                 break;
-            cap = (n > cap ? n : cap) * 2; // n = what the stream needed so far
+            cap = n > cap ? n : cap * 2; // n = what the stream decodes to (bz2b200.h): one retry
         }
         if (rc == BZ2B200_E_FORMAT)
             throw std::runtime_error(bz2b200_last_error(handle)); // the reference's own exception text

@@ -174,7 +174,8 @@ int bz2b200_compress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_by
  * handle's.  Errors: BZ2B200_E_FORMAT with the reference's exception text in bz2b200_last_error ("Invalid BZip2 header",
  * "BZip2 stream format error", "BZip2 stream CRC error", "BZip2 block CRC error", "block Huffman tables invalid",
  * "BZip2 block exceeds declared block size", "Error decoding  block", "BZip2 start pointer invalid", "Insufficient data");
- * BZ2B200_E_OUTPUT when out_capacity is too small (*out_bytes = bytes decoded so far + the block that did not fit).
+ * BZ2B200_E_OUTPUT when out_capacity is too small: *out_bytes = the number of bytes the input decodes to (the decoder goes on without
+ * writing, so one retry with a buffer of that size succeeds).
  */
 int bz2b200_decompress_stream(bz2b200_t *handle, const uint8_t *input, size_t n_bytes, uint8_t *out, size_t out_capacity, size_t *out_bytes);
 

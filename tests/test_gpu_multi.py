@@ -260,6 +260,28 @@ def test_facade_zero_runs_written_byte_by_byte(tmp_path):
     assert (tmp_path / "zeros.bz2").read_bytes() == oracle.compress(d, 9, 100000)
 
 
+def test_decompress_reports_the_size_it_needs():
+    """an output buffer that is too small costs ONE more call, not a doubling loop -- BZ2B200_E_OUTPUT carries the number of bytes
+    the stream decodes to (the decoder goes on without writing)"""
+    d = bytes(30_000_000) + corpus.word_text(2_000_000, 3) + bytes(10_000_000)
+    c = api.Compressor(9, 8, 100000)
+    stream = c.compress(d) + c.compress(b"second stream " * 1000)
+    src = np.frombuffer(stream, dtype=np.uint8)
+    for cap in (0, 1000, 29_000_000, len(d) - 1):
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = c.lib.bz2b200_decompress_stream(c.h, src.ctypes.data_as(C.c_void_p), len(stream), out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+        assert rc == api.E_OUTPUT and n.value == len(d), (cap, n.value)
+    ns = C.c_uint64(0)
+    n = C.c_size_t(0)
+    out = np.zeros(100, dtype=np.uint8)
+    rc = c.lib.bz2b200_decompress_concat(c.h, src.ctypes.data_as(C.c_void_p), len(stream), out.ctypes.data_as(C.c_void_p), 100, C.byref(n), C.byref(ns))
+    assert rc == api.E_OUTPUT and n.value == len(d) + 14000
+    assert c.decompress(stream) == d                                  # (the binding retries with the reported size)
+    assert c.decompress(stream, multi=True) == d + b"second stream " * 1000
+    c.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------- crafted streams
 class _Bits:
     def __init__(self):
