@@ -151,6 +151,33 @@ def run_reference(args, rank):
     emit_line(line)
 
 
+def build_roofline(ktimes, prof_steps, ms_dev, stats):
+    """roofline of the dominant main-stream kernel from per-kernel CUDA-event times (profiled passes, batches one at a time)"""
+    peak, peak_src = load_peaks()
+    side_stream = ("k_rle_walk", "k_rle_tile_seg", "k_rle_reduce")   # overlapped with the main-stream kernels: not part of the step's critical path
+    top = max(((k, v) for k, v in ktimes.items() if k not in side_stream), key=lambda kv: kv[1][0])
+    name, (k_ms, k_n, k_bytes) = top
+    achieved = (k_bytes / 1e9) / (k_ms / 1e3) if k_ms > 0 and k_bytes else None
+    step_kernel_ms = sum(v[0] for v in ktimes.values()) / prof_steps
+    # DRAM traffic of that kernel per launch from the committed ncu capture of the N = 1 command (profiles/), if there is one
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if name in tj["kernels"]:
+            traffic, traffic_src = int(tj["kernels"][name]["dram_bytes_per_launch"]), tj.get("source")
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "launches_per_step": k_n // prof_steps, "avg_launch_ms": round(k_ms / max(1, k_n), 4),
+            "share_of_step": round(k_ms / prof_steps / ms_dev, 4),
+            "algorithmic_bytes_per_launch": k_bytes // max(1, k_n),
+            "kernels_ms_per_step": {k: round(v[0] / prof_steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
+            "sum_kernel_ms_per_step": round(step_kernel_ms, 3),
+            "stage_ms_last_step": {k[3:]: round(float(stats[k]), 3) for k in ("ms_total", "ms_rle", "ms_bwt_sort0", "ms_bwt_rounds", "ms_bwt_finish", "ms_mtf",
+                                                                              "ms_huffman", "ms_emit", "ms_walk")}}
+
+
 def lcg_bytes_device(lo: int, hi: int, seed: int, device):
     """bytes [lo, hi) of corpus.rand_bytes(., seed) (config C4: top byte of the LCG state), generated on the GPU with the corpus
     module's own jump tables (the 64-bit products wrap in int64 exactly as in uint64)."""
@@ -354,6 +381,24 @@ def run_multi(args, rank, local_rank, world):
                                                                     sampler if name == "weak" else None)
         clocks = sampler.stop() if (rank == 0 and name == "weak") else None
         st = comp.stats()
+        if name == "weak":
+            # per-kernel times of rank 0's own slice (one profiled compress call outside the timed region): the roofline of the dominant
+            # kernel is a per-GPU figure and is reported as such
+            roof = None
+            if rank == 0:
+                own = src(job.lo, job.hi)
+                capo = comp.max_output_bytes(own.numel()) + 64
+                oo = torch.empty(capo, dtype=torch.uint8, device="cuda")
+                comp.set_profiling(True)
+                comp.compress_blocks_ptr(own.data_ptr(), own.numel(), oo.data_ptr(), capo)
+                torch.cuda.synchronize()
+                kt = comp.kernel_times()
+                comp.set_profiling(False)
+                pst = comp.stats()
+                roof = build_roofline(kt, 1, ms_dev, pst)
+                roof["what"] = "rank 0's slice compressed alone with CUDA events around every launch (one GPU); share_of_step is against the N-GPU step"
+                del own, oo
+            out["roofline"] = roof
         n_rle = sum_over_ranks(st["n_rle"])
         rho = sum_over_ranks(st["bwt_active_volume"]) / max(1.0, n_rle)
         walk_ms = max_over_ranks(float(st["ms_walk"]))
@@ -392,7 +437,9 @@ def run_multi(args, rank, local_rank, world):
                 "gpu_launches": w["launches"],
                 "strong": ({"workload": f"BASELINE config 4: {args.strong_mb} MiB of LCG bytes (corpus.rand_bytes, seed 4), one stream over {world} GPUs", **out["strong"]}
                            if "strong" in out else None),
-                "roofline": None, "cpu_baseline": None, "clocks": w["clocks"]}
+                "roofline": out.get("roofline"),
+                "cpu_baseline": None, "cpu_baseline_note": "measured at N = 1 only (bench contract): see the N = 1 line / --impl reference",
+                "clocks": w["clocks"]}
         line["config"]["phases_ms_per_rank"] = w["phases_ms_per_rank"]
         emit_line(line)
     dist.destroy_process_group()
@@ -527,29 +574,7 @@ def main():
     assert e2e_res["nbits"] == res["nbits"] and (e2e_res["crcs"] == res["crcs"]).all()
 
     # ---- roofline of the dominant kernel (summed CUDA-event time over the timed steps)
-    peak, peak_src = load_peaks()
-    side_stream = ("k_rle_walk", "k_rle_tile_seg", "k_rle_reduce")   # overlapped with the main-stream kernels: not part of the step's critical path
-    top = max(((k, v) for k, v in ktimes.items() if k not in side_stream), key=lambda kv: kv[1][0])
-    name, (k_ms, k_n, k_bytes) = top
-    achieved = (k_bytes / 1e9) / (k_ms / 1e3) if k_ms > 0 and k_bytes else None
-    step_kernel_ms = sum(v[0] for v in ktimes.values()) / prof_steps
-    # DRAM traffic of that kernel per launch from the committed ncu capture of this same command (profiles/), if there is one
-    traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if name in tj["kernels"]:
-            traffic, traffic_src = int(tj["kernels"][name]["dram_bytes_per_launch"]), tj.get("source")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "launches_per_step": k_n // prof_steps, "avg_launch_ms": round(k_ms / max(1, k_n), 4),
-                "share_of_step": round(k_ms / prof_steps / ms_dev, 4),
-                "algorithmic_bytes_per_launch": k_bytes // max(1, k_n),
-                "kernels_ms_per_step": {k: round(v[0] / prof_steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
-                "sum_kernel_ms_per_step": round(step_kernel_ms, 3),
-                "stage_ms_last_step": {k[3:]: round(float(stats[k]), 3) for k in ("ms_total", "ms_rle", "ms_bwt_sort0", "ms_bwt_rounds", "ms_bwt_finish", "ms_mtf",
-                                                                                  "ms_huffman", "ms_emit", "ms_walk")}}
+    roofline = build_roofline(ktimes, prof_steps, ms_dev, stats)
     n_rle_total = sum_over_ranks(stats["n_rle"])
     rho = sum_over_ranks(stats["bwt_active_volume"]) / max(1.0, n_rle_total)
 

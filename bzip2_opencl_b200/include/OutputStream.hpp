@@ -329,11 +329,11 @@ public:
             if (rc != BZ2B200_OK)
                 throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
         }
-        worker = std::thread([this] { workerMain(); });
-        writer = std::thread([this] { writerMain(); });
-        // stream header, reference :126-128
+        // stream header, reference :126-128 (before the threads exist: a throwing ostream must not leave them behind)
         const char hdr[4] = {'B', 'Z', 'h', static_cast<char>('0' + blockSizeMultiplier)};
         outputStream.write(hdr, 4);
+        worker = std::thread([this] { workerMain(); });
+        writer = std::thread([this] { writerMain(); });
     }
 
     OutputStream(const OutputStream &) = delete;
