@@ -1834,10 +1834,11 @@ static int multi_compress_blocks(bz2b200 *P, const uint8_t *input, size_t n_byte
                     pt.stats = c->stats;
                 }
             }
-        } else if (rc == BZ2B200_OK) {
+        } else { // nothing of this slice starts a block, or the chain failed upstream: the preparation is dropped
             cudaStreamSynchronize(c->side);
             cudaStreamSynchronize(c->h2d);
             c->prepared = false;
+            c->host_src = nullptr;
         }
         if (!published) chain_publish(ch, d + 1, s, rc, c->err); // nothing walked (or a failure): the chain passes through
         if (rc) chain_publish(ch, k + 1, 0, rc, c->err);
