@@ -265,6 +265,40 @@ private:
         target = target * 2 < cap - head ? target * 2 : cap - head;
     }
 
+    // threads joined (after their work is done), pinned buffers and the handle released; also the way out of a constructor that fails half way
+    void release()
+    {
+        if (worker.joinable())
+        {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return jobDone; });
+                quit = true;
+            }
+            cv.notify_all();
+            worker.join();
+        }
+        if (writer.joinable())
+        {
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return wDone; });
+                wQuit = true;
+            }
+            wcv.notify_all();
+            writer.join();
+        }
+        for (int i = 0; i < 2; ++i)
+        {
+            bz2b200_host_free(stage[i]);
+            bz2b200_host_free(outBuf[i]);
+            stage[i] = outBuf[i] = nullptr;
+        }
+        bz2b200_destroy(handle);
+        handle = nullptr;
+    }
+
+
 public:
     OutputStream(std::ostream &out, int blockSizeMultiplier, int parallelBlockCnt)
         : outputStream(out), streamBlockSize(BLOCKSIZE_DEFAULT * blockSizeMultiplier), parallelBlockCnt(parallelBlockCnt)
@@ -273,6 +307,20 @@ public:
             throw std::invalid_argument("Invalid block size");
         if (parallelBlockCnt < 1)
             throw std::invalid_argument("Invalid parallel block count");
+        try
+        {
+            construct(blockSizeMultiplier);
+        }
+        catch (...)
+        {
+            release(); // (a constructor that throws runs no destructor)
+            throw;
+        }
+    }
+
+private:
+    void construct(int blockSizeMultiplier)
+    {
         const std::vector<int> ids = deviceList();
         if (ids.empty())
             throw std::runtime_error("bz2b200_create: no CUDA device (a CUDA device is required; there is no CPU fallback)");
@@ -336,37 +384,11 @@ public:
         writer = std::thread([this] { writerMain(); });
     }
 
+public:
     OutputStream(const OutputStream &) = delete;
     OutputStream &operator=(const OutputStream &) = delete;
 
-    ~OutputStream()
-    {
-        if (worker.joinable())
-        {
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return jobDone; });
-                quit = true;
-            }
-            cv.notify_all();
-            worker.join();
-        }
-        if (writer.joinable())
-        {
-            {
-                std::unique_lock<std::mutex> lk(wmu);
-                wcv.wait(lk, [&] { return wDone; });
-                wQuit = true;
-            }
-            wcv.notify_all();
-            writer.join();
-        }
-        bz2b200_host_free(stage[0]);
-        bz2b200_host_free(stage[1]);
-        bz2b200_host_free(outBuf[0]);
-        bz2b200_host_free(outBuf[1]);
-        bz2b200_destroy(handle);
-    }
+    ~OutputStream() { release(); }
 
     void write(int value) // reference :131-142
     {
