@@ -79,7 +79,9 @@ def tail_of(last_two: bytes, nbits: int) -> int:
 def place_parts(nbits_all, tails_all, start_bit: int = 0):
     """Where every rank's bits go.  Returns [(bit offset, shift, carry byte, first stream byte, bytes to copy)] per rank:
     the part is shifted right by `shift` bits with `carry` (the trailing bits of the part in front) in the top of its first byte,
-    and copies `n_copy` bytes to stream byte `byte0`; the byte a later part starts in belongs to that later part."""
+    and copies `n_copy` bytes to stream byte `byte0`; the byte a later part starts in belongs to that later part.  A non-empty part
+    holds at least one block, i.e. more than the 7 bits a carry can be long (a block header alone is 105 bits)."""
+    assert all(int(nb) == 0 or int(nb) >= 8 for nb in nbits_all)
     k = len(nbits_all)
     off, pos = [], start_bit
     for nb in nbits_all:

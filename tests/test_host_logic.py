@@ -250,6 +250,37 @@ def test_byte_slices_chain_walk_and_bit_placement():
     assert multi.head_bytes(900000) >= 255 * ((900000 - 6) // 5 + 1)
 
 
+def test_bit_placement_of_parts_against_plain_bit_concatenation():
+    # property: parts of arbitrary bit lengths (some empty), packed from bit 0 each, shifted and placed as multi.place_parts says, give the
+    # bytes of the plain concatenation of all bits behind the 32 header bits
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        k = int(rng.integers(1, 9))
+        lens = [0 if rng.random() < 0.2 else int(rng.integers(9, 400)) for _ in range(k)]
+        bits = [rng.integers(0, 2, n).astype(np.uint8) for n in lens]
+        packed = [np.packbits(b).tobytes() for b in bits]
+        tails = [multi.tail_of(p[max(0, ((n - 1) >> 3) - 1):((n - 1) >> 3) + 1], n) if n else 0 for p, n in zip(packed, lens)]
+        placement = multi.place_parts(lens, tails, 32)
+        shifted = [multi.shift_bits_host(p, n, pl[1], pl[2]) for p, n, pl in zip(packed, lens, placement)]
+        body = bytearray(4)
+        for (off, shift, carry, byte0, n_copy), sh in zip(placement, shifted):
+            if n_copy:
+                assert byte0 == len(body)
+                body += sh[:n_copy]
+        allbits = np.concatenate([np.zeros(32, dtype=np.uint8)] + bits) if sum(lens) else np.zeros(32, dtype=np.uint8)
+        assert bytes(body) == np.packbits(allbits).tobytes(), (trial, lens)
+        # and the trailer continues the last partial byte
+        if sum(lens):
+            end_bit = 32 + sum(lens)
+            last = body[-1] if end_bit & 7 else 0
+            tr = multi.trailer_bytes(end_bit, last, 0xdeadbeef)
+            tail_bits = np.unpackbits(np.frombuffer(tr, dtype=np.uint8))
+            used = end_bit & 7
+            want = np.concatenate([allbits[len(allbits) - used:] if used else np.zeros(0, dtype=np.uint8),
+                                   np.unpackbits(np.frombuffer((0x177245385090).to_bytes(6, "big") + (0xdeadbeef).to_bytes(4, "big"), dtype=np.uint8))])
+            assert (tail_bits[:len(want)] == want).all() and not tail_bits[len(want):].any()
+
+
 WORKER2 = r'''
 import os, sys
 sys.path.insert(0, {root!r})
