@@ -286,13 +286,22 @@ def one_stream_job(comp, job, make_dev, make_host, steps, warmup, rank, world, b
     for _ in range(steps):
         r2 = step_e2e()
     ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0)) / steps
+    e2e_phases = dict(job.phases)
     assert r2["nbits_all"] == res["nbits_all"] and r2["crc"] == res["crc"]
     assert torch.equal(hout[:r2["n_copy"]].cuda(), job.shifted[:r2["n_copy"]])
-    del hbuf, hout
-    # host-clock phases of the last device-resident step, every rank's (the chain shows as wait_for_start growing with the rank)
-    allp = [None] * world
+    # the end-to-end parts assembled once more (untimed) must be the stream of the device-resident steps, byte for byte
+    dst2 = torch.zeros(total_cap if rank == 0 else 16, dtype=torch.uint8, device="cuda")
+    n2 = job.gather_device(r2, dst2)
+    same = bool(n2 == nbytes and torch.equal(dst2[:n2], dst[:nbytes])) if rank == 0 else True
+    del hbuf, hout, dst2
+    # host-clock phases of the last device-resident and of the last end-to-end step, every rank's (the chain shows as wait_for_start
+    # growing with the rank; with host buffers a rank's walk cannot end before its slice has been copied)
+    allp, alle = [None] * world, [None] * world
     dist.all_gather_object(allp, phases)
+    dist.all_gather_object(alle, e2e_phases)
     res["phases_ms_per_rank"] = allp
+    res["e2e_phases_ms_per_rank"] = alle
+    res["e2e_stream_equals_device_stream"] = same
     return ms_dev, ms_e2e, res, dst, nbytes, launches
 
 
@@ -414,6 +423,7 @@ def run_multi(args, rank, local_rank, world):
                          "stream_bytes": int(nbytes), "blocks_per_rank": res["blocks_all"], "slice_bytes_per_rank": [hi - lo for _, lo, hi in job.plan],
                          "halo_bytes": multi.head_bytes(comp.block_size), "slice_ratio": ratio, "rho_prefix_doubling": round(rho, 3),
                          "walk_ms_max_rank": round(walk_ms, 3), "launches": launches_all, "clocks": clocks, "phases_ms_per_rank": res.get("phases_ms_per_rank"),
+                         "e2e_phases_ms_per_rank": res.get("e2e_phases_ms_per_rank"), "e2e_stream_equals_device_stream": res.get("e2e_stream_equals_device_stream"),
                          "sha256_n_gpu_stream": multi_sha, "sha256_1_gpu_stream": ref[0],
                          "parity_check": ("sha256(N-GPU stream) == sha256(1-GPU stream)" if same else "MISMATCH between the N-GPU and the 1-GPU stream")}
         barrier()
@@ -441,6 +451,8 @@ def run_multi(args, rank, local_rank, world):
                 "cpu_baseline": None, "cpu_baseline_note": "measured at N = 1 only (bench contract): see the N = 1 line / --impl reference",
                 "clocks": w["clocks"]}
         line["config"]["phases_ms_per_rank"] = w["phases_ms_per_rank"]
+        line["e2e"]["phases_ms_per_rank"] = w["e2e_phases_ms_per_rank"]
+        line["e2e"]["stream_equals_device_stream"] = w["e2e_stream_equals_device_stream"]
         emit_line(line)
     dist.destroy_process_group()
     return 0
