@@ -51,6 +51,15 @@ def test_c_abi_exports_every_declared_symbol():
     assert set(api.EXPORTS) <= declared
 
 
+def test_header_is_plain_c99_and_links(tmp_path):
+    # the boundary is a C ABI: a C99 translation unit (-pedantic -Werror) includes the header, binds the new entry points and links
+    exe = str(tmp_path / "c_abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(HOST, "c_abi_check.c"), "-L" + os.path.join(ROOT, "bzip2_opencl_b200"), "-lbz2b200", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "bzip2_opencl_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    assert subprocess.run([exe], env=env).returncode in (0, 1)   # (1: a device exists and pinned memory could be allocated)
+
+
 def test_c_abi_argument_errors_without_gpu():
     lib = api.load_library()
     h = C.c_void_p()
