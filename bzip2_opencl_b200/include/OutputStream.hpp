@@ -85,6 +85,7 @@ private:
     size_t leftBegin = 0, leftEnd = 0; // bytes of the finished job that belong to the next batch
     int leftBuf = 0;
     std::exception_ptr failure;
+    bool broken = false; // a batch failed: the exception has been thrown once, the stream is unusable from then on
 
     static std::vector<int> deviceList()
     {
@@ -120,7 +121,7 @@ private:
         if (rc != BZ2B200_OK)
             throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
         for (uint64_t i = 0; i < nblocks; ++i) // reference :201-202
-            streamCRC = ((streamCRC << 1) | (static_cast<unsigned int>(streamCRC) >> 31)) ^ static_cast<int>(blockCRCs[i]);
+            streamCRC = static_cast<int>(((static_cast<unsigned int>(streamCRC) << 1) | (static_cast<unsigned int>(streamCRC) >> 31)) ^ blockCRCs[i]);
         if (nbits)
         {
             // OR the carried bits into the top of the first byte, write whole bytes, keep the new carry
@@ -229,8 +230,11 @@ private:
         {
             std::exception_ptr f = failure;
             failure = nullptr;
+            broken = true;
             std::rethrow_exception(f);
         }
+        if (broken)
+            throw std::runtime_error("the stream failed earlier");
     }
 
     // hands the filled buffer to the worker (after the previous batch has finished: its unfinished tail goes in front) and

@@ -381,3 +381,67 @@ def test_cli_front_end_argument_handling(tmp_path):
     f.write_bytes(b"x")
     r = subprocess.run([exe, str(f), "-d"], env=env, capture_output=True)
     assert r.returncode == 1 and b".bz2 extenstion" in r.stderr and f.exists()
+
+
+def _build_stub_facade(tmp_path, sanitizer, base):
+    """the OutputStream facade over tests/host/stub_abi.c (the oracle behind the C ABI's names) -- the facade's host pipeline without a GPU"""
+    exe = str(tmp_path / f"facade_stub_{sanitizer.split(',')[0]}_{base}")
+    obj = []
+    for src, cc, std in (("stub_abi.c", "gcc", "-std=c11"), (os.path.join(ROOT, "oracle", "bz2_oracle.c"), "gcc", "-std=c11")):
+        o = str(tmp_path / (os.path.basename(src) + f".{sanitizer.split(',')[0]}.o"))
+        subprocess.check_call([cc, std, "-O1", "-g", "-fsanitize=" + sanitizer, "-I" + os.path.join(ROOT, "include"), "-c",
+                               src if os.path.isabs(src) else os.path.join(HOST, src), "-o", o])
+        obj.append(o)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-fsanitize=" + sanitizer, f"-DBZ2B200_BLOCKSIZE_DEFAULT={base}",
+                           "-I" + os.path.join(ROOT, "bzip2_opencl_b200", "include"), "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(HOST, "facade_stub_driver.cpp"), *obj, "-lpthread", "-o", exe])
+    return exe
+
+
+def _facade_stub_data():
+    # several batches at base 2000: text, long runs that cross batch edges (the carried-over bytes), random bytes, a run at the very end
+    return (corpus.word_text(30000, 3) + b"\x00" * 70000 + corpus.rand_bytes(20000, 4) + b"ab" * 9000 + b"\xff" * 3000 + corpus.code_text(25000, 5)
+            + b"z" * 1021)
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_facade_host_pipeline_over_a_stub_abi(tmp_path, sanitizer):
+    """SURVEY N2 on the CPU: batching, the unfinished block carried into the next batch, the < 8 carried bits, the worker and writer
+    threads and readFrom(), with the oracle answering behind the C ABI's names, under ThreadSanitizer and AddressSanitizer/UBSan.
+    Every way of feeding the stream gives the oracle's stream, for several batch sizes."""
+    base = 2000
+    exe = _build_stub_facade(tmp_path, sanitizer, base)
+    data = _facade_stub_data()
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1")
+    for mult, blocks, mode in ((1, 3, "mixed"), (1, 1, "fd"), (3, 2, "byte"), (9, 4, "vec"), (2, 7, "ptr"), (9, 50, "fd")):
+        want = oracle.compress(data, mult, base)
+        dst = tmp_path / f"out_{mult}_{blocks}_{mode}.bz2"
+        r = subprocess.run([exe, mode, str(src), str(dst), str(mult), "1"], env=dict(env, BZ2B200_FACADE_BLOCKS=str(blocks), STUB_TRACE="1"),
+                           capture_output=True)
+        assert r.returncode == 0, (mult, blocks, mode, r.stderr.decode()[-2000:])
+        assert dst.read_bytes() == want, (mult, blocks, mode)
+        calls = int(re.search(rb"stub: (\d+) compress_blocks calls", r.stderr).group(1))
+        if blocks * base * mult * 4 < len(data):
+            assert calls > 3, (calls, mult, blocks)   # really several batches (1 call is the constructor's empty one)
+    # an empty stream and a one-byte stream
+    for payload in (b"", b"q"):
+        src.write_bytes(payload)
+        dst = tmp_path / "small.bz2"
+        r = subprocess.run([exe, "byte", str(src), str(dst), "9", "4"], env=env, capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        assert dst.read_bytes() == oracle.compress(payload, 9, base)
+
+
+def test_facade_reports_a_failed_batch_and_shuts_down(tmp_path):
+    """a batch that fails inside the worker thread surfaces as std::runtime_error in the caller (write or close), and the destructor still
+    joins both threads; with the failure in the very first (constructor) call, the constructor throws and leaves nothing behind"""
+    exe = _build_stub_facade(tmp_path, "address,undefined", 2000)
+    src = tmp_path / "in.bin"
+    src.write_bytes(_facade_stub_data())
+    for k in (1, 2, 3, 5):
+        r = subprocess.run([exe, "fail", str(src), str(tmp_path / "o.bz2"), "1", "1"],
+                           env=dict(os.environ, BZ2B200_FACADE_BLOCKS="2", STUB_FAIL_CALL=str(k), ASAN_OPTIONS="detect_leaks=1"), capture_output=True, timeout=120)
+        assert r.returncode == 0, (k, r.stdout, r.stderr.decode()[-2000:])
+        assert b"injected failure in call %d" % k in r.stdout
