@@ -21,7 +21,9 @@
 #ifndef OUTPUT_STREAM_HPP
 #define OUTPUT_STREAM_HPP
 
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +58,13 @@ private:
     size_t head = 0, cap = 0; // new input goes to [head, cap)
     size_t target = 0;        // bytes of new input that make a batch: small at first (the GPUs start early), then doubling up to cap - head
     size_t limit() const { return head + target; }
+    size_t maxTarget() const { return cap - head; }
+    int readers = 8;          // threads readFrom() copies a regular file with (BZ2B200_FACADE_READERS)
+    size_t parallelReadMin = size_t(8) << 20; // shorter reads are not worth the threads (BZ2B200_FACADE_READ_MIN, bytes; tests lower it)
+    size_t firstTarget = 0;   // readFrom() on a regular file: the first batch (short: the GPUs start early), the rest in equal batches
+    bool trace = false;       // BZ2B200_FACADE_TRACE=1: a host-clock timeline of batches on stderr (development aid)
+    double t0ms = 0;
+    static double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     int cur = 0;              // buffer being filled
     size_t fill = 0;          // next free byte in stage[cur]
     uint8_t *outBuf[2] = {nullptr, nullptr}; // pinned: packed bits of a batch; one is written to the ostream while the next batch fills the other
@@ -116,8 +125,12 @@ private:
     {
         uint64_t nbits = 0, nblocks = 0;
         size_t consumed = 0;
+        const double tc = trace ? nowMs() : 0;
         int rc = bz2b200_compress_blocks(handle, buf + begin, end - begin, final ? 1 : 0, static_cast<unsigned>(carryCount), outBits, outCap, &nbits,
                                          &consumed, blockCRCs.data(), nullptr, blockCRCs.size(), &nblocks);
+        if (trace)
+            std::fprintf(stderr, "[facade %8.2f] batch of %zu bytes compressed in %.2f ms (%llu blocks, %zu bytes carried over)\n", nowMs() - t0ms, end - begin,
+                         nowMs() - tc, static_cast<unsigned long long>(nblocks), end - begin - consumed);
         if (rc != BZ2B200_OK)
             throw std::runtime_error(std::string(bz2b200_strerror(rc)) + ": " + bz2b200_last_error(handle));
         for (uint64_t i = 0; i < nblocks; ++i) // reference :201-202
@@ -241,7 +254,10 @@ private:
     // goes on with the other buffer
     void submit(bool final)
     {
+        const double tw = trace ? nowMs() : 0;
         waitIdle();
+        if (trace)
+            std::fprintf(stderr, "[facade %8.2f] submit: %zu new bytes, waited %.2f ms for the batch in front\n", nowMs() - t0ms, fill - head, nowMs() - tw);
         size_t begin = head;
         const size_t left = leftEnd - leftBegin;
         if (left)
@@ -357,6 +373,27 @@ private:
         batch *= static_cast<size_t>(deviceCount);
         cap = head + batch;
         target = batch < (static_cast<size_t>(128) << 20) * static_cast<size_t>(deviceCount) ? batch : (static_cast<size_t>(128) << 20) * static_cast<size_t>(deviceCount);
+        // readFrom(): a regular file is copied out of the page cache by several threads (one thread moves 3-4 GB/s, a GPU compresses 10);
+        // its first batch is short, the rest of the file goes in equal batches
+        {
+            const unsigned hw = std::thread::hardware_concurrency();
+            // (half the cores, eight at most: measured on a 16-core B200 host, 8 threads already read 2-4 times faster than the GPU compresses,
+            // and 16 get in the way of the worker, lane and writer threads -- profiles/r02_facade_sweep.json)
+            readers = hw == 0 ? 8 : static_cast<int>(hw / 2 < 2 ? 2 : hw / 2 > 8 ? 8 : hw / 2);
+            if (const char *e = std::getenv("BZ2B200_FACADE_READERS"))
+                readers = std::atoi(e) > 0 ? (std::atoi(e) > 64 ? 64 : std::atoi(e)) : readers;
+            if (const char *e = std::getenv("BZ2B200_FACADE_READ_MIN"))
+                parallelReadMin = std::atol(e) > 0 ? static_cast<size_t>(std::atol(e)) : parallelReadMin;
+            size_t firstMb = 128;
+            if (const char *e = std::getenv("BZ2B200_FACADE_FIRST_MB"))
+                firstMb = std::atoi(e) > 0 ? static_cast<size_t>(std::atoi(e)) : firstMb;
+            firstTarget = (firstMb << 20) * static_cast<size_t>(deviceCount);
+            if (firstTarget > batch)
+                firstTarget = batch;
+            if (const char *e = std::getenv("BZ2B200_FACADE_TRACE"))
+                trace = std::atoi(e) != 0;
+            t0ms = nowMs();
+        }
         for (int i = 0; i < 2; ++i)
         {
             stage[i] = static_cast<uint8_t *>(bz2b200_host_alloc(cap));
@@ -439,10 +476,24 @@ public:
         {
             size_t pos = static_cast<size_t>(at);
             const size_t end = static_cast<size_t>(sb.st_size);
+            // the size is known: a short first batch, then what is left in equal batches (no small batch at the end, none larger than the buffers)
+            auto plan = [&](bool first) {
+                const size_t left = end > pos ? end - pos : 0;
+                if (fill != head || left == 0)
+                    return; // a batch is being filled already: it keeps its size
+                size_t t = first && firstTarget ? firstTarget : maxTarget();
+                if (!first || left <= t)
+                {
+                    const size_t k = (left + maxTarget() - 1) / maxTarget();
+                    t = ((left + k - 1) / k + 4095) / 4096 * 4096;
+                }
+                target = t < maxTarget() ? t : maxTarget();
+            };
+            plan(true);
             while (pos < end)
             {
                 const size_t n = end - pos < limit() - fill ? end - pos : limit() - fill;
-                const int T = n >= (size_t(8) << 20) ? 8 : 1;
+                const int T = n >= parallelReadMin ? readers : 1;
                 std::vector<std::thread> th;
                 bool ok = true;
                 uint8_t *dst = stage[cur] + fill;
@@ -465,7 +516,10 @@ public:
                 pos += n;
                 total += n;
                 if (fill == limit())
+                {
                     submit(false);
+                    plan(false);
+                }
             }
             ::lseek(fd, static_cast<off_t>(end), SEEK_SET);
             return total;

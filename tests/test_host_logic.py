@@ -418,7 +418,10 @@ def test_facade_host_pipeline_over_a_stub_abi(tmp_path, sanitizer):
     for mult, blocks, mode in ((1, 3, "mixed"), (1, 1, "fd"), (3, 2, "byte"), (9, 4, "vec"), (2, 7, "ptr"), (9, 50, "fd")):
         want = oracle.compress(data, mult, base)
         dst = tmp_path / f"out_{mult}_{blocks}_{mode}.bz2"
-        r = subprocess.run([exe, mode, str(src), str(dst), str(mult), "1"], env=dict(env, BZ2B200_FACADE_BLOCKS=str(blocks), STUB_TRACE="1"),
+        # (readFrom() with several reader threads even on this small file; a trace line per batch must not disturb anything)
+        r = subprocess.run([exe, mode, str(src), str(dst), str(mult), "1"], env=dict(env, BZ2B200_FACADE_BLOCKS=str(blocks), STUB_TRACE="1",
+                                                                                        BZ2B200_FACADE_READ_MIN="1000", BZ2B200_FACADE_READERS=str(1 + blocks % 5),
+                                                                                        BZ2B200_FACADE_TRACE=str(blocks & 1)),
                            capture_output=True)
         assert r.returncode == 0, (mult, blocks, mode, r.stderr.decode()[-2000:])
         assert dst.read_bytes() == want, (mult, blocks, mode)
@@ -445,3 +448,26 @@ def test_facade_reports_a_failed_batch_and_shuts_down(tmp_path):
                            env=dict(os.environ, BZ2B200_FACADE_BLOCKS="2", STUB_FAIL_CALL=str(k), ASAN_OPTIONS="detect_leaks=1"), capture_output=True, timeout=120)
         assert r.returncode == 0, (k, r.stdout, r.stderr.decode()[-2000:])
         assert b"injected failure in call %d" % k in r.stdout
+
+
+def test_facade_read_plan_short_first_batch_then_equal_batches(tmp_path):
+    """readFrom() on a regular file: a short first batch (BZ2B200_FACADE_FIRST_MB), the rest of the file in equal batches, several reader
+    threads -- the stream does not depend on any of it"""
+    base = 2000
+    exe = _build_stub_facade(tmp_path, "address,undefined", base)
+    data = _facade_stub_data() * 24          # 4.3 MB
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    want = oracle.compress(data, 9, base)
+    for first_mb, blocks in ((1, 70), (2, 70), (1, 200)):
+        dst = tmp_path / f"o_{first_mb}_{blocks}.bz2"
+        r = subprocess.run([exe, "fd", str(src), str(dst), "9", "1"], capture_output=True, timeout=600,
+                           env=dict(os.environ, BZ2B200_FACADE_BLOCKS=str(blocks), BZ2B200_FACADE_FIRST_MB=str(first_mb), BZ2B200_FACADE_READ_MIN="65536",
+                                    BZ2B200_FACADE_READERS="5", BZ2B200_FACADE_TRACE="1", ASAN_OPTIONS="detect_leaks=1"))
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        assert dst.read_bytes() == want
+        sizes = [int(m) for m in re.findall(rb"submit: (\d+) new bytes", r.stderr)]
+        assert sizes[0] == min(first_mb << 20, blocks * base * 9), sizes
+        rest = sizes[1:-1] if len(sizes) > 2 else []
+        assert all(abs(a - b) <= 4096 for a, b in zip(rest, rest[1:])), sizes      # equal batches
+        assert sum(sizes) == len(data), sizes
