@@ -222,6 +222,21 @@ def mixed_corpus(n: int, seg: int = 16 << 20, workers: int = 1) -> bytes:
     return b"".join(parts)
 
 
+def skewed_bytes(n: int, seed: int, alpha: int = 40, num: int = 5, den: int = 3) -> bytes:
+    """i.i.d. bytes 0..alpha-1 with P(i) proportional to (den/num)^i, thresholds in exact integer arithmetic.  With the default ratio 5/3
+    the symbol counts of a 900k block fall off like a Fibonacci sequence: an unrestricted Huffman code would be 21-22 bits deep, so the
+    length-limited allocator (HUFFMAN_ENCODE_MAXIMUM_CODE_LENGTH = 20, kernel.cpp:2748-2805) has to relocate nodes."""
+    if n == 0:
+        return b""
+    w = [den ** i * num ** (alpha - 1 - i) for i in range(alpha)]
+    tot, acc, thr = sum(w), 0, []
+    for x in w:
+        acc += x
+        thr.append((acc << 32) // tot)
+    u = LCG(seed).states(n) >> np.uint64(32)
+    return np.minimum(np.searchsorted(np.array(thr, dtype=np.uint64), u, side="right"), alpha - 1).astype(np.uint8).tobytes()
+
+
 def repetitive_corpus(n: int) -> bytes:
     """Config C3 scaled to n bytes (n/4 each): zeros; short periods + 'a' run; long-LCP text; near-periodic 'ab'."""
     q = n // 4

@@ -265,6 +265,22 @@ def test_alphabet_sizes_and_mixed_batches():
         assert (c.stage(b, api.STAGE_BWT) == o["L"]).all() and c.stage(b, api.STAGE_ORIGPTR)[0] == o["orig_ptr"]
 
 
+def test_code_lengths_limited_to_20_bits():
+    # symbol counts that fall off like Fibonacci numbers make a plain Huffman code 21-22 bits deep; the allocator's
+    # relocation path (kernel.cpp:2748-2805, huff.cuh mk_allocate) caps the lengths at 20.  tests/test_oracle.py shows that this input
+    # hits the limit and that the oracle equals the reference's own code on it.
+    d = corpus.skewed_bytes(880000, 1, 48, 13, 8) + corpus.skewed_bytes(880000, 2) + corpus.skewed_bytes(880000, 7)
+    c = comp(9, 100000, 4)
+    out = c.compress(d)
+    assert out == oracle.compress(d, 9, 100000)
+    assert bz2.decompress(out) == d
+    c.compress_blocks(d, True)
+    _stage_check(c, d, 9, 100000, [2])                          # the call's last block is resident: every stage, code lengths included
+    assert int(c.stage(2, api.STAGE_LENGTHS).max()) == 20
+    out2 = comp(9, 10000, 16).compress(d)                       # the stock base: 90k blocks, 30 of them
+    assert out2 == oracle.compress(d, 9, 10000)
+
+
 def test_lanes_never_change_the_stream(monkeypatch):
     # batches of a call run on 1..3 lanes (own stream + host thread each); the bit position passes from batch to batch in order,
     # so the stream, the per-block tables and the bytes drained so far are the same whatever the lane count or batch size

@@ -106,6 +106,57 @@ def test_oracle_equals_real_reference_on_the_alphabet_sweep():
             assert bz2.decompress(out) == d
 
 
+def length_limit_input() -> bytes:
+    # three 900k blocks whose MTF symbol counts fall off like Fibonacci numbers (tests/test_gpu_parity.py uses the same input)
+    return corpus.skewed_bytes(880000, 1, 48, 13, 8) + corpus.skewed_bytes(880000, 2) + corpus.skewed_bytes(880000, 7)
+
+
+def _unrestricted_depth(freqs) -> int:
+    import heapq
+    h = [(int(f), i, 0) for i, f in enumerate(freqs)]
+    heapq.heapify(h)
+    c = len(h)
+    while len(h) > 1:
+        a, b = heapq.heappop(h), heapq.heappop(h)
+        heapq.heappush(h, (a[0] + b[0], c, max(a[2], b[2]) + 1))
+        c += 1
+    return h[0][2]
+
+
+def test_length_limit_input_really_hits_the_20_bit_limit():
+    # the allocator caps code lengths at 20 (HUFFMAN_ENCODE_MAXIMUM_CODE_LENGTH, kernel.cpp:2748-2805).  On this input
+    # a plain Huffman code over a table's counts would be 21-22 bits deep, the coded lengths stop at 20, and the codes stay complete.
+    d = length_limit_input()
+    limited = 0
+    for b in range(3):
+        st = oracle.block_stages(d, b, 9, 100000)
+        a, mtf, sel, cl = st["alphabet_size"], st["mtf"], st["selectors"], st["code_lengths"]
+        for t in range(st["n_tables"]):
+            f = np.zeros(a, dtype=np.int64)
+            for g in np.nonzero(sel == t)[0]:
+                np.add.at(f, mtf[g * 50:(g + 1) * 50], 1)
+            lens = cl[t, :a].astype(np.int64)
+            assert lens.max() <= 20 and lens.min() >= 1
+            assert sum(1 << (20 - int(l)) for l in lens) == 1 << 20          # Kraft equality: a complete prefix code
+            if _unrestricted_depth(f) > 20:
+                limited += 1
+                assert lens.max() == 20
+    assert limited >= 3
+    assert bz2.decompress(oracle.compress(d, 9, 100000)) == d
+
+
+@pytest.mark.skipif(not have_ref(100000) or not have_ref(10000), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_real_reference_where_code_lengths_are_limited():
+    d = length_limit_input()
+    for mult, base in ((9, 100000), (9, 10000)):
+        out, offs, nonprim = oracle.compress_ex(d, mult, base)
+        ref = refimpl.compress(d, mult, base, threads=4)
+        assert not nonprim.any() and out == ref
+    for b in range(3):
+        o, r = oracle.block_stages(d, b, 9, 100000), refimpl.block_stages(d, b, 9, 100000)
+        assert (o["mtf"] == r["mtf"]).all() and (o["freq"] == r["freq"]).all() and (o["selectors"] == r["selectors"]).all()
+
+
 @pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built")
 def test_oracle_stage_dumps_equal_reference():
     d = corpus.word_text(250000, 77) + bytes(5000) + corpus.rand_bytes(40000, 3)
