@@ -265,6 +265,24 @@ def test_alphabet_sizes_and_mixed_batches():
         assert (c.stage(b, api.STAGE_BWT) == o["L"]).all() and c.stage(b, api.STAGE_ORIGPTR)[0] == o["orig_ptr"]
 
 
+def test_table_count_thresholds_and_unused_tables():
+    # one small block each: MTF lengths on both sides of 200 / 600 / 1200 / 2400 symbols (2 .. 6 tables, kernel.cpp:2808-2818) for alphabets
+    # of 2 .. 256 values; with few symbols most tables get no group at all.  Same list as tests/test_oracle.py::small_block_cases, where the
+    # oracle is pinned to the reference's own code on it.
+    c = comp(9, 100000, 2)
+    for alpha in (2, 3, 5, 30, 256):
+        for n in (1, 2, 3, 49, 50, 51, 99, 100, 101, 150, 197, 198, 199, 200, 201, 202, 597, 598, 599, 600, 601, 1197, 1198, 1199, 1200, 1201,
+                  2397, 2398, 2399, 2400, 2401, 2402, 3000, 5000):
+            raw = np.frombuffer(corpus.rand_bytes(n, 1000 * alpha + n), dtype=np.uint8).astype(np.int64)
+            d = (raw % alpha).astype(np.uint8).tobytes()
+            assert c.compress(d) == oracle.compress(d, 9, 100000), (alpha, n)
+    # and all of them as the blocks of ONE stream (base 1000: the C ABI's smallest block): batches of blocks with 2 .. 6 tables side by side
+    raw = np.frombuffer(corpus.rand_bytes(150_000, 4242), dtype=np.uint8).astype(np.int64)
+    d = b"".join((raw[i:i + 5000] % a).astype(np.uint8).tobytes() for i, a in zip(range(0, 150_000, 5000), [2, 3, 5, 30, 256, 4] * 5))
+    assert comp(1, 1000, 64).compress(d) == oracle.compress(d, 1, 1000)
+    assert comp(3, 1000, 7).compress(d) == oracle.compress(d, 3, 1000)
+
+
 def test_code_lengths_limited_to_20_bits():
     # symbol counts that fall off like Fibonacci numbers make a plain Huffman code 21-22 bits deep; the allocator's
     # relocation path (kernel.cpp:2748-2805, huff.cuh mk_allocate) caps the lengths at 20.  tests/test_oracle.py shows that this input

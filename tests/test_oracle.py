@@ -106,6 +106,33 @@ def test_oracle_equals_real_reference_on_the_alphabet_sweep():
             assert bz2.decompress(out) == d
 
 
+def small_block_cases():
+    # one small block each: MTF lengths on both sides of the table-count thresholds (selectTableCount, kernel.cpp:2808-2818: 200 / 600 /
+    # 1200 / 2400 symbols) for alphabets of 2 .. 256 values -- with few symbols most of the 2 .. 6 tables end up without a single group
+    # (all-zero counts).  tests/test_gpu_parity.py builds the same list.
+    cases = []
+    for alpha in (2, 3, 5, 30, 256):
+        for n in (1, 2, 3, 49, 50, 51, 99, 100, 101, 150, 197, 198, 199, 200, 201, 202, 597, 598, 599, 600, 601, 1197, 1198, 1199, 1200, 1201,
+                  2397, 2398, 2399, 2400, 2401, 2402, 3000, 5000):
+            raw = np.frombuffer(corpus.rand_bytes(n, 1000 * alpha + n), dtype=np.uint8).astype(np.int64)
+            cases.append((raw % alpha).astype(np.uint8).tobytes())
+    return cases
+
+
+@pytest.mark.skipif(not have_ref(100000), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_real_reference_around_the_table_count_thresholds():
+    seen, lengths = set(), set()
+    for d in small_block_cases():
+        assert oracle.compress(d, 9, 100000) == refimpl.compress(d, 9, 100000)
+        st = oracle.block_stages(d, 0, 9, 100000)
+        seen.add((st["n_tables"], len(set(st["selectors"].tolist()))))
+        lengths.add(st["mtf_length"])
+    assert {2, 3, 4, 5, 6} <= {t for t, _ in seen}
+    assert any(used < t for t, used in seen if t == 6) and any(used == 1 for _, used in seen)      # tables nobody selects
+    for edge in (200, 600, 1200, 2400):
+        assert {edge - 1, edge, edge + 1} <= lengths
+
+
 def length_limit_input() -> bytes:
     # three 900k blocks whose MTF symbol counts fall off like Fibonacci numbers (tests/test_gpu_parity.py uses the same input)
     return corpus.skewed_bytes(880000, 1, 48, 13, 8) + corpus.skewed_bytes(880000, 2) + corpus.skewed_bytes(880000, 7)
