@@ -459,6 +459,25 @@ def test_decompress_matches_libbzip2_and_reference_decoder():
     assert comp(9, 10000, 16).decompress(s) == d
 
 
+def test_decompress_long_codes_and_degenerate_tables():
+    # the decoder's lookup window is 10 bits: 20-bit codes (the allocator's limit, above libbzip2's 17) go through the limit search; small
+    # blocks carry tables nobody selects (all-zero counts) next to used ones.  Streams of the oracle (= the reference's own bytes).
+    c = comp(9, 100000, 4)
+    d = corpus.skewed_bytes(880000, 1, 48, 13, 8) + corpus.skewed_bytes(880000, 2) + corpus.skewed_bytes(880000, 7)
+    assert c.decompress(oracle.compress(d, 9, 100000)) == d
+    if have_ref(100000):
+        assert refimpl.decompress(c.compress(d), len(d) + 16, 100000) == d
+    for alpha in (2, 3, 5, 30, 256):
+        for n in (1, 3, 50, 199, 200, 201, 599, 600, 601, 1199, 1200, 1201, 2399, 2400, 2401, 5000):
+            raw = np.frombuffer(corpus.rand_bytes(n, 1000 * alpha + n), dtype=np.uint8).astype(np.int64)
+            x = (raw % alpha).astype(np.uint8).tobytes()
+            assert c.decompress(oracle.compress(x, 9, 100000)) == x, (alpha, n)
+    raw = np.frombuffer(corpus.rand_bytes(150_000, 4242), dtype=np.uint8).astype(np.int64)
+    x = b"".join((raw[i:i + 5000] % a).astype(np.uint8).tobytes() for i, a in zip(range(0, 150_000, 5000), [2, 3, 5, 30, 256, 4] * 5))
+    c1 = comp(1, 1000, 64)                                      # 152 one-kilobyte blocks, 2 .. 6 tables side by side in the batches
+    assert c1.decompress(oracle.compress(x, 1, 1000)) == x
+
+
 def test_decompress_device_pointers_and_batches():
     import torch
     d = corpus.mixed_corpus(12 << 20, 2 << 20)
