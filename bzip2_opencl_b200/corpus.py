@@ -237,6 +237,33 @@ def skewed_bytes(n: int, seed: int, alpha: int = 40, num: int = 5, den: int = 3)
     return np.minimum(np.searchsorted(np.array(thr, dtype=np.uint64), u, side="right"), alpha - 1).astype(np.uint8).tobytes()
 
 
+def run_fuzz(n: int, seed: int) -> bytes:
+    """About n bytes of run-structured noise for the parity fuzz tests: runs whose lengths sit on the RLE1 edges (3/4/5, 254..261, 510..515:
+    BlockCompressor.hpp:134-154 writes a run as 4 bytes + count, at most 255 + 4 per chunk), literal stretches over small and full alphabets,
+    short periods, and copies of earlier stretches -- so that block ends fall into every phase of a run."""
+    g = LCG(seed)
+    edges = (1, 2, 3, 4, 5, 6, 7, 254, 255, 256, 257, 258, 259, 260, 261, 262, 300, 510, 513, 514, 515, 516, 1000, 2600)
+    out = bytearray()
+    while len(out) < n:
+        kind, a, b, c = (int(v) for v in g.draws(4))
+        if kind % 5 == 0:
+            out += bytes([a & 0xff]) * edges[b % len(edges)]
+        elif kind % 5 == 1:
+            k = 1 + c % 400
+            alpha = (2, 3, 4, 16, 256)[b % 5]
+            out += bytes((int(v) % alpha + (a & 0x3f)) & 0xff for v in g.draws(k))
+        elif kind % 5 == 2:
+            p = 1 + b % 7
+            pat = bytes((a + 31 * i) & 0xff for i in range(p))
+            out += (pat * (c % 300 // p + 2))[:c % 300 + 1]
+        elif kind % 5 == 3 and len(out) > 16:
+            lo = a % (len(out) - 8)
+            out += out[lo:lo + 1 + b % 700]
+        else:
+            out += bytes([a & 0xff]) * (1 + b % 9) + bytes([c & 0xff])
+    return bytes(out[:n])
+
+
 def repetitive_corpus(n: int) -> bytes:
     """Config C3 scaled to n bytes (n/4 each): zeros; short periods + 'a' run; long-LCP text; near-periodic 'ab'."""
     q = n // 4

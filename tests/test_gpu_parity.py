@@ -283,6 +283,27 @@ def test_table_count_thresholds_and_unused_tables():
     assert comp(3, 1000, 7).compress(d) == oracle.compress(d, 3, 1000)
 
 
+def test_run_structured_fuzz():
+    # corpus.run_fuzz (run lengths on the RLE1 edges 3/4/5, 254..262, 510..516, small alphabets, short periods, copies of earlier stretches):
+    # one-kilobyte to 90k blocks, so that block ends fall into every phase of a run and the sort meets every kind of tie.  The oracle is pinned
+    # to the reference's own code on the same generator in tests/test_oracle.py.
+    blocks = 0
+    for i in range(60):
+        d = corpus.run_fuzz(20000 + 1777 * i, 9000 + i)
+        for mult, base, par in ((1, 1000, 64), (1 + i % 9, 1000, 5), (1 + (i * 5) % 9, 10000, 3)):
+            c = comp(mult, base, par)
+            r = c.compress_blocks(d)
+            out = c.compress(d)
+            assert out == oracle.compress(d, mult, base), (i, mult, base)
+            starts, lens, crcs = oracle.rle1_blocks(d, mult, base)
+            assert (r["crcs"] == crcs).all()
+            blocks += len(crcs)
+    assert blocks > 2500
+    d = corpus.run_fuzz(3_000_000, 77)                           # and at real block sizes
+    for mult in (1, 9):
+        assert comp(mult, 100000, 8).compress(d) == oracle.compress(d, mult, 100000)
+
+
 def test_code_lengths_limited_to_20_bits():
     # symbol counts that fall off like Fibonacci numbers make a plain Huffman code 21-22 bits deep; the allocator's
     # relocation path (kernel.cpp:2748-2805, huff.cuh mk_allocate) caps the lengths at 20.  tests/test_oracle.py shows that this input

@@ -133,6 +133,24 @@ def test_oracle_equals_real_reference_around_the_table_count_thresholds():
         assert {edge - 1, edge, edge + 1} <= lengths
 
 
+@pytest.mark.skipif(not have_ref(10000) or not have_ref(100000), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_real_reference_on_run_structured_fuzz():
+    # corpus.run_fuzz: run lengths on the RLE1 edges, small alphabets, short periods, copies -- block ends in every phase of a run
+    # (tests/test_gpu_parity.py::test_run_structured_fuzz compares the CUDA path with the oracle on the same generator)
+    blocks = 0
+    for i in range(40):
+        d = corpus.run_fuzz(60000 + 3001 * i, 9000 + i)
+        for mult, base in ((1, 10000), (1 + i % 9, 10000), (1, 100000)):
+            out, offs, nonprim = oracle.compress_ex(d, mult, base)
+            ref = refimpl.compress(d, mult, base, threads=2)
+            assert oracle.mask_origptr(out, offs, nonprim) == oracle.mask_origptr(ref, offs, nonprim), (i, mult, base)
+            s1, l1, c1 = oracle.rle1_blocks(d, mult, base)
+            s2, l2, c2 = refimpl.rle1_blocks(d, mult, base)
+            assert (s1 == s2).all() and (l1 == l2).all() and (c1 == c2).all()
+            blocks += len(offs)
+    assert blocks > 350
+
+
 def length_limit_input() -> bytes:
     # three 900k blocks whose MTF symbol counts fall off like Fibonacci numbers (tests/test_gpu_parity.py uses the same input)
     return corpus.skewed_bytes(880000, 1, 48, 13, 8) + corpus.skewed_bytes(880000, 2) + corpus.skewed_bytes(880000, 7)
