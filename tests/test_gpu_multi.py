@@ -193,6 +193,20 @@ def test_multi_device_handle_long_runs_and_tiny_inputs():
     m.close()
 
 
+def test_multi_device_handle_on_run_structured_fuzz(monkeypatch):
+    # corpus.run_fuzz through the slice chain: slice edges (multiples of 4096) fall into runs, count bytes and period stretches, and every
+    # device starts its walk from the state the prefix tables give it at the position the device in front handed on
+    for ratio in ("0.95", "0.6"):
+        monkeypatch.setenv("BZ2B200_MULTI_RATIO", ratio)
+        for ndev in (2, 5):
+            m = api.Compressor(1, 6, 1000, devices=_devices(ndev))
+            for i in range(12):
+                d = corpus.run_fuzz(90_000 + 7919 * i, 500 + i)
+                assert m.compress(d) == oracle.compress(d, 1, 1000), (ratio, ndev, i)
+                assert (m.scan_blocks(d) == oracle.rle1_blocks(d, 1, 1000)[0]).all()
+            m.close()
+
+
 def test_multi_device_handle_900k_blocks_device_pointers():
     import torch
     d = corpus.mixed_corpus(96 << 20, 1 << 22)
