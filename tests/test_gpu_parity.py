@@ -499,6 +499,17 @@ def test_decompress_long_codes_and_degenerate_tables():
     assert c1.decompress(oracle.compress(x, 1, 1000)) == x
 
 
+def test_decompress_run_structured_fuzz():
+    # the inverse of RLE1 on run lengths around its edges (count bytes 0, 1, 250, 251 and chunks of 255 + 4), small blocks and real ones
+    for i in range(25):
+        d = corpus.run_fuzz(30_000 + 4111 * i, 300 + i)
+        for mult, base, par in ((1, 1000, 64), (1 + i % 9, 10000, 4)):
+            assert comp(mult, base, par).decompress(oracle.compress(d, mult, base)) == d, (i, mult, base)
+    d = corpus.run_fuzz(2_500_000, 78)
+    assert comp(9, 100000, 4).decompress(oracle.compress(d, 9, 100000)) == d
+    assert comp(9, 100000, 4).decompress(bz2.compress(d, 5)) == d
+
+
 def test_decompress_device_pointers_and_batches():
     import torch
     d = corpus.mixed_corpus(12 << 20, 2 << 20)
