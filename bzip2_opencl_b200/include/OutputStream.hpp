@@ -463,7 +463,7 @@ public:
     }
 
     // extension: everything the file descriptor still holds, read straight into the staging buffers (no intermediate copy).
-    // A regular file is read by eight threads at once (pread on disjoint ranges: one thread copies out of the page cache at a
+    // A regular file is read by `readers` threads at once (pread on disjoint ranges: one thread copies out of the page cache at a
     // few GB/s, less than a GPU compresses).
     size_t readFrom(int fd)
     {
